@@ -1,0 +1,129 @@
+// common.cuh -- shared host/device helpers for libigneous_b200 (sm_100a only)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/igneous_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libigneous_b200 targets sm_100a (Blackwell B200) only"
+#endif
+
+namespace ign {
+
+void set_error(const char* fmt, ...);
+
+#define IGN_CUDA(call)                                                          \
+  do {                                                                          \
+    cudaError_t _e = (call);                                                    \
+    if (_e != cudaSuccess) {                                                    \
+      ign::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,              \
+                     cudaGetErrorString(_e));                                   \
+      return IGN_ERR_CUDA;                                                      \
+    }                                                                           \
+  } while (0)
+
+#define IGN_TRY(call)                 \
+  do {                                \
+    int _s = (call);                  \
+    if (_s != IGN_OK) return _s;      \
+  } while (0)
+
+#define IGN_REQUIRE(cond, status, ...)   \
+  do {                                   \
+    if (!(cond)) {                       \
+      ign::set_error(__VA_ARGS__);       \
+      return (status);                   \
+    }                                    \
+  } while (0)
+
+static inline int dtype_size(int dt) {
+  switch (dt) {
+    case IGN_U8: return 1;
+    case IGN_U16: return 2;
+    case IGN_U32: return 4;
+    case IGN_U64: return 8;
+    case IGN_F32: return 4;
+    default: return 0;
+  }
+}
+
+}  // namespace ign
+
+// grow-only device scratch arena, bump allocated per API call
+struct ign_ctx {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  cudaStream_t copy_stream;
+  char* scratch;
+  size_t scratch_bytes;
+  size_t scratch_used;
+  char* pinned;  // staging for scalars / small results
+  size_t pinned_bytes;
+  cudaEvent_t timers[16][2];
+  uint64_t launches;
+};
+
+namespace ign {
+
+// Make `ctx->device` current (one ctx per process is the contract, but be safe).
+int activate(ign_ctx* ctx);
+// Reset the bump pointer; call at the start of every public API function.
+void scratch_reset(ign_ctx* ctx);
+// Bump-allocate `bytes` (256B aligned) from the arena.  The arena never moves
+// while allocations of the current call are alive: scratch_reserve() must be
+// called first with the total the call needs.
+int scratch_reserve(ign_ctx* ctx, size_t total_bytes);
+void* scratch_take(ign_ctx* ctx, size_t bytes);
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// launch bookkeeping: every kernel launch in this library goes through
+// IGN_LAUNCH so ign_launch_count() is exact.
+#define IGN_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
+  do {                                                                           \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
+    (ctx)->launches++;                                                           \
+    IGN_CUDA(cudaGetLastError());                                                \
+  } while (0)
+
+static inline unsigned blocks_for(uint64_t n, unsigned threads) {
+  return (unsigned)((n + threads - 1) / threads);
+}
+
+}  // namespace ign
+
+// ------------------------------------------------------------------ device
+#ifdef __CUDACC__
+namespace ign {
+
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  // streaming 128-bit load: read-only path, do not allocate in L1
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(void* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream(void* p, uint2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y)
+               : "memory");
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+}  // namespace ign
+#endif

@@ -1,0 +1,77 @@
+"""Drop-in for the `tinybrain` calls on the igneous hot path, running on B200.
+
+Reference call sites (seung-lab/igneous):
+  igneous/tasks/image/image.py:46-55  downsample_method_to_fn binds
+      tinybrain.downsample_with_averaging / downsample_segmentation (+sparse)
+  igneous/tasks/image/image.py:91     mips = fn(image, factors[0], num_mips=num_mips)
+
+Same names, argument meaning and return convention (a list of `num_mips`
+Fortran-ordered arrays with the input's number of dimensions).  Everything is
+computed by libigneous_b200 on the GPU; there is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _shim
+
+__all__ = ["downsample_segmentation", "downsample_with_averaging"]
+
+# upstream render rule for integer averaging; parity unpinned offline
+# (SURVEY.md 8(c)), so it stays a runtime knob.
+DEFAULT_ROUNDING = _shim.ROUND_FLOOR
+
+
+def _check_factor(factor):
+  f = tuple(int(v) for v in factor)
+  if f[:3] != (2, 2, 1) or any(v != 1 for v in f[3:]):
+    raise NotImplementedError(
+      "igneous_b200 pooling implements factor (2,2,1) only (got %r); "
+      "2x2x2 / striding / min / max pooling are listed as next rows in DESIGN.md" % (factor,))
+
+
+def _out_shapes(shape, num_mips):
+  shapes = []
+  sx, sy = shape[0], shape[1]
+  for _ in range(num_mips):
+    sx, sy = (sx + 1) // 2, (sy + 1) // 2
+    shapes.append((sx, sy) + tuple(shape[2:]))
+  return shapes
+
+
+def _pool(img, factor, num_mips, mode, flag, ctx):
+  _check_factor(factor)
+  num_mips = int(num_mips)
+  if num_mips < 1:
+    return []
+  img = np.asarray(img)
+  ndim = img.ndim
+  arr, sx, sy, nz = _shim.as_fortran_volume(img)
+  code = _shim.dtype_code(arr.dtype)
+  if not mode and code == _shim.IGN_U64:
+    raise NotImplementedError("igneous_b200 averaging: uint64 images are not supported")
+  ctx = ctx or _shim.default_context()
+  shapes = _out_shapes(arr.shape, num_mips)
+  outs = [np.empty(s, dtype=arr.dtype, order="F") for s in shapes]
+  if arr.size:
+    fn = ctx.lib.ign_pool_mode_2x2x1 if mode else ctx.lib.ign_pool_avg_2x2x1
+    _shim.check(fn(ctx.handle, _shim.ptr(arr), ctypes.c_int(code), ctypes.c_uint64(sx),
+                   ctypes.c_uint64(sy), ctypes.c_uint64(nz), ctypes.c_int(num_mips),
+                   ctypes.c_int(int(flag)), _shim.void_pp([o.ctypes.data for o in outs])))
+  if ndim == 2:
+    outs = [o[:, :, 0] for o in outs]
+  return outs
+
+
+def downsample_segmentation(img, factor, num_mips=1, sparse=False, ctx=None):
+  """2x2x1 mode pooling pyramid (COUNTLESS 2-D, recursive per mip)."""
+  return _pool(img, factor, num_mips, True, bool(sparse), ctx)
+
+
+def downsample_with_averaging(img, factor, num_mips=1, sparse=False, ctx=None,
+                              rounding=None):
+  """2x2x1 average pooling pyramid (exact sums in groups of four mips)."""
+  if sparse:
+    raise NotImplementedError("igneous_b200 averaging: sparse=True is not implemented")
+  return _pool(img, factor, num_mips, False,
+               DEFAULT_ROUNDING if rounding is None else rounding, ctx)

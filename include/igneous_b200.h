@@ -1,0 +1,220 @@
+/*
+ * igneous_b200.h -- C ABI of libigneous_b200.so
+ *
+ * B200 (sm_100a) implementation of the igneous per-chunk hot path.  Every
+ * entry point replaces one call the reference (seung-lab/igneous @ 3b6e5b6)
+ * makes into a third-party CPU library; the reference call site is cited
+ * beside each declaration (paths relative to the igneous repo root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types.
+ *   - all volumes are Fortran order: index = x + sx*(y + sy*z); a 4-D
+ *     (x,y,z,c) array is passed as sz*sc slices.
+ *   - every function returns IGN_OK (0) or a negative ign_status; the message
+ *     is available from ign_last_error() (thread local).
+ *   - functions without suffix take HOST buffers (pageable or pinned) and do
+ *     H2D / D2H themselves; *_dev variants take DEVICE pointers obtained from
+ *     ign_dev_alloc and run asynchronously on the context's stream.
+ *   - one ign_ctx per process per GPU; a ctx is not thread safe.
+ *   - there is no CPU fallback: without a usable CUDA device ign_init fails.
+ */
+#ifndef IGNEOUS_B200_H
+#define IGNEOUS_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define IGN_API __attribute__((visibility("default")))
+#else
+#define IGN_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ign_ctx ign_ctx;
+typedef struct ign_mesher ign_mesher;
+typedef struct ign_group ign_group;
+
+typedef enum {
+  IGN_OK = 0,
+  IGN_ERR_CUDA = -1,        /* CUDA runtime error (sticky errors kill the ctx) */
+  IGN_ERR_INVALID = -2,     /* bad argument */
+  IGN_ERR_UNSUPPORTED = -3, /* dtype / factor / option not implemented */
+  IGN_ERR_NOMEM = -4,
+  IGN_ERR_KEY = -5,         /* remap: label missing from the table (KeyError) */
+  IGN_ERR_OVERFLOW = -6,    /* capacity exceeded (e.g. > 2^31-2 voxels per CCL call) */
+  IGN_ERR_NCCL = -7
+} ign_status;
+
+typedef enum {
+  IGN_U8 = 1,
+  IGN_U16 = 2,
+  IGN_U32 = 3,
+  IGN_U64 = 4,
+  IGN_F32 = 5
+} ign_dtype;
+
+/* averaging render rule (tinybrain parity is unpinned offline: SURVEY 8(c)) */
+typedef enum { IGN_ROUND_FLOOR = 0, IGN_ROUND_HALF_UP = 1, IGN_ROUND_HALF_EVEN = 2 } ign_rounding;
+
+/* ------------------------------------------------------------------ context */
+IGN_API int ign_version(void);
+IGN_API const char* ign_last_error(void);
+IGN_API int ign_device_count(int* n);
+IGN_API int ign_init(int device, ign_ctx** out);
+IGN_API int ign_destroy(ign_ctx* ctx);
+IGN_API int ign_sync(ign_ctx* ctx);
+/* number of kernels this library launched on ctx since ign_init */
+IGN_API int ign_launch_count(ign_ctx* ctx, uint64_t* n);
+/* raw cudaStream_t of the context (for interop: events, NCCL, torch external stream) */
+IGN_API int ign_stream(ign_ctx* ctx, void** stream);
+
+/* device / pinned-host memory */
+IGN_API int ign_dev_alloc(ign_ctx* ctx, uint64_t bytes, void** dptr);
+IGN_API int ign_dev_free(ign_ctx* ctx, void* dptr);
+IGN_API int ign_host_alloc(ign_ctx* ctx, uint64_t bytes, void** hptr); /* pinned */
+IGN_API int ign_host_free(ign_ctx* ctx, void* hptr);
+IGN_API int ign_h2d(ign_ctx* ctx, void* dst, const void* src, uint64_t bytes);  /* async on ctx stream */
+IGN_API int ign_d2h(ign_ctx* ctx, void* dst, const void* src, uint64_t bytes);  /* async on ctx stream */
+IGN_API int ign_d2d(ign_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+IGN_API int ign_memset(ign_ctx* ctx, void* dst, int byte, uint64_t bytes);
+
+/* CUDA-event timers on the ctx stream: slot in [0,16) */
+IGN_API int ign_timer_start(ign_ctx* ctx, int slot);
+IGN_API int ign_timer_stop(ign_ctx* ctx, int slot);
+IGN_API int ign_timer_ms(ign_ctx* ctx, int slot, float* ms); /* synchronises on the stop event */
+
+/* ------------------------------------------------------------------ pooling
+ * tinybrain.downsample_segmentation(img, factor=(2,2,1), num_mips, sparse)
+ *   igneous/tasks/image/image.py:52-53 (bound) and :91 (called)
+ * tinybrain.downsample_with_averaging(img, factor=(2,2,1), num_mips, sparse)
+ *   igneous/tasks/image/image.py:50-51 and :91
+ * outs[m] receives mip m+1, shape (ceil(sx/2^(m+1)), ceil(sy/2^(m+1)), sz).
+ * Mode pooling is recursive per mip (COUNTLESS 2-D rule); averaging keeps
+ * exact sums inside groups of four mips and renders with `rounding`.
+ */
+IGN_API int ign_pool_mode_2x2x1(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, uint64_t sy,
+                        uint64_t sz, int num_mips, int sparse, void* const* outs);
+IGN_API int ign_pool_avg_2x2x1(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, uint64_t sy,
+                       uint64_t sz, int num_mips, int rounding, void* const* outs);
+IGN_API int ign_pool_mode_2x2x1_dev(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, uint64_t sy,
+                            uint64_t sz, int num_mips, int sparse, void* const* outs);
+IGN_API int ign_pool_avg_2x2x1_dev(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, uint64_t sy,
+                           uint64_t sz, int num_mips, int rounding, void* const* outs);
+
+/* ---------------------------------------------------------------------- CCL
+ * cc3d.connected_components(labels, connectivity=6, out_dtype=np.uint64, return_N)
+ *   igneous/tasks/image/ccl.py:173, :235-238, :339-342
+ * 6-connected, multi-label (equal non-zero values connect), 0 = background.
+ * Output ids 1..N in order of each component's first voxel in Fortran raster
+ * order.  in_dtype U8 also serves bool input (threshold_image output).
+ * out_dtype: IGN_U16 / IGN_U32 / IGN_U64 (overflow -> IGN_ERR_OVERFLOW).
+ */
+IGN_API int ign_ccl6(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+             void* out, int out_dtype, uint64_t* n_components);
+IGN_API int ign_ccl6_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
+                 uint64_t sz, void* out, int out_dtype, uint64_t* n_components);
+
+/* cc3d.dust(labels, threshold, connectivity=6, in_place=True)
+ *   igneous/tasks/image/ccl.py:169-172, :231-234, :335-338
+ * zeroes (in place) every 6-connected component with < threshold voxels. */
+IGN_API int ign_dust(ign_ctx* ctx, void* labels, int dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+             uint64_t threshold);
+IGN_API int ign_dust_dev(ign_ctx* ctx, void* labels, int dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+                 uint64_t threshold);
+
+/* Fused CCLFacesTask body (igneous/tasks/image/ccl.py:166-175): optional
+ * threshold (use_lte/use_gte), blackout_non_face_rails(shape), CCL,
+ * += label_offset, background re-zeroed; out is u64. */
+IGN_API int ign_ccl_task_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
+                     uint64_t sz, int use_gte, double gte, int use_lte, double lte,
+                     uint64_t rail_x, uint64_t rail_y, uint64_t rail_z, uint64_t dust_threshold,
+                     uint64_t label_offset, uint64_t* out, uint64_t* n_components);
+
+/* ---------------------------------------------------------------- fastremap
+ * fastremap.renumber(data, in_place=True)            igneous/tasks/mesh/mesh.py:206
+ *   ids 1..K by first appearance in memory order, 0 kept.  out is u32;
+ *   uniq[0..K) receives the original label of new id i+1.
+ * fastremap.remap(arr, table, in_place=True)         igneous/tasks/image/ccl.py:346,
+ *                                                    igneous/tasks/mesh/mesh.py:369
+ *   preserve_missing=0 -> IGN_ERR_KEY when a label is not in keys[].
+ * fastremap.unique(arr, return_counts=True)          igneous/tasks/mesh/mesh.py:318
+ *   sorted ascending; call with uniq==NULL to get K only.
+ * fastremap.mask / mask_except(arr, labels, in_place) igneous/tasks/mesh/mesh.py:201-204,320,368
+ * fastremap.inverse_component_map(parents, components) igneous/tasks/image/ccl.py:280
+ *   unique (parent, component) pairs sorted ascending; capacity in *n_pairs.
+ */
+IGN_API int ign_renumber(ign_ctx* ctx, const void* in, int dtype, uint64_t n, uint32_t* out,
+                 uint64_t* uniq, uint64_t uniq_capacity, uint64_t* k);
+IGN_API int ign_renumber_dev(ign_ctx* ctx, const void* in, int dtype, uint64_t n, uint32_t* out,
+                     uint64_t* uniq_dev, uint64_t uniq_capacity, uint64_t* k);
+IGN_API int ign_remap(ign_ctx* ctx, void* arr, int dtype, uint64_t n, const uint64_t* keys,
+              const uint64_t* vals, uint64_t n_keys, int preserve_missing);
+IGN_API int ign_remap_dev(ign_ctx* ctx, void* arr, int dtype, uint64_t n, const uint64_t* keys_host,
+                  const uint64_t* vals_host, uint64_t n_keys, int preserve_missing);
+IGN_API int ign_unique(ign_ctx* ctx, const void* in, int dtype, uint64_t n, uint64_t* uniq,
+               uint64_t* counts, uint64_t capacity, uint64_t* k);
+IGN_API int ign_mask(ign_ctx* ctx, void* arr, int dtype, uint64_t n, const uint64_t* labels,
+             uint64_t n_labels, int except, uint64_t value);
+IGN_API int ign_inverse_component_map(ign_ctx* ctx, const void* parents, const void* components,
+                              int dtype, uint64_t n, uint64_t* pairs, uint64_t* n_pairs);
+/* widen/narrow unsigned integer arrays on the device */
+IGN_API int ign_cast_dev(ign_ctx* ctx, const void* in, int in_dtype, void* out, int out_dtype, uint64_t n);
+
+/* --------------------------------------------------------------------- mesh
+ * zmesh.Mesher(resolution).mesh(data, preserve_order=False)  igneous/tasks/mesh/mesh.py:151,245
+ * Mesher.ids()                                                igneous/tasks/mesh/mesh.py:374
+ * Mesher.get(id, reduction_factor, max_error, voxel_centered) igneous/tasks/mesh/mesh.py:376-381
+ * Multi-label marching cubes over every 2x2x2 cube; per label a welded
+ * (vertices f32 [nv,3], faces u32 [nf,3]) mesh in physical units:
+ *   position = (half_voxel_coord/2 + (voxel_centered ? 0.5 : 0)) * resolution.
+ * Vertices are ordered by (z,y,x), faces by cube raster order.
+ * reduction_factor > 0 runs the quadric edge-collapse simplifier towards
+ * nf/reduction_factor faces with error bound max_error (physical units).
+ */
+IGN_API int ign_mesh_begin(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx, uint64_t sy,
+                   uint64_t sz, ign_mesher** out);
+IGN_API int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx, uint64_t sy,
+                       uint64_t sz, ign_mesher** out);
+IGN_API int ign_mesh_num_ids(ign_mesher* m, uint64_t* n);
+IGN_API int ign_mesh_ids(ign_mesher* m, uint64_t* ids, uint64_t capacity);
+IGN_API int ign_mesh_counts(ign_mesher* m, uint64_t id, uint64_t* nv, uint64_t* nf);
+IGN_API int ign_mesh_totals(ign_mesher* m, uint64_t* nv, uint64_t* nf);
+IGN_API int ign_mesh_get(ign_mesher* m, uint64_t id, const float resolution[3], int reduction_factor,
+                 float max_error, int voxel_centered, float* vertices, uint32_t* faces,
+                 uint64_t* nv, uint64_t* nf);
+IGN_API int ign_mesh_free(ign_mesher* m);
+
+/* --------------------------------------------------- synthetic volumes (bench)
+ * jittered-grid Voronoi segmentation / hash-byte image,
+ * bit-identical to oracle.synth_seg / oracle.synth_image. */
+IGN_API int ign_synth_seg_dev(ign_ctx* ctx, void* out, int dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+                      int64_t ox, int64_t oy, int64_t oz, uint32_t pitch, uint64_t num_ids,
+                      uint64_t seed, uint64_t id_base);
+IGN_API int ign_synth_image_dev(ign_ctx* ctx, uint8_t* out, uint64_t sx, uint64_t sy, uint64_t sz,
+                        int64_t ox, int64_t oy, int64_t oz, uint64_t seed);
+
+/* ------------------------------------------------------- multi-GPU CCL merge
+ * Replaces the file exchange of igneous/tasks/image/ccl.py:177-194 (faces),
+ * :245-294 (equivalences) and :358-420 (create_relabeling) with one NCCL
+ * all-gather of compacted (label_a,label_b) face-equivalence pairs.
+ * One process per GPU; unique_id is ncclUniqueId bytes (128) created on rank 0
+ * by ign_group_unique_id and broadcast by the host-side launcher. */
+IGN_API int ign_group_unique_id(void* id128);
+IGN_API int ign_group_init(ign_ctx* ctx, int rank, int nranks, const void* id128, ign_group** out);
+IGN_API int ign_group_destroy(ign_group* g);
+/* slab CCL: this rank holds a (sx,sy,sz_local) slab of a volume stacked along z,
+ * plus (rank+1<nranks) its upper neighbour's first plane is supplied by the
+ * caller in `halo_plane` (device pointer, sx*sy voxels) -- exactly the +1 voxel
+ * overlap of ccl.py:153.  out receives globally consistent ids (u64),
+ * n_global the global number of components. */
+IGN_API int ign_ccl6_sharded_dev(ign_group* g, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
+                         uint64_t sz_local, const void* halo_plane, uint64_t* out,
+                         uint64_t* n_global);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGNEOUS_B200_H */

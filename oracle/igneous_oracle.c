@@ -1,0 +1,348 @@
+/*
+ * igneous_oracle.c -- CPU restatement of the igneous per-chunk hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is product code: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library, and only as the checker.
+ *
+ * The reference (seung-lab/igneous @ 3b6e5b6) holds no arithmetic of its own
+ * for this path; it calls un-vendored third-party wheels that are absent from
+ * /root/reference and from this image:
+ *   tinybrain >= 1.5.0               (requirements.txt:22)
+ *   connected-components-3d >= 3.10.1 (requirements.txt:5)
+ *   zmesh >= 1.13.1,<2.0             (requirements.txt:26)
+ * This file restates their published algorithms, anchored on the reference's
+ * call sites:
+ *   igneous/tasks/image/image.py:46-55,91   (pooling)
+ *   igneous/tasks/image/ccl.py:169-175      (CCL + dust)
+ *   igneous/tasks/mesh/mesh.py:151,245,371-383 (mesher)
+ *
+ * PARITY STATUS (see DESIGN.md "Oracle"):
+ *   - CCL: pinned structurally by the reference's own tests
+ *     (test/test_ccl_tasks.py:188-208, 213-249) + cross-checked against
+ *     scipy.ndimage.label in tests/test_oracle.py.
+ *   - mode pooling: rule documented (COUNTLESS 2D); tie-break KATs in
+ *     SURVEY.md 8(c).  Odd-edge handling: parity unpinned.
+ *   - averaging: rounding rule (floor) and 4-mip renormalisation recalled
+ *     from upstream tinybrain; parity unpinned (kept as a runtime enum).
+ *   - marching cubes: classic Lorensen/Bourke table; corner convention,
+ *     winding and vertex order: parity unpinned (compared after
+ *     canonicalisation).
+ *
+ * All arrays are Fortran order: index = x + sx*(y + sy*z).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_OK 0
+#define ORC_EINVAL -1
+#define ORC_ENOMEM -2
+
+/* ------------------------------------------------------------------ */
+/* Mode pooling 2x2x1 (tinybrain.downsample_segmentation, one mip).    */
+/* Rule per 2x2 block a=(x,y) b=(x+1,y) c=(x,y+1) d=(x+1,y+1):         */
+/*   out = a if (a==b || a==c) else (b if b==c else d)                 */
+/* Odd extents: the lone column/row has only (a,c) / (a,b) -> a        */
+/* (two samples: mode is a whenever they agree; tie -> first).         */
+/* sparse: zeros are not counted (mode over the non-zero samples, ties  */
+/* resolved in a,b,c,d order; all zero -> 0).                          */
+/* ------------------------------------------------------------------ */
+#define DEF_MODE_POOL(T, NAME)                                              \
+  int NAME(const T* in, uint64_t sx, uint64_t sy, uint64_t sz, T* out,      \
+           int sparse) {                                                    \
+    const uint64_t ox = (sx + 1) / 2, oy = (sy + 1) / 2;                    \
+    for (uint64_t z = 0; z < sz; z++) {                                     \
+      for (uint64_t y = 0; y < oy; y++) {                                   \
+        for (uint64_t x = 0; x < ox; x++) {                                 \
+          const uint64_t x0 = 2 * x, y0 = 2 * y;                            \
+          const int hx = (x0 + 1 < sx), hy = (y0 + 1 < sy);                 \
+          const T a = in[x0 + sx * (y0 + sy * z)];                          \
+          T r;                                                              \
+          if (!sparse) {                                                    \
+            if (hx && hy) {                                                 \
+              const T b = in[x0 + 1 + sx * (y0 + sy * z)];                  \
+              const T c = in[x0 + sx * (y0 + 1 + sy * z)];                  \
+              const T d = in[x0 + 1 + sx * (y0 + 1 + sy * z)];              \
+              r = (a == b || a == c) ? a : ((b == c) ? b : d);              \
+            } else {                                                        \
+              r = a;                                                        \
+            }                                                               \
+          } else {                                                          \
+            T v[4];                                                         \
+            int n = 0;                                                      \
+            if (a) v[n++] = a;                                              \
+            if (hx) {                                                       \
+              T b = in[x0 + 1 + sx * (y0 + sy * z)];                        \
+              if (b) v[n++] = b;                                            \
+            }                                                               \
+            if (hy) {                                                       \
+              T c = in[x0 + sx * (y0 + 1 + sy * z)];                        \
+              if (c) v[n++] = c;                                            \
+            }                                                               \
+            if (hx && hy) {                                                 \
+              T d = in[x0 + 1 + sx * (y0 + 1 + sy * z)];                    \
+              if (d) v[n++] = d;                                            \
+            }                                                               \
+            if (n == 0) r = 0;                                              \
+            else if (n <= 2) r = v[0];                                      \
+            else if (n == 3)                                                \
+              r = (v[0] == v[1] || v[0] == v[2]) ? v[0]                     \
+                  : ((v[1] == v[2]) ? v[1] : v[0]);                         \
+            else                                                            \
+              r = (v[0] == v[1] || v[0] == v[2]) ? v[0]                     \
+                  : ((v[1] == v[2]) ? v[1] : v[3]);                         \
+          }                                                                 \
+          out[x + ox * (y + oy * z)] = r;                                   \
+        }                                                                   \
+      }                                                                     \
+    }                                                                       \
+    return ORC_OK;                                                          \
+  }
+
+DEF_MODE_POOL(uint8_t, orc_mode_pool_2x2x1_u8)
+DEF_MODE_POOL(uint16_t, orc_mode_pool_2x2x1_u16)
+DEF_MODE_POOL(uint32_t, orc_mode_pool_2x2x1_u32)
+DEF_MODE_POOL(uint64_t, orc_mode_pool_2x2x1_u64)
+
+/* ------------------------------------------------------------------ */
+/* Average pooling 2x2x1 (tinybrain.downsample_with_averaging).        */
+/* Upstream keeps un-normalised 2x2 sums in a wider integer: level k   */
+/* of a group of four is rendered as accum >> 2k (floor), after the    */
+/* fourth level the accumulator is renormalised (accum >>= 8) and the  */
+/* next group starts from those truncated values.  Odd extents mirror  */
+/* the lone row/column (counted twice) so the divisor stays 4.         */
+/* rounding: 0 floor (upstream, recalled), 1 half-up, 2 half-even.     */
+/* ------------------------------------------------------------------ */
+static uint64_t orc_render(uint64_t acc, unsigned shift, int rounding) {
+  if (rounding == 0 || shift == 0) return acc >> shift;
+  const uint64_t half = 1ull << (shift - 1);
+  if (rounding == 1) return (acc + half) >> shift;
+  /* half-even */
+  uint64_t q = acc >> shift, rem = acc & ((1ull << shift) - 1);
+  if (rem > half || (rem == half && (q & 1))) q++;
+  return q;
+}
+
+/* accumulate one 2x2x1 level of 64-bit sums (mirror odd edges) */
+static uint64_t* orc_accum_2x2(const uint64_t* in, uint64_t sx, uint64_t sy,
+                               uint64_t sz) {
+  const uint64_t ox = (sx + 1) / 2, oy = (sy + 1) / 2;
+  uint64_t* acc = (uint64_t*)malloc(sizeof(uint64_t) * ox * oy * sz);
+  if (!acc) return NULL;
+  for (uint64_t z = 0; z < sz; z++)
+    for (uint64_t y = 0; y < oy; y++)
+      for (uint64_t x = 0; x < ox; x++) {
+        const uint64_t x0 = 2 * x, y0 = 2 * y;
+        const uint64_t x1 = (x0 + 1 < sx) ? x0 + 1 : x0;
+        const uint64_t y1 = (y0 + 1 < sy) ? y0 + 1 : y0;
+        acc[x + ox * (y + oy * z)] =
+            in[x0 + sx * (y0 + sy * z)] + in[x1 + sx * (y0 + sy * z)] +
+            in[x0 + sx * (y1 + sy * z)] + in[x1 + sx * (y1 + sy * z)];
+      }
+  return acc;
+}
+
+#define DEF_AVG_POOL(T, NAME)                                                 \
+  int NAME(const T* in, uint64_t sx, uint64_t sy, uint64_t sz, int num_mips,  \
+           T** outs, int rounding) {                                          \
+    if (num_mips < 1) return ORC_EINVAL;                                      \
+    uint64_t n = sx * sy * sz;                                                \
+    uint64_t* cur = (uint64_t*)malloc(sizeof(uint64_t) * (n ? n : 1));        \
+    if (!cur) return ORC_ENOMEM;                                              \
+    for (uint64_t i = 0; i < n; i++) cur[i] = in[i];                          \
+    for (int mip = 0; mip < num_mips; mip++) {                                \
+      uint64_t* acc = orc_accum_2x2(cur, sx, sy, sz);                         \
+      free(cur);                                                              \
+      if (!acc) return ORC_ENOMEM;                                            \
+      sx = (sx + 1) / 2;                                                      \
+      sy = (sy + 1) / 2;                                                      \
+      n = sx * sy * sz;                                                       \
+      const unsigned shift = 2 * ((mip % 4) + 1);                             \
+      for (uint64_t i = 0; i < n; i++)                                        \
+        outs[mip][i] = (T)orc_render(acc[i], shift, rounding);                \
+      if (shift == 8)                                                         \
+        for (uint64_t i = 0; i < n; i++)                                      \
+          acc[i] = orc_render(acc[i], shift, rounding);                       \
+      cur = acc;                                                              \
+    }                                                                         \
+    free(cur);                                                                \
+    return ORC_OK;                                                            \
+  }
+
+DEF_AVG_POOL(uint8_t, orc_avg_pool_2x2x1_u8)
+DEF_AVG_POOL(uint16_t, orc_avg_pool_2x2x1_u16)
+DEF_AVG_POOL(uint32_t, orc_avg_pool_2x2x1_u32)
+
+/* float32: plain mean of the four (mirrored) samples at every level,   */
+/* op order ((a+b)+(c+d))*0.25f.  Parity unpinned.                     */
+int orc_avg_pool_2x2x1_f32(const float* in, uint64_t sx, uint64_t sy,
+                           uint64_t sz, int num_mips, float** outs,
+                           int rounding) {
+  (void)rounding;
+  const float* cur = in;
+  for (int mip = 0; mip < num_mips; mip++) {
+    const uint64_t ox = (sx + 1) / 2, oy = (sy + 1) / 2;
+    float* o = outs[mip];
+    for (uint64_t z = 0; z < sz; z++)
+      for (uint64_t y = 0; y < oy; y++)
+        for (uint64_t x = 0; x < ox; x++) {
+          const uint64_t x0 = 2 * x, y0 = 2 * y;
+          const uint64_t x1 = (x0 + 1 < sx) ? x0 + 1 : x0;
+          const uint64_t y1 = (y0 + 1 < sy) ? y0 + 1 : y0;
+          const float a = cur[x0 + sx * (y0 + sy * z)];
+          const float b = cur[x1 + sx * (y0 + sy * z)];
+          const float c = cur[x0 + sx * (y1 + sy * z)];
+          const float d = cur[x1 + sx * (y1 + sy * z)];
+          o[x + ox * (y + oy * z)] = ((a + b) + (c + d)) * 0.25f;
+        }
+    cur = o;
+    sx = ox;
+    sy = oy;
+  }
+  return ORC_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* 6-connected multi-label CCL (cc3d.connected_components,             */
+/* connectivity=6; called at igneous/tasks/image/ccl.py:173,235,339).  */
+/* Two voxels are connected iff they are face adjacent and hold the    */
+/* same non-zero value.  Output ids 1..N are assigned in order of the  */
+/* first voxel of each component in Fortran raster order (== rank of   */
+/* the component's minimum linear index); background stays 0.          */
+/* ------------------------------------------------------------------ */
+static uint64_t uf_find(uint64_t* p, uint64_t i) {
+  while (p[i] != i) {
+    p[i] = p[p[i]];
+    i = p[i];
+  }
+  return i;
+}
+static void uf_union(uint64_t* p, uint64_t a, uint64_t b) {
+  a = uf_find(p, a);
+  b = uf_find(p, b);
+  if (a < b) p[b] = a;
+  else if (b < a) p[a] = b;
+}
+
+#define DEF_CCL6(T, NAME)                                                    \
+  int NAME(const T* in, uint64_t sx, uint64_t sy, uint64_t sz,               \
+           uint64_t* out, uint64_t* n_out) {                                 \
+    const uint64_t n = sx * sy * sz;                                         \
+    uint64_t* p = (uint64_t*)malloc(sizeof(uint64_t) * (n ? n : 1));         \
+    if (!p) return ORC_ENOMEM;                                               \
+    for (uint64_t i = 0; i < n; i++) p[i] = i;                               \
+    for (uint64_t z = 0; z < sz; z++)                                        \
+      for (uint64_t y = 0; y < sy; y++)                                      \
+        for (uint64_t x = 0; x < sx; x++) {                                  \
+          const uint64_t i = x + sx * (y + sy * z);                          \
+          const T v = in[i];                                                 \
+          if (!v) continue;                                                  \
+          if (x && in[i - 1] == v) uf_union(p, i, i - 1);                    \
+          if (y && in[i - sx] == v) uf_union(p, i, i - sx);                  \
+          if (z && in[i - sx * sy] == v) uf_union(p, i, i - sx * sy);        \
+        }                                                                    \
+    uint64_t next = 0;                                                       \
+    /* roots are minimum indices: a raster scan meets the root first */      \
+    for (uint64_t i = 0; i < n; i++) {                                       \
+      if (!in[i]) { out[i] = 0; continue; }                                  \
+      const uint64_t r = uf_find(p, i);                                      \
+      if (r == i) out[i] = ++next;                                           \
+      else out[i] = out[r];                                                  \
+    }                                                                        \
+    free(p);                                                                 \
+    if (n_out) *n_out = next;                                                \
+    return ORC_OK;                                                           \
+  }
+
+DEF_CCL6(uint8_t, orc_ccl6_u8)
+DEF_CCL6(uint16_t, orc_ccl6_u16)
+DEF_CCL6(uint32_t, orc_ccl6_u32)
+DEF_CCL6(uint64_t, orc_ccl6_u64)
+
+/* ------------------------------------------------------------------ */
+/* Multi-label marching cubes (zmesh.Mesher.mesh, mesh.py:245).        */
+/* For every 2x2x2 cube and every distinct non-zero corner label L the */
+/* classic 256-case table is evaluated with bit i set iff corner i==L. */
+/* Vertices sit on edge midpoints; coordinates are emitted in integer  */
+/* half-voxel units (2*x + dx).  Triangles are emitted per label in    */
+/* cube raster order (x fastest), table order inside a cube.           */
+/*                                                                     */
+/* Corner numbering (Bourke): 0:(0,0,0) 1:(1,0,0) 2:(1,1,0) 3:(0,1,0)   */
+/*                            4:(0,0,1) 5:(1,0,1) 6:(1,1,1) 7:(0,1,1)   */
+/* Edge numbering: 0:0-1 1:1-2 2:2-3 3:3-0 4:4-5 5:5-6 6:6-7 7:7-4     */
+/*                 8:0-4 9:1-5 10:2-6 11:3-7                           */
+/* ------------------------------------------------------------------ */
+#include "mc_table.h"
+
+/* edge midpoint offsets in half-voxel units relative to 2*(x,y,z) */
+static const int8_t orc_edge_mid[12][3] = {
+    {1, 0, 0}, {2, 1, 0}, {1, 2, 0}, {0, 1, 0}, {1, 0, 2}, {2, 1, 2},
+    {1, 2, 2}, {0, 1, 2}, {0, 0, 1}, {2, 0, 1}, {2, 2, 1}, {0, 2, 1}};
+static const int8_t orc_corner[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0},
+                                        {0, 1, 0}, {0, 0, 1}, {1, 0, 1},
+                                        {1, 1, 1}, {0, 1, 1}};
+
+/*
+ * Two-call protocol: with tri_label == NULL only counts triangles.
+ * tri_label[t]  : label of triangle t
+ * tri_verts[9t..]: three vertices (x,y,z) in half-voxel integer units,
+ * ordered: all cubes in raster order, labels inside a cube in ascending
+ * corner order of first appearance, triangles in table order.
+ * flip != 0 reverses the winding of every triangle.
+ */
+#define DEF_MC(T, NAME)                                                       \
+  int NAME(const T* in, uint64_t sx, uint64_t sy, uint64_t sz,                \
+           uint64_t* n_tri, uint64_t* tri_label, uint32_t* tri_verts,         \
+           int flip) {                                                        \
+    uint64_t nt = 0;                                                          \
+    if (sx < 2 || sy < 2 || sz < 2) { *n_tri = 0; return ORC_OK; }            \
+    for (uint64_t z = 0; z + 1 < sz; z++)                                     \
+      for (uint64_t y = 0; y + 1 < sy; y++)                                   \
+        for (uint64_t x = 0; x + 1 < sx; x++) {                               \
+          T c[8];                                                             \
+          int any = 0;                                                        \
+          for (int k = 0; k < 8; k++) {                                       \
+            c[k] = in[(x + orc_corner[k][0]) +                                \
+                      sx * ((y + orc_corner[k][1]) +                          \
+                            sy * (z + orc_corner[k][2]))];                    \
+            any |= (c[k] != 0);                                               \
+          }                                                                   \
+          if (!any) continue;                                                 \
+          for (int k = 0; k < 8; k++) {                                       \
+            const T L = c[k];                                                 \
+            if (!L) continue;                                                 \
+            int seen = 0;                                                     \
+            for (int j = 0; j < k; j++) seen |= (c[j] == L);                  \
+            if (seen) continue;                                               \
+            int idx = 0;                                                      \
+            for (int j = 0; j < 8; j++) idx |= (c[j] == L) << j;              \
+            const int8_t* tt = mc_tri_table[idx];                             \
+            for (int e = 0; tt[e] >= 0; e += 3) {                             \
+              if (tri_label) {                                                \
+                tri_label[nt] = (uint64_t)L;                                  \
+                for (int v = 0; v < 3; v++) {                                 \
+                  const int ed = tt[e + (flip ? 2 - v : v)];                  \
+                  tri_verts[9 * nt + 3 * v + 0] =                             \
+                      (uint32_t)(2 * x + orc_edge_mid[ed][0]);                \
+                  tri_verts[9 * nt + 3 * v + 1] =                             \
+                      (uint32_t)(2 * y + orc_edge_mid[ed][1]);                \
+                  tri_verts[9 * nt + 3 * v + 2] =                             \
+                      (uint32_t)(2 * z + orc_edge_mid[ed][2]);                \
+                }                                                             \
+              }                                                               \
+              nt++;                                                           \
+            }                                                                 \
+          }                                                                   \
+        }                                                                     \
+    *n_tri = nt;                                                              \
+    return ORC_OK;                                                            \
+  }
+
+DEF_MC(uint8_t, orc_marching_cubes_u8)
+DEF_MC(uint16_t, orc_marching_cubes_u16)
+DEF_MC(uint32_t, orc_marching_cubes_u32)
+DEF_MC(uint64_t, orc_marching_cubes_u64)
+
+/* table accessors so tests can validate the table itself */
+const int8_t* orc_mc_tri_table(void) { return &mc_tri_table[0][0]; }

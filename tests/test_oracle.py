@@ -1,0 +1,239 @@
+"""CPU tests pinning the oracle (oracle/) against the reference's own known
+answers and against independent implementations available in
+this image (scipy.ndimage.label).  No GPU needed."""
+import numpy as np
+import pytest
+
+
+# ---------------------------------------------------------------- mode pooling
+MODE_KATS = [  # [a b; c d] -> out  (SURVEY.md 8(c) derived from the COUNTLESS rule)
+  ((1, 1, 2, 3), 1), ((1, 2, 1, 3), 1), ((1, 2, 2, 3), 2), ((1, 2, 3, 3), 3),
+  ((1, 2, 3, 4), 4), ((1, 1, 2, 2), 1), ((1, 2, 2, 1), 2), ((0, 0, 5, 5), 0),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64])
+def test_mode_pool_kats(oracle, dtype):
+  for (a, b, c, d), want in MODE_KATS:
+    img = np.zeros((2, 2, 1), dtype=dtype, order="F")
+    img[0, 0, 0], img[1, 0, 0], img[0, 1, 0], img[1, 1, 0] = a, b, c, d
+    out, = oracle.downsample_segmentation(img, (2, 2, 1))
+    assert out.shape == (1, 1, 1) and out[0, 0, 0] == want
+
+
+def test_mode_pool_is_true_mode_when_unique(oracle):
+  rng = np.random.default_rng(0)
+  img = rng.integers(1, 4, size=(64, 64, 4)).astype(np.uint32)
+  out, = oracle.downsample_segmentation(img, (2, 2, 1))
+  for x in range(32):
+    for y in range(32):
+      blk = img[2 * x:2 * x + 2, 2 * y:2 * y + 2, 0].ravel()
+      vals, cnt = np.unique(blk, return_counts=True)
+      if (cnt == cnt.max()).sum() == 1 and cnt.max() >= 2:
+        assert out[x, y, 0] == vals[np.argmax(cnt)]
+
+
+def test_mode_pool_checker_equals_striding(oracle):
+  # pooling invariant: block-constant volume -> mode pool == stride-2 subsample
+  data = np.zeros((128, 128, 4), dtype=np.uint8, order="F")
+  i = 1
+  for x in range(4):
+    for y in range(4):
+      data[32 * x:32 * (x + 1), 32 * y:32 * (y + 1), :] = i
+      i += 1
+  mips = oracle.downsample_segmentation(data, (2, 2, 1), num_mips=4)
+  cur = data
+  for m in mips:
+    cur = cur[::2, ::2, :]
+    assert np.array_equal(m, cur)
+
+
+def test_mode_pool_odd_and_4d(oracle):
+  rng = np.random.default_rng(1)
+  img = rng.integers(0, 3, size=(5, 7, 3, 2)).astype(np.uint16)
+  out, = oracle.downsample_segmentation(img, (2, 2, 1, 1))
+  assert out.shape == (3, 4, 3, 2)
+  assert out[2, 0, 0, 0] == img[4, 0, 0, 0]  # lone column -> a
+  assert out[0, 3, 1, 1] == img[0, 6, 1, 1]  # lone row -> a
+
+
+# ------------------------------------------------------------------- averaging
+def test_avg_pool_rounding_probes(oracle):
+  # first-contact probes of SURVEY.md 8(c): floor is the recalled upstream rule
+  def one(a, b, c, d, rounding):
+    img = np.array([[[a], [c]], [[b], [d]]], dtype=np.uint8)
+    return int(oracle.downsample_with_averaging(img, (2, 2, 1), rounding=rounding)[0][0, 0, 0])
+  assert one(0, 1, 1, 1, 0) == 0 and one(0, 1, 1, 1, 1) == 1
+  assert one(0, 0, 1, 1, 0) == 0 and one(0, 0, 1, 1, 1) == 1 and one(0, 0, 1, 1, 2) == 0
+  assert one(1, 1, 2, 2, 1) == 2 and one(1, 1, 2, 2, 2) == 2
+
+
+def test_avg_pool_exact_sums_in_groups_of_four(oracle):
+  rng = np.random.default_rng(2)
+  img = rng.integers(0, 255, size=(64, 64, 2), dtype=np.uint8)
+  mips = oracle.downsample_with_averaging(img, (2, 2, 1), num_mips=5)
+  wide = img.astype(np.uint64)
+  for k in range(1, 5):
+    f = 2 ** k
+    s = wide.reshape(64 // f, f, 64 // f, f, 2).sum(axis=(1, 3))
+    assert np.array_equal(mips[k - 1], (s >> (2 * k)).astype(np.uint8))
+  # level 5 restarts from the truncated level-4 values
+  m4 = mips[3].astype(np.uint64)
+  s = m4.reshape(2, 2, 2, 2, 2).sum(axis=(1, 3))
+  assert np.array_equal(mips[4], (s >> 2).astype(np.uint8))
+
+
+def test_avg_pool_constant_and_mirror(oracle):
+  img = np.full((7, 5, 2), 200, dtype=np.uint8)
+  for m in oracle.downsample_with_averaging(img, (2, 2, 1), num_mips=3):
+    assert (m == 200).all()
+
+
+# ------------------------------------------------------------------------- CCL
+def _scipy_ccl(labels):
+  from scipy import ndimage
+  out = np.zeros(labels.shape, dtype=np.uint64)
+  nxt = 0
+  for l in np.unique(labels):
+    if l == 0:
+      continue
+    cc, k = ndimage.label(labels == l)  # default structure = 6-connectivity
+    out[cc > 0] = cc[cc > 0].astype(np.uint64) + np.uint64(nxt)
+    nxt += k
+  return out, nxt
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint32, np.uint64])
+def test_ccl_matches_scipy_after_renumber(oracle, dtype):
+  rng = np.random.default_rng(3)
+  labels = rng.integers(0, 4, size=(33, 29, 17)).astype(dtype)
+  cc, n = oracle.connected_components(labels, return_N=True)
+  ref, n_ref = _scipy_ccl(labels)
+  assert n == n_ref
+  a, _ = oracle.renumber(cc)
+  b, _ = oracle.renumber(ref)
+  assert np.array_equal(a, b)
+  # the oracle numbers components by first voxel in Fortran order:
+  # renumber (first appearance) must be the identity.
+  assert np.array_equal(a, cc)
+
+
+def test_ccl_checker_kat(oracle):
+  # test/test_ccl_tasks.py:20-30 checker volume (scaled down 4x): 128 blocks
+  data = np.zeros((128, 128, 32), dtype=np.uint8)
+  i = 1
+  for x in range(8):
+    for y in range(8):
+      for z in range(2):
+        data[16 * x:16 * (x + 1), 16 * y:16 * (y + 1), 16 * z:16 * (z + 1)] = i
+        i += 1
+  cc, n = oracle.connected_components(data, return_N=True)
+  assert n == 128
+  assert np.array_equal(np.unique(cc), np.arange(1, 129))
+  _, counts = np.unique(cc, return_counts=True)
+  assert (counts == 16 ** 3).all()
+  # thresholded to one component (test_ccl_tasks.py:200-203): image <= 255
+  cc, n = oracle.connected_components(data <= 255, return_N=True)
+  assert n == 1
+  # dust removes components with fewer than threshold voxels (:113,192-198)
+  assert not oracle.dust(data, 16 ** 3 + 1).any()
+  assert np.array_equal(oracle.dust(data, 16 ** 3), data)
+
+
+def test_ccl_synthetic_voronoi(oracle):
+  seg = oracle.synth_seg((64, 48, 40), pitch=16, num_ids=6)
+  cc, n = oracle.connected_components(seg, return_N=True)
+  ref, n_ref = _scipy_ccl(seg)
+  assert n == n_ref and n > 6
+  assert np.array_equal(oracle.renumber(cc)[0], oracle.renumber(ref)[0])
+
+
+# ------------------------------------------------------------------- fastremap
+def test_renumber_remap_unique(oracle):
+  arr = np.array([[5, 0, 9], [9, 5, 7]], dtype=np.uint64, order="F")
+  out, mapping = oracle.renumber(arr)
+  assert mapping == {5: 1, 9: 2, 0: 0, 7: 3}  # F order: 5,9,0,5,9,7
+  assert out.dtype == np.uint8
+  assert np.array_equal(out, [[1, 0, 2], [2, 1, 3]])
+  back = oracle.remap(out, {v: k for k, v in mapping.items()})
+  assert np.array_equal(back, arr.astype(np.uint8))
+  with pytest.raises(KeyError):
+    oracle.remap(arr, {5: 1})
+  u, c = oracle.unique(arr, return_counts=True)
+  assert list(u) == [0, 5, 7, 9] and list(c) == [1, 2, 1, 2]
+  assert oracle.inverse_component_map([1, 1, 2, 0], [4, 5, 4, 0]) == {0: [0], 1: [4, 5], 2: [4]}
+
+
+# --------------------------------------------------------------- marching cubes
+def _edge_manifold(faces):
+  e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]])
+  fwd = {}
+  for a, b in e:
+    fwd[(a, b)] = fwd.get((a, b), 0) + 1
+  return all(fwd.get((b, a), 0) == c for (a, b), c in fwd.items())
+
+
+def _signed_volume(v, f):
+  a, b, c = v[f[:, 0]].astype(np.float64), v[f[:, 1]].astype(np.float64), v[f[:, 2]].astype(np.float64)
+  return np.einsum("ij,ij->i", a, np.cross(b, c)).sum() / 6.0
+
+
+def test_mc_box_kat(oracle):
+  # SURVEY.md 8(c) box KAT from test/test_tasks.py:413-415: n=62 voxel cube
+  n = 62
+  data = np.zeros((64, 64, 64), dtype=np.uint32, order="F")
+  data[1:-1, 1:-1, 1:-1] = 1
+  tl, tv = oracle.marching_cubes(data)
+  assert (tl == 1).all()
+  F = 12 * (n - 1) ** 2 + 24 * (n - 1) + 8
+  assert len(tl) == F == 46124
+  v, f = oracle.mesh_for_label(tl, tv, 1, resolution=(1, 1, 1), voxel_centered=False)
+  assert len(v) == F // 2 + 2 == 23064
+  assert _edge_manifold(f)
+  vol = _signed_volume(v, f)
+  want = (n - 1) ** 3 + 3 * (n - 1) ** 2 + 1.5 * (n - 1) + 1.0 / 6.0
+  assert abs(abs(vol) - want) < 1e-6 * want
+  assert vol > 0, "triangles must wind counter-clockwise seen from outside"
+  assert np.allclose(v * 2, np.round(v * 2))  # half-voxel lattice
+
+
+def test_mc_watertight_random_multilabel(oracle):
+  # every label's surface must be closed and consistently oriented when the
+  # volume is zero padded: validates the 256-case table in all configurations
+  rng = np.random.default_rng(5)
+  data = np.zeros((18, 17, 16), dtype=np.uint8, order="F")
+  data[1:-1, 1:-1, 1:-1] = rng.integers(0, 4, size=(16, 15, 14))
+  tl, tv = oracle.marching_cubes(data)
+  for l in (1, 2, 3):
+    v, f = oracle.mesh_for_label(tl, tv, l, voxel_centered=False)
+    assert len(f) > 0 and _edge_manifold(f)
+    assert _signed_volume(v, f) > 0
+
+
+def test_mc_all_256_cases_closed(oracle):
+  # each cube configuration on its own, embedded in a zero volume
+  for case in range(1, 255):
+    data = np.zeros((4, 4, 4), dtype=np.uint8, order="F")
+    for k, (cx, cy, cz) in enumerate([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0),
+                                      (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]):
+      if (case >> k) & 1:
+        data[1 + cx, 1 + cy, 1 + cz] = 1
+    tl, tv = oracle.marching_cubes(data)
+    v, f = oracle.mesh_for_label(tl, tv, 1, voxel_centered=False)
+    assert _edge_manifold(f), case
+    assert _signed_volume(v, f) > 0, case
+
+
+def test_canonicalise_mesh_is_order_independent(oracle):
+  data = np.zeros((8, 8, 8), dtype=np.uint8, order="F")
+  data[2:6, 2:5, 3:6] = 1
+  tl, tv = oracle.marching_cubes(data)
+  v, f = oracle.mesh_for_label(tl, tv, 1)
+  rng = np.random.default_rng(0)
+  perm = rng.permutation(len(v))
+  inv = np.argsort(perm)
+  f2 = inv[f][rng.permutation(len(f))]
+  f2 = np.roll(f2, 1, axis=1)
+  v1, c1 = oracle.canonicalise_mesh(v, f)
+  v2, c2 = oracle.canonicalise_mesh(v[perm], f2)
+  assert np.array_equal(v1, v2) and np.array_equal(c1, c2)

@@ -1,0 +1,124 @@
+"""GPU parity: pooling kernels (through the C ABI) vs the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _seg(rng, shape, dtype, nlab=5):
+  # blocky labels so that ties and majorities both occur
+  small = rng.integers(0, nlab, size=tuple((s + 2) // 3 for s in shape[:3]) + shape[3:])
+  big = np.repeat(np.repeat(small, 3, axis=0), 3, axis=1)[:shape[0], :shape[1]]
+  noise = rng.integers(0, nlab, size=shape)
+  pick = rng.random(shape) < 0.3
+  out = np.where(pick, noise, big[..., :shape[2]] if big.ndim == 3 else big)
+  if np.dtype(dtype).itemsize == 8:
+    out = out.astype(np.uint64) * np.uint64(0x100000001)
+  return np.asfortranarray(out.astype(dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64])
+@pytest.mark.parametrize("shape,num_mips", [
+  ((128, 128, 64), 1),    # BASELINE config C1
+  ((256, 64, 5), 4),      # fused multi-mip
+  ((64, 48, 3), 3),       # sy not divisible by 16 -> mixed fused/generic
+  ((37, 21, 2), 3),       # odd extents -> generic path
+  ((16, 16, 1), 5),       # deeper than the extent
+])
+def test_mode_pool_matches_oracle(ctx, oracle, dtype, shape, num_mips):
+  from igneous_b200 import tinybrain
+  rng = np.random.default_rng(hash((np.dtype(dtype).itemsize, shape, num_mips)) % (1 << 32))
+  img = _seg(rng, shape, dtype)
+  got = tinybrain.downsample_segmentation(img, (2, 2, 1), num_mips=num_mips)
+  want = oracle.downsample_segmentation(img, (2, 2, 1), num_mips=num_mips)
+  assert len(got) == num_mips
+  for g, w in zip(got, want):
+    assert g.dtype == w.dtype and g.shape == w.shape and g.flags.f_contiguous
+    assert np.array_equal(g, w)
+
+
+def test_mode_pool_kats_gpu(ctx):
+  from igneous_b200 import tinybrain
+  from test_oracle import MODE_KATS
+  for dtype in (np.uint8, np.uint32, np.uint64):
+    for (a, b, c, d), want in MODE_KATS:
+      img = np.zeros((2, 2, 1), dtype=dtype, order="F")
+      img[0, 0, 0], img[1, 0, 0], img[0, 1, 0], img[1, 1, 0] = a, b, c, d
+      out, = tinybrain.downsample_segmentation(img, (2, 2, 1))
+      assert out[0, 0, 0] == want
+    # same KATs through the vectorised path (tile them to a 64x64 image)
+    img = np.zeros((64, 64, 2), dtype=dtype, order="F")
+    wants = np.zeros((32, 32, 2), dtype=dtype)
+    for i, ((a, b, c, d), want) in enumerate(MODE_KATS * 128):
+      x, y = i % 32, (i // 32) % 32
+      img[2 * x, 2 * y, :], img[2 * x + 1, 2 * y, :] = a, b
+      img[2 * x, 2 * y + 1, :], img[2 * x + 1, 2 * y + 1, :] = c, d
+      wants[x, y, :] = want
+    out, = tinybrain.downsample_segmentation(img, (2, 2, 1))
+    assert np.array_equal(out, wants)
+
+
+def test_mode_pool_sparse_and_4d(ctx, oracle):
+  from igneous_b200 import tinybrain
+  rng = np.random.default_rng(7)
+  img = _seg(rng, (64, 32, 4, 2), np.uint32, nlab=3)
+  for sparse in (False, True):
+    got = tinybrain.downsample_segmentation(img, (2, 2, 1, 1), num_mips=2, sparse=sparse)
+    want = oracle.downsample_segmentation(img, (2, 2, 1, 1), num_mips=2, sparse=sparse)
+    for g, w in zip(got, want):
+      assert g.shape == w.shape and np.array_equal(g, w)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32])
+@pytest.mark.parametrize("shape,num_mips", [
+  ((512, 512, 8), 5),     # C2 shape class: 5-level pyramid, group of 4 + 1
+  ((64, 64, 3), 4),
+  ((48, 40, 2), 3),       # generic path (not a multiple of 16)
+  ((37, 21, 2), 6),       # odd extents, mirrored edges, two groups
+])
+@pytest.mark.parametrize("rounding", [0, 1, 2])
+def test_avg_pool_matches_oracle(ctx, oracle, dtype, shape, num_mips, rounding):
+  from igneous_b200 import tinybrain
+  rng = np.random.default_rng(11)
+  hi = np.iinfo(dtype).max
+  img = np.asfortranarray(rng.integers(0, hi, size=shape, dtype=dtype, endpoint=True))
+  got = tinybrain.downsample_with_averaging(img, (2, 2, 1), num_mips=num_mips, rounding=rounding)
+  want = oracle.downsample_with_averaging(img, (2, 2, 1), num_mips=num_mips, rounding=rounding)
+  for g, w in zip(got, want):
+    assert g.shape == w.shape and np.array_equal(g, w)
+
+
+def test_avg_pool_f32_within_tolerance(ctx, oracle):
+  from igneous_b200 import tinybrain
+  rng = np.random.default_rng(12)
+  img = np.asfortranarray(rng.random((65, 33, 3), dtype=np.float32))
+  got = tinybrain.downsample_with_averaging(img, (2, 2, 1), num_mips=3)
+  want = oracle.downsample_with_averaging(img, (2, 2, 1), num_mips=3)
+  for g, w in zip(got, want):
+    # same operation order, no FMA contraction on either side: bit exact
+    assert np.array_equal(g, w)
+
+
+def test_pool_invariants_large(ctx):
+  """Size-independent properties at a size the oracle would take minutes for."""
+  from igneous_b200 import tinybrain
+  data = np.zeros((1024, 1024, 16), dtype=np.uint32, order="F")
+  i = 1
+  for x in range(16):
+    for y in range(16):
+      data[64 * x:64 * (x + 1), 64 * y:64 * (y + 1), :] = i
+      i += 1
+  mips = tinybrain.downsample_segmentation(data, (2, 2, 1), num_mips=5)
+  cur = data
+  for m in mips:
+    cur = cur[::2, ::2, :]
+    assert np.array_equal(m, cur)
+  const = np.full((512, 512, 4), 173, dtype=np.uint8, order="F")
+  for m in tinybrain.downsample_with_averaging(const, (2, 2, 1), num_mips=5):
+    assert (m == 173).all()
+
+
+def test_unsupported_factor_raises(ctx):
+  from igneous_b200 import tinybrain
+  with pytest.raises(NotImplementedError):
+    tinybrain.downsample_segmentation(np.zeros((4, 4, 4), np.uint8), (2, 2, 2))
