@@ -1,0 +1,895 @@
+// ccl.cu -- 6-connected multi-label connected components (K3), dust (K4)
+//
+// Replaces cc3d.connected_components(labels, connectivity=6, out_dtype=uint64)
+// and cc3d.dust as called from igneous/tasks/image/ccl.py:169-175,231-240,335-344,
+// and fuses the surrounding passes of CCLFacesTask (threshold_image :89-101,
+// blackout_non_face_rails :103-124, `+= label_offset`, `[labels==0] = 0`
+// :174-175) into the same kernels.
+//
+// Algorithm (run/segment based union-find, union-by-minimum-index):
+//   A1 init   : a warp owns one 32-voxel word of an x-row; a ballot over
+//               "differs from my left neighbour" finds segment starts; every
+//               voxel's parent entry is set to the linear index of its segment
+//               start (background -> BG).  Dense coalesced 4 B/voxel write.
+//   A2 union  : same mapping; for y-1 / z-1 / word-boundary x neighbours with
+//               an equal non-zero value the two segments are united with an
+//               atomicMin union-find (path halving).  Only the first lane of
+//               each segment overlap issues the union, so the number of atomics
+//               is O(#segment adjacencies), not O(#voxels).  Segments with no
+//               lower-index neighbour are logged as root candidates.
+//   R  roots  : candidates that are still their own parent are the component
+//               roots (= minimum voxel index of each component).  They are
+//               sorted; rank+1 is cc3d's output id (first-voxel raster order)
+//               and is written back into the root's parent entry, flagged.
+//   F  label  : every voxel chases parent links to a flagged root and writes
+//               its id; lanes of one segment share the chase through shuffles.
+// HBM traffic: in (A1) + 4 (A1) + in (A2, neighbours hit L1/L2) + 4 + out (F)
+//   = 2*in + 8 + out bytes/voxel; algorithmic bytes (cc3d contract) = in + out.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace ign {
+
+constexpr uint32_t CCL_BG = 0xFFFFFFFFu;
+constexpr uint32_t CCL_FLAG = 0x80000000u;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+// ----------------------------------------------------------------- reader
+// How a voxel value is obtained: raw label, or threshold_image() -> {0,1};
+// rails of the +1 overlap shell are blacked out on the fly.
+template <typename T, bool THR>
+struct Reader {
+  using V = std::conditional_t<THR, uint32_t, T>;
+  const T* in;
+  double gte, lte;
+  int use_gte, use_lte;
+  uint32_t rx, ry, rz;  // rail coordinates (0xFFFFFFFF = none)
+  __device__ __forceinline__ V at(uint32_t idx, uint32_t x, uint32_t y, uint32_t z) const {
+    const T raw = in[idx];
+    V v;
+    if constexpr (THR) {
+      bool ok = true;
+      if constexpr (std::is_same<T, float>::value) {
+        if (use_gte) ok = ok && (raw >= (float)gte);
+        if (use_lte) ok = ok && (raw <= (float)lte);
+      } else {
+        if (use_gte) ok = ok && ((double)raw >= gte);
+        if (use_lte) ok = ok && ((double)raw <= lte);
+      }
+      v = ok ? 1u : 0u;
+    } else {
+      v = raw;
+    }
+    const int on = (int)(x == rx) + (int)(y == ry) + (int)(z == rz);
+    if (on >= 2) v = 0;
+    return v;
+  }
+};
+
+template <typename V>
+__device__ __forceinline__ V shfl_up1(V v) {
+  if constexpr (sizeof(V) <= 4) return (V)__shfl_up_sync(FULL, (uint32_t)v, 1);
+  else return (V)__shfl_up_sync(FULL, (unsigned long long)v, 1);
+}
+
+// ------------------------------------------------------------- union-find
+__device__ __forceinline__ uint32_t uf_find(volatile uint32_t* P, uint32_t i) {
+  uint32_t cur = i, p = P[cur];
+  while (p != cur) {
+    const uint32_t gp = P[p];
+    if (gp != p) P[cur] = gp;  // path halving; cur is not a root here
+    cur = p;
+    p = gp;
+  }
+  return cur;
+}
+
+__device__ __forceinline__ void uf_union(uint32_t* P, uint32_t a, uint32_t b) {
+  while (true) {
+    a = uf_find(P, a);
+    b = uf_find(P, b);
+    if (a == b) return;
+    if (a < b) {
+      const uint32_t t = a;
+      a = b;
+      b = t;
+    }
+    const uint32_t old = atomicMin(&P[a], b);  // hook the larger root under the smaller
+    if (old == a) return;
+    a = old;  // lost a race: a had a parent already; unite that with b
+  }
+}
+
+// ------------------------------------------------------------------ tiling
+// A CTA owns a TILE_X x TILE_Y x TILE_Z voxel tile; a warp walks whole tile
+// rows as SUBW sub-words of 32 voxels (one voxel per lane per sub-word, so all
+// global accesses are 128 B coalesced whatever the row pitch -- igneous's own
+// task shape is 513^3 -- and SUBW independent loads are in flight per lane).
+constexpr int TILE_X = 256, TILE_Y = 8, TILE_Z = 8;
+constexpr int SUBW = TILE_X / 32;             // sub-words per tile row
+constexpr int TILE_ROWS = TILE_Y * TILE_Z;    // 64
+constexpr int TILE_VOX = TILE_X * TILE_ROWS;  // 16384 -> 64 KB of u32 parents
+constexpr int CCL_THREADS = 512;
+constexpr int CCL_WARPS = CCL_THREADS / 32;
+constexpr int ROWS_PER_WARP = TILE_ROWS / CCL_WARPS;  // 4
+constexpr int TASKS_PER_WARP = 128;           // queued (a<<16|b) union tasks, 14-bit local indices
+
+struct TilePos {
+  uint32_t X0, Y0, Z0, warp, lane;
+};
+
+__device__ __forceinline__ TilePos tile_pos(uint32_t ntx, uint32_t nty) {
+  TilePos t;
+  const uint32_t b = blockIdx.x;
+  t.X0 = (b % ntx) * TILE_X;
+  t.Y0 = ((b / ntx) % nty) * TILE_Y;
+  t.Z0 = (b / (ntx * nty)) * TILE_Z;
+  t.warp = threadIdx.x >> 5;
+  t.lane = threadIdx.x & 31;
+  return t;
+}
+
+__device__ __forceinline__ uint32_t seg_start_lane(uint32_t sm, uint32_t lane) {
+  return 31 - __clz(sm & (0xFFFFFFFFu >> (31 - lane)));
+}
+
+// shared-memory union-find (same algorithm as the global one)
+__device__ __forceinline__ uint32_t sm_find(volatile uint32_t* L, uint32_t i) {
+  uint32_t cur = i, p = L[cur];
+  while (p != cur) {
+    const uint32_t gp = L[p];
+    if (gp != p) L[cur] = gp;
+    cur = p;
+    p = gp;
+  }
+  return cur;
+}
+__device__ __forceinline__ void sm_union(uint32_t* L, uint32_t a, uint32_t b) {
+  while (true) {
+    a = sm_find(L, a);
+    b = sm_find(L, b);
+    if (a == b) return;
+    if (a < b) {
+      const uint32_t t = a;
+      a = b;
+      b = t;
+    }
+    const uint32_t old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+// -------------------------------------------------------- L: tile-local CCL
+// Resolves every tile completely in shared memory and writes, for each voxel,
+// the GLOBAL linear index of its tile-local root (background -> BG).  Local
+// roots are logged as root candidates.
+template <typename R>
+__global__ void __launch_bounds__(CCL_THREADS)
+    k_ccl_local(R rd, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t ntx, uint32_t nty,
+                uint32_t* __restrict__ parent, uint32_t* __restrict__ cand, uint32_t cand_cap,
+                uint32_t* counters) {
+  extern __shared__ uint32_t L[];
+  uint32_t* tasks = L + TILE_VOX;
+  using V = typename R::V;
+  const TilePos t = tile_pos(ntx, nty);
+
+  // step 1: segment starts
+#pragma unroll 1
+  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+    const uint32_t r = t.warp * ROWS_PER_WARP + rr;
+    const uint32_t y = t.Y0 + (r % TILE_Y), z = t.Z0 + (r / TILE_Y);
+    const bool rowok = (y < sy) && (z < sz);
+    const uint32_t rowbase = (z * sy + y) * sx;
+    V v[SUBW];
+#pragma unroll
+    for (int k = 0; k < SUBW; k++) {
+      const uint32_t x = t.X0 + 32 * k + t.lane;
+      v[k] = (rowok && x < sx) ? rd.at(rowbase + x, x, y, z) : (V)0;
+    }
+#pragma unroll
+    for (int k = 0; k < SUBW; k++) {
+      const V vl = shfl_up1(v[k]);
+      const bool start = (v[k] != 0) && (t.lane == 0 || vl != v[k]);
+      const uint32_t sm = __ballot_sync(FULL, start);
+      const uint32_t li = r * TILE_X + 32 * k + t.lane;
+      L[li] = (v[k] != 0) ? (r * TILE_X + 32 * k + seg_start_lane(sm, t.lane)) : CCL_BG;
+    }
+  }
+  __syncthreads();
+
+  // step 2: unions inside the tile.  Union tasks (a,b) are queued per warp in
+  // shared memory and executed 32 at a time: the dependent-load chains of one
+  // sub-word's unions would otherwise run back to back on a single lane.
+  uint32_t* q = tasks + t.warp * TASKS_PER_WARP;
+  uint32_t nq = 0;
+  auto flush = [&]() {
+    __syncwarp();
+    for (uint32_t i = t.lane; i < nq; i += 32) {
+      const uint32_t ab = q[i];
+      sm_union(L, ab >> 16, ab & 0xFFFFu);
+    }
+    __syncwarp();
+    nq = 0;
+  };
+#pragma unroll 1
+  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+    const uint32_t r = t.warp * ROWS_PER_WARP + rr;
+    const uint32_t ly = r % TILE_Y, lz = r / TILE_Y;
+    const uint32_t y = t.Y0 + ly, z = t.Z0 + lz;
+    if (!((y < sy) && (z < sz))) continue;
+    const uint32_t rowbase = (z * sy + y) * sx;
+    const uint32_t sxy = sx * sy;
+    V v[SUBW], vy[SUBW], vz[SUBW];
+#pragma unroll
+    for (int k = 0; k < SUBW; k++) {
+      const uint32_t x = t.X0 + 32 * k + t.lane;
+      const bool inb = x < sx;
+      v[k] = inb ? rd.at(rowbase + x, x, y, z) : (V)0;
+      vy[k] = (inb && ly > 0) ? rd.at(rowbase + x - sx, x, y - 1, z) : (V)0;
+      vz[k] = (inb && lz > 0) ? rd.at(rowbase + x - sxy, x, y, z - 1) : (V)0;
+    }
+    V prev_last = 0;
+#pragma unroll
+    for (int k = 0; k < SUBW; k++) {
+      const V vl = shfl_up1(v[k]);
+      const bool same_left = (t.lane > 0) && (v[k] == vl);
+      const bool start = (v[k] != 0) && !same_left;
+      const uint32_t sm = __ballot_sync(FULL, start);
+      const bool cy = (v[k] != 0) && (v[k] == vy[k]);
+      const bool cz = (v[k] != 0) && (v[k] == vz[k]);
+      const bool cy_l = __shfl_up_sync(FULL, (int)cy, 1) != 0;
+      const bool cz_l = __shfl_up_sync(FULL, (int)cz, 1) != 0;
+      const bool tx = (t.lane == 0) && (k > 0) && (v[k] != 0) && (v[k] == prev_last);
+      const bool ty = cy && !(same_left && cy_l);
+      const bool tz = cz && !(same_left && cz_l);
+      const uint32_t li = r * TILE_X + 32 * k + t.lane;
+      const uint32_t node = r * TILE_X + 32 * k + seg_start_lane(sm | 1u, t.lane);
+      const uint32_t my = __ballot_sync(FULL, ty), mz = __ballot_sync(FULL, tz);
+      const uint32_t mx = __ballot_sync(FULL, tx);
+      const uint32_t below = (1u << t.lane) - 1u;
+      if (nq + __popc(my) + __popc(mz) + __popc(mx) > TASKS_PER_WARP) flush();
+      if (tx) q[nq] = (li << 16) | (li - 1);
+      uint32_t o = nq + __popc(mx);
+      if (ty) q[o + __popc(my & below)] = (node << 16) | (li - TILE_X);
+      o += __popc(my);
+      if (tz) q[o + __popc(mz & below)] = (node << 16) | (li - TILE_X * TILE_Y);
+      nq = o + __popc(mz);
+      if constexpr (sizeof(V) <= 4) prev_last = (V)__shfl_sync(FULL, (uint32_t)v[k], 31);
+      else prev_last = (V)__shfl_sync(FULL, (unsigned long long)v[k], 31);
+    }
+  }
+  flush();
+  __syncthreads();
+
+  // step 3: flatten, translate to global indices, log local roots
+#pragma unroll 1
+  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+    const uint32_t r = t.warp * ROWS_PER_WARP + rr;
+    const uint32_t y = t.Y0 + (r % TILE_Y), z = t.Z0 + (r / TILE_Y);
+    if (!((y < sy) && (z < sz))) continue;
+    const uint32_t rowbase = (z * sy + y) * sx;
+#pragma unroll
+    for (int k = 0; k < SUBW; k++) {
+      const uint32_t x = t.X0 + 32 * k + t.lane;
+      const uint32_t li = r * TILE_X + 32 * k + t.lane;
+      uint32_t p = L[li];
+      bool is_root = false;
+      uint32_t g = CCL_BG;
+      if (p != CCL_BG) {
+        is_root = (p == li);
+        uint32_t cur = p;
+        while (true) {  // read-only chase: no writer after the barrier
+          const uint32_t q = L[cur];
+          if (q == cur) break;
+          cur = q;
+        }
+        const uint32_t rr2 = cur / TILE_X, lx = cur % TILE_X;
+        g = ((t.Z0 + rr2 / TILE_Y) * sy + (t.Y0 + rr2 % TILE_Y)) * sx + t.X0 + lx;
+      }
+      if (x < sx) parent[rowbase + x] = g;
+      const uint32_t cm = __ballot_sync(FULL, is_root);
+      if (cm) {
+        const int leader = __ffs(cm) - 1;
+        uint32_t base = 0;
+        if ((int)t.lane == leader) base = atomicAdd(&counters[0], (uint32_t)__popc(cm));
+        base = __shfl_sync(FULL, base, leader);
+        if (is_root) {
+          const uint32_t pos = base + __popc(cm & ((1u << t.lane) - 1u));
+          if (pos < cand_cap) cand[pos] = g;
+          else counters[1] = 1;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------- G: merges across tile faces
+// Flat mapping over the voxel pairs that straddle a tile face, one 32-voxel
+// sub-word per warp (y and z faces) or 32 rows per warp (x faces), so that the
+// dependent global-memory chains of the unions are hidden by warp parallelism.
+template <typename R>
+__global__ void __launch_bounds__(256)
+    k_ccl_merge(R rd, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t nfy, uint32_t nfz,
+                uint32_t nfx, uint64_t items_y, uint64_t items_z, uint64_t items_x,
+                uint32_t* parent) {
+  using V = typename R::V;
+  const uint64_t wid = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t w32 = (sx + 31) / 32;
+  const uint32_t sxy = sx * sy;
+  if (wid < items_y + items_z) {
+    uint32_t x0, y, z, stride;
+    if (wid < items_y) {  // (k32, z, fy)
+      x0 = (uint32_t)(wid % w32) * 32;
+      const uint64_t r = wid / w32;
+      z = (uint32_t)(r % sz);
+      y = ((uint32_t)(r / sz) + 1) * TILE_Y;
+      stride = sx;
+    } else {  // (k32, y, fz)
+      const uint64_t w2 = wid - items_y;
+      x0 = (uint32_t)(w2 % w32) * 32;
+      const uint64_t r = w2 / w32;
+      y = (uint32_t)(r % sy);
+      z = ((uint32_t)(r / sy) + 1) * TILE_Z;
+      stride = sxy;
+    }
+    const uint32_t x = x0 + lane;
+    const bool inb = x < sx;
+    const uint32_t idx = (z * sy + y) * sx + x;
+    const V v = inb ? rd.at(idx, x, y, z) : (V)0;
+    const V vn = inb ? ((stride == sx) ? rd.at(idx - sx, x, y - 1, z) : rd.at(idx - sxy, x, y, z - 1))
+                     : (V)0;
+    const V vl = shfl_up1(v);
+    // a 32-voxel sub-word may straddle a tile x face: segments break there too,
+    // which only costs a redundant union.
+    const bool same_left = (lane > 0) && (v == vl);
+    const bool c = (v != 0) && (v == vn);
+    const bool c_l = __shfl_up_sync(FULL, (int)c, 1) != 0;
+    if (c && !(same_left && c_l)) uf_union(parent, idx, idx - stride);
+  } else if (wid < items_y + items_z + items_x) {  // (row block of 32, fx)
+    const uint64_t w2 = wid - items_y - items_z;
+    const uint64_t nrows = (uint64_t)sy * sz;
+    const uint64_t rb = (nrows + 31) / 32;
+    const uint32_t fx = (uint32_t)(w2 / rb) + 1;
+    const uint64_t row = (w2 % rb) * 32 + lane;
+    if (row < nrows) {
+      const uint32_t x = fx * TILE_X;
+      const uint32_t y = (uint32_t)(row % sy), z = (uint32_t)(row / sy);
+      const uint32_t idx = (uint32_t)row * sx + x;
+      const V a = rd.at(idx, x, y, z);
+      if (a != 0 && a == rd.at(idx - 1, x - 1, y, z)) uf_union(parent, idx, idx - 1);
+    }
+  }
+  (void)nfy; (void)nfz; (void)nfx;
+}
+
+// -------------------------------------------------------------------- roots
+__global__ void __launch_bounds__(256)
+    k_ccl_roots(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ cand,
+                uint32_t ncand, uint32_t* __restrict__ roots, uint32_t* counters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  bool is_root = false;
+  uint32_t c = 0;
+  if (i < ncand) {
+    c = cand[i];
+    is_root = (parent[c] == c);
+  }
+  const uint32_t m = __ballot_sync(FULL, is_root);
+  if (m) {
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(&counters[2], (uint32_t)__popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (is_root) roots[base + __popc(m & ((1u << lane) - 1u))] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_ccl_rank(uint32_t* __restrict__ parent, const uint32_t* __restrict__ roots_sorted,
+               uint32_t nroots) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nroots) parent[roots_sorted[i]] = CCL_FLAG | (i + 1);
+}
+
+// ------------------------------------------------------------------ F label
+// flat mapping: a warp owns ROWCHUNK = 256 consecutive voxels of one row
+struct ChunkPos {
+  uint32_t lane, rowbase, x0;
+  bool ok;
+};
+__device__ __forceinline__ ChunkPos chunk_pos(uint32_t sx, uint32_t cpr, uint64_t nchunks) {
+  ChunkPos c;
+  const uint64_t wid = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  c.ok = wid < nchunks;
+  c.lane = threadIdx.x & 31;
+  const uint32_t row = (uint32_t)(wid / cpr);
+  c.x0 = (uint32_t)(wid % cpr) * TILE_X;
+  c.rowbase = row * sx;
+  return c;
+}
+
+// rank (1..N) of the component of a voxel whose parent entry is e; BG -> BG
+__device__ __forceinline__ uint32_t chase(const uint32_t* __restrict__ parent, uint32_t e) {
+  while (!(e & CCL_FLAG)) e = parent[e];
+  return e;
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(256)
+    k_ccl_label(const uint32_t* __restrict__ parent, uint32_t sx, uint32_t cpr, uint64_t nchunks,
+                uint64_t offset, const uint32_t* __restrict__ rank_map, OUT* __restrict__ out) {
+  const ChunkPos c = chunk_pos(sx, cpr, nchunks);
+  if (!c.ok) return;
+  uint32_t e[SUBW];
+#pragma unroll
+  for (int k = 0; k < SUBW; k++) {
+    const uint32_t x = c.x0 + 32 * k + c.lane;
+    e[k] = (x < sx) ? parent[c.rowbase + x] : CCL_BG;
+  }
+#pragma unroll
+  for (int k = 0; k < SUBW; k++) e[k] = chase(parent, e[k]);
+#pragma unroll
+  for (int k = 0; k < SUBW; k++) {
+    const uint32_t x = c.x0 + 32 * k + c.lane;
+    uint32_t label = (e[k] == CCL_BG) ? 0u : (e[k] & ~CCL_FLAG);
+    if (rank_map != nullptr && label != 0) label = rank_map[label];  // dust: 0 = removed
+    if (x < sx) out[c.rowbase + x] = (label == 0) ? (OUT)0 : (OUT)((uint64_t)label + offset);
+  }
+}
+
+// component sizes: one atomicAdd per run of equal ids inside a sub-word
+__global__ void __launch_bounds__(256)
+    k_ccl_count(const uint32_t* __restrict__ parent, uint32_t sx, uint32_t cpr, uint64_t nchunks,
+                uint32_t* __restrict__ counts) {
+  const ChunkPos c = chunk_pos(sx, cpr, nchunks);
+  if (!c.ok) return;
+#pragma unroll 1
+  for (int k = 0; k < SUBW; k++) {
+    const uint32_t x = c.x0 + 32 * k + c.lane;
+    const uint32_t e = chase(parent, (x < sx) ? parent[c.rowbase + x] : CCL_BG);
+    const bool bg = (e == CCL_BG);
+    const uint32_t label = bg ? 0u : (e & ~CCL_FLAG);
+    const uint32_t ll = __shfl_up_sync(FULL, label, 1);
+    const bool head = !bg && (c.lane == 0 || ll != label);
+    const uint32_t hm = __ballot_sync(FULL, head || bg);
+    if (head) {
+      const uint32_t above = (c.lane == 31) ? 0u : (hm & ~((2u << c.lane) - 1u));
+      const uint32_t end = above ? (uint32_t)(__ffs(above) - 1) : 32u;
+      atomicAdd(&counts[label], end - c.lane);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_dust_flags(const uint32_t* __restrict__ counts, uint32_t n, uint64_t threshold,
+                 uint32_t* __restrict__ keep) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n && i > 0) keep[i] = ((uint64_t)counts[i] >= threshold) ? 1u : 0u;
+  if (i == 0) keep[0] = 0;
+}
+
+// single-block inclusive scan: component counts are tiny next to voxel counts
+__global__ void __launch_bounds__(1024)
+    k_scan_keep(const uint32_t* __restrict__ keep, uint32_t n_plus1, uint32_t* __restrict__ rank_map,
+                uint32_t* __restrict__ total) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_plus1; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t k = (i < n_plus1) ? keep[i] : 0;
+    uint32_t v = k;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, v, d);
+      if ((threadIdx.x & 31) >= d) v += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t s = warp_sums[threadIdx.x];
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, s, d);
+        if (threadIdx.x >= d) s += t;
+      }
+      warp_sums[threadIdx.x] = s;
+    }
+    __syncthreads();
+    const uint32_t prev_warps = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0;
+    const uint32_t incl = carry + prev_warps + v;
+    if (i < n_plus1) rank_map[i] = k ? incl : 0;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+// in-place dust on the caller's labels: zero voxels of removed components
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_dust_apply(const uint32_t* __restrict__ parent, uint32_t sx, uint32_t cpr, uint64_t nchunks,
+                 const uint32_t* __restrict__ keep, T* __restrict__ labels) {
+  const ChunkPos c = chunk_pos(sx, cpr, nchunks);
+  if (!c.ok) return;
+#pragma unroll
+  for (int k = 0; k < SUBW; k++) {
+    const uint32_t x = c.x0 + 32 * k + c.lane;
+    if (x >= sx) continue;
+    const uint32_t e = chase(parent, parent[c.rowbase + x]);
+    if (e != CCL_BG && keep[e & ~CCL_FLAG] == 0) labels[c.rowbase + x] = 0;
+  }
+}
+
+// ------------------------------------------------------------- host driver
+struct CclScratch {
+  uint32_t* parent;
+  uint32_t* cand;
+  uint32_t* roots;
+  uint32_t* roots_sorted;
+  uint32_t* counters;  // [0] ncand [1] overflow [2] nroots [3] kept
+  void* cub_tmp;
+  size_t cub_bytes;
+  uint32_t cap;
+};
+
+static size_t ccl_cub_bytes(uint32_t cap) {
+  size_t b = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)cap);
+  return b;
+}
+
+static size_t ccl_scratch_bytes(uint64_t n, uint32_t cap) {
+  return align_up(n * 4, 256) + 3 * align_up((size_t)cap * 4, 256) + 256 + align_up(ccl_cub_bytes(cap), 256) + 4096;
+}
+
+static int ccl_take(ign_ctx* ctx, uint64_t n, uint32_t cap, CclScratch& s) {
+  s.cap = cap;
+  s.parent = (uint32_t*)scratch_take(ctx, n * 4);
+  s.cand = (uint32_t*)scratch_take(ctx, (size_t)cap * 4);
+  s.roots = (uint32_t*)scratch_take(ctx, (size_t)cap * 4);
+  s.roots_sorted = (uint32_t*)scratch_take(ctx, (size_t)cap * 4);
+  s.counters = (uint32_t*)scratch_take(ctx, 256);
+  s.cub_bytes = ccl_cub_bytes(cap);
+  s.cub_tmp = scratch_take(ctx, s.cub_bytes);
+  IGN_REQUIRE(s.parent && s.cand && s.roots && s.roots_sorted && s.counters && s.cub_tmp,
+              IGN_ERR_NOMEM, "CCL scratch arena too small");
+  return IGN_OK;
+}
+
+static uint32_t default_cap(uint64_t n) {
+  uint64_t c = n / 8 + 4096;
+  return (uint32_t)c;
+}
+
+// runs A1, A2, roots, sort, rank.  On return parent[] holds flagged roots and
+// *n_roots the number of components.  *overflow set if the candidate buffer
+// was too small (nothing else valid then).
+template <typename R>
+static int ccl_core(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, uint32_t sz,
+                    CclScratch& s, uint32_t* n_roots, bool* overflow) {
+  const uint32_t ntx = (sx + TILE_X - 1) / TILE_X, nty = (sy + TILE_Y - 1) / TILE_Y,
+                 ntz = (sz + TILE_Z - 1) / TILE_Z;
+  const uint64_t n = (uint64_t)sx * sy * sz;
+  const uint64_t ntiles = (uint64_t)ntx * nty * ntz;
+  IGN_REQUIRE(ntiles < 0x7FFFFFFFull, IGN_ERR_OVERFLOW, "too many CCL tiles");
+  const unsigned grid = (unsigned)ntiles;
+  constexpr size_t smem = (TILE_VOX + CCL_WARPS * TASKS_PER_WARP) * sizeof(uint32_t);
+  *overflow = false;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    IGN_CUDA(cudaFuncSetAttribute(k_ccl_local<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  IGN_CUDA(cudaMemsetAsync(s.counters, 0, 256, ctx->stream));
+  IGN_LAUNCH(ctx, (k_ccl_local<R>), grid, CCL_THREADS, smem, rd, sx, sy, sz, ntx, nty, s.parent,
+             s.cand, s.cap, s.counters);
+  {
+    const uint32_t w32 = (sx + 31) / 32;
+    const uint64_t items_y = (uint64_t)(nty - 1) * sz * w32;
+    const uint64_t items_z = (uint64_t)(ntz - 1) * sy * w32;
+    const uint64_t items_x = (uint64_t)(ntx - 1) * (((uint64_t)sy * sz + 31) / 32);
+    const uint64_t items = items_y + items_z + items_x;
+    if (items > 0)
+      IGN_LAUNCH(ctx, (k_ccl_merge<R>), blocks_for(items * 32, 256), 256, 0, rd, sx, sy, sz, nty - 1,
+                 ntz - 1, ntx - 1, items_y, items_z, items_x, s.parent);
+  }
+  uint32_t* h = (uint32_t*)ctx->pinned;
+  IGN_CUDA(cudaMemcpyAsync(h, s.counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  IGN_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h[1] != 0 || h[0] > s.cap) {
+    *overflow = true;
+    return IGN_OK;
+  }
+  const uint32_t ncand = h[0];
+  uint32_t nroots = 0;
+  if (ncand > 0) {
+    IGN_LAUNCH(ctx, k_ccl_roots, blocks_for(ncand, 256), 256, 0, s.parent, s.cand, ncand, s.roots,
+               s.counters);
+    IGN_CUDA(cudaMemcpyAsync(h, s.counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    IGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    nroots = h[2];
+  }
+  if (nroots > 0) {
+    int end_bit = 1;
+    while (end_bit < 32 && (1ull << end_bit) < n) end_bit++;
+    size_t tb = s.cub_bytes;
+    IGN_CUDA(cub::DeviceRadixSort::SortKeys(s.cub_tmp, tb, s.roots, s.roots_sorted, (int)nroots, 0,
+                                            end_bit, ctx->stream));
+    ctx->launches += 2;  // cub radix sort: library kernels, counted conservatively
+    IGN_LAUNCH(ctx, k_ccl_rank, blocks_for(nroots, 256), 256, 0, s.parent, s.roots_sorted, nroots);
+  }
+  *n_roots = nroots;
+  return IGN_OK;
+}
+
+template <typename T>
+static Reader<T, false> plain_reader(const void* in) {
+  Reader<T, false> r;
+  r.in = (const T*)in;
+  r.gte = r.lte = 0;
+  r.use_gte = r.use_lte = 0;
+  r.rx = r.ry = r.rz = 0xFFFFFFFFu;
+  return r;
+}
+
+static int check_ccl_dims(uint64_t sx, uint64_t sy, uint64_t sz) {
+  IGN_REQUIRE(sx > 0 && sy > 0 && sz > 0, IGN_ERR_INVALID, "empty volume");
+  IGN_REQUIRE(sx * sy * sz <= 0x7FFFFFF0ull, IGN_ERR_OVERFLOW,
+              "CCL chunk of %llu voxels exceeds the 2^31 voxel limit of 32-bit provisional labels; "
+              "split the volume into tasks (igneous uses 512^3)",
+              (unsigned long long)(sx * sy * sz));
+  return IGN_OK;
+}
+
+static int launch_label(ign_ctx* ctx, const CclScratch& s, uint32_t sx, uint32_t sy, uint32_t sz,
+                        uint64_t offset, const uint32_t* rank_map, void* out, int out_dtype,
+                        uint64_t max_label) {
+  const uint32_t wpr = (sx + TILE_X - 1) / TILE_X;
+  const uint64_t nwords = (uint64_t)wpr * sy * sz;
+  const unsigned grid = blocks_for(nwords * 32, 256);
+  switch (out_dtype) {
+    case IGN_U16:
+      IGN_REQUIRE(max_label + offset <= 0xFFFFull, IGN_ERR_OVERFLOW, "%llu labels do not fit uint16", (unsigned long long)max_label);
+      IGN_LAUNCH(ctx, (k_ccl_label<uint16_t>), grid, 256, 0, s.parent, sx, wpr, nwords, offset, rank_map, (uint16_t*)out);
+      break;
+    case IGN_U32:
+      IGN_REQUIRE(max_label + offset <= 0xFFFFFFFFull, IGN_ERR_OVERFLOW, "labels do not fit uint32");
+      IGN_LAUNCH(ctx, (k_ccl_label<uint32_t>), grid, 256, 0, s.parent, sx, wpr, nwords, offset, rank_map, (uint32_t*)out);
+      break;
+    case IGN_U64:
+      IGN_LAUNCH(ctx, (k_ccl_label<uint64_t>), grid, 256, 0, s.parent, sx, wpr, nwords, offset, rank_map, (uint64_t*)out);
+      break;
+    default:
+      set_error("CCL out_dtype must be u16/u32/u64 (got %d)", out_dtype);
+      return IGN_ERR_UNSUPPORTED;
+  }
+  return IGN_OK;
+}
+
+// dust on the component structure held in s.parent: builds keep/rank maps.
+// returns device pointers (inside the arena) and the number of kept components.
+static int dust_maps(ign_ctx* ctx, const CclScratch& s, uint32_t sx, uint32_t sy, uint32_t sz,
+                     uint32_t nroots, uint64_t threshold, uint32_t** keep_out,
+                     uint32_t** rank_map_out, uint32_t* kept) {
+  const uint32_t wpr = (sx + TILE_X - 1) / TILE_X;
+  const uint64_t nwords = (uint64_t)wpr * sy * sz;
+  const unsigned grid = blocks_for(nwords * 32, 256);
+  const size_t bytes = ((size_t)nroots + 1) * 4;
+  uint32_t* counts = (uint32_t*)scratch_take(ctx, bytes);
+  uint32_t* keep = (uint32_t*)scratch_take(ctx, bytes);
+  uint32_t* rank_map = (uint32_t*)scratch_take(ctx, bytes);
+  IGN_REQUIRE(counts && keep && rank_map, IGN_ERR_NOMEM, "scratch arena too small for dust maps");
+  IGN_CUDA(cudaMemsetAsync(counts, 0, bytes, ctx->stream));
+  IGN_LAUNCH(ctx, k_ccl_count, grid, 256, 0, s.parent, sx, wpr, nwords, counts);
+  IGN_LAUNCH(ctx, k_dust_flags, blocks_for(nroots + 1, 256), 256, 0, counts, nroots, threshold, keep);
+  IGN_LAUNCH(ctx, k_scan_keep, 1, 1024, 0, keep, nroots + 1, rank_map, s.counters + 3);
+  uint32_t* h = (uint32_t*)ctx->pinned;
+  IGN_CUDA(cudaMemcpyAsync(h, s.counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  IGN_CUDA(cudaStreamSynchronize(ctx->stream));
+  *kept = h[3];
+  *keep_out = keep;
+  *rank_map_out = rank_map;
+  return IGN_OK;
+}
+
+// full pipeline for one reader type; out may be null when only dust-in-place is wanted
+template <typename R, typename TL>
+static int ccl_run(ign_ctx* ctx, const R& rd, uint64_t sx, uint64_t sy, uint64_t sz,
+                   uint64_t dust_threshold, uint64_t offset, void* out, int out_dtype,
+                   TL* dust_labels_inplace, uint64_t* n_components) {
+  IGN_TRY(check_ccl_dims(sx, sy, sz));
+  const uint64_t n = sx * sy * sz;
+  const bool own_arena = (ctx->scratch_used == 0);
+  uint32_t cap = default_cap(n);
+  for (int attempt = 0; attempt < 2; attempt++) {
+    const size_t keep_used = ctx->scratch_used;
+    const size_t need = ccl_scratch_bytes(n, cap) + 3 * ((size_t)cap + 1) * 4 + 1024;
+    if (own_arena) IGN_TRY(scratch_reserve(ctx, need));
+    CclScratch s;
+    IGN_TRY(ccl_take(ctx, n, cap, s));
+    uint32_t nroots = 0;
+    bool overflow = false;
+    int rc = ccl_core(ctx, rd, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, s, &nroots, &overflow);
+    if (rc != IGN_OK) {
+      ctx->scratch_used = keep_used;
+      return rc;
+    }
+    if (overflow) {
+      ctx->scratch_used = keep_used;
+      IGN_REQUIRE(attempt == 0, IGN_ERR_OVERFLOW,
+                  "CCL candidate buffer overflow (more than %u isolated segments)", cap);
+      cap = (uint32_t)n + 1024;  // worst case: every voxel its own component
+      continue;
+    }
+    uint32_t* rank_map = nullptr;
+    uint32_t* keep = nullptr;
+    uint32_t kept = nroots;
+    if (dust_threshold > 0 && nroots > 0) {
+      rc = dust_maps(ctx, s, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, nroots, dust_threshold, &keep, &rank_map, &kept);
+      if (rc != IGN_OK) {
+        ctx->scratch_used = keep_used;
+        return rc;
+      }
+    }
+    if (dust_labels_inplace != nullptr && keep != nullptr) {
+      const uint32_t wpr = ((uint32_t)sx + TILE_X - 1) / TILE_X;
+      const uint64_t nwords = (uint64_t)wpr * sy * sz;
+      IGN_LAUNCH(ctx, (k_dust_apply<TL>), blocks_for(nwords * 32, 256), 256, 0, s.parent, (uint32_t)sx, wpr, nwords, keep, dust_labels_inplace);
+    }
+    if (out != nullptr) {
+      rc = launch_label(ctx, s, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, offset, rank_map, out, out_dtype, kept);
+      if (rc != IGN_OK) {
+        ctx->scratch_used = keep_used;
+        return rc;
+      }
+    }
+    if (n_components) *n_components = kept;
+    ctx->scratch_used = keep_used;
+    return IGN_OK;
+  }
+  return IGN_ERR_OVERFLOW;
+}
+
+template <typename T>
+static int ccl_task_typed(ign_ctx* ctx, const void* in, uint64_t sx, uint64_t sy, uint64_t sz,
+                          int use_gte, double gte, int use_lte, double lte, uint64_t rx, uint64_t ry,
+                          uint64_t rz, uint64_t dust, uint64_t offset, uint64_t* out, uint64_t* n) {
+  auto rail = [](uint64_t r, uint64_t s) { return (r < s) ? (uint32_t)r : 0xFFFFFFFFu; };
+  if (use_gte || use_lte) {
+    Reader<T, true> r;
+    r.in = (const T*)in;
+    r.gte = gte;
+    r.lte = lte;
+    r.use_gte = use_gte;
+    r.use_lte = use_lte;
+    r.rx = rail(rx, sx);
+    r.ry = rail(ry, sy);
+    r.rz = rail(rz, sz);
+    return ccl_run(ctx, r, sx, sy, sz, dust, offset, out, IGN_U64, (uint8_t*)nullptr, n);
+  }
+  if constexpr (std::is_same<T, float>::value) {
+    set_error("CCL on float input requires a threshold");
+    return IGN_ERR_UNSUPPORTED;
+  } else {
+    Reader<T, false> r = plain_reader<T>(in);
+    r.rx = rail(rx, sx);
+    r.ry = rail(ry, sy);
+    r.rz = rail(rz, sz);
+    return ccl_run(ctx, r, sx, sy, sz, dust, offset, out, IGN_U64, (uint8_t*)nullptr, n);
+  }
+}
+
+}  // namespace ign
+
+using namespace ign;
+
+extern "C" {
+
+int ign_ccl6_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+                 void* out, int out_dtype, uint64_t* n_components) {
+  IGN_TRY(activate(ctx));
+  IGN_REQUIRE(in && out, IGN_ERR_INVALID, "null buffer");
+  switch (in_dtype) {
+    case IGN_U8: return ccl_run(ctx, plain_reader<uint8_t>(in), sx, sy, sz, 0, 0, out, out_dtype, (uint8_t*)nullptr, n_components);
+    case IGN_U16: return ccl_run(ctx, plain_reader<uint16_t>(in), sx, sy, sz, 0, 0, out, out_dtype, (uint16_t*)nullptr, n_components);
+    case IGN_U32: return ccl_run(ctx, plain_reader<uint32_t>(in), sx, sy, sz, 0, 0, out, out_dtype, (uint32_t*)nullptr, n_components);
+    case IGN_U64: return ccl_run(ctx, plain_reader<uint64_t>(in), sx, sy, sz, 0, 0, out, out_dtype, (uint64_t*)nullptr, n_components);
+  }
+  set_error("CCL: unsupported input dtype %d", in_dtype);
+  return IGN_ERR_UNSUPPORTED;
+}
+
+int ign_dust_dev(ign_ctx* ctx, void* labels, int dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+                 uint64_t threshold) {
+  IGN_TRY(activate(ctx));
+  IGN_REQUIRE(labels, IGN_ERR_INVALID, "null buffer");
+  if (threshold == 0) return IGN_OK;
+  switch (dtype) {
+    case IGN_U8: return ccl_run(ctx, plain_reader<uint8_t>(labels), sx, sy, sz, threshold, 0, nullptr, IGN_U64, (uint8_t*)labels, nullptr);
+    case IGN_U16: return ccl_run(ctx, plain_reader<uint16_t>(labels), sx, sy, sz, threshold, 0, nullptr, IGN_U64, (uint16_t*)labels, nullptr);
+    case IGN_U32: return ccl_run(ctx, plain_reader<uint32_t>(labels), sx, sy, sz, threshold, 0, nullptr, IGN_U64, (uint32_t*)labels, nullptr);
+    case IGN_U64: return ccl_run(ctx, plain_reader<uint64_t>(labels), sx, sy, sz, threshold, 0, nullptr, IGN_U64, (uint64_t*)labels, nullptr);
+  }
+  set_error("dust: unsupported dtype %d", dtype);
+  return IGN_ERR_UNSUPPORTED;
+}
+
+int ign_ccl_task_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
+                     uint64_t sz, int use_gte, double gte, int use_lte, double lte,
+                     uint64_t rail_x, uint64_t rail_y, uint64_t rail_z, uint64_t dust_threshold,
+                     uint64_t label_offset, uint64_t* out, uint64_t* n_components) {
+  IGN_TRY(activate(ctx));
+  IGN_REQUIRE(in && out, IGN_ERR_INVALID, "null buffer");
+  switch (in_dtype) {
+    case IGN_U8: return ccl_task_typed<uint8_t>(ctx, in, sx, sy, sz, use_gte, gte, use_lte, lte, rail_x, rail_y, rail_z, dust_threshold, label_offset, out, n_components);
+    case IGN_U16: return ccl_task_typed<uint16_t>(ctx, in, sx, sy, sz, use_gte, gte, use_lte, lte, rail_x, rail_y, rail_z, dust_threshold, label_offset, out, n_components);
+    case IGN_U32: return ccl_task_typed<uint32_t>(ctx, in, sx, sy, sz, use_gte, gte, use_lte, lte, rail_x, rail_y, rail_z, dust_threshold, label_offset, out, n_components);
+    case IGN_U64: return ccl_task_typed<uint64_t>(ctx, in, sx, sy, sz, use_gte, gte, use_lte, lte, rail_x, rail_y, rail_z, dust_threshold, label_offset, out, n_components);
+    case IGN_F32: return ccl_task_typed<float>(ctx, in, sx, sy, sz, use_gte, gte, use_lte, lte, rail_x, rail_y, rail_z, dust_threshold, label_offset, out, n_components);
+  }
+  set_error("CCL task: unsupported input dtype %d", in_dtype);
+  return IGN_ERR_UNSUPPORTED;
+}
+
+// ---- host-buffer wrappers
+int ign_ccl6(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+             void* out, int out_dtype, uint64_t* n_components) {
+  IGN_TRY(activate(ctx));
+  IGN_REQUIRE(in && out, IGN_ERR_INVALID, "null buffer");
+  IGN_TRY(check_ccl_dims(sx, sy, sz));
+  const int es = dtype_size(in_dtype), os = dtype_size(out_dtype);
+  IGN_REQUIRE(es > 0 && os > 0, IGN_ERR_UNSUPPORTED, "unsupported dtype");
+  const uint64_t n = sx * sy * sz;
+  scratch_reset(ctx);
+  const uint32_t cap = (uint32_t)n + 1024;  // host path: size for the worst case once
+  IGN_TRY(scratch_reserve(ctx, align_up(n * es, 256) + align_up(n * os, 256) + ccl_scratch_bytes(n, cap) + 3 * ((size_t)cap + 1) * 4 + 8192));
+  void* d_in = scratch_take(ctx, n * es);
+  void* d_out = scratch_take(ctx, n * os);
+  IGN_CUDA(cudaMemcpyAsync(d_in, in, n * es, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = ign_ccl6_dev(ctx, d_in, in_dtype, sx, sy, sz, d_out, out_dtype, n_components);
+  if (rc == IGN_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, d_out, n * os, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      set_error("CCL D2H: %s", cudaGetErrorString(e));
+      rc = IGN_ERR_CUDA;
+    }
+  }
+  scratch_reset(ctx);
+  return rc;
+}
+
+int ign_dust(ign_ctx* ctx, void* labels, int dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+             uint64_t threshold) {
+  IGN_TRY(activate(ctx));
+  IGN_REQUIRE(labels, IGN_ERR_INVALID, "null buffer");
+  if (threshold == 0) return IGN_OK;
+  IGN_TRY(check_ccl_dims(sx, sy, sz));
+  const int es = dtype_size(dtype);
+  IGN_REQUIRE(es > 0 && dtype != IGN_F32, IGN_ERR_UNSUPPORTED, "unsupported dtype");
+  const uint64_t n = sx * sy * sz;
+  scratch_reset(ctx);
+  const uint32_t cap = (uint32_t)n + 1024;
+  IGN_TRY(scratch_reserve(ctx, align_up(n * es, 256) + ccl_scratch_bytes(n, cap) + 3 * ((size_t)cap + 1) * 4 + 8192));
+  void* d = scratch_take(ctx, n * es);
+  IGN_CUDA(cudaMemcpyAsync(d, labels, n * es, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = ign_dust_dev(ctx, d, dtype, sx, sy, sz, threshold);
+  if (rc == IGN_OK) {
+    cudaError_t e = cudaMemcpyAsync(labels, d, n * es, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      set_error("dust D2H: %s", cudaGetErrorString(e));
+      rc = IGN_ERR_CUDA;
+    }
+  }
+  scratch_reset(ctx);
+  return rc;
+}
+
+}  // extern "C"

@@ -7,11 +7,6 @@ using namespace ign;
 #define IGN_STUB(name) \
   { set_error(name ": not implemented yet"); return IGN_ERR_UNSUPPORTED; }
 extern "C" {
-int ign_ccl6(ign_ctx*, const void*, int, uint64_t, uint64_t, uint64_t, void*, int, uint64_t*) IGN_STUB("ign_ccl6")
-int ign_ccl6_dev(ign_ctx*, const void*, int, uint64_t, uint64_t, uint64_t, void*, int, uint64_t*) IGN_STUB("ign_ccl6_dev")
-int ign_dust(ign_ctx*, void*, int, uint64_t, uint64_t, uint64_t, uint64_t) IGN_STUB("ign_dust")
-int ign_dust_dev(ign_ctx*, void*, int, uint64_t, uint64_t, uint64_t, uint64_t) IGN_STUB("ign_dust_dev")
-int ign_ccl_task_dev(ign_ctx*, const void*, int, uint64_t, uint64_t, uint64_t, int, double, int, double, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t*, uint64_t*) IGN_STUB("ign_ccl_task_dev")
 int ign_renumber(ign_ctx*, const void*, int, uint64_t, uint32_t*, uint64_t*, uint64_t, uint64_t*) IGN_STUB("ign_renumber")
 int ign_renumber_dev(ign_ctx*, const void*, int, uint64_t, uint32_t*, uint64_t*, uint64_t, uint64_t*) IGN_STUB("ign_renumber_dev")
 int ign_remap(ign_ctx*, void*, int, uint64_t, const uint64_t*, const uint64_t*, uint64_t, int) IGN_STUB("ign_remap")

@@ -6,12 +6,11 @@ pytestmark = pytest.mark.gpu
 
 
 def _seg(rng, shape, dtype, nlab=5):
-  # blocky labels so that ties and majorities both occur
-  small = rng.integers(0, nlab, size=tuple((s + 2) // 3 for s in shape[:3]) + shape[3:])
+  # blocky labels (3x3 in xy) plus 30% noise so that ties and majorities both occur
+  small = rng.integers(0, nlab, size=((shape[0] + 2) // 3, (shape[1] + 2) // 3) + tuple(shape[2:]))
   big = np.repeat(np.repeat(small, 3, axis=0), 3, axis=1)[:shape[0], :shape[1]]
   noise = rng.integers(0, nlab, size=shape)
-  pick = rng.random(shape) < 0.3
-  out = np.where(pick, noise, big[..., :shape[2]] if big.ndim == 3 else big)
+  out = np.where(rng.random(shape) < 0.3, noise, big)
   if np.dtype(dtype).itemsize == 8:
     out = out.astype(np.uint64) * np.uint64(0x100000001)
   return np.asfortranarray(out.astype(dtype))
