@@ -1,0 +1,112 @@
+"""GPU parity: marching cubes + weld (through the C ABI) vs the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare_all_labels(oracle, mesher, data, resolution, voxel_centered):
+  tl, tv = oracle.marching_cubes(data)
+  want_ids = sorted(int(i) for i in np.unique(tl))
+  assert sorted(mesher.ids()) == want_ids
+  for lab in want_ids:
+    got = mesher.get(lab, reduction_factor=0, voxel_centered=voxel_centered)
+    wv, wf = oracle.mesh_for_label(tl, tv, lab, resolution=resolution, voxel_centered=voxel_centered)
+    # the product already emits the canonical order: compare raw first
+    assert got.vertices.shape == wv.shape and got.faces.shape == wf.shape
+    assert np.abs(got.vertices - wv).max() <= 1e-5 * max(1.0, float(np.abs(wv).max()))
+    assert np.array_equal(got.vertices, wv)       # same f32 operation order: bit exact
+    assert np.array_equal(got.faces, wf)          # identical triangle topology and order
+    cv1, cf1 = oracle.canonicalise_mesh(got.vertices, got.faces)
+    cv2, cf2 = oracle.canonicalise_mesh(wv, wf)
+    assert np.array_equal(cf1, cf2) and np.array_equal(cv1, cv2)
+
+
+def test_mc_box_kat_gpu(ctx):
+  # reference mesh test volume (test/test_tasks.py:413-415): 62^3 box in 64^3
+  from igneous_b200 import zmesh
+  data = np.zeros((64, 64, 64), dtype=np.uint32, order="F")
+  data[1:-1, 1:-1, 1:-1] = 1
+  m = zmesh.Mesher((1, 1, 1))
+  m.mesh(data)
+  assert m.ids() == [1]
+  mesh = m.get(1, reduction_factor=0, voxel_centered=False)
+  assert mesh.faces.shape == (46124, 3) and mesh.vertices.shape == (23064, 3)
+  v, f = mesh.vertices.astype(np.float64), mesh.faces
+  vol = np.einsum("ij,ij->i", v[f[:, 0]], np.cross(v[f[:, 1]], v[f[:, 2]])).sum() / 6
+  n = 62
+  assert abs(vol - ((n - 1) ** 3 + 3 * (n - 1) ** 2 + 1.5 * (n - 1) + 1 / 6)) < 1e-3
+  binary = mesh.to_precomputed()
+  assert len(binary) == 4 + 12 * 23064 + 12 * 46124
+  back = zmesh.Mesh.from_precomputed(binary)
+  assert back == mesh
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64])
+def test_mc_random_multilabel_matches_oracle(ctx, oracle, dtype):
+  from igneous_b200 import zmesh
+  rng = np.random.default_rng(3)
+  data = np.zeros((23, 19, 17), dtype=dtype, order="F")
+  vals = np.array([0, 7, 9, 250], dtype=dtype)
+  if np.dtype(dtype).itemsize == 8:
+    vals = np.array([0, 7, 1 << 40, (1 << 63) + 5], dtype=np.uint64)
+  data[1:-1, 1:-1, 1:-1] = vals[rng.integers(0, 4, size=(21, 17, 15))]
+  res = (4.0, 4.0, 40.0)
+  m = zmesh.Mesher(res)
+  m.mesh(data)
+  for vc in (False, True):
+    _compare_all_labels(oracle, m, data, res, vc)
+
+
+def test_mc_synthetic_segmentation_unpadded(ctx, oracle):
+  # open surfaces at the chunk border (no zero padding), realistic labels
+  from igneous_b200 import zmesh
+  seg = oracle.synth_seg((65, 65, 33), pitch=16, num_ids=1 << 20)
+  m = zmesh.Mesher((16, 16, 40))
+  m.mesh(seg)
+  _compare_all_labels(oracle, m, seg, (16, 16, 40), True)
+
+
+def test_mc_empty_and_degenerate(ctx):
+  from igneous_b200 import zmesh
+  m = zmesh.Mesher((1, 1, 1))
+  m.mesh(np.zeros((8, 8, 8), dtype=np.uint32))
+  assert m.ids() == []
+  m.mesh(np.full((8, 8, 8), 5, dtype=np.uint32))  # no surface inside the chunk
+  assert m.ids() == []
+  m.mesh(np.ones((1, 5, 5), dtype=np.uint8))
+  assert m.ids() == []
+  with pytest.raises(KeyError):
+    m.get(3)
+
+
+def test_mc_properties_at_task_size(ctx):
+  """257^3 task (BASELINE config C4 task shape + overlap): every label's mesh
+  has only valid indices, no degenerate faces, and interior labels are closed."""
+  from igneous_b200 import zmesh, _shim
+  import ctypes as c
+  n = 257
+  d = ctx.alloc(n ** 3 * 4)
+  _shim.check(ctx.lib.ign_synth_seg_dev(ctx.handle, _shim.ptr(d), c.c_int(_shim.IGN_U32), c.c_uint64(n), c.c_uint64(n), c.c_uint64(n), c.c_int64(0), c.c_int64(0), c.c_int64(0), c.c_uint32(64), c.c_uint64(1 << 20), c.c_uint64(0), c.c_uint64(0)))
+  seg = ctx.to_host(d, (n, n, n), np.uint32)
+  d.free()
+  m = zmesh.Mesher((16, 16, 40))
+  m.mesh(seg)
+  ids = m.ids()
+  assert len(ids) > 50
+  inner = set(np.unique(seg[1:-1, 1:-1, 1:-1])) - set(np.unique(np.concatenate([
+    seg[0].ravel(), seg[-1].ravel(), seg[:, 0].ravel(), seg[:, -1].ravel(),
+    seg[:, :, 0].ravel(), seg[:, :, -1].ravel()])))
+  checked = 0
+  for lab in ids:
+    mesh = m.get(lab, voxel_centered=True)
+    f = mesh.faces
+    assert f.max() < len(mesh.vertices)
+    assert (f[:, 0] != f[:, 1]).all() and (f[:, 1] != f[:, 2]).all() and (f[:, 0] != f[:, 2]).all()
+    if lab in inner and checked < 10:
+      e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]).astype(np.int64)
+      fwd = e[:, 0] * (1 << 32) + e[:, 1]
+      bwd = e[:, 1] * (1 << 32) + e[:, 0]
+      assert np.array_equal(np.sort(fwd), np.sort(bwd))  # closed + consistently oriented
+      checked += 1
+  assert checked > 0
