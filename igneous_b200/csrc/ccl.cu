@@ -28,6 +28,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <type_traits>
+#include <vector>
 
 #include "common.cuh"
 
@@ -548,9 +549,10 @@ static size_t ccl_scratch_bytes(uint64_t n, uint32_t cap) {
   return align_up(n * 4, 256) + 3 * align_up((size_t)cap * 4, 256) + 256 + align_up(ccl_cub_bytes(cap), 256) + 4096;
 }
 
-static int ccl_take(ign_ctx* ctx, uint64_t n, uint32_t cap, CclScratch& s) {
+static int ccl_take(ign_ctx* ctx, uint64_t n, uint32_t cap, CclScratch& s,
+                    uint32_t* ext_parent = nullptr) {
   s.cap = cap;
-  s.parent = (uint32_t*)scratch_take(ctx, n * 4);
+  s.parent = ext_parent ? ext_parent : (uint32_t*)scratch_take(ctx, n * 4);
   s.cand = (uint32_t*)scratch_take(ctx, (size_t)cap * 4);
   s.roots = (uint32_t*)scratch_take(ctx, (size_t)cap * 4);
   s.roots_sorted = (uint32_t*)scratch_take(ctx, (size_t)cap * 4);
@@ -587,7 +589,7 @@ static int ccl_core(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, uint32_
     attr_set = true;
   }
   IGN_CUDA(cudaMemsetAsync(s.counters, 0, 256, ctx->stream));
-  IGN_LAUNCH(ctx, (k_ccl_local<R>), grid, CCL_THREADS, smem, rd, sx, sy, sz, ntx, nty, s.parent,
+  IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local<R>), grid, CCL_THREADS, smem, rd, sx, sy, sz, ntx, nty, s.parent,
              s.cand, s.cap, s.counters);
   {
     const uint32_t w32 = (sx + 31) / 32;
@@ -596,7 +598,7 @@ static int ccl_core(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, uint32_
     const uint64_t items_x = (uint64_t)(ntx - 1) * (((uint64_t)sy * sz + 31) / 32);
     const uint64_t items = items_y + items_z + items_x;
     if (items > 0)
-      IGN_LAUNCH(ctx, (k_ccl_merge<R>), blocks_for(items * 32, 256), 256, 0, rd, sx, sy, sz, nty - 1,
+      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, (k_ccl_merge<R>), blocks_for(items * 32, 256), 256, 0, rd, sx, sy, sz, nty - 1,
                  ntz - 1, ntx - 1, items_y, items_z, items_x, s.parent);
   }
   uint32_t* h = (uint32_t*)ctx->pinned;
@@ -656,14 +658,14 @@ static int launch_label(ign_ctx* ctx, const CclScratch& s, uint32_t sx, uint32_t
   switch (out_dtype) {
     case IGN_U16:
       IGN_REQUIRE(max_label + offset <= 0xFFFFull, IGN_ERR_OVERFLOW, "%llu labels do not fit uint16", (unsigned long long)max_label);
-      IGN_LAUNCH(ctx, (k_ccl_label<uint16_t>), grid, 256, 0, s.parent, sx, wpr, nwords, offset, rank_map, (uint16_t*)out);
+      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LABEL, (k_ccl_label<uint16_t>), grid, 256, 0, s.parent, sx, wpr, nwords, offset, rank_map, (uint16_t*)out);
       break;
     case IGN_U32:
       IGN_REQUIRE(max_label + offset <= 0xFFFFFFFFull, IGN_ERR_OVERFLOW, "labels do not fit uint32");
-      IGN_LAUNCH(ctx, (k_ccl_label<uint32_t>), grid, 256, 0, s.parent, sx, wpr, nwords, offset, rank_map, (uint32_t*)out);
+      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LABEL, (k_ccl_label<uint32_t>), grid, 256, 0, s.parent, sx, wpr, nwords, offset, rank_map, (uint32_t*)out);
       break;
     case IGN_U64:
-      IGN_LAUNCH(ctx, (k_ccl_label<uint64_t>), grid, 256, 0, s.parent, sx, wpr, nwords, offset, rank_map, (uint64_t*)out);
+      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LABEL, (k_ccl_label<uint64_t>), grid, 256, 0, s.parent, sx, wpr, nwords, offset, rank_map, (uint64_t*)out);
       break;
     default:
       set_error("CCL out_dtype must be u16/u32/u64 (got %d)", out_dtype);
@@ -785,6 +787,90 @@ static int ccl_task_typed(ign_ctx* ctx, const void* in, uint64_t sx, uint64_t sy
   }
 }
 
+
+// ------------------------------------------------------ multi-slab building blocks
+// (igneous/tasks/image/ccl.py passes 1-4 without the file exchange: slabs are
+// disjoint in z, linked through their facing planes.)
+
+// structure only (phases L, G, roots, rank) into a caller-owned parent array
+template <typename R>
+static int ccl_build(ign_ctx* ctx, const R& rd, uint64_t sx, uint64_t sy, uint64_t sz,
+                     uint32_t* parent, uint64_t* n_local) {
+  IGN_TRY(check_ccl_dims(sx, sy, sz));
+  const uint64_t n = sx * sy * sz;
+  const bool own_arena = (ctx->scratch_used == 0);
+  uint32_t cap = default_cap(n);
+  for (int attempt = 0; attempt < 2; attempt++) {
+    const size_t keep_used = ctx->scratch_used;
+    if (own_arena) IGN_TRY(scratch_reserve(ctx, ccl_scratch_bytes(0, cap) + 4096));
+    CclScratch s;
+    int rc = ccl_take(ctx, n, cap, s, parent);
+    if (rc != IGN_OK) {
+      ctx->scratch_used = keep_used;
+      return rc;
+    }
+    uint32_t nroots = 0;
+    bool overflow = false;
+    rc = ccl_core(ctx, rd, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, s, &nroots, &overflow);
+    ctx->scratch_used = keep_used;
+    if (rc != IGN_OK) return rc;
+    if (overflow) {
+      IGN_REQUIRE(attempt == 0, IGN_ERR_OVERFLOW, "CCL candidate buffer overflow");
+      cap = (uint32_t)n + 1024;
+      continue;
+    }
+    *n_local = nroots;
+    return IGN_OK;
+  }
+  return IGN_ERR_OVERFLOW;
+}
+
+// one z-plane of a slab: voxel values widened to u64 and local component ids
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_ccl_plane(const T* __restrict__ in, const uint32_t* __restrict__ parent, uint64_t plane_base,
+                uint64_t nplane, uint64_t* __restrict__ values, uint32_t* __restrict__ labels) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= nplane) return;
+  values[i] = (uint64_t)in[plane_base + i];
+  const uint32_t e = chase(parent, parent[plane_base + i]);
+  labels[i] = (e == CCL_BG) ? 0u : (e & ~CCL_FLAG);
+}
+
+// equivalence pairs between two facing planes (same x,y; adjacent z)
+__global__ void __launch_bounds__(256)
+    k_ccl_link(const uint64_t* __restrict__ va, const uint32_t* __restrict__ la, uint64_t offa,
+               const uint64_t* __restrict__ vb, const uint32_t* __restrict__ lb, uint64_t offb,
+               uint64_t nplane, uint64_t* __restrict__ pairs, uint32_t cap, uint32_t* counters) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  bool emit = false;
+  uint64_t a = 0, b = 0;
+  if (i < nplane) {
+    const uint64_t v = va[i];
+    if (v != 0 && v == vb[i]) {
+      a = offa + la[i];
+      b = offb + lb[i];
+      // runs of the same pair along x are emitted once
+      emit = !(i > 0 && la[i - 1] == la[i] && lb[i - 1] == lb[i] && va[i - 1] == v && vb[i - 1] == v);
+    }
+  }
+  const uint32_t m = __ballot_sync(FULL, emit);
+  if (m) {
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(&counters[0], (uint32_t)__popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (emit) {
+      const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+      if (pos < cap) {
+        pairs[2 * (uint64_t)pos] = a;
+        pairs[2 * (uint64_t)pos + 1] = b;
+      }
+    }
+  }
+}
+
 }  // namespace ign
 
 using namespace ign;
@@ -888,6 +974,217 @@ int ign_dust(ign_ctx* ctx, void* labels, int dtype, uint64_t sx, uint64_t sy, ui
       rc = IGN_ERR_CUDA;
     }
   }
+  scratch_reset(ctx);
+  return rc;
+}
+
+
+// ------------------------------------------------------------ multi-slab API
+int ign_ccl6_build_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
+                       uint64_t sz, uint32_t* work, uint64_t* n_local) {
+  IGN_TRY(activate(ctx));
+  IGN_REQUIRE(in && work && n_local, IGN_ERR_INVALID, "null argument");
+  switch (in_dtype) {
+    case IGN_U8: return ccl_build(ctx, plain_reader<uint8_t>(in), sx, sy, sz, work, n_local);
+    case IGN_U16: return ccl_build(ctx, plain_reader<uint16_t>(in), sx, sy, sz, work, n_local);
+    case IGN_U32: return ccl_build(ctx, plain_reader<uint32_t>(in), sx, sy, sz, work, n_local);
+    case IGN_U64: return ccl_build(ctx, plain_reader<uint64_t>(in), sx, sy, sz, work, n_local);
+  }
+  set_error("CCL build: unsupported input dtype %d", in_dtype);
+  return IGN_ERR_UNSUPPORTED;
+}
+
+int ign_ccl6_plane_dev(ign_ctx* ctx, const void* in, int in_dtype, const uint32_t* work, uint64_t sx,
+                       uint64_t sy, uint64_t sz, uint64_t z, uint64_t* values, uint32_t* labels) {
+  IGN_TRY(activate(ctx));
+  IGN_REQUIRE(in && work && values && labels && z < sz, IGN_ERR_INVALID, "bad plane argument");
+  const uint64_t np = sx * sy, base = z * np;
+  const unsigned g = blocks_for(np, 256);
+  switch (in_dtype) {
+    case IGN_U8: IGN_LAUNCH(ctx, (k_ccl_plane<uint8_t>), g, 256, 0, (const uint8_t*)in, work, base, np, values, labels); break;
+    case IGN_U16: IGN_LAUNCH(ctx, (k_ccl_plane<uint16_t>), g, 256, 0, (const uint16_t*)in, work, base, np, values, labels); break;
+    case IGN_U32: IGN_LAUNCH(ctx, (k_ccl_plane<uint32_t>), g, 256, 0, (const uint32_t*)in, work, base, np, values, labels); break;
+    case IGN_U64: IGN_LAUNCH(ctx, (k_ccl_plane<uint64_t>), g, 256, 0, (const uint64_t*)in, work, base, np, values, labels); break;
+    default: set_error("CCL plane: unsupported input dtype %d", in_dtype); return IGN_ERR_UNSUPPORTED;
+  }
+  return IGN_OK;
+}
+
+// device address of the pair list written by the last ign_ccl6_link_dev call on
+// this thread; valid until the next arena allocation at the same bump position
+static thread_local uint64_t* g_last_link_pairs = nullptr;
+static uint64_t* link_pairs_dev(ign_ctx*) { return g_last_link_pairs; }
+
+int ign_ccl6_link_dev(ign_ctx* ctx, const uint64_t* values_a, const uint32_t* labels_a,
+                      uint64_t offset_a, const uint64_t* values_b, const uint32_t* labels_b,
+                      uint64_t offset_b, uint64_t n_plane, uint64_t* pairs_host, uint64_t capacity,
+                      uint64_t* n_pairs) {
+  IGN_TRY(activate(ctx));
+  IGN_REQUIRE(values_a && labels_a && values_b && labels_b && n_pairs, IGN_ERR_INVALID, "null argument");
+  *n_pairs = 0;
+  if (n_plane == 0) return IGN_OK;
+  const size_t keep = ctx->scratch_used;
+  const bool own = (keep == 0);
+  const uint32_t cap = (uint32_t)(n_plane < 0x7FFFFFFFull ? n_plane : 0x7FFFFFFFull);
+  if (own) IGN_TRY(scratch_reserve(ctx, (size_t)cap * 16 + 8192));
+  uint64_t* d_pairs = (uint64_t*)scratch_take(ctx, (size_t)cap * 16);
+  uint32_t* counters = (uint32_t*)scratch_take(ctx, 256);
+  g_last_link_pairs = d_pairs;
+  if (!d_pairs || !counters) {
+    ctx->scratch_used = keep;
+    set_error("scratch arena too small (CCL link)");
+    return IGN_ERR_NOMEM;
+  }
+  IGN_CUDA(cudaMemsetAsync(counters, 0, 256, ctx->stream));
+  IGN_LAUNCH(ctx, k_ccl_link, blocks_for(n_plane, 256), 256, 0, values_a, labels_a, offset_a, values_b,
+             labels_b, offset_b, n_plane, d_pairs, cap, counters);
+  uint32_t* h = (uint32_t*)ctx->pinned;
+  IGN_CUDA(cudaMemcpyAsync(h, counters, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  IGN_CUDA(cudaStreamSynchronize(ctx->stream));
+  const uint64_t total = h[0];
+  *n_pairs = total;
+  if (pairs_host && total) {
+    const uint64_t m = total < capacity ? total : capacity;
+    IGN_CUDA(cudaMemcpy(pairs_host, d_pairs, m * 16, cudaMemcpyDeviceToHost));
+  }
+  ctx->scratch_used = keep;
+  return IGN_OK;
+}
+
+// Host-side global union-find over provisional ids 1..total (the B200-native
+// stand-in for create_relabeling, igneous/tasks/image/ccl.py:358-420):
+// smaller id wins (ccl.py:70-73); final ids are the ranks of the component
+// minima, i.e. identical to a whole-volume cc3d numbering.
+int ign_ccl6_solve(const uint64_t* pairs, uint64_t n_pairs, uint64_t total, uint32_t* lut,
+                   uint64_t* n_global) {
+  IGN_REQUIRE(lut && n_global && (n_pairs == 0 || pairs), IGN_ERR_INVALID, "null argument");
+  IGN_REQUIRE(total < 0xFFFFFFF0ull, IGN_ERR_OVERFLOW, "too many provisional components");
+  std::vector<uint32_t> p(total + 1);
+  for (uint64_t i = 0; i <= total; i++) p[i] = (uint32_t)i;
+  auto find = [&](uint32_t i) {
+    while (p[i] != i) {
+      p[i] = p[p[i]];
+      i = p[i];
+    }
+    return i;
+  };
+  for (uint64_t k = 0; k < n_pairs; k++) {
+    const uint64_t a64 = pairs[2 * k], b64 = pairs[2 * k + 1];
+    IGN_REQUIRE(a64 >= 1 && a64 <= total && b64 >= 1 && b64 <= total, IGN_ERR_INVALID,
+                "equivalence pair (%llu,%llu) out of range", (unsigned long long)a64, (unsigned long long)b64);
+    const uint32_t a = find((uint32_t)a64), b = find((uint32_t)b64);
+    if (a < b) p[b] = a;
+    else if (b < a) p[a] = b;
+  }
+  uint32_t next = 0;
+  lut[0] = 0;
+  for (uint64_t i = 1; i <= total; i++) {
+    const uint32_t r = find((uint32_t)i);
+    if (r == i) lut[i] = ++next;  // roots are minima: met before their members
+    else lut[i] = lut[r];
+  }
+  *n_global = next;
+  return IGN_OK;
+}
+
+int ign_ccl6_label_dev(ign_ctx* ctx, const uint32_t* work, uint64_t sx, uint64_t sy, uint64_t sz,
+                       const uint32_t* lut_dev, uint64_t offset, void* out, int out_dtype,
+                       uint64_t max_label) {
+  IGN_TRY(activate(ctx));
+  IGN_REQUIRE(work && out, IGN_ERR_INVALID, "null argument");
+  IGN_TRY(check_ccl_dims(sx, sy, sz));
+  CclScratch s;
+  s.parent = const_cast<uint32_t*>(work);
+  return launch_label(ctx, s, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, offset, lut_dev, out, out_dtype, max_label);
+}
+
+// Whole-volume CCL on one GPU for volumes beyond the 2^31-voxel slab limit:
+// z-slabs are resolved independently, linked through their facing planes and
+// labelled once with the composed lookup table.
+int ign_ccl6_volume_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
+                        uint64_t sz, void* out, int out_dtype, uint64_t max_slab_voxels,
+                        uint64_t* n_components) {
+  IGN_TRY(activate(ctx));
+  IGN_REQUIRE(in && out, IGN_ERR_INVALID, "null buffer");
+  IGN_REQUIRE(sx > 0 && sy > 0 && sz > 0, IGN_ERR_INVALID, "empty volume");
+  const int es = dtype_size(in_dtype), os = dtype_size(out_dtype);
+  IGN_REQUIRE(es > 0 && os > 0 && in_dtype != IGN_F32, IGN_ERR_UNSUPPORTED, "unsupported dtype");
+  const uint64_t np = sx * sy;
+  if (max_slab_voxels == 0 || max_slab_voxels > 0x40000000ull) max_slab_voxels = 0x40000000ull;
+  IGN_REQUIRE(np <= max_slab_voxels, IGN_ERR_OVERFLOW, "one z-plane exceeds the slab limit");
+  const uint64_t slab_sz = max_slab_voxels / np;
+  const uint64_t nslabs = (sz + slab_sz - 1) / slab_sz;
+  const uint64_t n = np * sz;
+  IGN_REQUIRE(ctx->scratch_used == 0, IGN_ERR_INVALID, "ign_ccl6_volume_dev must own the scratch arena");
+  const uint64_t slab_vox = np * (slab_sz < sz ? slab_sz : sz);
+  const uint32_t cap = (uint32_t)slab_vox + 1024;
+  const size_t need = align_up(n * 4, 256) + ccl_scratch_bytes(0, cap) + 2 * (align_up(np * 8, 256) + align_up(np * 4, 256)) +
+                      align_up(np * 16, 256) + align_up((n / 8 + 4096) * 4, 256) + (1 << 20);
+  IGN_TRY(scratch_reserve(ctx, need));
+  uint32_t* work = (uint32_t*)scratch_take(ctx, n * 4);
+  uint64_t* va = (uint64_t*)scratch_take(ctx, np * 8);
+  uint64_t* vb = (uint64_t*)scratch_take(ctx, np * 8);
+  uint32_t* la = (uint32_t*)scratch_take(ctx, np * 4);
+  uint32_t* lb = (uint32_t*)scratch_take(ctx, np * 4);
+  IGN_REQUIRE(work && va && vb && la && lb, IGN_ERR_NOMEM, "scratch arena too small (volume CCL)");
+  std::vector<uint64_t> nloc(nslabs), off(nslabs + 1, 0);
+  int rc = IGN_OK;
+  for (uint64_t s = 0; s < nslabs && rc == IGN_OK; s++) {
+    const uint64_t z0 = s * slab_sz, zs = (z0 + slab_sz <= sz) ? slab_sz : sz - z0;
+    rc = ign_ccl6_build_dev(ctx, (const char*)in + z0 * np * es, in_dtype, sx, sy, zs, work + z0 * np, &nloc[s]);
+    off[s + 1] = off[s] + nloc[s];
+  }
+  const uint64_t total = off[nslabs];
+  std::vector<uint64_t> pairs;
+  for (uint64_t s = 0; s + 1 < nslabs && rc == IGN_OK; s++) {
+    const uint64_t z0 = s * slab_sz, z1 = (s + 1) * slab_sz;
+    const uint64_t zs1 = (z1 + slab_sz <= sz) ? slab_sz : sz - z1;
+    rc = ign_ccl6_plane_dev(ctx, (const char*)in + z0 * np * es, in_dtype, work + z0 * np, sx, sy, slab_sz, slab_sz - 1, va, la);
+    if (rc == IGN_OK) rc = ign_ccl6_plane_dev(ctx, (const char*)in + z1 * np * es, in_dtype, work + z1 * np, sx, sy, zs1, 0, vb, lb);
+    if (rc != IGN_OK) break;
+    // exact-size transfer: the device list is counted first, then copied into
+    // the (tiny) host vector -- no plane-sized host staging per boundary
+    uint64_t cnt = 0;
+    rc = ign_ccl6_link_dev(ctx, va, la, off[s], vb, lb, off[s + 1], np, nullptr, 0, &cnt);
+    if (rc != IGN_OK) break;
+    if (cnt) {
+      const size_t at = pairs.size();
+      pairs.resize(at + 2 * cnt);
+      cudaError_t e = cudaMemcpy(pairs.data() + at, link_pairs_dev(ctx), cnt * 16, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) {
+        set_error("volume CCL: pairs D2H: %s", cudaGetErrorString(e));
+        rc = IGN_ERR_CUDA;
+      }
+    }
+  }
+  uint64_t nglobal = total;
+  uint32_t* d_lut = nullptr;
+  if (rc == IGN_OK && nslabs > 1) {
+    std::vector<uint32_t> lut(total + 1);
+    rc = ign_ccl6_solve(pairs.data(), pairs.size() / 2, total, lut.data(), &nglobal);
+    if (rc == IGN_OK) {
+      d_lut = (uint32_t*)scratch_take(ctx, (total + 1) * 4);
+      if (!d_lut) {
+        set_error("scratch arena too small for the relabel table (%llu components)", (unsigned long long)total);
+        rc = IGN_ERR_NOMEM;
+      } else {
+        cudaError_t e = cudaMemcpyAsync(d_lut, lut.data(), (total + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // lut is a host temporary
+        if (e != cudaSuccess) {
+          set_error("volume CCL: lut H2D: %s", cudaGetErrorString(e));
+          rc = IGN_ERR_CUDA;
+        }
+      }
+    }
+  }
+  for (uint64_t s = 0; s < nslabs && rc == IGN_OK; s++) {
+    const uint64_t z0 = s * slab_sz, zs = (z0 + slab_sz <= sz) ? slab_sz : sz - z0;
+    if (d_lut)
+      rc = ign_ccl6_label_dev(ctx, work + z0 * np, sx, sy, zs, d_lut + off[s], 0, (char*)out + z0 * np * os, out_dtype, nglobal);
+    else
+      rc = ign_ccl6_label_dev(ctx, work + z0 * np, sx, sy, zs, nullptr, 0, (char*)out + z0 * np * os, out_dtype, nglobal);
+  }
+  if (rc == IGN_OK && n_components) *n_components = nglobal;
   scratch_reset(ctx);
   return rc;
 }

@@ -65,7 +65,21 @@ struct ign_ctx {
   size_t pinned_bytes;
   cudaEvent_t timers[16][2];
   uint64_t launches;
+  // optional per-kernel-class profiling (ign_prof_enable): CUDA events recorded
+  // on the ctx stream around selected launches
+  int prof_on;
+  struct ProfRec { int cls; cudaEvent_t a, b; };
+  ProfRec* prof;
+  int prof_n, prof_cap;
+  // grow-only pool for the result buffers of the (normally single) live mesher:
+  // cudaMalloc/cudaFree per task serialise on the driver lock
+  char* mesh_pool;
+  size_t mesh_pool_bytes;
+  int mesh_pool_busy;
 };
+
+enum { IGN_PROF_CCL_LOCAL = 0, IGN_PROF_CCL_MERGE = 1, IGN_PROF_CCL_LABEL = 2, IGN_PROF_POOL = 3,
+       IGN_PROF_MC = 4, IGN_PROF_CLASSES = 8 };
 
 namespace ign {
 
@@ -87,6 +101,18 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
   do {                                                                           \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
     (ctx)->launches++;                                                           \
+    IGN_CUDA(cudaGetLastError());                                                \
+  } while (0)
+
+// profiled launch: like IGN_LAUNCH, plus an event pair when profiling is on
+int prof_begin(ign_ctx* ctx, int cls);
+void prof_end(ign_ctx* ctx, int slot);
+#define IGN_LAUNCH_PROF(ctx, cls, kernel, grid, block, smem, ...)                 \
+  do {                                                                           \
+    const int _slot = ign::prof_begin((ctx), (cls));                             \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
+    (ctx)->launches++;                                                           \
+    ign::prof_end((ctx), _slot);                                                 \
     IGN_CUDA(cudaGetLastError());                                                \
   } while (0)
 

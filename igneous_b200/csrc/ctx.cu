@@ -48,6 +48,39 @@ void* scratch_take(ign_ctx* ctx, size_t bytes) {
   return ctx->scratch + off;
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_copy_box(const T* __restrict__ src, uint64_t sx, uint64_t sy, uint64_t x0, uint64_t y0,
+               uint64_t z0, uint64_t bx, uint64_t by, uint64_t total, T* __restrict__ dst) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const uint64_t x = i % bx, r = i / bx, y = r % by, z = r / by;
+  dst[i] = src[((z0 + z) * sy + (y0 + y)) * sx + (x0 + x)];
+}
+
+int prof_begin(ign_ctx* ctx, int cls) {
+  if (!ctx->prof_on) return -1;
+  if (ctx->prof_n == ctx->prof_cap) {
+    const int ncap = ctx->prof_cap ? ctx->prof_cap * 2 : 256;
+    ign_ctx::ProfRec* np = (ign_ctx::ProfRec*)realloc(ctx->prof, sizeof(ign_ctx::ProfRec) * ncap);
+    if (!np) return -1;
+    for (int i = ctx->prof_cap; i < ncap; i++) {
+      cudaEventCreate(&np[i].a);
+      cudaEventCreate(&np[i].b);
+    }
+    ctx->prof = np;
+    ctx->prof_cap = ncap;
+  }
+  const int slot = ctx->prof_n++;
+  ctx->prof[slot].cls = cls;
+  cudaEventRecord(ctx->prof[slot].a, ctx->stream);
+  return slot;
+}
+
+void prof_end(ign_ctx* ctx, int slot) {
+  if (slot >= 0) cudaEventRecord(ctx->prof[slot].b, ctx->stream);
+}
+
 }  // namespace ign
 
 using namespace ign;
@@ -89,6 +122,12 @@ int ign_init(int device, ign_ctx** out) {
   ctx->scratch = nullptr;
   ctx->scratch_bytes = ctx->scratch_used = 0;
   ctx->launches = 0;
+  ctx->prof_on = 0;
+  ctx->prof = nullptr;
+  ctx->prof_n = ctx->prof_cap = 0;
+  ctx->mesh_pool = nullptr;
+  ctx->mesh_pool_bytes = 0;
+  ctx->mesh_pool_busy = 0;
   IGN_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   IGN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   ctx->pinned_bytes = 1 << 20;
@@ -107,6 +146,7 @@ int ign_destroy(ign_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->mesh_pool) cudaFree(ctx->mesh_pool);
   for (int i = 0; i < 16; i++) {
     cudaEventDestroy(ctx->timers[i][0]);
     cudaEventDestroy(ctx->timers[i][1]);
@@ -194,6 +234,53 @@ int ign_d2d(ign_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
 int ign_memset(ign_ctx* ctx, void* dst, int byte, uint64_t bytes) {
   IGN_TRY(activate(ctx));
   IGN_CUDA(cudaMemsetAsync(dst, byte, bytes, ctx->stream));
+  return IGN_OK;
+}
+
+int ign_prof_enable(ign_ctx* ctx, int on) {
+  IGN_REQUIRE(ctx, IGN_ERR_INVALID, "null ctx");
+  ctx->prof_on = on ? 1 : 0;
+  ctx->prof_n = 0;
+  return IGN_OK;
+}
+
+// sums the recorded launches of one kernel class since ign_prof_enable(ctx,1)
+int ign_prof_read(ign_ctx* ctx, int cls, float* total_ms, uint64_t* launches) {
+  IGN_TRY(activate(ctx));
+  IGN_REQUIRE(total_ms && launches, IGN_ERR_INVALID, "null argument");
+  IGN_CUDA(cudaStreamSynchronize(ctx->stream));
+  float sum = 0;
+  uint64_t cnt = 0;
+  for (int i = 0; i < ctx->prof_n; i++) {
+    if (ctx->prof[i].cls != cls) continue;
+    float ms = 0;
+    IGN_CUDA(cudaEventElapsedTime(&ms, ctx->prof[i].a, ctx->prof[i].b));
+    sum += ms;
+    cnt++;
+  }
+  *total_ms = sum;
+  *launches = cnt;
+  return IGN_OK;
+}
+
+// strided 3-D sub-box copy between device volumes (Fortran order).  A plain
+// coalesced kernel: cudaMemcpy3D takes a slow path for rows of ~1 KB.
+int ign_copy_box_dev(ign_ctx* ctx, const void* src, int dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+                     uint64_t x0, uint64_t y0, uint64_t z0, uint64_t bx, uint64_t by, uint64_t bz,
+                     void* dst) {
+  IGN_TRY(activate(ctx));
+  const size_t es = dtype_size(dtype);
+  IGN_REQUIRE(src && dst && es > 0, IGN_ERR_INVALID, "bad copy_box argument");
+  IGN_REQUIRE(x0 + bx <= sx && y0 + by <= sy && z0 + bz <= sz, IGN_ERR_INVALID, "box outside the volume");
+  const uint64_t total = bx * by * bz;
+  if (total == 0) return IGN_OK;
+  const unsigned g = blocks_for(total, 256);
+  switch (es) {
+    case 1: IGN_LAUNCH(ctx, (k_copy_box<uint8_t>), g, 256, 0, (const uint8_t*)src, sx, sy, x0, y0, z0, bx, by, total, (uint8_t*)dst); break;
+    case 2: IGN_LAUNCH(ctx, (k_copy_box<uint16_t>), g, 256, 0, (const uint16_t*)src, sx, sy, x0, y0, z0, bx, by, total, (uint16_t*)dst); break;
+    case 4: IGN_LAUNCH(ctx, (k_copy_box<uint32_t>), g, 256, 0, (const uint32_t*)src, sx, sy, x0, y0, z0, bx, by, total, (uint32_t*)dst); break;
+    default: IGN_LAUNCH(ctx, (k_copy_box<uint64_t>), g, 256, 0, (const uint64_t*)src, sx, sy, x0, y0, z0, bx, by, total, (uint64_t*)dst); break;
+  }
   return IGN_OK;
 }
 

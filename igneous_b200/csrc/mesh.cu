@@ -228,6 +228,7 @@ struct ign_mesher {
   uint64_t T, U;         // triangles, unique vertices
   uint64_t* d_uniq_vkeys;  // [U]
   uint32_t* d_faces;       // [3T] label-local vertex indices
+  bool pooled;             // buffers live in ctx->mesh_pool
   std::vector<uint64_t> ids;       // original label of dense id i+1
   std::vector<uint32_t> tri_off;   // [K+2]
   std::vector<uint32_t> vert_off;  // [K+2]
@@ -260,8 +261,12 @@ extern "C" {
 int ign_mesh_free(ign_mesher* m) {
   if (!m) return IGN_OK;
   cudaSetDevice(m->ctx->device);
-  if (m->d_uniq_vkeys) cudaFree(m->d_uniq_vkeys);
-  if (m->d_faces) cudaFree(m->d_faces);
+  if (m->pooled) {
+    m->ctx->mesh_pool_busy = 0;
+  } else {
+    if (m->d_uniq_vkeys) cudaFree(m->d_uniq_vkeys);
+    if (m->d_faces) cudaFree(m->d_faces);
+  }
   delete m;
   return IGN_OK;
 }
@@ -285,6 +290,7 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
   m->K = m->T = m->U = 0;
   m->d_uniq_vkeys = nullptr;
   m->d_faces = nullptr;
+  m->pooled = false;
   int rc = IGN_OK;
   auto fail = [&](int code) {
     ctx->scratch_used = keep;
@@ -441,8 +447,27 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
   MESH_CUDA(cudaStreamSynchronize(ctx->stream));
   const uint64_t U = (uint64_t)last[0] + last[1];
   m->U = U;
-  MESH_CUDA(cudaMalloc((void**)&m->d_faces, 3 * T * 4));
-  MESH_CUDA(cudaMalloc((void**)&m->d_uniq_vkeys, U * 8));
+  {
+    const size_t fbytes = align_up(3 * T * 4, 256), vbytes = align_up(U * 8, 256);
+    if (!ctx->mesh_pool_busy) {
+      if (ctx->mesh_pool_bytes < fbytes + vbytes) {
+        MESH_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->mesh_pool) cudaFree(ctx->mesh_pool);
+        ctx->mesh_pool = nullptr;
+        ctx->mesh_pool_bytes = 0;
+        const size_t want = (fbytes + vbytes) * 5 / 4;
+        MESH_CUDA(cudaMalloc((void**)&ctx->mesh_pool, want));
+        ctx->mesh_pool_bytes = want;
+      }
+      m->d_faces = (uint32_t*)ctx->mesh_pool;
+      m->d_uniq_vkeys = (uint64_t*)(ctx->mesh_pool + fbytes);
+      m->pooled = true;
+      ctx->mesh_pool_busy = 1;
+    } else {
+      MESH_CUDA(cudaMalloc((void**)&m->d_faces, 3 * T * 4));
+      MESH_CUDA(cudaMalloc((void**)&m->d_uniq_vkeys, U * 8));
+    }
+  }
   MESH_LAUNCH(k_vertex_assign, blocks_for(3 * T, 256), 256, vkeys_s, corner_s, heads, rank,
               (uint64_t)(3 * T), uniq_vk, m->d_faces);
   MESH_CUDA(cudaMemcpyAsync(m->d_uniq_vkeys, uniq_vk, U * 8, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -299,15 +299,15 @@ static int mode_pyramid(ign_ctx* ctx, const T* in, uint64_t sx, uint64_t sy, uin
       const unsigned grid = blocks_for(total, 256);
       if (total > 0) {
         switch (nm) {
-          case 1: IGN_LAUNCH(ctx, (k_mode_fused<T, 1>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, o[0], o[1], o[2], o[3]); break;
+          case 1: IGN_LAUNCH_PROF(ctx, IGN_PROF_POOL, (k_mode_fused<T, 1>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, o[0], o[1], o[2], o[3]); break;
           case 2:
-            if constexpr (VEC >= 4) { IGN_LAUNCH(ctx, (k_mode_fused<T, 2>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, o[0], o[1], o[2], o[3]); }
+            if constexpr (VEC >= 4) { IGN_LAUNCH_PROF(ctx, IGN_PROF_POOL, (k_mode_fused<T, 2>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, o[0], o[1], o[2], o[3]); }
             break;
           case 3:
-            if constexpr (VEC >= 8) { IGN_LAUNCH(ctx, (k_mode_fused<T, 3>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, o[0], o[1], o[2], o[3]); }
+            if constexpr (VEC >= 8) { IGN_LAUNCH_PROF(ctx, IGN_PROF_POOL, (k_mode_fused<T, 3>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, o[0], o[1], o[2], o[3]); }
             break;
           default:
-            if constexpr (VEC >= 16) { IGN_LAUNCH(ctx, (k_mode_fused<T, 4>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, o[0], o[1], o[2], o[3]); }
+            if constexpr (VEC >= 16) { IGN_LAUNCH_PROF(ctx, IGN_PROF_POOL, (k_mode_fused<T, 4>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, o[0], o[1], o[2], o[3]); }
             break;
         }
       }
@@ -348,15 +348,15 @@ static int avg_pyramid(ign_ctx* ctx, const T* in, uint64_t sx, uint64_t sy, uint
       const unsigned grid = blocks_for(total, 256);
       if (total > 0) {
         switch (g) {
-          case 1: IGN_LAUNCH(ctx, (k_avg_fused<T, A, 1>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, rounding, o[0], o[1], o[2], o[3]); break;
+          case 1: IGN_LAUNCH_PROF(ctx, IGN_PROF_POOL, (k_avg_fused<T, A, 1>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, rounding, o[0], o[1], o[2], o[3]); break;
           case 2:
-            if constexpr (VEC >= 4) { IGN_LAUNCH(ctx, (k_avg_fused<T, A, 2>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, rounding, o[0], o[1], o[2], o[3]); }
+            if constexpr (VEC >= 4) { IGN_LAUNCH_PROF(ctx, IGN_PROF_POOL, (k_avg_fused<T, A, 2>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, rounding, o[0], o[1], o[2], o[3]); }
             break;
           case 3:
-            if constexpr (VEC >= 8) { IGN_LAUNCH(ctx, (k_avg_fused<T, A, 3>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, rounding, o[0], o[1], o[2], o[3]); }
+            if constexpr (VEC >= 8) { IGN_LAUNCH_PROF(ctx, IGN_PROF_POOL, (k_avg_fused<T, A, 3>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, rounding, o[0], o[1], o[2], o[3]); }
             break;
           default:
-            if constexpr (VEC >= 16) { IGN_LAUNCH(ctx, (k_avg_fused<T, A, 4>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, rounding, o[0], o[1], o[2], o[3]); }
+            if constexpr (VEC >= 16) { IGN_LAUNCH_PROF(ctx, IGN_PROF_POOL, (k_avg_fused<T, A, 4>), grid, 256, 0, cur, sx, sy, tiles_x, tiles_y, total, rounding, o[0], o[1], o[2], o[3]); }
             break;
         }
       }

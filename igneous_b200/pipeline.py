@@ -1,0 +1,174 @@
+"""Device-resident downsample -> CCL -> mesh pipeline over one volume (one GPU
+holds one z-slab of the dataset; BASELINE.json config C5 / the headline metric).
+
+The three stages are exactly the per-task bodies of the reference, chained in
+HBM instead of through CloudVolume files:
+  * DownsampleTask          igneous/tasks/image/image.py:518-549 (2 mode mips)
+  * CCL passes 1-4          igneous/tasks/image/ccl.py:126-420
+  * MeshTask (mip 2, 256^3) igneous/tasks/mesh/mesh.py:140-265
+Host code only sequences kernels; all arithmetic runs in libigneous_b200.
+"""
+import ctypes as c
+
+import numpy as np
+
+from . import _shim
+
+PROF_CLASSES = {"ccl_local": 0, "ccl_merge": 1, "ccl_label": 2, "pool": 3, "mc": 4}
+
+
+def _u64(v):
+  return c.c_uint64(int(v))
+
+
+class VolumePipeline:
+  def __init__(self, ctx, shape, dtype=np.uint32, num_mips=2, mesh_shape=(256, 256, 256),
+               resolution=(16, 16, 40), pitch=64, num_ids=1 << 20, seed=0, offset=(0, 0, 0),
+               ccl_out_dtype=np.uint32, simplification_factor=100, max_simplification_error=40,
+               group=None):
+    self.ctx = ctx
+    self.lib = ctx.lib
+    self.shape = tuple(int(s) for s in shape)
+    self.dtype = np.dtype(dtype)
+    self.code = _shim.dtype_code(self.dtype)
+    self.num_mips = int(num_mips)
+    self.mesh_shape = tuple(mesh_shape)
+    self.resolution = tuple(resolution)
+    self.pitch, self.num_ids, self.seed, self.offset = pitch, num_ids, seed, tuple(offset)
+    self.ccl_out_dtype = np.dtype(ccl_out_dtype)
+    self.simplification_factor = simplification_factor
+    self.max_simplification_error = max_simplification_error
+    self.group = group
+    sx, sy, sz = self.shape
+    self.n = sx * sy * sz
+    es = self.dtype.itemsize
+    self.d_in = ctx.alloc(self.n * es)
+    self.mip_shapes = []
+    x, y = sx, sy
+    for _ in range(self.num_mips):
+      x, y = (x + 1) // 2, (y + 1) // 2
+      self.mip_shapes.append((x, y, sz))
+    self.d_mips = [ctx.alloc(int(np.prod(s)) * es) for s in self.mip_shapes]
+    self.d_cc = ctx.alloc(self.n * self.ccl_out_dtype.itemsize)
+    mx, my, mz = self.mesh_shape
+    self.d_task = ctx.alloc((mx + 1) * (my + 1) * (mz + 1) * es)
+    self.n_components = 0
+    self.mesh_stats = {}
+
+  def free(self):
+    for b in [self.d_in, self.d_cc, self.d_task] + self.d_mips:
+      b.free()
+
+  # ------------------------------------------------------------------ inputs
+  def synth(self):
+    sx, sy, sz = self.shape
+    ox, oy, oz = self.offset
+    _shim.check(self.lib.ign_synth_seg_dev(
+      self.ctx.handle, _shim.ptr(self.d_in), c.c_int(self.code), _u64(sx), _u64(sy), _u64(sz),
+      c.c_int64(ox), c.c_int64(oy), c.c_int64(oz), c.c_uint32(self.pitch), _u64(self.num_ids),
+      _u64(self.seed), _u64(0)))
+
+  def load_host(self, arr):
+    self.ctx.h2d(self.d_in, arr)
+
+  # ------------------------------------------------------------------ stages
+  def pool(self):
+    sx, sy, sz = self.shape
+    _shim.check(self.lib.ign_pool_mode_2x2x1_dev(
+      self.ctx.handle, _shim.ptr(self.d_in), c.c_int(self.code), _u64(sx), _u64(sy), _u64(sz),
+      c.c_int(self.num_mips), c.c_int(0), _shim.void_pp([m.ptr for m in self.d_mips])))
+
+  def ccl(self):
+    sx, sy, sz = self.shape
+    n = c.c_uint64(0)
+    if self.group is not None:
+      n_glob = self.group.ccl_sharded(self, n)
+      self.n_components = n_glob
+      return
+    _shim.check(self.lib.ign_ccl6_volume_dev(
+      self.ctx.handle, _shim.ptr(self.d_in), c.c_int(self.code), _u64(sx), _u64(sy), _u64(sz),
+      _shim.ptr(self.d_cc), c.c_int(_shim.dtype_code(self.ccl_out_dtype)), _u64(0), c.byref(n)))
+    self.n_components = int(n.value)
+
+  def mesh_tasks(self):
+    """(x0,y0,z0,bx,by,bz) cutouts of the mesh mip: task shape + 1 voxel high padding
+    (igneous/tasks/mesh/mesh.py:158-160), clamped to the volume."""
+    msx, msy, msz = self.mip_shapes[-1] if self.num_mips else self.shape
+    mx, my, mz = self.mesh_shape
+    for z0 in range(0, msz, mz):
+      for y0 in range(0, msy, my):
+        for x0 in range(0, msx, mx):
+          yield (x0, y0, z0, min(mx + 1, msx - x0), min(my + 1, msy - y0), min(mz + 1, msz - z0))
+
+  def mesh(self, export=None):
+    """MeshTask bodies over the mesh mip.  `export(task, mesher_handle)` may pull
+    results to the host (e2e); without it only the totals are read back."""
+    src = self.d_mips[-1] if self.num_mips else self.d_in
+    msx, msy, msz = self.mip_shapes[-1] if self.num_mips else self.shape
+    tris = verts = labels = tasks = 0
+    for (x0, y0, z0, bx, by, bz) in self.mesh_tasks():
+      _shim.check(self.lib.ign_copy_box_dev(
+        self.ctx.handle, _shim.ptr(src), c.c_int(self.code), _u64(msx), _u64(msy), _u64(msz),
+        _u64(x0), _u64(y0), _u64(z0), _u64(bx), _u64(by), _u64(bz), _shim.ptr(self.d_task)))
+      h = c.c_void_p()
+      _shim.check(self.lib.ign_mesh_begin_dev(
+        self.ctx.handle, _shim.ptr(self.d_task), c.c_int(self.code), _u64(bx), _u64(by), _u64(bz),
+        c.byref(h)))
+      try:
+        if self.simplification_factor and self.simplification_factor > 0:
+          _shim.check(self.lib.ign_mesh_simplify(
+            h, (c.c_float * 3)(*[float(r) for r in self.resolution]),
+            c.c_int(int(self.simplification_factor)), c.c_float(float(self.max_simplification_error))))
+        nv, nf, nl = c.c_uint64(0), c.c_uint64(0), c.c_uint64(0)
+        _shim.check(self.lib.ign_mesh_totals(h, c.byref(nv), c.byref(nf)))
+        _shim.check(self.lib.ign_mesh_num_ids(h, c.byref(nl)))
+        if export is not None:
+          export((x0, y0, z0, bx, by, bz), h, int(nv.value), int(nf.value), int(nl.value))
+        tris += nf.value
+        verts += nv.value
+        labels += nl.value
+        tasks += 1
+      finally:
+        self.lib.ign_mesh_free(h)
+    self.mesh_stats = {"tasks": tasks, "triangles": int(tris), "vertices": int(verts),
+                       "label_fragments": int(labels)}
+
+  def step(self, timers=True):
+    """One pass of the hot path over the resident volume."""
+    ctx = self.ctx
+    if timers:
+      ctx.timer_start(1)
+    self.pool()
+    if timers:
+      ctx.timer_stop(1)
+      ctx.timer_start(2)
+    self.ccl()
+    if timers:
+      ctx.timer_stop(2)
+      ctx.timer_start(3)
+    self.mesh()
+    if timers:
+      ctx.timer_stop(3)
+
+  def stage_ms(self):
+    return {"pool_ms": self.ctx.timer_ms(1), "ccl_ms": self.ctx.timer_ms(2),
+            "mesh_ms": self.ctx.timer_ms(3)}
+
+  # --------------------------------------------------------------- profiling
+  def prof_enable(self, on=True):
+    _shim.check(self.lib.ign_prof_enable(self.ctx.handle, c.c_int(int(on))))
+
+  def prof_read(self):
+    out = {}
+    for name, cls in PROF_CLASSES.items():
+      ms, cnt = c.c_float(0), c.c_uint64(0)
+      _shim.check(self.lib.ign_prof_read(self.ctx.handle, c.c_int(cls), c.byref(ms), c.byref(cnt)))
+      out[name] = (float(ms.value), int(cnt.value))
+    return out
+
+  # ------------------------------------------------------------- host results
+  def results_to_host(self, host):
+    """D2H of every product of one step into preallocated (pinned) arrays."""
+    for dst, src in zip(host["mips"], self.d_mips):
+      self.ctx.d2h(dst, src)
+    self.ctx.d2h(host["cc"], self.d_cc)

@@ -86,6 +86,16 @@ IGN_API int ign_timer_start(ign_ctx* ctx, int slot);
 IGN_API int ign_timer_stop(ign_ctx* ctx, int slot);
 IGN_API int ign_timer_ms(ign_ctx* ctx, int slot, float* ms); /* synchronises on the stop event */
 
+/* per-kernel-class CUDA-event profiling on the ctx stream (bench.py roofline):
+ * classes 0 ccl_local, 1 ccl_merge, 2 ccl_label, 3 pool, 4 marching cubes */
+IGN_API int ign_prof_enable(ign_ctx* ctx, int on);
+IGN_API int ign_prof_read(ign_ctx* ctx, int cls, float* total_ms, uint64_t* launches);
+
+/* strided 3-D sub-box copy between device volumes (task cutouts, +1 overlap) */
+IGN_API int ign_copy_box_dev(ign_ctx* ctx, const void* src, int dtype, uint64_t sx, uint64_t sy,
+                             uint64_t sz, uint64_t x0, uint64_t y0, uint64_t z0, uint64_t bx,
+                             uint64_t by, uint64_t bz, void* dst);
+
 /* ------------------------------------------------------------------ pooling
  * tinybrain.downsample_segmentation(img, factor=(2,2,1), num_mips, sparse)
  *   igneous/tasks/image/image.py:52-53 (bound) and :91 (called)
@@ -116,6 +126,33 @@ IGN_API int ign_ccl6(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, ui
              void* out, int out_dtype, uint64_t* n_components);
 IGN_API int ign_ccl6_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
                  uint64_t sz, void* out, int out_dtype, uint64_t* n_components);
+
+/* Multi-slab building blocks.  A volume too large for one call (or spread
+ * over several GPUs) is cut into z-slabs; each slab's component structure is
+ * built into a caller-owned `work` array (4 bytes per voxel), facing planes are
+ * compared, the equivalences are solved on the host, and every slab is labelled
+ * once through the composed lookup table.  This replaces the four file-based
+ * passes of igneous/tasks/image/ccl.py (CCLFacesTask :126-194,
+ * CCLEquivalancesTask :196-294, create_relabeling :358-420, RelabelCCLTask
+ * :296-356) for data that is resident in HBM.  The result is bit-identical to
+ * one whole-volume ign_ccl6 call. */
+IGN_API int ign_ccl6_build_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
+                               uint64_t sz, uint32_t* work, uint64_t* n_local);
+IGN_API int ign_ccl6_plane_dev(ign_ctx* ctx, const void* in, int in_dtype, const uint32_t* work,
+                               uint64_t sx, uint64_t sy, uint64_t sz, uint64_t z, uint64_t* values,
+                               uint32_t* labels);
+IGN_API int ign_ccl6_link_dev(ign_ctx* ctx, const uint64_t* values_a, const uint32_t* labels_a,
+                              uint64_t offset_a, const uint64_t* values_b, const uint32_t* labels_b,
+                              uint64_t offset_b, uint64_t n_plane, uint64_t* pairs_host,
+                              uint64_t capacity, uint64_t* n_pairs);
+IGN_API int ign_ccl6_solve(const uint64_t* pairs, uint64_t n_pairs, uint64_t total, uint32_t* lut,
+                           uint64_t* n_global);
+IGN_API int ign_ccl6_label_dev(ign_ctx* ctx, const uint32_t* work, uint64_t sx, uint64_t sy,
+                               uint64_t sz, const uint32_t* lut_dev, uint64_t offset, void* out,
+                               int out_dtype, uint64_t max_label);
+IGN_API int ign_ccl6_volume_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
+                                uint64_t sz, void* out, int out_dtype, uint64_t max_slab_voxels,
+                                uint64_t* n_components);
 
 /* cc3d.dust(labels, threshold, connectivity=6, in_place=True)
  *   igneous/tasks/image/ccl.py:169-172, :231-234, :335-338

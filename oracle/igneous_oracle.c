@@ -346,3 +346,113 @@ DEF_MC(uint64_t, orc_marching_cubes_u64)
 
 /* table accessors so tests can validate the table itself */
 const int8_t* orc_mc_tri_table(void) { return &mc_tri_table[0][0]; }
+
+/* ------------------------------------------------------------------ */
+/* Weld (Mesher.get without simplification, mesh.py:376-381): per      */
+/* label, unique vertices ordered by packed (z,y,x) key; faces keep    */
+/* cube raster order.  Outputs are grouped by ascending label.         */
+/*   tri_order[T]   : input triangle index of output triangle t        */
+/*   uniq_label[U], uniq_xyz[3U] : unique vertices (label major)       */
+/*   faces[3T]      : index into the unique vertex list (GLOBAL index; */
+/*                    subtract the label's first vertex for local ids) */
+/* ------------------------------------------------------------------ */
+typedef struct { uint64_t label, key; uint64_t corner; } orc_vrec;
+typedef struct { uint64_t label, idx; } orc_trec;
+
+static int orc_cmp_v(const void* a, const void* b) {
+  const orc_vrec *x = (const orc_vrec*)a, *y = (const orc_vrec*)b;
+  if (x->label != y->label) return x->label < y->label ? -1 : 1;
+  if (x->key != y->key) return x->key < y->key ? -1 : 1;
+  return 0;
+}
+static int orc_cmp_t(const void* a, const void* b) {
+  const orc_trec *x = (const orc_trec*)a, *y = (const orc_trec*)b;
+  if (x->label != y->label) return x->label < y->label ? -1 : 1;
+  return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+int orc_weld(const uint64_t* tri_label, const uint32_t* tri_verts, uint64_t T,
+             uint64_t* tri_order, uint64_t* uniq_label, uint32_t* uniq_xyz,
+             uint32_t* faces, uint64_t* n_uniq) {
+  *n_uniq = 0;
+  if (T == 0) return ORC_OK;
+  orc_trec* tr = (orc_trec*)malloc(sizeof(orc_trec) * T);
+  orc_vrec* vr = (orc_vrec*)malloc(sizeof(orc_vrec) * 3 * T);
+  uint64_t* newpos = (uint64_t*)malloc(sizeof(uint64_t) * T);
+  if (!tr || !vr || !newpos) { free(tr); free(vr); free(newpos); return ORC_ENOMEM; }
+  for (uint64_t t = 0; t < T; t++) { tr[t].label = tri_label[t]; tr[t].idx = t; }
+  qsort(tr, T, sizeof(orc_trec), orc_cmp_t);
+  for (uint64_t t = 0; t < T; t++) { tri_order[t] = tr[t].idx; newpos[tr[t].idx] = t; }
+  for (uint64_t t = 0; t < T; t++)
+    for (int v = 0; v < 3; v++) {
+      const uint32_t* p = tri_verts + 9 * t + 3 * v;
+      vr[3 * t + v].label = tri_label[t];
+      vr[3 * t + v].key = ((uint64_t)p[2] << 42) | ((uint64_t)p[1] << 21) | p[0];
+      vr[3 * t + v].corner = 3 * newpos[t] + v;
+    }
+  qsort(vr, 3 * T, sizeof(orc_vrec), orc_cmp_v);
+  uint64_t u = 0;
+  for (uint64_t i = 0; i < 3 * T; i++) {
+    if (i == 0 || vr[i].label != vr[i - 1].label || vr[i].key != vr[i - 1].key) {
+      uniq_label[u] = vr[i].label;
+      uniq_xyz[3 * u + 0] = (uint32_t)(vr[i].key & 0x1FFFFF);
+      uniq_xyz[3 * u + 1] = (uint32_t)((vr[i].key >> 21) & 0x1FFFFF);
+      uniq_xyz[3 * u + 2] = (uint32_t)(vr[i].key >> 42);
+      u++;
+    }
+    faces[vr[i].corner] = (uint32_t)(u - 1);
+  }
+  *n_uniq = u;
+  free(tr); free(vr); free(newpos);
+  return ORC_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* Synthetic jittered-Voronoi segmentation; same      */
+/* integer hash as igneous_b200/csrc/synth.cu and oracle.synth_seg_np. */
+/* ------------------------------------------------------------------ */
+static uint64_t orc_mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static uint64_t orc_cell_hash(uint64_t seed, int64_t cx, int64_t cy, int64_t cz) {
+  uint64_t h = orc_mix64(seed + (uint64_t)cx * 0x100000001B3ull);
+  h = orc_mix64(h ^ ((uint64_t)cy * 0xC2B2AE3D27D4EB4Full));
+  h = orc_mix64(h ^ ((uint64_t)cz * 0x165667B19E3779F9ull));
+  return h;
+}
+static int64_t orc_floordiv(int64_t a, int64_t b) {
+  int64_t q = a / b;
+  if ((a % b != 0) && ((a < 0) != (b < 0))) q--;
+  return q;
+}
+
+int orc_synth_seg_u64(uint64_t* out, uint64_t sx, uint64_t sy, uint64_t sz,
+                      int64_t ox, int64_t oy, int64_t oz, int pitch,
+                      uint64_t num_ids, uint64_t seed, uint64_t id_base) {
+  for (uint64_t z = 0; z < sz; z++)
+    for (uint64_t y = 0; y < sy; y++)
+      for (uint64_t x = 0; x < sx; x++) {
+        const int64_t X = (int64_t)x + ox, Y = (int64_t)y + oy, Z = (int64_t)z + oz;
+        const int64_t cx = orc_floordiv(X, pitch), cy = orc_floordiv(Y, pitch),
+                      cz = orc_floordiv(Z, pitch);
+        int64_t d1 = INT64_MAX, d2 = INT64_MAX;
+        uint64_t id1 = 0;
+        for (int dz = -1; dz <= 1; dz++)
+          for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+              const int64_t ccx = cx + dx, ccy = cy + dy, ccz = cz + dz;
+              const uint64_t h = orc_cell_hash(seed, ccx, ccy, ccz);
+              const int64_t px = ccx * pitch + (int64_t)((h & 0xFFFF) % (uint64_t)pitch);
+              const int64_t py = ccy * pitch + (int64_t)(((h >> 16) & 0xFFFF) % (uint64_t)pitch);
+              const int64_t pz = ccz * pitch + (int64_t)(((h >> 32) & 0xFFFF) % (uint64_t)pitch);
+              const int64_t d = (X - px) * (X - px) + (Y - py) * (Y - py) + (Z - pz) * (Z - pz);
+              if (d < d1) { d2 = d1; d1 = d; id1 = id_base + 1 + orc_mix64(h) % num_ids; }
+              else if (d < d2) { d2 = d; }
+            }
+        out[x + sx * (y + sy * z)] = ((d2 - d1) < 2 * (int64_t)pitch) ? 0 : id1;
+      }
+  return ORC_OK;
+}

@@ -254,6 +254,47 @@ def marching_cubes(labels, flip=True):
   return tl, tv
 
 
+class WeldedMeshes:
+  """All labels of one marching-cubes run welded at once (oracle of
+  Mesher.get with reduction_factor=0, igneous/tasks/mesh/mesh.py:376-381)."""
+
+  def __init__(self, tl, tv):
+    T = len(tl)
+    self.tri_order = np.zeros(T, dtype=np.uint64)
+    ulabel = np.zeros(3 * T, dtype=np.uint64)
+    uxyz = np.zeros((3 * T, 3), dtype=np.uint32)
+    faces = np.zeros((T, 3), dtype=np.uint32)
+    n = ctypes.c_uint64(0)
+    tl = np.ascontiguousarray(tl, dtype=np.uint64)
+    tv = np.ascontiguousarray(tv, dtype=np.uint32)
+    rc = lib().orc_weld(_ptr(tl), _ptr(tv), ctypes.c_uint64(T), _ptr(self.tri_order), _ptr(ulabel),
+                        _ptr(uxyz), _ptr(faces), ctypes.byref(n))
+    assert rc == 0
+    U = int(n.value)
+    self.ulabel, self.uxyz, self.faces = ulabel[:U], uxyz[:U], faces
+    self.tlabel = tl[self.tri_order.astype(np.int64)] if T else tl
+    self.labels = np.unique(self.tlabel)
+    self.v0 = np.searchsorted(self.ulabel, self.labels, side="left")
+    self.v1 = np.searchsorted(self.ulabel, self.labels, side="right")
+    self.f0 = np.searchsorted(self.tlabel, self.labels, side="left")
+    self.f1 = np.searchsorted(self.tlabel, self.labels, side="right")
+
+  def ids(self):
+    return [int(l) for l in self.labels]
+
+  def get(self, label, resolution=(1, 1, 1), voxel_centered=True):
+    j = int(np.searchsorted(self.labels, np.uint64(label)))
+    if j >= len(self.labels) or self.labels[j] != label:
+      raise KeyError(label)
+    xyz = self.uxyz[self.v0[j]:self.v1[j]].astype(np.float32)
+    verts = xyz * np.float32(0.5)
+    if voxel_centered:
+      verts = verts + np.float32(0.5)
+    verts = verts * np.asarray(resolution, dtype=np.float32)
+    faces = self.faces[self.f0[j]:self.f1[j]] - np.uint32(self.v0[j])
+    return verts.astype(np.float32), faces.astype(np.uint32)
+
+
 def pack_vertex(v):
   """(x,y,z) half-voxel integer coords -> sortable 63-bit key (z major)."""
   v = np.asarray(v, dtype=np.uint64)
@@ -314,9 +355,10 @@ def cell_hash(seed, cx, cy, cz):
   return h
 
 
-def synth_seg(shape, pitch=16, num_ids=1 << 20, seed=0, offset=(0, 0, 0),
+def synth_seg_np(shape, pitch=16, num_ids=1 << 20, seed=0, offset=(0, 0, 0),
               dtype=np.uint32, id_base=0):
-  """Jittered-grid Voronoi segmentation with membranes,
+  """numpy statement of synth_seg (slow; used to cross-check the C version).
+  Jittered-grid Voronoi segmentation with membranes,
   bit-identical to ign_synth_seg (igneous_b200/csrc/synth.cu).
 
   One seed point per pitch^3 cell at a hashed offset.  The 27 surrounding
@@ -361,3 +403,23 @@ def synth_image(shape, seed=0, offset=(0, 0, 0)):
                         np.arange(sz, dtype=np.int64) + offset[2], indexing="ij")
   h = cell_hash(seed, X, Y, Z)
   return np.asfortranarray(((h >> np.uint64(11)) % np.uint64(255)).astype(np.uint8))
+
+
+def synth_seg(shape, pitch=16, num_ids=1 << 20, seed=0, offset=(0, 0, 0),
+              dtype=np.uint32, id_base=0):
+  """C version of synth_seg_np (same integer hash, bit identical)."""
+  sx, sy, sz = (int(v) for v in shape)
+  out = np.zeros((sx, sy, sz), dtype=np.uint64, order="F")
+  rc = lib().orc_synth_seg_u64(_ptr(out), ctypes.c_uint64(sx), ctypes.c_uint64(sy), ctypes.c_uint64(sz),
+                               ctypes.c_int64(offset[0]), ctypes.c_int64(offset[1]),
+                               ctypes.c_int64(offset[2]), ctypes.c_int(pitch), ctypes.c_uint64(num_ids),
+                               ctypes.c_uint64(seed), ctypes.c_uint64(id_base))
+  assert rc == 0
+  return np.asfortranarray(out.astype(dtype))
+
+
+def synth_tiled(shape, seed):
+  """Bench chunk for the CPU reference arm: a distinct region of the bench
+  dataset per (seed), generated by the C synthesiser."""
+  return synth_seg(shape, pitch=64, num_ids=1 << 20, seed=0,
+                   offset=(0, 0, (seed % 100000) * shape[2]))

@@ -114,3 +114,26 @@ def test_ccl_rejects_other_connectivity(ctx):
   from igneous_b200 import cc3d
   with pytest.raises(NotImplementedError):
     cc3d.connected_components(np.zeros((4, 4, 4), np.uint8), connectivity=26)
+
+
+@pytest.mark.parametrize("shape,slab_vox", [((64, 48, 40), 64 * 48 * 7), ((33, 29, 17), 33 * 29 * 1),
+                                            ((70, 65, 9), 70 * 65 * 4), ((40, 40, 40), 40 * 40 * 40)])
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint64])
+def test_multislab_volume_ccl_equals_whole_volume(ctx, oracle, shape, slab_vox, dtype):
+  """z-slabs + plane linkage + host union-find + one label pass must be
+  bit-identical to a single whole-volume CCL (and to the oracle)."""
+  import ctypes as c
+  from igneous_b200 import _shim
+  rng = np.random.default_rng(21)
+  labels = _blobs(rng, shape, 3, dtype, p_bg=0.2)
+  want, n_want = oracle.connected_components(labels, return_N=True)
+  d_in = ctx.to_device(labels)
+  d_out = ctx.alloc(labels.size * 4)
+  n = c.c_uint64(0)
+  _shim.check(ctx.lib.ign_ccl6_volume_dev(
+    ctx.handle, _shim.ptr(d_in), c.c_int(_shim.dtype_code(dtype)), c.c_uint64(shape[0]),
+    c.c_uint64(shape[1]), c.c_uint64(shape[2]), _shim.ptr(d_out), c.c_int(_shim.IGN_U32),
+    c.c_uint64(slab_vox), c.byref(n)))
+  got = ctx.to_host(d_out, shape, np.uint32)
+  assert n.value == n_want
+  assert np.array_equal(got, want.astype(np.uint32))
