@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------- CPU legs
-def oracle_pipeline(seg):
+def oracle_pipeline(seg, simplify=100):
   """The CPU restatement of one step on a host array: returns voxels processed."""
   from oracle import oracle as O
   mips = O.downsample_segmentation(seg, (2, 2, 1), num_mips=2)
@@ -96,7 +96,9 @@ def oracle_pipeline(seg):
     for y0 in range(0, m2.shape[1], 256):
       for x0 in range(0, m2.shape[0], 256):
         tl, tv = O.marching_cubes(m2[x0:x0 + 257, y0:y0 + 257, z0:z0 + 257])
-        O.WeldedMeshes(tl, tv)
+        W = O.WeldedMeshes(tl, tv)
+        if simplify:
+          O.simplify_welded(W, RESOLUTION, simplify, 40.0, True)
   return seg.size
 
 
@@ -162,7 +164,7 @@ def cpu_baseline_sample(pipe, ctx, budget_s=20.0):
   O.build()
   sx, sy, sz = pipe.shape
   bz = min(sz, 256)
-  bx, by = min(sx, 512), min(sy, 512)
+  bx, by = min(sx, 256), min(sy, 256)
   from igneous_b200 import _shim
   d_box = ctx.alloc(bx * by * bz * 4)
   _shim.check(ctx.lib.ign_copy_box_dev(ctx.handle, _shim.ptr(pipe.d_in), c.c_int(pipe.code),
@@ -174,7 +176,7 @@ def cpu_baseline_sample(pipe, ctx, budget_s=20.0):
   t = time.perf_counter()
   vox, reps = 0, 0
   while True:
-    vox += oracle_pipeline(seg)
+    vox += oracle_pipeline(seg, pipe.simplification_factor)
     reps += 1
     if time.perf_counter() - t > budget_s / 2 or reps >= 8:
       break

@@ -11,7 +11,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(CSRC, "libigneous_b200.so")
+ASAN = bool(os.environ.get("IGN_ASAN"))
+LIB = os.path.join(CSRC, "libigneous_b200_asan.so" if ASAN else "libigneous_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
@@ -30,8 +31,13 @@ def _stale(target, deps):
   return any(os.path.getmtime(d) > t for d in deps)
 
 
+# simplify.cu must match the CPU oracle bit for bit: no FMA contraction
+PER_FILE_FLAGS = {"simplify.cu": ["-fmad=false"]}
+
+
 def _compile(src, obj, log):
-  cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+  extra = ["-Xcompiler", "-fsanitize=address,-fno-omit-frame-pointer", "-g"] if ASAN else []
+  cmd = [NVCC] + NVCC_FLAGS + extra + PER_FILE_FLAGS.get(os.path.basename(src), []) + ["-c", src, "-o", obj]
   p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
   with open(log, "w") as f:
     f.write(" ".join(cmd) + "\n" + p.stdout)
@@ -49,7 +55,7 @@ def build(force=False, verbose=False):
   objs = []
   for s in srcs:
     base = os.path.splitext(os.path.basename(s))[0]
-    o = os.path.join(CSRC, "build", base + ".o")
+    o = os.path.join(CSRC, "build", base + (".asan.o" if ASAN else ".o"))
     objs.append(o)
     if force or _stale(o, [s] + hdrs):
       jobs.append((s, o, os.path.join(CSRC, "build", base + ".log")))
@@ -57,7 +63,8 @@ def build(force=False, verbose=False):
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
       list(ex.map(lambda j: _compile(*j), jobs))
   if force or jobs or _stale(LIB, objs):
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"] + \
+        (["-Xcompiler", "-fsanitize=address"] if ASAN else [])
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if p.returncode != 0:
       raise RuntimeError("link failed:\n" + p.stdout[-4000:])

@@ -221,21 +221,29 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace ign
 
-// persistent result of ign_mesh_begin*
-struct ign_mesher {
-  ign_ctx* ctx;
-  uint64_t K;            // dense labels 1..K
-  uint64_t T, U;         // triangles, unique vertices
-  uint64_t* d_uniq_vkeys;  // [U]
-  uint32_t* d_faces;       // [3T] label-local vertex indices
-  bool pooled;             // buffers live in ctx->mesh_pool
-  std::vector<uint64_t> ids;       // original label of dense id i+1
-  std::vector<uint32_t> tri_off;   // [K+2]
-  std::vector<uint32_t> vert_off;  // [K+2]
-  std::vector<uint64_t> present;   // original ids with at least one triangle
-};
+#include "mesher.h"
 
+namespace ign {
+int simp_export_positions(ign_ctx* ctx, const float* pos_f, uint64_t first, uint64_t count,
+                          const float shift[3], float* d_out);
+}
 using namespace ign;
+
+// positions of vertices [first, first+count) into d_out (device), whichever form the mesher holds
+static int mesher_positions(ign_mesher* m, uint64_t first, uint64_t count, const float resolution[3],
+                            int voxel_centered, float* d_out) {
+  ign_ctx* ctx = m->ctx;
+  if (m->simplified) {
+    IGN_REQUIRE(resolution[0] == m->res[0] && resolution[1] == m->res[1] && resolution[2] == m->res[2],
+                IGN_ERR_INVALID, "resolution differs from the one the mesher was simplified with");
+    const float shift[3] = {voxel_centered ? 0.5f * m->res[0] : 0.0f, voxel_centered ? 0.5f * m->res[1] : 0.0f,
+                            voxel_centered ? 0.5f * m->res[2] : 0.0f};
+    return simp_export_positions(ctx, m->d_pos_f, first, count, shift, d_out);
+  }
+  IGN_LAUNCH(ctx, k_vertex_positions, blocks_for(count, 256), 256, 0, m->d_uniq_vkeys, first, count,
+             resolution[0], resolution[1], resolution[2], voxel_centered ? 0.5f : 0.0f, d_out);
+  return IGN_OK;
+}
 
 static bool g_tables_loaded[64] = {false};
 
@@ -291,6 +299,11 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
   m->d_uniq_vkeys = nullptr;
   m->d_faces = nullptr;
   m->pooled = false;
+  m->simplified = false;
+  m->d_pos_f = nullptr;
+  m->simp_factor = 0;
+  m->simp_max_error = 0;
+  m->simp_rounds = 0;
   int rc = IGN_OK;
   auto fail = [&](int code) {
     ctx->scratch_used = keep;
@@ -448,7 +461,7 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
   const uint64_t U = (uint64_t)last[0] + last[1];
   m->U = U;
   {
-    const size_t fbytes = align_up(3 * T * 4, 256), vbytes = align_up(U * 8, 256);
+    const size_t fbytes = align_up(3 * T * 4, 256), vbytes = align_up(U * 12, 256);  // 12: float3 after simplify
     if (!ctx->mesh_pool_busy) {
       if (ctx->mesh_pool_bytes < fbytes + vbytes) {
         MESH_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -562,9 +575,15 @@ int ign_mesh_get(ign_mesher* m, uint64_t id, const float resolution[3], int redu
   IGN_REQUIRE(m && resolution && nv && nf, IGN_ERR_INVALID, "null argument");
   ign_ctx* ctx = m->ctx;
   IGN_TRY(activate(ctx));
-  IGN_REQUIRE(reduction_factor <= 0, IGN_ERR_UNSUPPORTED,
-              "mesh simplification (reduction_factor=%d, max_error=%g) is not implemented yet",
-              reduction_factor, (double)max_error);
+  if (reduction_factor > 0 && !m->simplified) {
+    scratch_reset(ctx);
+    IGN_TRY(ign_mesh_simplify(m, resolution, reduction_factor, max_error));
+  }
+  if (m->simplified) {
+    IGN_REQUIRE(reduction_factor == m->simp_factor && max_error == m->simp_max_error, IGN_ERR_INVALID,
+                "mesher was simplified with reduction_factor=%d max_error=%g; call mesh() again to change",
+                m->simp_factor, (double)m->simp_max_error);
+  }
   const int64_t l = dense_of(m, id);
   IGN_REQUIRE(l > 0, IGN_ERR_KEY, "%llu", (unsigned long long)id);
   const uint64_t v0 = m->vert_off[l], v1 = m->vert_off[l + 1];
@@ -575,8 +594,7 @@ int ign_mesh_get(ign_mesher* m, uint64_t id, const float resolution[3], int redu
   scratch_reset(ctx);
   IGN_TRY(scratch_reserve(ctx, (v1 - v0) * 12 + 4096));
   float* d_pos = (float*)scratch_take(ctx, (v1 - v0) * 12);
-  IGN_LAUNCH(ctx, k_vertex_positions, blocks_for(v1 - v0, 256), 256, 0, m->d_uniq_vkeys, v0, v1 - v0,
-             resolution[0], resolution[1], resolution[2], voxel_centered ? 0.5f : 0.0f, d_pos);
+  IGN_TRY(mesher_positions(m, v0, v1 - v0, resolution, voxel_centered, d_pos));
   IGN_CUDA(cudaMemcpyAsync(vertices, d_pos, (v1 - v0) * 12, cudaMemcpyDeviceToHost, ctx->stream));
   IGN_CUDA(cudaMemcpyAsync(faces, m->d_faces + 3 * t0, (t1 - t0) * 12, cudaMemcpyDeviceToHost, ctx->stream));
   IGN_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -603,8 +621,7 @@ int ign_mesh_export(ign_mesher* m, const float resolution[3], int voxel_centered
   scratch_reset(ctx);
   IGN_TRY(scratch_reserve(ctx, m->U * 12 + 4096));
   float* d_pos = (float*)scratch_take(ctx, m->U * 12);
-  IGN_LAUNCH(ctx, k_vertex_positions, blocks_for(m->U, 256), 256, 0, m->d_uniq_vkeys, 0ull, m->U,
-             resolution[0], resolution[1], resolution[2], voxel_centered ? 0.5f : 0.0f, d_pos);
+  IGN_TRY(mesher_positions(m, 0, m->U, resolution, voxel_centered, d_pos));
   IGN_CUDA(cudaMemcpyAsync(vertices, d_pos, m->U * 12, cudaMemcpyDeviceToHost, ctx->stream));
   IGN_CUDA(cudaMemcpyAsync(faces, m->d_faces, m->T * 12, cudaMemcpyDeviceToHost, ctx->stream));
   IGN_CUDA(cudaStreamSynchronize(ctx->stream));

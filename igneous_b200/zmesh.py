@@ -72,6 +72,7 @@ class Mesher:
     self._ctx = ctx
     self._handle = None
     self._export = {}
+    self._simp = None  # (reduction_factor, max_error) the resident meshes were simplified with
 
   # -- lifecycle
   def _free(self):
@@ -79,6 +80,7 @@ class Mesher:
       _shim.load().ign_mesh_free(self._handle)
       self._handle = None
     self._export = {}
+    self._simp = None
 
   def clear(self):
     self._free()
@@ -124,6 +126,19 @@ class Mesher:
       _shim.check(lib.ign_mesh_ids(self._handle, _shim.ptr(ids), ctypes.c_uint64(n.value)))
     return [int(i) for i in ids]
 
+  def _simplify(self, reduction_factor, max_error):
+    want = (int(reduction_factor), float(max_error)) if reduction_factor and reduction_factor > 0 else None
+    if want == self._simp:
+      return
+    if self._simp is not None or (want is None and self._simp is not None):
+      raise ValueError("igneous_b200.zmesh: the resident meshes were simplified with %r; call mesh() "
+                       "again to extract with %r" % (self._simp, want))
+    res = (ctypes.c_float * 3)(*[float(r) for r in self.voxel_res])
+    _shim.check(self._ctx.lib.ign_mesh_simplify(self._handle, res, ctypes.c_int(want[0]),
+                                                ctypes.c_float(want[1])))
+    self._simp = want
+    self._export = {}
+
   def _exported(self, voxel_centered):
     key = bool(voxel_centered)
     if key not in self._export:
@@ -149,6 +164,7 @@ class Mesher:
       raise ValueError("Mesher.get called before Mesher.mesh")
     if normals:
       raise NotImplementedError("igneous_b200.zmesh: normals=True is not implemented")
+    self._simplify(reduction_factor, max_error)
     verts, faces, voff, foff, index = self._exported(voxel_centered)
     label = int(label)
     if label not in index:
@@ -156,11 +172,7 @@ class Mesher:
     j = index[label]
     v = verts[int(voff[j]):int(voff[j + 1])].copy()
     f = faces[int(foff[j]):int(foff[j + 1])].copy()
-    mesh = Mesh(v, f, id=label)
-    if reduction_factor and reduction_factor > 0 and len(f) > 0:
-      from . import simplify
-      mesh = simplify.simplify(mesh, int(reduction_factor), float(max_error), ctx=self._ctx)
-    return mesh
+    return Mesh(v, f, id=label)
 
   def get_mesh(self, *args, **kwargs):  # legacy alias
     return self.get(*args, **kwargs)

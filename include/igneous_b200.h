@@ -222,7 +222,13 @@ IGN_API int ign_mesh_totals(ign_mesher* m, uint64_t* nv, uint64_t* nf);
 IGN_API int ign_mesh_get(ign_mesher* m, uint64_t id, const float resolution[3], int reduction_factor,
                  float max_error, int voxel_centered, float* vertices, uint32_t* faces,
                  uint64_t* nv, uint64_t* nf);
-/* bulk export of every label's unsimplified mesh in ign_mesh_ids order:
+/* Simplify every label of the mesher in place (round-based quadric edge collapse
+ * towards nf/reduction_factor faces per label, collapse cost <= max_error^2 in
+ * physical units, boundary vertices locked).  ign_mesh_get(reduction_factor>0)
+ * calls it on first use; ign_mesh_export then returns the simplified meshes. */
+IGN_API int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int reduction_factor,
+                              float max_error);
+/* bulk export of every label's mesh (simplified if ign_mesh_simplify ran) in ign_mesh_ids order:
  * vertices f32 [U,3], faces u32 [T,3] (label-local indices), offsets [n_ids+1] */
 IGN_API int ign_mesh_export(ign_mesher* m, const float resolution[3], int voxel_centered,
                             float* vertices, uint32_t* faces, uint64_t* vert_offsets,

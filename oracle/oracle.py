@@ -295,6 +295,45 @@ class WeldedMeshes:
     return verts.astype(np.float32), faces.astype(np.uint32)
 
 
+def simplify_welded(W, resolution=(1, 1, 1), reduction_factor=100, max_error=40.0,
+                    voxel_centered=True, max_rounds=400):
+  """Mesher.get(id, reduction_factor, max_error, voxel_centered) for every label of a
+  WeldedMeshes (igneous/tasks/mesh/mesh.py:376-381): round-based quadric edge
+  collapse (see orc_simplify; parity with zmesh unpinned).  Returns
+  ({label: (vertices f32, faces u32)}, rounds)."""
+  U, T = len(W.ulabel), len(W.faces)
+  res = np.asarray(resolution, dtype=np.float64)
+  pos = np.ascontiguousarray(W.uxyz.astype(np.float64) * 0.5 * res)
+  faces = np.ascontiguousarray(W.faces.astype(np.uint32))
+  dense = np.searchsorted(W.labels, W.tlabel).astype(np.uint32) + np.uint32(1)
+  K = len(W.labels)
+  nf = (W.f1 - W.f0).astype(np.uint64)
+  target = np.zeros(K + 1, dtype=np.uint32)
+  target[1:] = (nf // np.uint64(max(int(reduction_factor), 1))).astype(np.uint32)
+  valive = np.zeros(max(U, 1), dtype=np.uint8)
+  falive = np.zeros(max(T, 1), dtype=np.uint8)
+  rounds = ctypes.c_int(0)
+  tri_off = np.zeros(K + 1, dtype=np.uint32)
+  tri_off[1:] = W.f0.astype(np.uint32)
+  rc = lib().orc_simplify(ctypes.c_uint64(U), ctypes.c_uint64(T), _ptr(pos), _ptr(faces), _ptr(dense),
+                          ctypes.c_uint32(K), _ptr(target), _ptr(tri_off), ctypes.c_double(float(max_error) ** 2),
+                          ctypes.c_int(max_rounds), _ptr(valive), _ptr(falive), ctypes.byref(rounds))
+  assert rc == 0
+  out = {}
+  shift = (np.float32(0.5) * np.asarray(resolution, dtype=np.float32)) if voxel_centered else np.zeros(3, np.float32)
+  newid = np.cumsum(valive[:U].astype(np.int64)) - 1
+  for j, lab in enumerate(W.labels):
+    v0, v1, f0, f1 = int(W.v0[j]), int(W.v1[j]), int(W.f0[j]), int(W.f1[j])
+    va = valive[v0:v1].astype(bool)
+    fa = falive[f0:f1].astype(bool)
+    verts = pos[v0:v1][va].astype(np.float32) + shift
+    base = newid[v0] - (1 if valive[v0] else 0) + 1 if v1 > v0 else 0
+    f = faces[f0:f1][fa].astype(np.int64)
+    f = (newid[f] - base).astype(np.uint32)
+    out[int(lab)] = (verts.astype(np.float32), f)
+  return out, int(rounds.value)
+
+
 def pack_vertex(v):
   """(x,y,z) half-voxel integer coords -> sortable 63-bit key (z major)."""
   v = np.asarray(v, dtype=np.uint64)

@@ -110,3 +110,55 @@ def test_mc_properties_at_task_size(ctx):
       assert np.array_equal(np.sort(fwd), np.sort(bwd))  # closed + consistently oriented
       checked += 1
   assert checked > 0
+
+
+def _closed(f):
+  e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]).astype(np.int64)
+  return np.array_equal(np.sort(e[:, 0] * (1 << 32) + e[:, 1]), np.sort(e[:, 1] * (1 << 32) + e[:, 0]))
+
+
+def test_simplify_box_matches_oracle_bit_exact(ctx, oracle):
+  """62^3 box (reference mesh test volume): the GPU simplifier reproduces the
+  CPU restatement of the same round-based algorithm bit for bit (parity with
+  zmesh's own simplifier is unpinned)."""
+  from igneous_b200 import zmesh
+  data = np.zeros((64, 64, 64), dtype=np.uint32, order="F")
+  data[1:-1, 1:-1, 1:-1] = 1
+  m = zmesh.Mesher((1, 1, 1))
+  m.mesh(data)
+  got = m.get(1, reduction_factor=100, max_error=40, voxel_centered=False)
+  tl, tv = oracle.marching_cubes(data)
+  want, rounds = oracle.simplify_welded(oracle.WeldedMeshes(tl, tv), (1, 1, 1), 100, 40.0, False)
+  wv, wf = want[1]
+  assert got.faces.shape == wf.shape and got.vertices.shape == wv.shape
+  assert np.array_equal(got.faces, wf) and np.array_equal(got.vertices, wv)
+  assert len(got.faces) <= 46124 // 100 + 2 and len(got.faces) >= 0.8 * (46124 // 100)
+  assert _closed(got.faces)
+  v = got.vertices.astype(np.float64)
+  vol = np.einsum("ij,ij->i", v[got.faces[:, 0]], np.cross(v[got.faces[:, 1]], v[got.faces[:, 2]])).sum() / 6
+  assert abs(vol - 238235.6667) < 1e-3 * 238235  # flat faces: volume preserved
+
+
+@pytest.mark.parametrize("factor,max_error", [(100, 40.0), (4, 1e9), (10, 8.0)])
+def test_simplify_multilabel_matches_oracle(ctx, oracle, factor, max_error):
+  from igneous_b200 import zmesh
+  seg = oracle.synth_seg((49, 45, 41), pitch=16, num_ids=1 << 20)
+  res = (16, 16, 40)
+  m = zmesh.Mesher(res)
+  m.mesh(seg)
+  tl, tv = oracle.marching_cubes(seg)
+  W = oracle.WeldedMeshes(tl, tv)
+  want, rounds = oracle.simplify_welded(W, res, factor, max_error, True)
+  assert sorted(m.ids()) == sorted(want.keys())
+  before = {l: len(W.get(l)[1]) for l in W.ids()}
+  for lab in m.ids():
+    got = m.get(lab, reduction_factor=factor, max_error=max_error, voxel_centered=True)
+    wv, wf = want[lab]
+    assert got.vertices.shape == wv.shape and got.faces.shape == wf.shape, lab
+    assert np.abs(got.vertices - wv).max(initial=0) <= 1e-5 * max(1.0, float(np.abs(wv).max(initial=0)))
+    assert np.array_equal(got.vertices, wv) and np.array_equal(got.faces, wf), lab
+    assert len(got.faces) <= before[lab]
+  total_after = sum(len(f) for v, f in want.values())
+  assert total_after < sum(before.values())
+  with pytest.raises(ValueError):
+    m.get(m.ids()[0], reduction_factor=factor + 1, max_error=max_error)
