@@ -81,3 +81,37 @@ def dust(img, threshold, connectivity=6, in_place=False, ctx=None):
       src[...] = res  # caller's array was not Fortran contiguous
     return img if isinstance(img, np.ndarray) else src
   return res
+
+
+def ccl_task(image, shape, threshold_gte=None, threshold_lte=None, dust_threshold=0,
+             label_offset=0, ctx=None):
+  """The fused body shared by CCLFacesTask / CCLEquivalancesTask / RelabelCCLTask
+  (igneous/tasks/image/ccl.py:165-175, 228-240, 331-344): threshold_image ->
+  blackout_non_face_rails(shape) -> dust -> 6-connected CCL -> += label_offset
+  with the background re-zeroed, in one pass over HBM.  Returns (uint64 labels, N)."""
+  import ctypes as c
+  arr = _volume(image)
+  if arr.dtype == np.bool_:
+    arr = arr.view(np.uint8)
+  ctx = ctx or _shim.default_context()
+  sx, sy, sz = arr.shape
+  out = np.zeros(arr.shape, dtype=np.uint64, order="F")
+  n = c.c_uint64(0)
+  if arr.size:
+    d_in = ctx.to_device(arr)
+    d_out = ctx.alloc(arr.size * 8)
+    try:
+      _shim.check(ctx.lib.ign_ccl_task_dev(
+        ctx.handle, _shim.ptr(d_in), c.c_int(_shim.dtype_code(arr.dtype)), c.c_uint64(sx), c.c_uint64(sy),
+        c.c_uint64(sz), c.c_int(int(threshold_gte is not None)),
+        c.c_double(float(threshold_gte) if threshold_gte is not None else 0.0),
+        c.c_int(int(threshold_lte is not None)),
+        c.c_double(float(threshold_lte) if threshold_lte is not None else 0.0),
+        c.c_uint64(int(shape[0])), c.c_uint64(int(shape[1])), c.c_uint64(int(shape[2])),
+        c.c_uint64(int(dust_threshold or 0)), c.c_uint64(int(label_offset)), _shim.ptr(d_out), c.byref(n)))
+      ctx.d2h(out, d_out)
+      ctx.sync()
+    finally:
+      d_in.free()
+      d_out.free()
+  return out, int(n.value)
