@@ -829,12 +829,15 @@ static int ccl_build(ign_ctx* ctx, const R& rd, uint64_t sx, uint64_t sy, uint64
 template <typename T>
 __global__ void __launch_bounds__(256)
     k_ccl_plane(const T* __restrict__ in, const uint32_t* __restrict__ parent, uint64_t plane_base,
-                uint64_t nplane, uint64_t* __restrict__ values, uint32_t* __restrict__ labels) {
+                uint64_t nplane, const uint32_t* __restrict__ lut, uint64_t* __restrict__ values,
+                uint32_t* __restrict__ labels) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= nplane) return;
   values[i] = (uint64_t)in[plane_base + i];
   const uint32_t e = chase(parent, parent[plane_base + i]);
-  labels[i] = (e == CCL_BG) ? 0u : (e & ~CCL_FLAG);
+  uint32_t l = (e == CCL_BG) ? 0u : (e & ~CCL_FLAG);
+  if (lut != nullptr && l != 0) l = lut[l];
+  labels[i] = l;
 }
 
 // equivalence pairs between two facing planes (same x,y; adjacent z)
@@ -994,17 +997,27 @@ int ign_ccl6_build_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, 
   return IGN_ERR_UNSUPPORTED;
 }
 
+static int ccl_plane(ign_ctx* ctx, const void* in, int in_dtype, const uint32_t* work, uint64_t sx,
+                     uint64_t sy, uint64_t sz, uint64_t z, const uint32_t* lut, uint64_t* values,
+                     uint32_t* labels);
+
 int ign_ccl6_plane_dev(ign_ctx* ctx, const void* in, int in_dtype, const uint32_t* work, uint64_t sx,
                        uint64_t sy, uint64_t sz, uint64_t z, uint64_t* values, uint32_t* labels) {
+  return ccl_plane(ctx, in, in_dtype, work, sx, sy, sz, z, nullptr, values, labels);
+}
+
+static int ccl_plane(ign_ctx* ctx, const void* in, int in_dtype, const uint32_t* work, uint64_t sx,
+                     uint64_t sy, uint64_t sz, uint64_t z, const uint32_t* lut, uint64_t* values,
+                     uint32_t* labels) {
   IGN_TRY(activate(ctx));
   IGN_REQUIRE(in && work && values && labels && z < sz, IGN_ERR_INVALID, "bad plane argument");
   const uint64_t np = sx * sy, base = z * np;
   const unsigned g = blocks_for(np, 256);
   switch (in_dtype) {
-    case IGN_U8: IGN_LAUNCH(ctx, (k_ccl_plane<uint8_t>), g, 256, 0, (const uint8_t*)in, work, base, np, values, labels); break;
-    case IGN_U16: IGN_LAUNCH(ctx, (k_ccl_plane<uint16_t>), g, 256, 0, (const uint16_t*)in, work, base, np, values, labels); break;
-    case IGN_U32: IGN_LAUNCH(ctx, (k_ccl_plane<uint32_t>), g, 256, 0, (const uint32_t*)in, work, base, np, values, labels); break;
-    case IGN_U64: IGN_LAUNCH(ctx, (k_ccl_plane<uint64_t>), g, 256, 0, (const uint64_t*)in, work, base, np, values, labels); break;
+    case IGN_U8: IGN_LAUNCH(ctx, (k_ccl_plane<uint8_t>), g, 256, 0, (const uint8_t*)in, work, base, np, lut, values, labels); break;
+    case IGN_U16: IGN_LAUNCH(ctx, (k_ccl_plane<uint16_t>), g, 256, 0, (const uint16_t*)in, work, base, np, lut, values, labels); break;
+    case IGN_U32: IGN_LAUNCH(ctx, (k_ccl_plane<uint32_t>), g, 256, 0, (const uint32_t*)in, work, base, np, lut, values, labels); break;
+    case IGN_U64: IGN_LAUNCH(ctx, (k_ccl_plane<uint64_t>), g, 256, 0, (const uint64_t*)in, work, base, np, lut, values, labels); break;
     default: set_error("CCL plane: unsupported input dtype %d", in_dtype); return IGN_ERR_UNSUPPORTED;
   }
   return IGN_OK;
@@ -1098,43 +1111,76 @@ int ign_ccl6_label_dev(ign_ctx* ctx, const uint32_t* work, uint64_t sx, uint64_t
   return launch_label(ctx, s, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, offset, lut_dev, out, out_dtype, max_label);
 }
 
-// Whole-volume CCL on one GPU for volumes beyond the 2^31-voxel slab limit:
-// z-slabs are resolved independently, linked through their facing planes and
-// labelled once with the composed lookup table.
-int ign_ccl6_volume_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
-                        uint64_t sz, void* out, int out_dtype, uint64_t max_slab_voxels,
-                        uint64_t* n_components) {
+// ---------------------------------------------------------------- volume CCL
+// z-slabs of <= 2^30 voxels are resolved independently, linked through their
+// facing planes, solved on the host and labelled once through the composed
+// lookup table.  begin/finish are split so that a multi-GPU run can exchange the
+// outer planes of every rank's volume in between (ONE all-gather) and fold the
+// global relabelling into the same single label pass.
+struct ign_ccl_volume {
+  ign_ctx* ctx;
+  const void* in;
+  int in_dtype;
+  uint64_t sx, sy, sz, slab_sz, nslabs;
+  uint32_t* work;
+  std::vector<uint64_t> nloc, off;   // per slab component counts / offsets
+  std::vector<uint32_t> local_lut;   // provisional slab id -> volume-local id (1..n_local)
+  uint64_t n_local;
+};
+
+int ign_ccl6_volume_abort(ign_ccl_volume* v) {
+  if (!v) return IGN_OK;
+  scratch_reset(v->ctx);
+  delete v;
+  return IGN_OK;
+}
+
+int ign_ccl6_volume_begin_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
+                              uint64_t sz, uint64_t max_slab_voxels, uint64_t* first_values,
+                              uint32_t* first_labels, uint64_t* last_values, uint32_t* last_labels,
+                              ign_ccl_volume** out, uint64_t* n_local) {
   IGN_TRY(activate(ctx));
-  IGN_REQUIRE(in && out, IGN_ERR_INVALID, "null buffer");
+  IGN_REQUIRE(in && out && n_local, IGN_ERR_INVALID, "null argument");
+  *out = nullptr;
   IGN_REQUIRE(sx > 0 && sy > 0 && sz > 0, IGN_ERR_INVALID, "empty volume");
-  const int es = dtype_size(in_dtype), os = dtype_size(out_dtype);
-  IGN_REQUIRE(es > 0 && os > 0 && in_dtype != IGN_F32, IGN_ERR_UNSUPPORTED, "unsupported dtype");
+  const int es = dtype_size(in_dtype);
+  IGN_REQUIRE(es > 0 && in_dtype != IGN_F32, IGN_ERR_UNSUPPORTED, "unsupported dtype");
   const uint64_t np = sx * sy;
   if (max_slab_voxels == 0 || max_slab_voxels > 0x40000000ull) max_slab_voxels = 0x40000000ull;
   IGN_REQUIRE(np <= max_slab_voxels, IGN_ERR_OVERFLOW, "one z-plane exceeds the slab limit");
-  const uint64_t slab_sz = max_slab_voxels / np;
-  const uint64_t nslabs = (sz + slab_sz - 1) / slab_sz;
-  const uint64_t n = np * sz;
-  IGN_REQUIRE(ctx->scratch_used == 0, IGN_ERR_INVALID, "ign_ccl6_volume_dev must own the scratch arena");
+  IGN_REQUIRE(ctx->scratch_used == 0, IGN_ERR_INVALID, "volume CCL must own the scratch arena");
+  ign_ccl_volume* v = new ign_ccl_volume();
+  v->ctx = ctx;
+  v->in = in;
+  v->in_dtype = in_dtype;
+  v->sx = sx; v->sy = sy; v->sz = sz;
+  v->slab_sz = max_slab_voxels / np;
+  v->nslabs = (sz + v->slab_sz - 1) / v->slab_sz;
+  const uint64_t n = np * sz, slab_sz = v->slab_sz, nslabs = v->nslabs;
   const uint64_t slab_vox = np * (slab_sz < sz ? slab_sz : sz);
   const uint32_t cap = (uint32_t)slab_vox + 1024;
   const size_t need = align_up(n * 4, 256) + ccl_scratch_bytes(0, cap) + 2 * (align_up(np * 8, 256) + align_up(np * 4, 256)) +
-                      align_up(np * 16, 256) + align_up((n / 8 + 4096) * 4, 256) + (1 << 20);
-  IGN_TRY(scratch_reserve(ctx, need));
-  uint32_t* work = (uint32_t*)scratch_take(ctx, n * 4);
+                      2 * align_up(np * 16, 256) + 2 * align_up((n / 8 + 4096) * 4, 256) + (4 << 20);
+  int rc = scratch_reserve(ctx, need);
+  if (rc != IGN_OK) { delete v; return rc; }
+  uint32_t* work = v->work = (uint32_t*)scratch_take(ctx, n * 4);
   uint64_t* va = (uint64_t*)scratch_take(ctx, np * 8);
   uint64_t* vb = (uint64_t*)scratch_take(ctx, np * 8);
   uint32_t* la = (uint32_t*)scratch_take(ctx, np * 4);
   uint32_t* lb = (uint32_t*)scratch_take(ctx, np * 4);
-  IGN_REQUIRE(work && va && vb && la && lb, IGN_ERR_NOMEM, "scratch arena too small (volume CCL)");
-  std::vector<uint64_t> nloc(nslabs), off(nslabs + 1, 0);
-  int rc = IGN_OK;
+  if (!work || !va || !vb || !la || !lb) {
+    set_error("scratch arena too small (volume CCL)");
+    ign_ccl6_volume_abort(v);
+    return IGN_ERR_NOMEM;
+  }
+  v->nloc.assign(nslabs, 0);
+  v->off.assign(nslabs + 1, 0);
   for (uint64_t s = 0; s < nslabs && rc == IGN_OK; s++) {
     const uint64_t z0 = s * slab_sz, zs = (z0 + slab_sz <= sz) ? slab_sz : sz - z0;
-    rc = ign_ccl6_build_dev(ctx, (const char*)in + z0 * np * es, in_dtype, sx, sy, zs, work + z0 * np, &nloc[s]);
-    off[s + 1] = off[s] + nloc[s];
+    rc = ign_ccl6_build_dev(ctx, (const char*)in + z0 * np * es, in_dtype, sx, sy, zs, work + z0 * np, &v->nloc[s]);
+    v->off[s + 1] = v->off[s] + v->nloc[s];
   }
-  const uint64_t total = off[nslabs];
+  const uint64_t total = v->off[nslabs];
   std::vector<uint64_t> pairs;
   for (uint64_t s = 0; s + 1 < nslabs && rc == IGN_OK; s++) {
     const uint64_t z0 = s * slab_sz, z1 = (s + 1) * slab_sz;
@@ -1142,10 +1188,8 @@ int ign_ccl6_volume_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx,
     rc = ign_ccl6_plane_dev(ctx, (const char*)in + z0 * np * es, in_dtype, work + z0 * np, sx, sy, slab_sz, slab_sz - 1, va, la);
     if (rc == IGN_OK) rc = ign_ccl6_plane_dev(ctx, (const char*)in + z1 * np * es, in_dtype, work + z1 * np, sx, sy, zs1, 0, vb, lb);
     if (rc != IGN_OK) break;
-    // exact-size transfer: the device list is counted first, then copied into
-    // the (tiny) host vector -- no plane-sized host staging per boundary
     uint64_t cnt = 0;
-    rc = ign_ccl6_link_dev(ctx, va, la, off[s], vb, lb, off[s + 1], np, nullptr, 0, &cnt);
+    rc = ign_ccl6_link_dev(ctx, va, la, v->off[s], vb, lb, v->off[s + 1], np, nullptr, 0, &cnt);
     if (rc != IGN_OK) break;
     if (cnt) {
       const size_t at = pairs.size();
@@ -1157,36 +1201,97 @@ int ign_ccl6_volume_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx,
       }
     }
   }
-  uint64_t nglobal = total;
-  uint32_t* d_lut = nullptr;
-  if (rc == IGN_OK && nslabs > 1) {
-    std::vector<uint32_t> lut(total + 1);
-    rc = ign_ccl6_solve(pairs.data(), pairs.size() / 2, total, lut.data(), &nglobal);
-    if (rc == IGN_OK) {
-      d_lut = (uint32_t*)scratch_take(ctx, (total + 1) * 4);
-      if (!d_lut) {
-        set_error("scratch arena too small for the relabel table (%llu components)", (unsigned long long)total);
-        rc = IGN_ERR_NOMEM;
-      } else {
-        cudaError_t e = cudaMemcpyAsync(d_lut, lut.data(), (total + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // lut is a host temporary
-        if (e != cudaSuccess) {
-          set_error("volume CCL: lut H2D: %s", cudaGetErrorString(e));
-          rc = IGN_ERR_CUDA;
-        }
-      }
+  if (rc == IGN_OK) {
+    v->local_lut.assign(total + 1, 0);
+    if (nslabs > 1) {
+      rc = ign_ccl6_solve(pairs.data(), pairs.size() / 2, total, v->local_lut.data(), &v->n_local);
+    } else {
+      for (uint64_t i = 0; i <= total; i++) v->local_lut[i] = (uint32_t)i;
+      v->n_local = total;
     }
   }
-  for (uint64_t s = 0; s < nslabs && rc == IGN_OK; s++) {
-    const uint64_t z0 = s * slab_sz, zs = (z0 + slab_sz <= sz) ? slab_sz : sz - z0;
-    if (d_lut)
-      rc = ign_ccl6_label_dev(ctx, work + z0 * np, sx, sy, zs, d_lut + off[s], 0, (char*)out + z0 * np * os, out_dtype, nglobal);
-    else
-      rc = ign_ccl6_label_dev(ctx, work + z0 * np, sx, sy, zs, nullptr, 0, (char*)out + z0 * np * os, out_dtype, nglobal);
+  // outer planes with volume-local ids, for a caller that links several volumes
+  if (rc == IGN_OK && first_values && first_labels && last_values && last_labels) {
+    uint32_t* d_lut = (uint32_t*)scratch_take(ctx, (total + 1) * 4);
+    if (!d_lut) {
+      set_error("scratch arena too small for the relabel table (%llu components)", (unsigned long long)total);
+      rc = IGN_ERR_NOMEM;
+    } else {
+      cudaError_t e = cudaMemcpyAsync(d_lut, v->local_lut.data(), (total + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) { set_error("volume CCL: lut H2D: %s", cudaGetErrorString(e)); rc = IGN_ERR_CUDA; }
+      const uint64_t zl = (nslabs - 1) * slab_sz, zsl = sz - zl;
+      if (rc == IGN_OK) rc = ccl_plane(ctx, in, in_dtype, work, sx, sy, (slab_sz < sz ? slab_sz : sz), 0, d_lut + v->off[0], first_values, first_labels);
+      if (rc == IGN_OK) rc = ccl_plane(ctx, (const char*)in + zl * np * es, in_dtype, work + zl * np, sx, sy, zsl, zsl - 1, d_lut + v->off[nslabs - 1], last_values, last_labels);
+      if (rc == IGN_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("volume CCL: sync failed"); rc = IGN_ERR_CUDA; }
+    }
   }
-  if (rc == IGN_OK && n_components) *n_components = nglobal;
+  if (rc != IGN_OK) {
+    ign_ccl6_volume_abort(v);
+    return rc;
+  }
+  // the arena stays held (work[] lives in it) until finish/abort; later
+  // allocations of this call sequence bump above the structure
+  *n_local = v->n_local;
+  *out = v;
+  return IGN_OK;
+}
+
+// global_lut: NULL, or [n_local+1] volume-local id -> final id (from the caller's
+// cross-volume solve).  Labels every slab once and releases the arena.
+int ign_ccl6_volume_finish_dev(ign_ccl_volume* v, const uint32_t* global_lut, uint64_t max_label,
+                               void* out, int out_dtype) {
+  IGN_REQUIRE(v && out, IGN_ERR_INVALID, "null argument");
+  ign_ctx* ctx = v->ctx;
+  IGN_TRY(activate(ctx));
+  const int os = dtype_size(out_dtype);
+  const uint64_t np = v->sx * v->sy, total = v->off[v->nslabs];
+  int rc = IGN_OK;
+  uint32_t* d_lut = nullptr;
+  std::vector<uint32_t> composed;
+  const uint32_t* lut_host = nullptr;
+  if (global_lut) {
+    composed.resize(total + 1);
+    for (uint64_t i = 0; i <= total; i++) composed[i] = global_lut[v->local_lut[i]];
+    lut_host = composed.data();
+  } else if (v->nslabs > 1) {
+    lut_host = v->local_lut.data();
+    max_label = v->n_local;
+  } else {
+    max_label = v->n_local;
+  }
+  if (os <= 0) { set_error("unsupported out dtype"); rc = IGN_ERR_UNSUPPORTED; }
+  if (rc == IGN_OK && lut_host) {
+    d_lut = (uint32_t*)scratch_take(ctx, (total + 1) * 4);
+    if (!d_lut) {
+      set_error("scratch arena too small for the relabel table (%llu components)", (unsigned long long)total);
+      rc = IGN_ERR_NOMEM;
+    } else {
+      cudaError_t e = cudaMemcpyAsync(d_lut, lut_host, (total + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // host table is a temporary
+      if (e != cudaSuccess) { set_error("volume CCL: lut H2D: %s", cudaGetErrorString(e)); rc = IGN_ERR_CUDA; }
+    }
+  }
+  for (uint64_t s = 0; s < v->nslabs && rc == IGN_OK; s++) {
+    const uint64_t z0 = s * v->slab_sz, zs = (z0 + v->slab_sz <= v->sz) ? v->slab_sz : v->sz - z0;
+    rc = ign_ccl6_label_dev(ctx, v->work + z0 * np, v->sx, v->sy, zs, d_lut ? d_lut + v->off[s] : nullptr, 0,
+                            (char*)out + z0 * np * os, out_dtype, max_label);
+  }
   scratch_reset(ctx);
+  delete v;
   return rc;
+}
+
+int ign_ccl6_volume_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
+                        uint64_t sz, void* out, int out_dtype, uint64_t max_slab_voxels,
+                        uint64_t* n_components) {
+  IGN_REQUIRE(in && out, IGN_ERR_INVALID, "null buffer");
+  ign_ccl_volume* v = nullptr;
+  uint64_t n = 0;
+  IGN_TRY(ign_ccl6_volume_begin_dev(ctx, in, in_dtype, sx, sy, sz, max_slab_voxels, nullptr, nullptr, nullptr,
+                                    nullptr, &v, &n));
+  IGN_TRY(ign_ccl6_volume_finish_dev(v, nullptr, n, out, out_dtype));
+  if (n_components) *n_components = n;
+  return IGN_OK;
 }
 
 }  // extern "C"

@@ -153,6 +153,20 @@ IGN_API int ign_ccl6_label_dev(ign_ctx* ctx, const uint32_t* work, uint64_t sx, 
 IGN_API int ign_ccl6_volume_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
                                 uint64_t sz, void* out, int out_dtype, uint64_t max_slab_voxels,
                                 uint64_t* n_components);
+/* The same in two halves, so that several volumes (one per GPU) can be linked in
+ * between: begin resolves the volume and fills its outer z-planes (voxel values
+ * widened to u64 and volume-local ids 1..n_local; device buffers of sx*sy
+ * entries, may be NULL); finish takes the caller's [n_local+1] table from
+ * volume-local to final ids (NULL = identity) and writes the labels. */
+typedef struct ign_ccl_volume ign_ccl_volume;
+IGN_API int ign_ccl6_volume_begin_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx,
+                                      uint64_t sy, uint64_t sz, uint64_t max_slab_voxels,
+                                      uint64_t* first_values, uint32_t* first_labels,
+                                      uint64_t* last_values, uint32_t* last_labels,
+                                      ign_ccl_volume** out, uint64_t* n_local);
+IGN_API int ign_ccl6_volume_finish_dev(ign_ccl_volume* v, const uint32_t* global_lut,
+                                       uint64_t max_label, void* out, int out_dtype);
+IGN_API int ign_ccl6_volume_abort(ign_ccl_volume* v);
 
 /* cc3d.dust(labels, threshold, connectivity=6, in_place=True)
  *   igneous/tasks/image/ccl.py:169-172, :231-234, :335-338
@@ -249,18 +263,15 @@ IGN_API int ign_synth_image_dev(ign_ctx* ctx, uint8_t* out, uint64_t sx, uint64_
  * :245-294 (equivalences) and :358-420 (create_relabeling) with one NCCL
  * all-gather of compacted (label_a,label_b) face-equivalence pairs.
  * One process per GPU; unique_id is ncclUniqueId bytes (128) created on rank 0
- * by ign_group_unique_id and broadcast by the host-side launcher. */
+ * by ign_group_unique_id and broadcast by the host-side launcher.  NCCL is
+ * dlopen()ed on first use (libnccl.so.2), so the library itself has no link-time
+ * dependency on it.  Host orchestration: igneous_b200/multigpu.py. */
 IGN_API int ign_group_unique_id(void* id128);
 IGN_API int ign_group_init(ign_ctx* ctx, int rank, int nranks, const void* id128, ign_group** out);
 IGN_API int ign_group_destroy(ign_group* g);
-/* slab CCL: this rank holds a (sx,sy,sz_local) slab of a volume stacked along z,
- * plus (rank+1<nranks) its upper neighbour's first plane is supplied by the
- * caller in `halo_plane` (device pointer, sx*sy voxels) -- exactly the +1 voxel
- * overlap of ccl.py:153.  out receives globally consistent ids (u64),
- * n_global the global number of components. */
-IGN_API int ign_ccl6_sharded_dev(ign_group* g, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
-                         uint64_t sz_local, const void* halo_plane, uint64_t* out,
-                         uint64_t* n_global);
+/* the single collective of the path: every rank contributes `bytes` bytes (its
+ * component count + outer planes), everyone receives nranks*bytes */
+IGN_API int ign_group_allgather(ign_group* g, const void* send_dev, uint64_t bytes, void* recv_dev);
 
 #ifdef __cplusplus
 }
