@@ -52,8 +52,8 @@ struct Simp {
   const uint32_t* target;  // [K+2]
   uint8_t* label_active;   // [K+2]
   const uint32_t* tri_off; // [K+2] first face of each label: keys use label-local half-edge ids
-  uint8_t* estate;  // [3T] 1 = parked: the edge won a round but failed validation
-  float* ecost;     // [3T] (unused)
+  uint8_t* estate;  // [3T] see k_simp_edge_keys
+  float* ecost;     // [3T] cached float cost of state 2
   uint8_t* vdirty;  // [U] ring changed by a collapse of the previous round
   // compacted work lists (rebuilt every few rounds; pure work skipping)
   uint32_t* elist;  // candidate half-edges
@@ -362,14 +362,28 @@ __global__ void __launch_bounds__(128) k_simp_edge_keys(Simp s, double max_err2,
   if (!s.falive[f] || !s.label_active[s.flabel[f]]) return;
   const uint32_t u = s.face[3 * (uint64_t)f + c], v = s.face[3 * (uint64_t)f + (c + 1) % 3];
   if (!(u < v)) return;  // one key per edge
-  if (s.estate[h] == 1) {
-    if (s.vdirty[u] || s.vdirty[v]) s.estate[h] = 0;  // neighbourhood changed: try again
-    else return;
+  // estate: 0 unknown, 1 parked (won a round, failed validation), 2 cost cached in
+  // ecost, 3 known to exceed max_error.  Any cached state is dropped when one of the
+  // endpoints' rings changed in the previous round (pure memoisation).
+  uint8_t st = s.estate[h];
+  if (st != 0 && (s.vdirty[u] || s.vdirty[v])) st = 0;
+  if (st == 1 || st == 3) return;
+  float cf;
+  if (st == 2) {
+    cf = s.ecost[h];
+  } else {
+    SEval e;
+    s_cost(s, u, v, max_err2, &e);
+    if (!e.valid) {
+      s.estate[h] = 3;
+      return;
+    }
+    cf = __double2float_rn(e.cost);
+    s.ecost[h] = cf;
+    s.estate[h] = 2;
   }
-  SEval e;
-  s_cost(s, u, v, max_err2, &e);
-  if (!e.valid) return;
-  const unsigned long long key = s_key(e.cost, (uint32_t)h - 3 * s.tri_off[s.flabel[f]], salt);
+  const unsigned long long key = ((unsigned long long)__float_as_uint(cf) << 32) |
+                                 s_mix(((uint32_t)h - 3 * s.tri_off[s.flabel[f]]) ^ salt);
   atomicMin(&s.key1[u], key);
   atomicMin(&s.key1[v], key);
 }
@@ -395,57 +409,87 @@ __global__ void __launch_bounds__(256) k_simp_key2(Simp s) {
   s.key2[w] = m;
 }
 
-__global__ void __launch_bounds__(128)
-    k_simp_collapse(Simp s, double max_err2, uint32_t salt, uint32_t* flags) {
+// winners of the round -> dense list (one winner per ~50 vertices: processing
+// them in place would leave one active lane per warp)
+__global__ void __launch_bounds__(256)
+    k_simp_select(Simp s, uint32_t salt, uint32_t* wlist, uint32_t* counters) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= s.nv) return;
-  const uint32_t a = s.vlist[i];
-  const unsigned long long key = s.key1[a];
-  if (!s.valive[a] || key == S_KEYMAX) return;
-  // the key holds a label-local half-edge id; a's label is that of any of its faces
-  const uint32_t hl = s_unmix((uint32_t)(key & 0xFFFFFFFFu)) ^ salt;
-  const uint32_t h = hl + 3 * s.tri_off[s.flabel[s.head[a] / 3]];
-  const uint32_t f = h / 3, c = h % 3;
-  const uint32_t u = s.face[3 * (uint64_t)f + c], v = s.face[3 * (uint64_t)f + (c + 1) % 3];
-  if (a != u) return;
-  if (s.key2[u] != key || s.key2[v] != key) return;
-  SEval e;
-  s_evaluate(s, u, v, max_err2, &e);
-  if (!e.valid) {  // park the edge until one of its endpoints' rings changes
-    s.estate[h] = 1;
-    flags[1] = 1;
-    return;
-  }
-  const uint32_t k = e.keep, rm = e.remove;
-  s.pos[3 * (uint64_t)k + 0] = e.p[0];
-  s.pos[3 * (uint64_t)k + 1] = e.p[1];
-  s.pos[3 * (uint64_t)k + 2] = e.p[2];
-  for (int i = 0; i < 10; i++)
-    s.Q[10 * (uint64_t)k + i] = s.Q[10 * (uint64_t)k + i] + s.Q[10 * (uint64_t)rm + i];
-  for (uint32_t hh = s.head[rm]; hh != S_NONE; hh = s.next[hh]) {
-    const uint32_t g = hh / 3;
-    if (!s.falive[g]) continue;
-    uint32_t* fv = s.face + 3 * (uint64_t)g;
-    if (fv[0] == k || fv[1] == k || fv[2] == k) {
-      s.falive[g] = 0;
-      atomicSub(&s.alive_faces[s.flabel[g]], 1u);
-    } else {
-      fv[hh % 3] = k;
+  bool win = false;
+  uint32_t h = 0;
+  if (i < s.nv) {
+    const uint32_t a = s.vlist[i];
+    const unsigned long long key = s.key1[a];
+    if (s.valive[a] && key != S_KEYMAX) {
+      // the key holds a label-local half-edge id; a's label is that of any of its faces
+      const uint32_t hl = s_unmix((uint32_t)(key & 0xFFFFFFFFu)) ^ salt;
+      h = hl + 3 * s.tri_off[s.flabel[s.head[a] / 3]];
+      const uint32_t f = h / 3, c = h % 3;
+      const uint32_t u = s.face[3 * (uint64_t)f + c], v = s.face[3 * (uint64_t)f + (c + 1) % 3];
+      win = (a == u) && s.key2[u] == key && s.key2[v] == key;
     }
   }
-  s.next[s.tail[k]] = s.head[rm];
-  s.tail[k] = s.tail[rm];
-  s.valive[rm] = 0;
-  flags[1] = 1;
-  atomicAdd(&flags[2], 1u);
-  s.vdirty[k] = 1;
-  for (uint32_t hh = s.head[k]; hh != S_NONE; hh = s.next[hh]) {
-    const uint32_t g = hh / 3;
-    if (!s.falive[g]) continue;
-    const uint32_t* fv = s.face + 3 * (uint64_t)g;
-    s.vdirty[fv[0]] = 1;
-    s.vdirty[fv[1]] = 1;
-    s.vdirty[fv[2]] = 1;
+  s_append(win, h, wlist, &counters[3]);
+}
+
+__global__ void __launch_bounds__(128)
+    k_simp_collapse(Simp s, double max_err2, const uint32_t* __restrict__ wlist, uint32_t* flags) {
+  const uint32_t nw = flags[3];  // written by k_simp_select (stream ordered)
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nw;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t h = wlist[i];
+    const uint32_t f = h / 3, c = h % 3;
+    const uint32_t u = s.face[3 * (uint64_t)f + c], v = s.face[3 * (uint64_t)f + (c + 1) % 3];
+    SEval e;
+    s_evaluate(s, u, v, max_err2, &e);
+    if (!e.valid) {  // park the edge until one of its endpoints' rings changes
+      s.estate[h] = 1;
+      flags[1] = 1;
+      continue;
+    }
+    const uint32_t k = e.keep, rm = e.remove;
+    s.pos[3 * (uint64_t)k + 0] = e.p[0];
+    s.pos[3 * (uint64_t)k + 1] = e.p[1];
+    s.pos[3 * (uint64_t)k + 2] = e.p[2];
+    for (int q = 0; q < 10; q++)
+      s.Q[10 * (uint64_t)k + q] = s.Q[10 * (uint64_t)k + q] + s.Q[10 * (uint64_t)rm + q];
+    for (uint32_t hh = s.head[rm]; hh != S_NONE; hh = s.next[hh]) {
+      const uint32_t g = hh / 3;
+      if (!s.falive[g]) continue;
+      uint32_t* fv = s.face + 3 * (uint64_t)g;
+      if (fv[0] == k || fv[1] == k || fv[2] == k) {
+        s.falive[g] = 0;
+        atomicSub(&s.alive_faces[s.flabel[g]], 1u);
+      } else {
+        fv[hh % 3] = k;
+      }
+    }
+    // k's new incident list = k's ++ rm's with the dead faces unlinked (the lists
+    // would otherwise keep every face either vertex ever had, and every later
+    // ring walk would pay for them).  Only this thread touches k and rm this round.
+    uint32_t nhead = S_NONE, ntail = S_NONE;
+    for (int pass = 0; pass < 2; pass++) {
+      uint32_t hh = pass ? s.head[rm] : s.head[k];
+      while (hh != S_NONE) {
+        const uint32_t nxt = s.next[hh];
+        if (s.falive[hh / 3]) {
+          if (ntail == S_NONE) nhead = hh;
+          else s.next[ntail] = hh;
+          ntail = hh;
+          const uint32_t* fv = s.face + 3 * (uint64_t)(hh / 3);
+          s.vdirty[fv[0]] = 1;
+          s.vdirty[fv[1]] = 1;
+          s.vdirty[fv[2]] = 1;
+        }
+        hh = nxt;
+      }
+    }
+    if (ntail != S_NONE) s.next[ntail] = S_NONE;
+    s.head[k] = nhead;
+    s.tail[k] = ntail;
+    s.vdirty[k] = 1;
+    s.valive[rm] = 0;
+    flags[1] = 1;
+    atomicAdd(&flags[2], 1u);
   }
 }
 
@@ -537,7 +581,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
                       3 * align_up(T * 4, 256) + 2 * align_up(T, 256) + 3 * align_up(U, 256) +
                       4 * align_up(U * 4, 256) + 2 * align_up(U * 8, 256) + 6 * align_up((K + 2) * 4, 256) +
                       2 * align_up(3 * T * 4, 256) + align_up(3 * T, 256) + align_up(3 * T * 4, 256) +
-                      align_up(U, 256) + align_up(3 * T * 4, 256) + align_up(U * 4, 256) + tmpb + (1 << 20);
+                      align_up(U, 256) + align_up(3 * T * 4, 256) + 2 * align_up(U * 4, 256) + tmpb + (1 << 20);
   IGN_TRY(scratch_reserve(ctx, need));
   Simp s;
   s.U = U;
@@ -571,6 +615,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   s.vdirty = (uint8_t*)scratch_take(ctx, U);
   s.elist = (uint32_t*)scratch_take(ctx, 3 * T * 4);
   s.vlist = (uint32_t*)scratch_take(ctx, U * 4);
+  uint32_t* wlist = (uint32_t*)scratch_take(ctx, U * 4);
   s.ne = s.nv = 0;
   void* tmp = scratch_take(ctx, tmpb);
   uint32_t* sorted_v = (uint32_t*)scratch_take(ctx, 3 * T * 4);
@@ -579,7 +624,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
       !s.vbound || !s.head || !s.tail || !vscan || !vflag || !s.key1 || !s.key2 || !s.alive_faces ||
       !d_target || !s.label_active || !d_tri_off || !d_vert_off || !d_new_tri_off || !d_new_vert_off ||
       !flags || !tmp || !sorted_v || !sorted_h || !s.estate || !s.ecost || !s.vdirty || !s.elist ||
-      !s.vlist) {
+      !s.vlist || !wlist) {
     // the plan above under-counted: grow once with slack and retry
     scratch_reset(ctx);
     set_error("scratch arena too small (simplify: %llu faces)", (unsigned long long)T);
@@ -656,15 +701,18 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
       s.ne = hflags[8];
       s.nv = hflags[9];
     }
-    S_CUDA(cudaMemsetAsync(flags, 0, 12, ctx->stream));
+    S_CUDA(cudaMemsetAsync(flags, 0, 16, ctx->stream));
     const uint64_t nb = (s.nv > K + 1 ? s.nv : K + 1);
     S_LAUNCH(k_simp_round_begin, blocks_for(nb, 256), 256, s, (uint32_t)K, flags);
     if (s.ne) S_LAUNCH(k_simp_edge_keys, blocks_for(s.ne, 128), 128, s, max_err2, salt);
     if (s.nv) {
       S_LAUNCH(k_simp_key2, blocks_for(s.nv, 256), 256, s);
-      S_LAUNCH(k_simp_collapse, blocks_for(s.nv, 128), 128, s, max_err2, salt, flags);
+      S_LAUNCH(k_simp_select, blocks_for(s.nv, 256), 256, s, salt, wlist, flags);
+      // grid-stride over the device-side winner count: no host round trip in between
+      const unsigned cg = blocks_for(s.nv / 16 + 1, 128);
+      S_LAUNCH(k_simp_collapse, cg < 1184 ? cg : 1184, 128, s, max_err2, wlist, flags);
     }
-    S_CUDA(cudaMemcpyAsync(hflags, flags, 12, cudaMemcpyDeviceToHost, ctx->stream));
+    S_CUDA(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, ctx->stream));
     S_CUDA(cudaStreamSynchronize(ctx->stream));
     if (hflags[0] == 0) break;           // every label reached its target before this round
     if (hflags[1] == 0) { r++; break; }  // nothing collapsed or parked: fixed point
