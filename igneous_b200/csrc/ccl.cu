@@ -541,6 +541,73 @@ __global__ void __launch_bounds__(256)
   (void)nfy; (void)nfz; (void)nfx;
 }
 
+// ----------------------------------------- G2: face merges, deduplicated per tile
+// One CTA per tile handles the tile's low y / z / x faces.  Along a face the same
+// pair of tile-local components meets in up to 64 sub-words; instead of running
+// a global union-find for each meeting, the (local root A, local root B) pairs
+// are first collected in a shared-memory hash set and only the unique pairs are
+// united in global memory.
+constexpr int MERGE_SLOTS = 1024;  // power of two, 8 KB of u64
+
+__device__ __forceinline__ void merge_emit(unsigned long long* set, uint32_t* parent, uint32_t a,
+                                           uint32_t b) {
+  const unsigned long long key = ((unsigned long long)a << 32) | b;
+  uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 54) & (MERGE_SLOTS - 1);
+  for (int probe = 0; probe < 16; probe++) {
+    const unsigned long long cur = atomicCAS(&set[h], 0xFFFFFFFFFFFFFFFFull, key);
+    if (cur == 0xFFFFFFFFFFFFFFFFull || cur == key) return;
+    h = (h + 1) & (MERGE_SLOTS - 1);
+  }
+  uf_union(parent, a, b);  // table crowded: unite directly
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+    k_ccl_merge_tiles(R rd, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t ntx, uint32_t nty,
+                      uint32_t* parent) {
+  using V = typename R::V;
+  __shared__ unsigned long long set[MERGE_SLOTS];
+  for (int i = threadIdx.x; i < MERGE_SLOTS; i += blockDim.x) set[i] = 0xFFFFFFFFFFFFFFFFull;
+  __syncthreads();
+  const TilePos t = tile_pos(ntx, nty);
+  const uint32_t sxy = sx * sy;
+  const uint32_t nwarps = blockDim.x >> 5;
+  // faces as (row list, neighbour stride): y face = rows (ly=0, lz=0..7); z face = rows (lz=0, ly=0..7)
+  for (uint32_t item = t.warp; item < 2 * TILE_Y * SUBW; item += nwarps) {
+    const uint32_t face = item / (TILE_Y * SUBW);      // 0: y face, 1: z face
+    const uint32_t rowi = (item / SUBW) % TILE_Y, k = item % SUBW;
+    const uint32_t ly = face == 0 ? 0 : rowi, lz = face == 0 ? rowi : 0;
+    const uint32_t y = t.Y0 + ly, z = t.Z0 + lz;
+    if (y >= sy || z >= sz) continue;
+    if (face == 0 ? (y == 0) : (z == 0)) continue;
+    const uint32_t stride = face == 0 ? sx : sxy;
+    const uint32_t x = t.X0 + 32 * k + t.lane;
+    const bool inb = x < sx;
+    const uint32_t idx = (z * sy + y) * sx + x;
+    const V v = inb ? rd.at(idx, x, y, z) : (V)0;
+    const V vn = inb ? (face == 0 ? rd.at(idx - sx, x, y - 1, z) : rd.at(idx - sxy, x, y, z - 1)) : (V)0;
+    const V vl = shfl_up1(v);
+    const bool same_left = (t.lane > 0) && (v == vl);
+    const bool c = (v != 0) && (v == vn);
+    const bool c_l = __shfl_up_sync(FULL, (int)c, 1) != 0;
+    if (c && !(same_left && c_l)) merge_emit(set, parent, parent[idx], parent[idx - stride]);
+  }
+  if (t.X0 > 0) {  // x face: one voxel pair per tile row
+    for (uint32_t r = threadIdx.x; r < TILE_ROWS; r += blockDim.x) {
+      const uint32_t y = t.Y0 + (r % TILE_Y), z = t.Z0 + (r / TILE_Y);
+      if (y >= sy || z >= sz) continue;
+      const uint32_t idx = (z * sy + y) * sx + t.X0;
+      const V a = rd.at(idx, t.X0, y, z);
+      if (a != 0 && a == rd.at(idx - 1, t.X0 - 1, y, z)) merge_emit(set, parent, parent[idx], parent[idx - 1]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < MERGE_SLOTS; i += blockDim.x) {
+    const unsigned long long key = set[i];
+    if (key != 0xFFFFFFFFFFFFFFFFull) uf_union(parent, (uint32_t)(key >> 32), (uint32_t)(key & 0xFFFFFFFFu));
+  }
+}
+
 // -------------------------------------------------------------------- roots
 __global__ void __launch_bounds__(256)
     k_ccl_roots(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ cand,
@@ -775,15 +842,19 @@ static int ccl_core(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, uint32_
   if (!fast)
     IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local<R>), grid, CCL_THREADS, smem, rd, sx, sy, sz, ntx, nty,
                     s.parent, s.cand, s.cap, s.counters);
-  {
-    const uint32_t w32 = (sx + 31) / 32;
-    const uint64_t items_y = (uint64_t)(nty - 1) * sz * w32;
-    const uint64_t items_z = (uint64_t)(ntz - 1) * sy * w32;
-    const uint64_t items_x = (uint64_t)(ntx - 1) * (((uint64_t)sy * sz + 31) / 32);
-    const uint64_t items = items_y + items_z + items_x;
-    if (items > 0)
-      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, (k_ccl_merge<R>), blocks_for(items * 32, 256), 256, 0, rd, sx, sy, sz, nty - 1,
-                 ntz - 1, ntx - 1, items_y, items_z, items_x, s.parent);
+  if (ntiles > 1) {
+    if (getenv("IGN_CCL_FLATMERGE") == nullptr) {
+      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, (k_ccl_merge_tiles<R>), grid, 256, 0, rd, sx, sy, sz, ntx, nty, s.parent);
+    } else {
+      const uint32_t w32 = (sx + 31) / 32;
+      const uint64_t items_y = (uint64_t)(nty - 1) * sz * w32;
+      const uint64_t items_z = (uint64_t)(ntz - 1) * sy * w32;
+      const uint64_t items_x = (uint64_t)(ntx - 1) * (((uint64_t)sy * sz + 31) / 32);
+      const uint64_t items = items_y + items_z + items_x;
+      if (items > 0)
+        IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, (k_ccl_merge<R>), blocks_for(items * 32, 256), 256, 0, rd, sx, sy, sz, nty - 1,
+                   ntz - 1, ntx - 1, items_y, items_z, items_x, s.parent);
+    }
   }
   uint32_t* h = (uint32_t*)ctx->pinned;
   IGN_CUDA(cudaMemcpyAsync(h, s.counters, 16, cudaMemcpyDeviceToHost, ctx->stream));

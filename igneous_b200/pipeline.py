@@ -25,7 +25,7 @@ class VolumePipeline:
   def __init__(self, ctx, shape, dtype=np.uint32, num_mips=2, mesh_shape=(256, 256, 256),
                resolution=(16, 16, 40), pitch=64, num_ids=1 << 20, seed=0, offset=(0, 0, 0),
                ccl_out_dtype=np.uint32, simplification_factor=100, max_simplification_error=40,
-               group=None):
+               group=None, mesh_streams=4):
     self.ctx = ctx
     self.lib = ctx.lib
     self.shape = tuple(int(s) for s in shape)
@@ -52,12 +52,23 @@ class VolumePipeline:
     self.d_cc = ctx.alloc(self.n * self.ccl_out_dtype.itemsize)
     mx, my, mz = self.mesh_shape
     self.d_task = ctx.alloc((mx + 1) * (my + 1) * (mz + 1) * es)
+    # MeshTask bodies are independent and latency bound (sorts, simplification
+    # rounds): run several of them concurrently, each on its own ign_ctx (own
+    # stream, scratch arena and mesher pool) of the same device.
+    self.mesh_streams = max(1, int(mesh_streams))
+    self._workers = [(ctx, self.d_task)]
+    for _ in range(self.mesh_streams - 1):
+      wctx = _shim.Context(ctx.device)
+      self._workers.append((wctx, wctx.alloc((mx + 1) * (my + 1) * (mz + 1) * es)))
     self.n_components = 0
     self.mesh_stats = {}
 
   def free(self):
     for b in [self.d_in, self.d_cc, self.d_task] + self.d_mips:
       b.free()
+    for wctx, buf in self._workers[1:]:
+      buf.free()
+      wctx.close()
 
   # ------------------------------------------------------------------ inputs
   def synth(self):
@@ -100,38 +111,57 @@ class VolumePipeline:
         for x0 in range(0, msx, mx):
           yield (x0, y0, z0, min(mx + 1, msx - x0), min(my + 1, msy - y0), min(mz + 1, msz - z0))
 
-  def mesh(self, export=None):
-    """MeshTask bodies over the mesh mip.  `export(task, mesher_handle)` may pull
-    results to the host (e2e); without it only the totals are read back."""
+  def _mesh_one(self, wctx, d_task, task, export):
+    lib = wctx.lib
     src = self.d_mips[-1] if self.num_mips else self.d_in
     msx, msy, msz = self.mip_shapes[-1] if self.num_mips else self.shape
-    tris = verts = labels = tasks = 0
-    for (x0, y0, z0, bx, by, bz) in self.mesh_tasks():
-      _shim.check(self.lib.ign_copy_box_dev(
-        self.ctx.handle, _shim.ptr(src), c.c_int(self.code), _u64(msx), _u64(msy), _u64(msz),
-        _u64(x0), _u64(y0), _u64(z0), _u64(bx), _u64(by), _u64(bz), _shim.ptr(self.d_task)))
-      h = c.c_void_p()
-      _shim.check(self.lib.ign_mesh_begin_dev(
-        self.ctx.handle, _shim.ptr(self.d_task), c.c_int(self.code), _u64(bx), _u64(by), _u64(bz),
-        c.byref(h)))
-      try:
-        if self.simplification_factor and self.simplification_factor > 0:
-          _shim.check(self.lib.ign_mesh_simplify(
-            h, (c.c_float * 3)(*[float(r) for r in self.resolution]),
-            c.c_int(int(self.simplification_factor)), c.c_float(float(self.max_simplification_error))))
-        nv, nf, nl = c.c_uint64(0), c.c_uint64(0), c.c_uint64(0)
-        _shim.check(self.lib.ign_mesh_totals(h, c.byref(nv), c.byref(nf)))
-        _shim.check(self.lib.ign_mesh_num_ids(h, c.byref(nl)))
-        if export is not None:
-          export((x0, y0, z0, bx, by, bz), h, int(nv.value), int(nf.value), int(nl.value))
-        tris += nf.value
-        verts += nv.value
-        labels += nl.value
-        tasks += 1
-      finally:
-        self.lib.ign_mesh_free(h)
-    self.mesh_stats = {"tasks": tasks, "triangles": int(tris), "vertices": int(verts),
-                       "label_fragments": int(labels)}
+    x0, y0, z0, bx, by, bz = task
+    _shim.check(lib.ign_copy_box_dev(
+      wctx.handle, _shim.ptr(src), c.c_int(self.code), _u64(msx), _u64(msy), _u64(msz),
+      _u64(x0), _u64(y0), _u64(z0), _u64(bx), _u64(by), _u64(bz), _shim.ptr(d_task)))
+    h = c.c_void_p()
+    _shim.check(lib.ign_mesh_begin_dev(
+      wctx.handle, _shim.ptr(d_task), c.c_int(self.code), _u64(bx), _u64(by), _u64(bz), c.byref(h)))
+    try:
+      if self.simplification_factor and self.simplification_factor > 0:
+        _shim.check(lib.ign_mesh_simplify(
+          h, (c.c_float * 3)(*[float(r) for r in self.resolution]),
+          c.c_int(int(self.simplification_factor)), c.c_float(float(self.max_simplification_error))))
+      nv, nf, nl = c.c_uint64(0), c.c_uint64(0), c.c_uint64(0)
+      _shim.check(lib.ign_mesh_totals(h, c.byref(nv), c.byref(nf)))
+      _shim.check(lib.ign_mesh_num_ids(h, c.byref(nl)))
+      if export is not None:
+        export(task, h, int(nv.value), int(nf.value), int(nl.value), wctx)
+      return int(nf.value), int(nv.value), int(nl.value)
+    finally:
+      lib.ign_mesh_free(h)
+
+  def mesh(self, export=None):
+    """MeshTask bodies over the mesh mip.  `export(task, mesher, nv, nf, nl, ctx)` may
+    pull results to the host (e2e); without it only the totals are read back."""
+    tasks = list(self.mesh_tasks())
+    self.ctx.sync()  # the mip pyramid (main stream) must be complete before other streams read it
+    results = []
+    if self.mesh_streams == 1 or len(tasks) == 1:
+      for t in tasks:
+        results.append(self._mesh_one(self.ctx, self.d_task, t, export))
+    else:
+      from concurrent.futures import ThreadPoolExecutor
+
+      def run(widx):
+        wctx, buf = self._workers[widx]
+        out = [self._mesh_one(wctx, buf, t, export) for t in tasks[widx::self.mesh_streams]]
+        wctx.sync()
+        return out
+      with ThreadPoolExecutor(max_workers=self.mesh_streams) as ex:
+        for part in ex.map(run, range(self.mesh_streams)):
+          results.extend(part)
+    self.mesh_stats = {"tasks": len(tasks), "triangles": int(sum(r[0] for r in results)),
+                       "vertices": int(sum(r[1] for r in results)),
+                       "label_fragments": int(sum(r[2] for r in results)), "streams": self.mesh_streams}
+
+  def launch_count(self):
+    return sum(w[0].launch_count() for w in self._workers)
 
   def step(self, timers=True):
     """One pass of the hot path over the resident volume."""
