@@ -149,8 +149,9 @@ def run_reference_arm(args):
     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
     "data": "synthetic", "gpu_launches": 0,
     "config": {"workload": "oracle port of the igneous CPU path: per step %d chunks of 256^3 uint32 "
-                           "(one per host core): mode pool 2 mips + cc3d-style CCL + marching cubes/weld "
-                           "at mip 2" % cores, "chunk": list(shape)},
+                           "(one per host core, jittered-Voronoi pitch 64): mode pool 2 mips + 6-connected CCL + "
+                           "marching cubes / weld / quadric simplification x100 at mip 2" % cores,
+               "chunk": list(shape), "simplification_factor": 100},
     "cpu_baseline": {"value": value, "unit": "Mvoxels/s", "cores": cores, "kind": "port",
                      "sample": "%d x 256^3 chunks per step, %d steps" % (cores, args.steps)},
     "e2e": {"value": value, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -197,6 +198,7 @@ def main():
   ap.add_argument("--no-cpu", action="store_true")
   ap.add_argument("--e2e-steps", type=int, default=2)
   ap.add_argument("--simplify", type=int, default=None, help="simplification factor (default 100)")
+  ap.add_argument("--mesh-streams", type=int, default=4, help="concurrent MeshTask bodies per GPU")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == "b200":
     args.warmup = 3
@@ -228,7 +230,8 @@ def main():
     group = multigpu.Group(ctx, rank, world, dist)
   pipe = pipeline.VolumePipeline(ctx, shape, np.uint32, num_mips=2, mesh_shape=(256, 256, 256),
                                  resolution=RESOLUTION, pitch=PITCH, num_ids=NUM_IDS, seed=0,
-                                 offset=(0, 0, rank * S), simplification_factor=simplify, group=group)
+                                 offset=(0, 0, rank * S), simplification_factor=simplify, group=group,
+                                 mesh_streams=args.mesh_streams)
   pipe.synth()
   ctx.sync()
 
