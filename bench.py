@@ -289,12 +289,20 @@ def main():
   achieved = (dom_bytes_per_launch / 1e9) / (dom_ms / dom_launches * 1e-3) if dom_ms > 0 else 0.0
   roofline = {
     "bound": "hbm", "kernel": "k_" + dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    "frac": achieved / peak,
+    # dram__bytes_read+write of this kernel from the ncu --set full capture in
+    # profiles/r01_ccl_local_fast_full_512_raw.csv: 7.657 B/voxel (537+491 MB at 512^3), scaled per launch
+    "traffic": (7.657 * pipe.n / dom_launches) if dominant == "ccl_local" else None,
+    "traffic_source": "ncu capture at 512^3 scaled by voxels per launch (profiles/r01_ccl_local_fast_full_512_raw.csv)",
+    "peak_source": peak_src,
     "algorithmic_bytes_per_voxel": alg[dominant],
     "avg_launch_ms": dom_ms / dom_launches, "launches_per_step": dom_launches,
     "stage_ccl": {"algorithmic_bytes_per_voxel": in_b + out_b, "ms_per_step": ccl_ms,
                   "achieved": pipe.n * (in_b + out_b) / 1e9 / (ccl_ms * 1e-3) if ccl_ms > 0 else 0.0},
     "kernels": kern,
+    "note": "dominant own streaming kernel; the mesh stage (cub sorts + latency-bound simplification rounds on "
+            "%d concurrent streams) takes %.0f%% of the step and has no bandwidth roofline"
+            % (pipe.mesh_streams, 100.0 * stage["mesh_ms"] / max(sum(stage.values()), 1e-9)),
   }
   roofline["stage_ccl"]["frac"] = roofline["stage_ccl"]["achieved"] / peak
 

@@ -302,11 +302,6 @@ __global__ void __launch_bounds__(256) k_simp_boundary(Simp s) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_simp_count_faces(Simp s) {
-  const uint64_t f = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (f < s.T) atomicAdd(&s.alive_faces[s.flabel[f]], 1u);
-}
-
 // work-list construction (warp-aggregated append; order is irrelevant)
 __device__ __forceinline__ void s_append(bool take, uint32_t value, uint32_t* list, uint32_t* counter) {
   const uint32_t lane = threadIdx.x & 31;
