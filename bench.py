@@ -198,7 +198,7 @@ def main():
   ap.add_argument("--no-cpu", action="store_true")
   ap.add_argument("--e2e-steps", type=int, default=2)
   ap.add_argument("--simplify", type=int, default=None, help="simplification factor (default 100)")
-  ap.add_argument("--mesh-streams", type=int, default=4, help="concurrent MeshTask bodies per GPU")
+  ap.add_argument("--mesh-streams", type=int, default=8, help="concurrent MeshTask bodies per GPU")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == "b200":
     args.warmup = 3

@@ -284,6 +284,15 @@ int ign_copy_box_dev(ign_ctx* ctx, const void* src, int dtype, uint64_t sx, uint
   return IGN_OK;
 }
 
+// make `waiter`'s stream wait for the point where `producer` last called
+// ign_timer_start(producer, slot) -- cross-stream ordering without a host sync
+int ign_stream_wait_mark(ign_ctx* waiter, ign_ctx* producer, int slot) {
+  IGN_REQUIRE(waiter && producer && slot >= 0 && slot < 16, IGN_ERR_INVALID, "bad stream_wait argument");
+  IGN_TRY(activate(waiter));
+  IGN_CUDA(cudaStreamWaitEvent(waiter->stream, producer->timers[slot][0], 0));
+  return IGN_OK;
+}
+
 int ign_timer_start(ign_ctx* ctx, int slot) {
   IGN_TRY(activate(ctx));
   IGN_REQUIRE(slot >= 0 && slot < 16, IGN_ERR_INVALID, "timer slot %d out of range", slot);

@@ -28,6 +28,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
+
 #include "mesher.h"
 
 namespace ign {
@@ -716,6 +718,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
     cum_collapses += hflags[2];
     const uint64_t alive_total = T - 2 * cum_collapses;
     if ((uint64_t)hflags[2] * 1000 < alive_total) slow++; else slow = 0;
+    if (getenv("IGN_SIMP_TRACE")) fprintf(stderr, "round %d collapses %u alive %llu ne %u nv %u\n", r, hflags[2], (unsigned long long)alive_total, s.ne, s.nv);
     if (slow >= 4) { r++; break; }
   }
   m->simp_rounds = r;

@@ -25,7 +25,7 @@ class VolumePipeline:
   def __init__(self, ctx, shape, dtype=np.uint32, num_mips=2, mesh_shape=(256, 256, 256),
                resolution=(16, 16, 40), pitch=64, num_ids=1 << 20, seed=0, offset=(0, 0, 0),
                ccl_out_dtype=np.uint32, simplification_factor=100, max_simplification_error=40,
-               group=None, mesh_streams=4):
+               group=None, mesh_streams=8):
     self.ctx = ctx
     self.lib = ctx.lib
     self.shape = tuple(int(s) for s in shape)
@@ -55,9 +55,11 @@ class VolumePipeline:
     # MeshTask bodies are independent and latency bound (sorts, simplification
     # rounds): run several of them concurrently, each on its own ign_ctx (own
     # stream, scratch arena and mesher pool) of the same device.
+    # The main context's stream is left free during the mesh stage so that the D2H
+    # of the CCL labels / mips (e2e) overlaps with meshing.
     self.mesh_streams = max(1, int(mesh_streams))
-    self._workers = [(ctx, self.d_task)]
-    for _ in range(self.mesh_streams - 1):
+    self._workers = []
+    for _ in range(self.mesh_streams):
       wctx = _shim.Context(ctx.device)
       self._workers.append((wctx, wctx.alloc((mx + 1) * (my + 1) * (mz + 1) * es)))
     self.n_components = 0
@@ -66,7 +68,7 @@ class VolumePipeline:
   def free(self):
     for b in [self.d_in, self.d_cc, self.d_task] + self.d_mips:
       b.free()
-    for wctx, buf in self._workers[1:]:
+    for wctx, buf in self._workers:
       buf.free()
       wctx.close()
 
@@ -88,6 +90,7 @@ class VolumePipeline:
     _shim.check(self.lib.ign_pool_mode_2x2x1_dev(
       self.ctx.handle, _shim.ptr(self.d_in), c.c_int(self.code), _u64(sx), _u64(sy), _u64(sz),
       c.c_int(self.num_mips), c.c_int(0), _shim.void_pp([m.ptr for m in self.d_mips])))
+    self.ctx.timer_start(15)  # "mips ready" mark for the mesh streams
 
   def ccl(self):
     sx, sy, sz = self.shape
@@ -140,19 +143,19 @@ class VolumePipeline:
     """MeshTask bodies over the mesh mip.  `export(task, mesher, nv, nf, nl, ctx)` may
     pull results to the host (e2e); without it only the totals are read back."""
     tasks = list(self.mesh_tasks())
-    self.ctx.sync()  # the mip pyramid (main stream) must be complete before other streams read it
+    for wctx, _ in self._workers:  # mesh streams start when the mip pyramid is complete
+      _shim.check(self.lib.ign_stream_wait_mark(wctx.handle, self.ctx.handle, c.c_int(15)))
     results = []
-    if self.mesh_streams == 1 or len(tasks) == 1:
-      for t in tasks:
-        results.append(self._mesh_one(self.ctx, self.d_task, t, export))
-    else:
-      from concurrent.futures import ThreadPoolExecutor
+    from concurrent.futures import ThreadPoolExecutor
 
-      def run(widx):
-        wctx, buf = self._workers[widx]
-        out = [self._mesh_one(wctx, buf, t, export) for t in tasks[widx::self.mesh_streams]]
-        wctx.sync()
-        return out
+    def run(widx):
+      wctx, buf = self._workers[widx]
+      out = [self._mesh_one(wctx, buf, t, export) for t in tasks[widx::self.mesh_streams]]
+      wctx.sync()
+      return out
+    if self.mesh_streams == 1:
+      results = run(0)
+    else:
       with ThreadPoolExecutor(max_workers=self.mesh_streams) as ex:
         for part in ex.map(run, range(self.mesh_streams)):
           results.extend(part)
@@ -161,7 +164,7 @@ class VolumePipeline:
                        "label_fragments": int(sum(r[2] for r in results)), "streams": self.mesh_streams}
 
   def launch_count(self):
-    return sum(w[0].launch_count() for w in self._workers)
+    return self.ctx.launch_count() + sum(w[0].launch_count() for w in self._workers)
 
   def step(self, timers=True):
     """One pass of the hot path over the resident volume."""

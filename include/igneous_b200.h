@@ -85,6 +85,9 @@ IGN_API int ign_memset(ign_ctx* ctx, void* dst, int byte, uint64_t bytes);
 IGN_API int ign_timer_start(ign_ctx* ctx, int slot);
 IGN_API int ign_timer_stop(ign_ctx* ctx, int slot);
 IGN_API int ign_timer_ms(ign_ctx* ctx, int slot, float* ms); /* synchronises on the stop event */
+/* cross-context ordering on one device: waiter's stream waits for the point where
+ * producer last called ign_timer_start(producer, slot); no host synchronisation */
+IGN_API int ign_stream_wait_mark(ign_ctx* waiter, ign_ctx* producer, int slot);
 
 /* per-kernel-class CUDA-event profiling on the ctx stream (bench.py roofline):
  * classes 0 ccl_local, 1 ccl_merge, 2 ccl_label, 3 pool, 4 marching cubes */
