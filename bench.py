@@ -340,10 +340,18 @@ def run_e2e(ctx, pipe, args, dist, world):
   all mesh fragments) back D2H."""
   from igneous_b200 import _shim
   n = pipe.n
-  host_in = ctx.pinned_empty(pipe.shape, np.uint32)
+  host_kind = "pinned (cudaHostAlloc)"
+  try:
+    host_in = ctx.pinned_empty(pipe.shape, np.uint32)
+    host = {"mips": [ctx.pinned_empty(s, np.uint32) for s in pipe.mip_shapes],
+            "cc": ctx.pinned_empty(pipe.shape, pipe.ccl_out_dtype)}
+  except (MemoryError, _shim.IgneousB200Error):
+    # the host could not page-lock ~80 GB for this rank: fall back to pageable buffers
+    host_kind = "pageable (pinned allocation failed)"
+    host_in = np.empty(pipe.shape, dtype=np.uint32, order="F")
+    host = {"mips": [np.empty(s, dtype=np.uint32, order="F") for s in pipe.mip_shapes],
+            "cc": np.empty(pipe.shape, dtype=pipe.ccl_out_dtype, order="F")}
   ctx.d2h(host_in, pipe.d_in)
-  host = {"mips": [ctx.pinned_empty(s, np.uint32) for s in pipe.mip_shapes],
-          "cc": ctx.pinned_empty(pipe.shape, pipe.ccl_out_dtype)}
   cap_v, cap_f = 1 << 22, 1 << 23
   ctx.sync()
   mesh_bytes = [0]
@@ -399,7 +407,7 @@ def run_e2e(ctx, pipe, args, dist, world):
   d2h = sum(int(np.prod(s)) * 4 for s in pipe.mip_shapes) + n * pipe.ccl_out_dtype.itemsize + mesh_bytes[0]
   return {"value": n * world / (ms / steps * 1e-3) / 1e6, "unit": "Mvoxels/s",
           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": steps,
-          "ms_per_step": ms / steps, "host_memory": "pinned (cudaHostAlloc)"}
+          "ms_per_step": ms / steps, "host_memory": host_kind}
 
 
 if __name__ == "__main__":

@@ -477,6 +477,7 @@ int orc_synth_seg_u64(uint64_t* out, uint64_t sx, uint64_t sy, uint64_t sz,
 /* All arithmetic in double without FMA contraction.                   */
 /* ------------------------------------------------------------------ */
 #include <math.h>
+#include <stdio.h>
 #define SIMP_NONE 0xFFFFFFFFu
 #define SIMP_MAXV 32
 #define SIMP_KEYMAX 0xFFFFFFFFFFFFFFFFull
@@ -782,6 +783,7 @@ int orc_simplify(uint64_t U, uint64_t T, double* pos, uint32_t* face, const uint
         vdirty[face[3 * (uint64_t)g]] = 1; vdirty[face[3 * (uint64_t)g + 1]] = 1; vdirty[face[3 * (uint64_t)g + 2]] = 1;
       }
     }
+    if (getenv("ORC_SIMP_TRACE")) fprintf(stderr, "round %d winners %llu collapses %llu\n", r, (unsigned long long)nsel, (unsigned long long)ncol);
     if (nsel == 0) { r++; break; }
     /* early stop: four consecutive rounds that each remove < 0.2% of the remaining faces */
     cum_collapses += ncol;
