@@ -257,6 +257,30 @@ __global__ void __launch_bounds__(256)
   out[t] = __fmul_rn(__fadd_rn(__fadd_rn(a, b), __fadd_rn(c, d)), 0.25f);
 }
 
+// min / max pooling and striding over fx x fy x fz blocks (factors 1 or 2 per axis;
+// partial edge blocks reduce over the samples that exist).  op: 0 min, 1 max, 2 striding.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_pool_select(const T* __restrict__ in, uint64_t sx, uint64_t sy, uint64_t sz, uint32_t fx,
+                  uint32_t fy, uint32_t fz, int op, T* __restrict__ out) {
+  const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy, oz = (sz + fz - 1) / fz;
+  const uint64_t total = ox * oy * oz;
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const uint64_t x = t % ox, r = t / ox, y = r % oy, z = r / oy;
+  const uint64_t x0 = x * fx, y0 = y * fy, z0 = z * fz;
+  T acc = in[(z0 * sy + y0) * sx + x0];
+  if (op != 2) {
+    for (uint32_t dz = 0; dz < fz && z0 + dz < sz; dz++)
+      for (uint32_t dy = 0; dy < fy && y0 + dy < sy; dy++)
+        for (uint32_t dx = 0; dx < fx && x0 + dx < sx; dx++) {
+          const T v = in[((z0 + dz) * sy + (y0 + dy)) * sx + (x0 + dx)];
+          acc = (op == 0) ? (v < acc ? v : acc) : (v > acc ? v : acc);
+        }
+  }
+  out[t] = acc;
+}
+
 template <typename A>
 __global__ void __launch_bounds__(256)
     k_widen_from(const void* __restrict__ in, int dtype, uint64_t n, A* __restrict__ out) {
@@ -422,6 +446,21 @@ static int check_pool_args(const void* in, int dtype, uint64_t sx, uint64_t sy, 
   return IGN_OK;
 }
 
+template <typename T>
+static int select_pyramid(ign_ctx* ctx, const void* in, uint64_t sx, uint64_t sy, uint64_t sz, uint32_t fx,
+                          uint32_t fy, uint32_t fz, int num_mips, int op, void* const* outs) {
+  const T* cur = (const T*)in;
+  for (int m = 0; m < num_mips; m++) {
+    const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy, oz = (sz + fz - 1) / fz;
+    const uint64_t total = ox * oy * oz;
+    if (total > 0)
+      IGN_LAUNCH(ctx, (k_pool_select<T>), blocks_for(total, 256), 256, 0, cur, sx, sy, sz, fx, fy, fz, op, (T*)outs[m]);
+    cur = (const T*)outs[m];
+    sx = ox; sy = oy; sz = oz;
+  }
+  return IGN_OK;
+}
+
 }  // namespace ign
 
 using namespace ign;
@@ -460,6 +499,55 @@ int ign_pool_avg_2x2x1_dev(ign_ctx* ctx, const void* in, int dtype, uint64_t sx,
   }
   set_error("averaging: unsupported dtype %d", dtype);
   return IGN_ERR_UNSUPPORTED;
+}
+
+int ign_pool_select_dev(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+                        uint32_t fx, uint32_t fy, uint32_t fz, int num_mips, int op, void* const* outs) {
+  IGN_TRY(activate(ctx));
+  IGN_TRY(check_pool_args(in, dtype, sx, sy, sz, num_mips, outs));
+  IGN_REQUIRE(fx >= 1 && fx <= 2 && fy >= 1 && fy <= 2 && fz >= 1 && fz <= 2, IGN_ERR_UNSUPPORTED,
+              "pooling factors must be 1 or 2 per axis (got %u,%u,%u)", fx, fy, fz);
+  IGN_REQUIRE(op >= 0 && op <= 2, IGN_ERR_INVALID, "op must be 0 (min), 1 (max) or 2 (striding)");
+  switch (dtype) {
+    case IGN_U8: return select_pyramid<uint8_t>(ctx, in, sx, sy, sz, fx, fy, fz, num_mips, op, outs);
+    case IGN_U16: return select_pyramid<uint16_t>(ctx, in, sx, sy, sz, fx, fy, fz, num_mips, op, outs);
+    case IGN_U32: return select_pyramid<uint32_t>(ctx, in, sx, sy, sz, fx, fy, fz, num_mips, op, outs);
+    case IGN_U64: return select_pyramid<uint64_t>(ctx, in, sx, sy, sz, fx, fy, fz, num_mips, op, outs);
+    case IGN_F32: return select_pyramid<float>(ctx, in, sx, sy, sz, fx, fy, fz, num_mips, op, outs);
+  }
+  set_error("unsupported dtype %d", dtype);
+  return IGN_ERR_UNSUPPORTED;
+}
+
+int ign_pool_select(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+                    uint32_t fx, uint32_t fy, uint32_t fz, int num_mips, int op, void* const* outs) {
+  IGN_TRY(activate(ctx));
+  IGN_TRY(check_pool_args(in, dtype, sx, sy, sz, num_mips, outs));
+  IGN_REQUIRE(fx >= 1 && fx <= 2 && fy >= 1 && fy <= 2 && fz >= 1 && fz <= 2, IGN_ERR_UNSUPPORTED,
+              "pooling factors must be 1 or 2 per axis (got %u,%u,%u)", fx, fy, fz);
+  const size_t es = dtype_size(dtype);
+  size_t total = align_up(sx * sy * sz * es, 256);
+  size_t ob[32];
+  uint64_t x = sx, y = sy, z = sz;
+  for (int m = 0; m < num_mips; m++) {
+    x = (x + fx - 1) / fx; y = (y + fy - 1) / fy; z = (z + fz - 1) / fz;
+    ob[m] = x * y * z * es;
+    total += align_up(ob[m], 256);
+  }
+  scratch_reset(ctx);
+  IGN_TRY(scratch_reserve(ctx, total + 4096));
+  void* d_in = scratch_take(ctx, sx * sy * sz * es);
+  void* d_out[32];
+  for (int m = 0; m < num_mips; m++) d_out[m] = scratch_take(ctx, ob[m]);
+  IGN_CUDA(cudaMemcpyAsync(d_in, in, sx * sy * sz * es, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = ign_pool_select_dev(ctx, d_in, dtype, sx, sy, sz, fx, fy, fz, num_mips, op, d_out);
+  if (rc == IGN_OK) {
+    for (int m = 0; m < num_mips; m++)
+      IGN_CUDA(cudaMemcpyAsync(outs[m], d_out[m], ob[m], cudaMemcpyDeviceToHost, ctx->stream));
+    IGN_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  scratch_reset(ctx);
+  return rc;
 }
 
 static int pool_host(ign_ctx* ctx, bool mode, const void* in, int dtype, uint64_t sx, uint64_t sy,

@@ -23,9 +23,11 @@ def downsample_method_to_fn(method, sparse, vol):
     return partial(tinybrain.downsample_with_averaging, sparse=sparse)
   if method == DownsampleMethods.MODE_POOLING:
     return partial(tinybrain.downsample_segmentation, sparse=sparse)
-  raise NotImplementedError(
-    "igneous_b200 implements average and mode pooling (DownsampleTask always uses AUTO, "
-    "image.py:548); %r is a next row in DESIGN.md" % DownsampleMethods(method).name)
+  if method == DownsampleMethods.MIN_POOLING:
+    return tinybrain.downsample_with_min_pooling
+  if method == DownsampleMethods.MAX_POOLING:
+    return tinybrain.downsample_with_max_pooling
+  return tinybrain.downsample_with_striding
 
 
 def downsample_and_upload(image, bounds, vol, ds_shape, mip=0, axis="z", skip_first=False,

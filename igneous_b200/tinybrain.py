@@ -15,7 +15,8 @@ import numpy as np
 
 from . import _shim
 
-__all__ = ["downsample_segmentation", "downsample_with_averaging"]
+__all__ = ["downsample_segmentation", "downsample_with_averaging", "downsample_with_min_pooling",
+           "downsample_with_max_pooling", "downsample_with_striding"]
 
 # upstream render rule for integer averaging; parity unpinned offline
 # (SURVEY.md 8(c)), so it stays a runtime knob.
@@ -75,3 +76,49 @@ def downsample_with_averaging(img, factor, num_mips=1, sparse=False, ctx=None,
     raise NotImplementedError("igneous_b200 averaging: sparse=True is not implemented")
   return _pool(img, factor, num_mips, False,
                DEFAULT_ROUNDING if rounding is None else rounding, ctx)
+
+
+def _select(img, factor, num_mips, op, ctx):
+  f = tuple(int(v) for v in factor)
+  if len(f) < 3 or any(v not in (1, 2) for v in f[:3]) or any(v != 1 for v in f[3:]):
+    raise NotImplementedError("igneous_b200 min/max/striding pooling: factors must be 1 or 2 per axis, got %r" % (factor,))
+  num_mips = int(num_mips)
+  img = np.asarray(img)
+  if num_mips < 1:
+    return []
+  arr = np.asfortranarray(img)
+  if arr.ndim == 2:
+    arr = arr[:, :, np.newaxis]
+  chans = [arr] if arr.ndim == 3 else [arr[..., c] for c in range(arr.shape[3])]
+  ctx = ctx or _shim.default_context()
+  per_chan = []
+  for ch in chans:
+    ch = np.asfortranarray(ch)
+    sx, sy, sz = ch.shape
+    outs, shp = [], (sx, sy, sz)
+    for _ in range(num_mips):
+      shp = tuple((s + ff - 1) // ff for s, ff in zip(shp, f[:3]))
+      outs.append(np.empty(shp, dtype=ch.dtype, order="F"))
+    if ch.size:
+      _shim.check(ctx.lib.ign_pool_select(
+        ctx.handle, _shim.ptr(ch), ctypes.c_int(_shim.dtype_code(ch.dtype)), ctypes.c_uint64(sx),
+        ctypes.c_uint64(sy), ctypes.c_uint64(sz), ctypes.c_uint32(f[0]), ctypes.c_uint32(f[1]),
+        ctypes.c_uint32(f[2]), ctypes.c_int(num_mips), ctypes.c_int(op),
+        _shim.void_pp([o.ctypes.data for o in outs])))
+    per_chan.append(outs)
+  if img.ndim == 4:
+    return [np.asfortranarray(np.stack([pc[m] for pc in per_chan], axis=3)) for m in range(num_mips)]
+  res = per_chan[0]
+  return [o[:, :, 0] for o in res] if img.ndim == 2 else res
+
+
+def downsample_with_min_pooling(img, factor, num_mips=1, ctx=None):
+  return _select(img, factor, num_mips, 0, ctx)
+
+
+def downsample_with_max_pooling(img, factor, num_mips=1, ctx=None):
+  return _select(img, factor, num_mips, 1, ctx)
+
+
+def downsample_with_striding(img, factor, num_mips=1, ctx=None):
+  return _select(img, factor, num_mips, 2, ctx)

@@ -117,6 +117,17 @@ IGN_API int ign_pool_mode_2x2x1_dev(ign_ctx* ctx, const void* in, int dtype, uin
 IGN_API int ign_pool_avg_2x2x1_dev(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, uint64_t sy,
                            uint64_t sz, int num_mips, int rounding, void* const* outs);
 
+/* tinybrain.downsample_with_min_pooling / _max_pooling / _striding
+ *   igneous/tasks/image/image.py:46-49,55 (reachable through TransferTask(downsample_method=...))
+ * factors 1 or 2 per axis; op 0 = min, 1 = max, 2 = striding; partial edge blocks
+ * reduce over the samples that exist.  [SURVEY 8(f) row 3, not on the headline path] */
+IGN_API int ign_pool_select(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, uint64_t sy,
+                            uint64_t sz, uint32_t fx, uint32_t fy, uint32_t fz, int num_mips, int op,
+                            void* const* outs);
+IGN_API int ign_pool_select_dev(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, uint64_t sy,
+                                uint64_t sz, uint32_t fx, uint32_t fy, uint32_t fz, int num_mips,
+                                int op, void* const* outs);
+
 /* ---------------------------------------------------------------------- CCL
  * cc3d.connected_components(labels, connectivity=6, out_dtype=np.uint64, return_N)
  *   igneous/tasks/image/ccl.py:173, :235-238, :339-342

@@ -110,6 +110,33 @@ def downsample_with_averaging(img, factor=(2, 2, 1), num_mips=1, sparse=False,
   return [r[0] for r in results]
 
 
+def downsample_select(img, factor, num_mips=1, op="min"):
+  """tinybrain.downsample_with_{min,max}_pooling / _striding
+  (igneous/tasks/image/image.py:46-49,55): block min / max / first sample; partial
+  edge blocks reduce over the samples that exist."""
+  f = tuple(int(v) for v in factor)[:3]
+  cur = np.asarray(img)
+  outs = []
+  for _ in range(num_mips):
+    if op == "stride":
+      cur = cur[::f[0], ::f[1], ::f[2]]
+    else:
+      big, fn = (np.iinfo(cur.dtype).max if cur.dtype.kind in "ui" else np.inf), (np.minimum if op == "min" else np.maximum)
+      fill = big if op == "min" else (np.iinfo(cur.dtype).min if cur.dtype.kind in "ui" else -np.inf)
+      pad = [(0, (-s) % ff) for s, ff in zip(cur.shape[:3], f)] + [(0, 0)] * (cur.ndim - 3)
+      p = np.pad(cur, pad, constant_values=fill)
+      acc = None
+      for dx in range(f[0]):
+        for dy in range(f[1]):
+          for dz in range(f[2]):
+            part = p[dx::f[0], dy::f[1], dz::f[2]]
+            acc = part if acc is None else fn(acc, part)
+      cur = acc
+    cur = np.asfortranarray(cur)
+    outs.append(cur)
+  return outs
+
+
 # -------------------------------------------------------------------- CCL
 def connected_components(labels, connectivity=6, out_dtype=np.uint64, return_N=False):
   """cc3d.connected_components(labels, connectivity=6, out_dtype=np.uint64)

@@ -142,3 +142,21 @@ def test_synth_matches_oracle(ctx, oracle):
   _shim.check(ctx.lib.ign_synth_image_dev(ctx.handle, _shim.ptr(d), c.c_uint64(shape[0]), c.c_uint64(shape[1]),
                                           c.c_uint64(shape[2]), c.c_int64(1), c.c_int64(2), c.c_int64(3), c.c_uint64(9)))
   assert np.array_equal(ctx.to_host(d, shape, np.uint8), oracle.synth_image(shape, seed=9, offset=(1, 2, 3)))
+
+
+@pytest.mark.parametrize("op,name", [(0, "min"), (1, "max"), (2, "stride")])
+@pytest.mark.parametrize("factor", [(2, 2, 1), (2, 2, 2), (1, 2, 2)])
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint32, np.float32])
+def test_min_max_striding_pooling(ctx, oracle, op, name, factor, dtype):
+  """DownsampleMethods MIN / MAX / STRIDING (igneous/types.py:9-11), SURVEY 8(f) row 3."""
+  from igneous_b200 import tinybrain
+  rng = np.random.default_rng(31)
+  shape = (37, 22, 9)
+  img = rng.random(shape).astype(np.float32) if dtype == np.float32 else rng.integers(0, 250, size=shape).astype(dtype)
+  img = np.asfortranarray(img)
+  fn = [tinybrain.downsample_with_min_pooling, tinybrain.downsample_with_max_pooling,
+        tinybrain.downsample_with_striding][op]
+  got = fn(img, factor, num_mips=3)
+  want = oracle.downsample_select(img, factor, num_mips=3, op=name)
+  for g, w in zip(got, want):
+    assert g.shape == w.shape and g.dtype == w.dtype and np.array_equal(g, w)
