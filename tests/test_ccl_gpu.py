@@ -137,3 +137,44 @@ def test_multislab_volume_ccl_equals_whole_volume(ctx, oracle, shape, slab_vox, 
   got = ctx.to_host(d_out, shape, np.uint32)
   assert n.value == n_want
   assert np.array_equal(got, want.astype(np.uint32))
+
+
+def test_ccl_device_resident_properties_1024(ctx):
+  """BASELINE config C3 size (1024^3, uint64 ids >= 2^32, ~5.7k objects), device resident:
+  idempotence (CCL of the CCL output is the identity), component count stable across
+  slab splits, every id in 1..N used.  The oracle needs minutes at this size."""
+  import ctypes as c
+  from igneous_b200 import _shim
+  S = 1024
+  n = S ** 3
+  d_in = ctx.alloc(n * 8)
+  d_cc = ctx.alloc(n * 4)
+  d_cc2 = ctx.alloc(n * 4)
+  try:
+    _shim.check(ctx.lib.ign_synth_seg_dev(ctx.handle, _shim.ptr(d_in), c.c_int(_shim.IGN_U64), c.c_uint64(S),
+                                          c.c_uint64(S), c.c_uint64(S), c.c_int64(0), c.c_int64(0), c.c_int64(0),
+                                          c.c_uint32(64), c.c_uint64(4096), c.c_uint64(0), c.c_uint64(1 << 32)))
+    n1, n2, n3 = c.c_uint64(0), c.c_uint64(0), c.c_uint64(0)
+    args = (c.c_uint64(S), c.c_uint64(S), c.c_uint64(S))
+    _shim.check(ctx.lib.ign_ccl6_dev(ctx.handle, _shim.ptr(d_in), c.c_int(_shim.IGN_U64), *args, _shim.ptr(d_cc),
+                                     c.c_int(_shim.IGN_U32), c.byref(n1)))
+    _shim.check(ctx.lib.ign_ccl6_dev(ctx.handle, _shim.ptr(d_cc), c.c_int(_shim.IGN_U32), *args, _shim.ptr(d_cc2),
+                                     c.c_int(_shim.IGN_U32), c.byref(n2)))
+    assert n1.value == n2.value and 4000 < n1.value < 8000
+    a = ctx.to_host(d_cc, (S, S, 64), np.uint32)   # first 64 z-planes
+    b = ctx.to_host(d_cc2, (S, S, 64), np.uint32)
+    assert np.array_equal(a, b)
+    # 4 z-slabs + plane linkage must give the same labelling as the single call
+    _shim.check(ctx.lib.ign_ccl6_volume_dev(ctx.handle, _shim.ptr(d_in), c.c_int(_shim.IGN_U64), *args,
+                                            _shim.ptr(d_cc2), c.c_int(_shim.IGN_U32), c.c_uint64(S * S * 256),
+                                            c.byref(n3)))
+    assert n3.value == n1.value
+    assert np.array_equal(ctx.to_host(d_cc2, (S, S, 64), np.uint32), a)
+    tail = np.empty((S, S, 8), dtype=np.uint32, order="F")
+    ctx.d2h(tail, d_cc.ptr + (S - 8) * S * S * 4)
+    tail2 = np.empty((S, S, 8), dtype=np.uint32, order="F")
+    ctx.d2h(tail2, d_cc2.ptr + (S - 8) * S * S * 4)
+    ctx.sync()
+    assert np.array_equal(tail, tail2) and int(max(a.max(), tail.max())) <= n1.value
+  finally:
+    d_in.free(); d_cc.free(); d_cc2.free()
