@@ -135,11 +135,11 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// triangle records (sorted) -> 3 vertex keys each; also per-label triangle counts
+// triangle records (sorted) -> 3 vertex keys each
 __global__ void __launch_bounds__(256)
     k_tri_vertices(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ cases, uint64_t T,
                    uint32_t cx, uint32_t cy, uint64_t* __restrict__ vkeys,
-                   uint32_t* __restrict__ corner, uint32_t* __restrict__ tri_count) {
+                   uint32_t* __restrict__ corner) {
   const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (t >= T) return;
   const uint64_t key = keys[t];
@@ -159,7 +159,6 @@ __global__ void __launch_bounds__(256)
     vkeys[3 * t + v] = (label << V_LABEL_SHIFT) | (vz << (2 * V_COORD_BITS)) | (vy << V_COORD_BITS) | vx;
     corner[3 * t + v] = (uint32_t)(3 * t + v);
   }
-  (void)tri_count;
 }
 
 // boundaries in a sorted array of keys -> per-label [start) markers
@@ -445,7 +444,7 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
 
   // ---- weld
   MESH_LAUNCH(k_tri_vertices, blocks_for(T, 256), 256, keys_s, cases_s, (uint64_t)T, (uint32_t)(sx - 1),
-              (uint32_t)(sy - 1), vkeys, corner, (uint32_t*)nullptr);
+              (uint32_t)(sy - 1), vkeys, corner);
   tb = tmp_bytes;
   MESH_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, vkeys, vkeys_s, corner, corner_s, (int)(3 * T), 0,
                                             V_LABEL_SHIFT + label_bits, ctx->stream));

@@ -7,8 +7,8 @@
 //
 //   init    per-vertex Garland-Heckbert plane quadrics (unit normals, summed in
 //           face order), boundary vertices locked (chunk borders must stitch),
-//           per-vertex incident-face lists (linked lists of half-edge nodes,
-//           concatenated on collapse).
+//           per-vertex incident-face arrays (half-edge nodes, fixed capacity,
+//           merged and compacted on collapse).
 //   round   E  one thread per half-edge: the half-edge with u < v of every edge
 //              of a label still above its face target computes the cheap
 //              quadric cost (min over {u, v, midpoint} of p^T (Qu+Qv) p) and,
@@ -37,6 +37,7 @@ namespace ign {
 constexpr uint32_t S_NONE = 0xFFFFFFFFu;
 constexpr uint64_t S_KEYMAX = 0xFFFFFFFFFFFFFFFFull;
 constexpr int S_MAXV = 32;
+constexpr int S_VCAP = 64;  // two rings of < S_MAXV alive faces always fit after a collapse
 constexpr int VB = 11;  // vertex key coordinate bits (mesh.cu V_COORD_BITS)
 
 struct Simp {
@@ -48,7 +49,10 @@ struct Simp {
   uint8_t* falive;
   uint8_t* valive;
   uint8_t* vbound;
-  uint32_t *next, *head, *tail;
+  // incident half-edge nodes (3f+c) of every vertex as a fixed-capacity array: ring
+  // enumeration is a set of independent loads instead of a linked-list pointer chase
+  uint32_t* vf;   // [U * S_VCAP]
+  uint32_t* vn;   // [U] entries in use (dead faces are skipped, compacted when the vertex is kept)
   unsigned long long *key1, *key2;
   uint32_t* alive_faces;   // [K+2]
   const uint32_t* target;  // [K+2]
@@ -84,7 +88,10 @@ __device__ __forceinline__ double s_qeval(const double* q, const double* p) {
 
 __device__ int s_twins(const Simp& s, uint32_t f, uint32_t u, uint32_t v, uint32_t* twin) {
   int cnt = 0;
-  for (uint32_t h = s.head[u]; h != S_NONE; h = s.next[h]) {
+  const uint32_t* lu = s.vf + (uint64_t)u * S_VCAP;
+  const uint32_t cu = s.vn[u];
+  for (uint32_t j = 0; j < cu; j++) {
+    const uint32_t h = lu[j];
     const uint32_t g = h / 3;
     if (g == f || !s.falive[g]) continue;
     const uint32_t* fv = s.face + 3 * (uint64_t)g;
@@ -99,7 +106,10 @@ __device__ int s_twins(const Simp& s, uint32_t f, uint32_t u, uint32_t v, uint32
 __device__ bool s_ring(const Simp& s, uint32_t w, uint32_t* faces, uint32_t* nbr, int* nf, int* nn) {
   *nf = 0;
   *nn = 0;
-  for (uint32_t h = s.head[w]; h != S_NONE; h = s.next[h]) {
+  const uint32_t* lw = s.vf + (uint64_t)w * S_VCAP;
+  const uint32_t cw = s.vn[w];
+  for (uint32_t j = 0; j < cw; j++) {
+    const uint32_t h = lw[j];
     const uint32_t g = h / 3;
     if (!s.falive[g]) continue;
     if (*nf >= S_MAXV) return false;
@@ -211,8 +221,7 @@ __device__ void s_evaluate(const Simp& s, uint32_t u, uint32_t v, double max_err
 __global__ void __launch_bounds__(256)
     k_simp_init_verts(const uint64_t* __restrict__ vkeys, uint64_t U, double rx, double ry, double rz,
                       double* __restrict__ pos, uint8_t* __restrict__ valive,
-                      uint8_t* __restrict__ vbound, uint32_t* __restrict__ head,
-                      uint32_t* __restrict__ tail) {
+                      uint8_t* __restrict__ vbound, uint32_t* __restrict__ vn) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= U) return;
   const uint64_t k = vkeys[i];
@@ -224,8 +233,7 @@ __global__ void __launch_bounds__(256)
   pos[3 * i + 2] = z * 0.5 * rz;
   valive[i] = 1;
   vbound[i] = 0;
-  head[i] = S_NONE;
-  tail[i] = S_NONE;
+  vn[i] = 0;
 }
 
 // faces: local ids + per-label vertex base -> global ids; flabel by offsets search
@@ -254,18 +262,24 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// sorted (vertex, node) pairs -> linked lists in ascending node order
+// sorted (vertex, node) pairs -> per-vertex arrays in ascending node order
 __global__ void __launch_bounds__(256)
     k_simp_link(const uint32_t* __restrict__ sv, const uint32_t* __restrict__ sh, uint64_t n,
-                uint32_t* __restrict__ next, uint32_t* __restrict__ head, uint32_t* __restrict__ tail) {
+                uint32_t* __restrict__ vf, uint32_t* __restrict__ vn, uint32_t* overflow) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t v = sv[i], h = sh[i];
-  const bool first = (i == 0) || (sv[i - 1] != v);
-  const bool last = (i + 1 == n) || (sv[i + 1] != v);
-  next[h] = last ? S_NONE : sh[i + 1];
-  if (first) head[v] = h;
-  if (last) tail[v] = h;
+  const uint32_t v = sv[i];
+  if (i > 0 && sv[i - 1] == v) return;  // the first pair of a run writes the whole run
+  uint32_t c = 0;
+  for (uint64_t j = i; j < n && sv[j] == v; j++) {
+    if (c < S_VCAP) vf[(uint64_t)v * S_VCAP + c] = sh[j];
+    c++;
+  }
+  if (c > S_VCAP) {
+    *overflow = 1;
+    c = S_VCAP;
+  }
+  vn[v] = c;
 }
 
 __global__ void __launch_bounds__(128) k_simp_quadrics(Simp s) {
@@ -273,7 +287,8 @@ __global__ void __launch_bounds__(128) k_simp_quadrics(Simp s) {
   if (v >= s.U) return;
   double q[10];
   for (int i = 0; i < 10; i++) q[i] = 0.0;
-  for (uint32_t h = s.head[v]; h != S_NONE; h = s.next[h]) {
+  for (uint32_t j = 0; j < s.vn[v]; j++) {
+    const uint32_t h = s.vf[(uint64_t)v * S_VCAP + j];
     const uint32_t* fv = s.face + 3 * (uint64_t)(h / 3);
     const double* a = s.pos + 3 * (uint64_t)fv[0];
     const double* b = s.pos + 3 * (uint64_t)fv[1];
@@ -334,7 +349,7 @@ __global__ void __launch_bounds__(256) k_simp_build_vlist(Simp s, uint32_t* coun
   const uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   bool take = false;
   if (v < s.U && s.valive[v]) {
-    const uint32_t l = s.flabel[s.head[v] / 3];
+    const uint32_t l = s.flabel[s.vf[(uint64_t)v * S_VCAP] / 3];
     take = s.alive_faces[l] > s.target[l];
   }
   s_append(take, (uint32_t)v, s.vlist, &counters[1]);
@@ -395,8 +410,10 @@ __global__ void __launch_bounds__(256) k_simp_key2(Simp s) {
     return;
   }
   unsigned long long m = s.key1[w];
-  for (uint32_t h = s.head[w]; h != S_NONE; h = s.next[h]) {
-    const uint32_t g = h / 3;
+  const uint32_t* lw = s.vf + (uint64_t)w * S_VCAP;
+  const uint32_t cw = s.vn[w];
+  for (uint32_t j = 0; j < cw; j++) {
+    const uint32_t g = lw[j] / 3;
     if (!s.falive[g]) continue;
     for (int k = 0; k < 3; k++) {
       const unsigned long long kk = s.key1[s.face[3 * (uint64_t)g + k]];
@@ -419,7 +436,7 @@ __global__ void __launch_bounds__(256)
     if (s.valive[a] && key != S_KEYMAX) {
       // the key holds a label-local half-edge id; a's label is that of any of its faces
       const uint32_t hl = s_unmix((uint32_t)(key & 0xFFFFFFFFu)) ^ salt;
-      h = hl + 3 * s.tri_off[s.flabel[s.head[a] / 3]];
+      h = hl + 3 * s.tri_off[s.flabel[s.vf[(uint64_t)a * S_VCAP] / 3]];
       const uint32_t f = h / 3, c = h % 3;
       const uint32_t u = s.face[3 * (uint64_t)f + c], v = s.face[3 * (uint64_t)f + (c + 1) % 3];
       win = (a == u) && s.key2[u] == key && s.key2[v] == key;
@@ -449,7 +466,11 @@ __global__ void __launch_bounds__(128)
     s.pos[3 * (uint64_t)k + 2] = e.p[2];
     for (int q = 0; q < 10; q++)
       s.Q[10 * (uint64_t)k + q] = s.Q[10 * (uint64_t)k + q] + s.Q[10 * (uint64_t)rm + q];
-    for (uint32_t hh = s.head[rm]; hh != S_NONE; hh = s.next[hh]) {
+    uint32_t* lk = s.vf + (uint64_t)k * S_VCAP;
+    const uint32_t* lr = s.vf + (uint64_t)rm * S_VCAP;
+    const uint32_t ck = s.vn[k], cr = s.vn[rm];
+    for (uint32_t j = 0; j < cr; j++) {
+      const uint32_t hh = lr[j];
       const uint32_t g = hh / 3;
       if (!s.falive[g]) continue;
       uint32_t* fv = s.face + 3 * (uint64_t)g;
@@ -460,29 +481,24 @@ __global__ void __launch_bounds__(128)
         fv[hh % 3] = k;
       }
     }
-    // k's new incident list = k's ++ rm's with the dead faces unlinked (the lists
-    // would otherwise keep every face either vertex ever had, and every later
-    // ring walk would pay for them).  Only this thread touches k and rm this round.
-    uint32_t nhead = S_NONE, ntail = S_NONE;
+    // k's new ring = alive entries of k's array (compacted in place) ++ alive entries of
+    // rm's.  Both rings had < S_MAXV alive faces (validated), so S_VCAP entries suffice.
+    // Only this thread touches k and rm this round.
+    uint32_t nk = 0;
     for (int pass = 0; pass < 2; pass++) {
-      uint32_t hh = pass ? s.head[rm] : s.head[k];
-      while (hh != S_NONE) {
-        const uint32_t nxt = s.next[hh];
-        if (s.falive[hh / 3]) {
-          if (ntail == S_NONE) nhead = hh;
-          else s.next[ntail] = hh;
-          ntail = hh;
-          const uint32_t* fv = s.face + 3 * (uint64_t)(hh / 3);
-          s.vdirty[fv[0]] = 1;
-          s.vdirty[fv[1]] = 1;
-          s.vdirty[fv[2]] = 1;
-        }
-        hh = nxt;
+      const uint32_t* src = pass ? lr : lk;
+      const uint32_t cnt = pass ? cr : ck;
+      for (uint32_t j = 0; j < cnt; j++) {
+        const uint32_t hh = src[j];
+        if (!s.falive[hh / 3]) continue;
+        lk[nk++] = hh;
+        const uint32_t* fv = s.face + 3 * (uint64_t)(hh / 3);
+        s.vdirty[fv[0]] = 1;
+        s.vdirty[fv[1]] = 1;
+        s.vdirty[fv[2]] = 1;
       }
     }
-    if (ntail != S_NONE) s.next[ntail] = S_NONE;
-    s.head[k] = nhead;
-    s.tail[k] = ntail;
+    s.vn[k] = nk;
     s.vdirty[k] = 1;
     s.valive[rm] = 0;
     flags[1] = 1;
@@ -575,6 +591,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
                                 (int)(3 * T));
   const size_t tmpb = (sortb > scanb ? sortb : scanb) + 256;
   const size_t need = align_up(U * 24, 256) + align_up(U * 80, 256) + 4 * align_up(3 * T * 4, 256) +
+                      align_up(U * S_VCAP * 4, 256) +
                       3 * align_up(T * 4, 256) + 2 * align_up(T, 256) + 3 * align_up(U, 256) +
                       4 * align_up(U * 4, 256) + 2 * align_up(U * 8, 256) + 6 * align_up((K + 2) * 4, 256) +
                       2 * align_up(3 * T * 4, 256) + align_up(3 * T, 256) + align_up(3 * T * 4, 256) +
@@ -586,15 +603,14 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   s.pos = (double*)scratch_take(ctx, U * 24);
   s.Q = (double*)scratch_take(ctx, U * 80);
   s.face = (uint32_t*)scratch_take(ctx, 3 * T * 4);
-  s.next = (uint32_t*)scratch_take(ctx, 3 * T * 4);
+  s.vf = (uint32_t*)scratch_take(ctx, U * S_VCAP * 4);
   uint32_t* node_v = (uint32_t*)scratch_take(ctx, 3 * T * 4);   // reused as face scan later
   uint32_t* node_h = (uint32_t*)scratch_take(ctx, 3 * T * 4);
   s.flabel = (uint32_t*)scratch_take(ctx, T * 4);
   s.falive = (uint8_t*)scratch_take(ctx, T);
   s.valive = (uint8_t*)scratch_take(ctx, U);
   s.vbound = (uint8_t*)scratch_take(ctx, U);
-  s.head = (uint32_t*)scratch_take(ctx, U * 4);
-  s.tail = (uint32_t*)scratch_take(ctx, U * 4);
+  s.vn = (uint32_t*)scratch_take(ctx, U * 4);
   uint32_t* vscan = (uint32_t*)scratch_take(ctx, U * 4);
   uint32_t* vflag = (uint32_t*)scratch_take(ctx, U * 4);
   s.key1 = (unsigned long long*)scratch_take(ctx, U * 8);
@@ -617,8 +633,8 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   void* tmp = scratch_take(ctx, tmpb);
   uint32_t* sorted_v = (uint32_t*)scratch_take(ctx, 3 * T * 4);
   uint32_t* sorted_h = (uint32_t*)scratch_take(ctx, 3 * T * 4);
-  if (!s.pos || !s.Q || !s.face || !s.next || !node_v || !node_h || !s.flabel || !s.falive || !s.valive ||
-      !s.vbound || !s.head || !s.tail || !vscan || !vflag || !s.key1 || !s.key2 || !s.alive_faces ||
+  if (!s.pos || !s.Q || !s.face || !s.vf || !node_v || !node_h || !s.flabel || !s.falive || !s.valive ||
+      !s.vbound || !s.vn || !vscan || !vflag || !s.key1 || !s.key2 || !s.alive_faces ||
       !d_target || !s.label_active || !d_tri_off || !d_vert_off || !d_new_tri_off || !d_new_vert_off ||
       !flags || !tmp || !sorted_v || !sorted_h || !s.estate || !s.ecost || !s.vdirty || !s.elist ||
       !s.vlist || !wlist) {
@@ -660,7 +676,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   S_CUDA(cudaMemsetAsync(s.estate, 0, 3 * T, ctx->stream));
   S_CUDA(cudaMemsetAsync(s.vdirty, 0, U, ctx->stream));
   S_LAUNCH(k_simp_init_verts, blocks_for(U, 256), 256, m->d_uniq_vkeys, U, (double)resolution[0],
-           (double)resolution[1], (double)resolution[2], s.pos, s.valive, s.vbound, s.head, s.tail);
+           (double)resolution[1], (double)resolution[2], s.pos, s.valive, s.vbound, s.vn);
   S_LAUNCH(k_simp_init_faces, blocks_for(T, 256), 256, m->d_faces, d_tri_off, d_vert_off, (uint32_t)K, T,
            s.face, s.flabel, s.falive, node_v, node_h);
   {
@@ -671,8 +687,18 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
                                            ctx->stream));
     ctx->launches += 3;
   }
-  S_LAUNCH(k_simp_link, blocks_for(3 * T, 256), 256, sorted_v, sorted_h, (uint64_t)(3 * T), s.next, s.head,
-           s.tail);
+  S_CUDA(cudaMemsetAsync(flags, 0, 64, ctx->stream));
+  S_LAUNCH(k_simp_link, blocks_for(3 * T, 256), 256, sorted_v, sorted_h, (uint64_t)(3 * T), s.vf, s.vn,
+           flags + 12);
+  {
+    uint32_t* hf = (uint32_t*)ctx->pinned;
+    S_CUDA(cudaMemcpyAsync(hf, flags + 12, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    S_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hf[0] != 0) {
+      set_error("simplify: a vertex has more than %d incident faces", S_VCAP);
+      return done(IGN_ERR_UNSUPPORTED);
+    }
+  }
   S_LAUNCH(k_simp_quadrics, blocks_for(U, 128), 128, s);
   S_LAUNCH(k_simp_boundary, blocks_for(3 * T, 256), 256, s);
   {
