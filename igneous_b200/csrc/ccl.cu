@@ -125,7 +125,8 @@ constexpr int TILE_VOX = TILE_X * TILE_ROWS;  // 16384 -> 64 KB of u32 parents
 constexpr int CCL_THREADS = 512;
 constexpr int CCL_WARPS = CCL_THREADS / 32;
 constexpr int ROWS_PER_WARP = TILE_ROWS / CCL_WARPS;  // 4
-constexpr int TASKS_PER_WARP = 128;           // queued (a<<16|b) union tasks, 14-bit local indices
+constexpr int TASKS_PER_WARP = 128;
+static_assert(TILE_X == 256 && TILE_Y == 8, "k_ccl_local_fast decodes local indices with shifts");           // queued (a<<16|b) union tasks, 14-bit local indices
 
 struct TilePos {
   uint32_t X0, Y0, Z0, warp, lane;
@@ -400,7 +401,6 @@ __device__ __forceinline__ void local_tile_fast(const T* __restrict__ in, uint32
       vy[k] = (inb && ly > 0) ? *(p + 32 * k - sx) : (T)0;
       vz[k] = (inb && lz > 0) ? *(p + 32 * k - sxy) : (T)0;
     }
-    uint32_t carry = 0;
     T prev_last = 0;
     uint32_t cy_prev = 0, cz_prev = 0;  // bit 31 of the previous sub-word's masks
 #pragma unroll
@@ -410,24 +410,26 @@ __device__ __forceinline__ void local_tile_fast(const T* __restrict__ in, uint32
       const bool cont = (k > 0) && (v0 != 0) && (v0 == prev_last);
       const bool nz = v[k] != 0;
       const bool same = (t.lane > 0) ? (v[k] == vl) : cont;
-      const uint32_t m_start = __ballot_sync(FULL, nz && !same);
       const uint32_t m_same = __ballot_sync(FULL, nz && same);
       const uint32_t m_cy = __ballot_sync(FULL, nz && (v[k] == vy[k]));
       const uint32_t m_cz = __ballot_sync(FULL, nz && (v[k] == vz[k]));
       // a union is needed where the connection starts or the x-run breaks
       const uint32_t t_y = m_cy & ~(m_same & ((m_cy << 1) | cy_prev));
       const uint32_t t_z = m_cz & ~(m_same & ((m_cz << 1) | cz_prev));
-      const uint32_t base = r * TILE_X + 32 * k;
-      const uint32_t below = m_start & lemask;
-      const uint32_t node = below ? (base + 31 - __clz(below)) : carry;
-      const uint32_t ny = __popc(t_y), nz_ = __popc(t_z);
-      if (ny + nz_) {
+      const uint32_t both = t_y | t_z;
+      if (both) {
+        const uint32_t ny = __popc(t_y), nz_ = __popc(t_z);
         if (nq + ny + nz_ > TASKS_PER_WARP) flush();
-        if ((t_y >> t.lane) & 1u) q[nq + __popc(t_y & ltmask)] = (node << 16) | (base + t.lane - TILE_X);
-        if ((t_z >> t.lane) & 1u) q[nq + ny + __popc(t_z & ltmask)] = (node << 16) | (base + t.lane - TILE_X * TILE_Y);
+        if ((both >> t.lane) & 1u) {
+          const uint32_t li = r * TILE_X + 32 * k + t.lane;
+          // any member of my run's set represents it: the entry written in phase 1
+          // (or an ancestor another warp's path halving put there meanwhile)
+          const uint32_t node = ((volatile uint32_t*)L)[li];
+          if ((t_y >> t.lane) & 1u) q[nq + __popc(t_y & ltmask)] = (node << 16) | (li - TILE_X);
+          if ((t_z >> t.lane) & 1u) q[nq + ny + __popc(t_z & ltmask)] = (node << 16) | (li - TILE_X * TILE_Y);
+        }
         nq += ny + nz_;
       }
-      if (m_start) carry = base + 31 - __clz(m_start);
       prev_last = shfl_idx(v[k], 31);
       cy_prev = m_cy >> 31;
       cz_prev = m_cz >> 31;
@@ -447,27 +449,24 @@ __device__ __forceinline__ void local_tile_fast(const T* __restrict__ in, uint32
     for (int k = 0; k < SUBW; k++) {
       const uint32_t li = r * TILE_X + 32 * k + t.lane;
       const uint32_t p0 = L[li];
-      uint32_t g = CCL_BG;
-      bool is_root = false;
-      if (p0 != CCL_BG) {
-        is_root = (p0 == li);
-        uint32_t cur = p0, nxt;
-        while ((nxt = L[cur]) != cur) cur = nxt;  // read-only: no writer after the barrier
-        const uint32_t rr2 = cur / TILE_X;
-        g = tile_g0 + (rr2 / TILE_Y) * sxy + (rr2 % TILE_Y) * sx + (cur % TILE_X);
-      }
-      if (FULLTILE || (t.X0 + 32 * k + t.lane < sx)) out[32 * k] = g;
-      const uint32_t cm = __ballot_sync(FULL, is_root);
-      if (cm) {
-        const int leader = __ffs(cm) - 1;
-        uint32_t base = 0;
-        if ((int)t.lane == leader) base = atomicAdd(&counters[0], (uint32_t)__popc(cm));
-        base = __shfl_sync(FULL, base, leader);
-        if (is_root) {
-          const uint32_t pos = base + __popc(cm & ltmask);
-          if (pos < cand_cap) cand[pos] = g;
-          else counters[1] = 1;
+      const bool bgv = (p0 == CCL_BG);
+      // two unrolled hops cover almost every voxel after path halving (voxel -> run
+      // start -> root); the loop only runs for the rare deeper chains
+      uint32_t cur = bgv ? li : p0;
+      uint32_t nxt = L[cur];
+      if (__any_sync(FULL, !bgv && nxt != cur)) {
+        while (!bgv && nxt != cur) {
+          cur = nxt;
+          nxt = L[cur];
         }
+      }
+      const uint32_t rr2 = cur >> 8;  // TILE_X == 256
+      const uint32_t g = bgv ? CCL_BG : (tile_g0 + (rr2 >> 3) * sxy + (rr2 & 7) * sx + (cur & 255));
+      if (FULLTILE || (t.X0 + 32 * k + t.lane < sx)) out[32 * k] = g;
+      if (!bgv && p0 == li) {  // tile-local root (a handful per tile): log it as a root candidate
+        const uint32_t pos = atomicAdd(&counters[0], 1u);
+        if (pos < cand_cap) cand[pos] = g;
+        else counters[1] = 1;
       }
     }
   }
