@@ -135,7 +135,7 @@ def run_reference_arm(args):
   from oracle import oracle as O
   O.build()
   cores = os.cpu_count() or 1
-  shape = (256, 256, 128)
+  shape = (256, 256, 64)  # ~14 s per step on a 128-thread host under full contention
   ctx = mp.get_context("spawn")
   counter = ctx.Value("i", 0)
   times, per_chunk = [], []
