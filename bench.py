@@ -389,11 +389,8 @@ def run_e2e(ctx, pipe, args, dist, world):
 
   def one():
     mesh_bytes[0] = 0
-    pipe.load_host(host_in)
-    pipe.pool()
-    pipe.ccl()
-    pipe.results_to_host(host)
-    pipe.mesh(export=export)
+    # upload in z-layers; pooling, meshing, CCL and the D2H of the products overlap
+    pipe.step_streamed(host_in, host, export)
 
   one()  # warm-up (pinned pages touched, arena sized)
   ctx.sync()

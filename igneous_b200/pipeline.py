@@ -139,18 +139,27 @@ class VolumePipeline:
     finally:
       lib.ign_mesh_free(h)
 
-  def mesh(self, export=None):
+  def mesh(self, export=None, wait_for=None):
     """MeshTask bodies over the mesh mip.  `export(task, mesher, nv, nf, nl, ctx)` may
-    pull results to the host (e2e); without it only the totals are read back."""
+    pull results to the host (e2e); without it only the totals are read back.
+    `wait_for(task)` (streamed step) blocks the calling mesh thread until the host
+    has enqueued the mip planes the task reads; the mesh stream then waits on the
+    device for mark 15, which by then covers those planes."""
     tasks = list(self.mesh_tasks())
-    for wctx, _ in self._workers:  # mesh streams start when the mip pyramid is complete
-      _shim.check(self.lib.ign_stream_wait_mark(wctx.handle, self.ctx.handle, c.c_int(15)))
+    if wait_for is None:
+      for wctx, _ in self._workers:  # mesh streams start when the mip pyramid is complete
+        _shim.check(self.lib.ign_stream_wait_mark(wctx.handle, self.ctx.handle, c.c_int(15)))
     results = []
     from concurrent.futures import ThreadPoolExecutor
 
     def run(widx):
       wctx, buf = self._workers[widx]
-      out = [self._mesh_one(wctx, buf, t, export) for t in tasks[widx::self.mesh_streams]]
+      out = []
+      for t in tasks[widx::self.mesh_streams]:
+        if wait_for is not None:
+          wait_for(t)
+          _shim.check(self.lib.ign_stream_wait_mark(wctx.handle, self.ctx.handle, c.c_int(15)))
+        out.append(self._mesh_one(wctx, buf, t, export))
       wctx.sync()
       return out
     if self.mesh_streams == 1:
@@ -182,6 +191,68 @@ class VolumePipeline:
     self.mesh()
     if timers:
       ctx.timer_stop(3)
+
+  def step_streamed(self, host_in, host_out=None, export=None):
+    """One pass of the hot path from a HOST volume: the volume is uploaded in z-layers
+    of the mesh task height; each layer is pooled as soon as it has landed (2x2x1
+    pooling never mixes z planes) and the MeshTasks of a layer start when the layer
+    above it is pooled (they read one plane of it: mesh.py:158-160 high padding), so
+    meshing overlaps the rest of the upload, the CCL passes and the D2H of the
+    products.  Results are identical to load_host() + step()."""
+    import threading
+    sx, sy, sz = self.shape
+    es = self.dtype.itemsize
+    mz = self.mesh_shape[2]
+    n_layers = -(-sz // mz)
+    cond = threading.Condition()
+    state = {"ready": 0, "error": None}
+
+    def wait_for(task):
+      need = min(n_layers, task[2] // mz + 2)
+      with cond:
+        cond.wait_for(lambda: state["ready"] >= need or state["error"] is not None)
+        if state["error"] is not None:
+          raise RuntimeError("upload failed") from state["error"]
+
+    mesh_err = []
+
+    def mesh_thread():
+      try:
+        self.mesh(export=export, wait_for=wait_for)
+      except BaseException as e:  # re-raised on the caller's thread
+        mesh_err.append(e)
+
+    th = threading.Thread(target=mesh_thread)
+    th.start()
+    try:
+      src = host_in.ctypes.data
+      for k in range(n_layers):
+        z0, z1 = k * mz, min(sz, (k + 1) * mz)
+        off = z0 * sx * sy * es
+        _shim.check(self.lib.ign_h2d(self.ctx.handle, c.c_void_p(self.d_in.ptr + off),
+                                     c.c_void_p(src + off), _u64((z1 - z0) * sx * sy * es)))
+        if self.num_mips:
+          outs = [m.ptr + z0 * s[0] * s[1] * es for m, s in zip(self.d_mips, self.mip_shapes)]
+          _shim.check(self.lib.ign_pool_mode_2x2x1_dev(
+            self.ctx.handle, c.c_void_p(self.d_in.ptr + off), c.c_int(self.code), _u64(sx), _u64(sy),
+            _u64(z1 - z0), c.c_int(self.num_mips), c.c_int(0), _shim.void_pp(outs)))
+        self.ctx.timer_start(15)
+        with cond:
+          state["ready"] = k + 1
+          cond.notify_all()
+      self.ccl()
+      if host_out is not None:
+        self.results_to_host(host_out)
+    except BaseException as e:
+      with cond:
+        state["error"] = e
+        cond.notify_all()
+      th.join()
+      raise
+    th.join()
+    if mesh_err:
+      raise mesh_err[0]
+    self.ctx.sync()
 
   def stage_ms(self):
     return {"pool_ms": self.ctx.timer_ms(1), "ccl_ms": self.ctx.timer_ms(2),
