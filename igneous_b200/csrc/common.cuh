@@ -76,6 +76,13 @@ struct ign_ctx {
   char* mesh_pool;
   size_t mesh_pool_bytes;
   int mesh_pool_busy;
+  // mapped pinned window for small control transfers (see ign::small_d2h)
+  char* win;      // host address
+  char* win_dev;  // the same bytes as seen by kernels
+  size_t win_fetch_used, win_push_used;
+  struct FetchRec { void* dst; size_t off, bytes; };
+  FetchRec fetch[32];
+  int fetch_n;
 };
 
 enum { IGN_PROF_CCL_LOCAL = 0, IGN_PROF_CCL_MERGE = 1, IGN_PROF_CCL_LABEL = 2, IGN_PROF_POOL = 3,
@@ -94,6 +101,19 @@ int scratch_reserve(ign_ctx* ctx, size_t total_bytes);
 void* scratch_take(ign_ctx* ctx, size_t bytes);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Small control transfers (counters, per-label offset tables) that sit between kernels
+// of one call.  cudaMemcpyAsync would put them on a copy engine, where they queue behind
+// multi-GB transfers issued by other contexts of the same device (the volume upload /
+// label download that overlap the mesh stage).  Instead a copy kernel on the ctx stream
+// moves them through a mapped pinned window, so only the SMs and the stream order are
+// involved.  Transfers that do not fit the window fall back to cudaMemcpyAsync.
+//   small_d2h: host_dst is valid after small_sync().
+//   small_h2d: host_src is consumed before the call returns.
+//   small_sync: cudaStreamSynchronize(ctx->stream) + delivery of pending small_d2h results.
+int small_d2h(ign_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
+int small_h2d(ign_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
+int small_sync(ign_ctx* ctx);
 
 // launch bookkeeping: every kernel launch in this library goes through
 // IGN_LAUNCH so ign_launch_count() is exact.

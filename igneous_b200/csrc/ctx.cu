@@ -1,5 +1,6 @@
 // ctx.cu -- context, memory, timers, error plumbing of libigneous_b200
 #include <stdarg.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -56,6 +57,67 @@ __global__ void __launch_bounds__(256)
   if (i >= total) return;
   const uint64_t x = i % bx, r = i / bx, y = r % by, z = r / by;
   dst[i] = src[((z0 + z) * sy + (y0 + y)) * sx + (x0 + x)];
+}
+
+// ---- mapped pinned window (small control transfers)
+enum : size_t { WIN_FETCH_BYTES = 256 << 10, WIN_PUSH_BYTES = 768 << 10 };
+
+__global__ void __launch_bounds__(256) k_copy_small(void* __restrict__ dst, const void* __restrict__ src,
+                                                    uint32_t n_words, uint32_t tail_bytes) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_words) ((uint32_t*)dst)[i] = ((const uint32_t*)src)[i];
+  if (i < tail_bytes) ((uint8_t*)dst)[4ull * n_words + i] = ((const uint8_t*)src)[4ull * n_words + i];
+}
+
+static int copy_small_launch(ign_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  const bool words = ((uintptr_t)dst % 4 == 0) && ((uintptr_t)src % 4 == 0);
+  const uint32_t nw = words ? (uint32_t)(bytes / 4) : 0;
+  const uint32_t tail = (uint32_t)(bytes - 4ull * nw);
+  const uint32_t work = nw > tail ? nw : tail;
+  IGN_LAUNCH(ctx, k_copy_small, blocks_for(work, 256), 256, 0, dst, src, nw, tail);
+  return IGN_OK;
+}
+
+int small_d2h(ign_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
+  if (bytes == 0) return IGN_OK;
+  const size_t off = align_up(ctx->win_fetch_used, 16);
+  if (!ctx->win || ctx->fetch_n == 32 || off + bytes > WIN_FETCH_BYTES) {
+    IGN_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return IGN_OK;
+  }
+  IGN_TRY(copy_small_launch(ctx, ctx->win_dev + off, dev_src, bytes));
+  ctx->fetch[ctx->fetch_n++] = {host_dst, off, bytes};
+  ctx->win_fetch_used = off + bytes;
+  return IGN_OK;
+}
+
+int small_sync(ign_ctx* ctx) {
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess)
+    for (int i = 0; i < ctx->fetch_n; i++)
+      memcpy(ctx->fetch[i].dst, ctx->win + ctx->fetch[i].off, ctx->fetch[i].bytes);
+  ctx->fetch_n = 0;
+  ctx->win_fetch_used = 0;
+  ctx->win_push_used = 0;  // every queued push kernel has run
+  IGN_CUDA(e);
+  return IGN_OK;
+}
+
+int small_h2d(ign_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes) {
+  if (bytes == 0) return IGN_OK;
+  if (!ctx->win || bytes > WIN_PUSH_BYTES) {
+    IGN_CUDA(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return IGN_OK;
+  }
+  size_t off = align_up(ctx->win_push_used, 16);
+  if (off + bytes > WIN_PUSH_BYTES) {  // window full: wait until the queued copy kernels have read it
+    IGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    off = 0;
+  }
+  char* stage = ctx->win + WIN_FETCH_BYTES + off;
+  memcpy(stage, host_src, bytes);
+  ctx->win_push_used = off + bytes;
+  return copy_small_launch(ctx, dev_dst, ctx->win_dev + WIN_FETCH_BYTES + off, bytes);
 }
 
 int prof_begin(ign_ctx* ctx, int cls) {
@@ -136,6 +198,17 @@ int ign_init(int device, ign_ctx** out) {
     IGN_CUDA(cudaEventCreate(&ctx->timers[i][0]));
     IGN_CUDA(cudaEventCreate(&ctx->timers[i][1]));
   }
+  ctx->win = ctx->win_dev = nullptr;
+  ctx->win_fetch_used = ctx->win_push_used = 0;
+  ctx->fetch_n = 0;
+  if (cudaHostAlloc((void**)&ctx->win, WIN_FETCH_BYTES + WIN_PUSH_BYTES,
+                    cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&ctx->win_dev, ctx->win, 0) != cudaSuccess) {
+    // no mapped host memory: small transfers use the copy engines
+    cudaGetLastError();
+    if (ctx->win) cudaFreeHost(ctx->win);
+    ctx->win = ctx->win_dev = nullptr;
+  }
   *out = ctx;
   return IGN_OK;
 }
@@ -146,6 +219,7 @@ int ign_destroy(ign_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->win) cudaFreeHost(ctx->win);
   if (ctx->mesh_pool) cudaFree(ctx->mesh_pool);
   for (int i = 0; i < 16; i++) {
     cudaEventDestroy(ctx->timers[i][0]);
@@ -213,15 +287,26 @@ int ign_host_free(ign_ctx* ctx, void* hptr) {
   return IGN_OK;
 }
 
+// Bulk copies are issued in 64 MiB pieces so that transfers of other contexts sharing
+// the copy engines (mesh fragment exports) interleave instead of waiting for a
+// multi-GB transfer to drain.
+static const uint64_t BULK_PIECE = 64ull << 20;
+
 int ign_h2d(ign_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
   IGN_TRY(activate(ctx));
-  IGN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  for (uint64_t at = 0; at < bytes; at += BULK_PIECE) {
+    const uint64_t nb = bytes - at < BULK_PIECE ? bytes - at : BULK_PIECE;
+    IGN_CUDA(cudaMemcpyAsync((char*)dst + at, (const char*)src + at, nb, cudaMemcpyHostToDevice, ctx->stream));
+  }
   return IGN_OK;
 }
 
 int ign_d2h(ign_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
   IGN_TRY(activate(ctx));
-  IGN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  for (uint64_t at = 0; at < bytes; at += BULK_PIECE) {
+    const uint64_t nb = bytes - at < BULK_PIECE ? bytes - at : BULK_PIECE;
+    IGN_CUDA(cudaMemcpyAsync((char*)dst + at, (const char*)src + at, nb, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   return IGN_OK;
 }
 

@@ -330,11 +330,9 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
   m->K = K;
   m->ids.resize(K);
   if (K) {
-    if (cudaMemcpyAsync(m->ids.data(), d_uniq, K * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-      set_error("mesher: D2H of label ids failed");
-      return fail(IGN_ERR_CUDA);
-    }
+    rc = small_d2h(ctx, m->ids.data(), d_uniq, K * 8);
+    if (rc == IGN_OK) rc = small_sync(ctx);
+    if (rc != IGN_OK) return fail(rc);
   }
   m->tri_off.assign(K + 2, 0);
   m->vert_off.assign(K + 2, 0);
@@ -364,6 +362,11 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
       return fail(IGN_ERR_CUDA);                                                   \
     }                                                                              \
   } while (0)
+#define MESH_TRY(call)                    \
+  do {                                    \
+    const int _s = (call);                \
+    if (_s != IGN_OK) return fail(_s);    \
+  } while (0)
 #define MESH_LAUNCH(kernel, g, b, ...)                    \
   do {                                                    \
     kernel<<<(g), (b), 0, ctx->stream>>>(__VA_ARGS__);    \
@@ -373,8 +376,8 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
   MESH_CUDA(cudaMemsetAsync(d_total, 0, 8, ctx->stream));
   MESH_LAUNCH((k_mc<false>), grid, 256, d_lab, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, d_total,
               (uint64_t*)nullptr, (uint8_t*)nullptr, 0ull);
-  MESH_CUDA(cudaMemcpyAsync(&T, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  MESH_CUDA(cudaStreamSynchronize(ctx->stream));
+  MESH_TRY(small_d2h(ctx, &T, d_total, 8));
+  MESH_TRY(small_sync(ctx));
   m->T = T;
   if (T == 0) {
     ctx->scratch_used = keep;
@@ -397,7 +400,7 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
   if (scanb > tmp_bytes) tmp_bytes = scanb;
   const size_t need = align_up(n * 4, 256) + 2 * align_up(T * 8, 256) + 2 * align_up(T, 256) +
                       2 * align_up(3 * T * 8, 256) + 4 * align_up(3 * T * 4, 256) +
-                      align_up(3 * T * 8, 256) + 2 * align_up((K + 2) * 4, 256) + tmp_bytes + (1 << 20);
+                      2 * align_up((K + 2) * 4, 256) + tmp_bytes + (1 << 20);
   if (own && need > ctx->scratch_bytes) {
     // growing the arena invalidates d_lab: re-run the (cheap) renumber into the new arena
     ctx->scratch_used = keep;
@@ -422,12 +425,11 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
   uint32_t* corner_s = (uint32_t*)scratch_take(ctx, 3 * T * 4);
   uint32_t* heads = (uint32_t*)scratch_take(ctx, 3 * T * 4);
   uint32_t* rank = (uint32_t*)scratch_take(ctx, 3 * T * 4);
-  uint64_t* uniq_vk = (uint64_t*)scratch_take(ctx, 3 * T * 8);
   uint32_t* d_tri_off = (uint32_t*)scratch_take(ctx, (K + 2) * 4);
   uint32_t* d_vert_off = (uint32_t*)scratch_take(ctx, (K + 2) * 4);
   void* tmp = scratch_take(ctx, tmp_bytes);
   if (!keys || !keys_s || !cases || !cases_s || !vkeys || !vkeys_s || !corner || !corner_s || !heads ||
-      !rank || !uniq_vk || !d_tri_off || !d_vert_off || !tmp) {
+      !rank || !d_tri_off || !d_vert_off || !tmp) {
     set_error("scratch arena too small (mesher: %llu triangles)", T);
     return fail(IGN_ERR_NOMEM);
   }
@@ -454,9 +456,9 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
   MESH_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, heads, rank, (int)(3 * T), ctx->stream));
   ctx->launches += 2;
   uint32_t last[2];
-  MESH_CUDA(cudaMemcpyAsync(&last[0], rank + (3 * T - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-  MESH_CUDA(cudaMemcpyAsync(&last[1], heads + (3 * T - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-  MESH_CUDA(cudaStreamSynchronize(ctx->stream));
+  MESH_TRY(small_d2h(ctx, &last[0], rank + (3 * T - 1), 4));
+  MESH_TRY(small_d2h(ctx, &last[1], heads + (3 * T - 1), 4));
+  MESH_TRY(small_sync(ctx));
   const uint64_t U = (uint64_t)last[0] + last[1];
   m->U = U;
   {
@@ -481,23 +483,22 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
     }
   }
   MESH_LAUNCH(k_vertex_assign, blocks_for(3 * T, 256), 256, vkeys_s, corner_s, heads, rank,
-              (uint64_t)(3 * T), uniq_vk, m->d_faces);
-  MESH_CUDA(cudaMemcpyAsync(m->d_uniq_vkeys, uniq_vk, U * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+              (uint64_t)(3 * T), m->d_uniq_vkeys, m->d_faces);
 
   // ---- per-label offsets (labels are 1..K; slot K+1 is the end sentinel)
   MESH_LAUNCH(k_fill_u32, blocks_for(K + 2, 256), 256, d_tri_off, (uint32_t)T, (uint32_t)(K + 2));
   MESH_LAUNCH(k_fill_u32, blocks_for(K + 2, 256), 256, d_vert_off, (uint32_t)U, (uint32_t)(K + 2));
   MESH_LAUNCH(k_label_starts, blocks_for(T, 256), 256, keys_s, (uint64_t)T, TRI_LABEL_SHIFT, d_tri_off);
   MESH_LAUNCH(k_label_starts, blocks_for(U, 256), 256, m->d_uniq_vkeys, U, V_LABEL_SHIFT, d_vert_off);
-  MESH_CUDA(cudaMemcpyAsync(m->tri_off.data(), d_tri_off, (K + 2) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  MESH_CUDA(cudaMemcpyAsync(m->vert_off.data(), d_vert_off, (K + 2) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  MESH_CUDA(cudaStreamSynchronize(ctx->stream));
+  MESH_TRY(small_d2h(ctx, m->tri_off.data(), d_tri_off, (K + 2) * 4));
+  MESH_TRY(small_d2h(ctx, m->vert_off.data(), d_vert_off, (K + 2) * 4));
+  MESH_TRY(small_sync(ctx));
   // absent labels hold the end marker: a suffix minimum turns starts into offsets
   for (int64_t l = (int64_t)K; l >= 0; l--) {
     if (m->tri_off[l] > m->tri_off[l + 1]) m->tri_off[l] = m->tri_off[l + 1];
     if (m->vert_off[l] > m->vert_off[l + 1]) m->vert_off[l] = m->vert_off[l + 1];
   }
-  MESH_CUDA(cudaMemcpyAsync(d_vert_off, m->vert_off.data(), (K + 2) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MESH_TRY(small_h2d(ctx, d_vert_off, m->vert_off.data(), (K + 2) * 4));
   MESH_LAUNCH(k_faces_local, blocks_for(3 * T, 256), 256, keys_s, d_vert_off, (uint64_t)T, m->d_faces);
   MESH_CUDA(cudaStreamSynchronize(ctx->stream));
   for (uint64_t l = 1; l <= K; l++)

@@ -272,11 +272,8 @@ static int table_alloc(ign_ctx* ctx, uint32_t cap, uint64_t val_init_byte, HashT
 }
 
 static int read_counters(ign_ctx* ctx, const uint32_t* counters, uint32_t* h8) {
-  uint32_t* h = (uint32_t*)ctx->pinned;
-  IGN_CUDA(cudaMemcpyAsync(h, counters, 32, cudaMemcpyDeviceToHost, ctx->stream));
-  IGN_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < 8; i++) h8[i] = h[i];
-  return IGN_OK;
+  IGN_TRY(small_d2h(ctx, h8, counters, 32));
+  return small_sync(ctx);
 }
 
 #define DISPATCH_UINT(dtype, FN, ...)                                      \

@@ -658,6 +658,11 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
       return done(IGN_ERR_CUDA);                                                      \
     }                                                                                 \
   } while (0)
+#define S_TRY(call)                       \
+  do {                                    \
+    const int _s = (call);                \
+    if (_s != IGN_OK) return done(_s);    \
+  } while (0)
 #define S_LAUNCH(kernel, g, b, ...)                       \
   do {                                                    \
     kernel<<<(g), (b), 0, ctx->stream>>>(__VA_ARGS__);    \
@@ -668,9 +673,9 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   std::vector<uint32_t> target(K + 2, 0);
   for (uint64_t l = 1; l <= K; l++)
     target[l] = (m->tri_off[l + 1] - m->tri_off[l]) / (uint32_t)reduction_factor;
-  S_CUDA(cudaMemcpyAsync(d_target, target.data(), (K + 2) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  S_CUDA(cudaMemcpyAsync(d_tri_off, m->tri_off.data(), (K + 2) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  S_CUDA(cudaMemcpyAsync(d_vert_off, m->vert_off.data(), (K + 2) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  S_TRY(small_h2d(ctx, d_target, target.data(), (K + 2) * 4));
+  S_TRY(small_h2d(ctx, d_tri_off, m->tri_off.data(), (K + 2) * 4));
+  S_TRY(small_h2d(ctx, d_vert_off, m->vert_off.data(), (K + 2) * 4));
   S_CUDA(cudaMemsetAsync(s.alive_faces, 0, (K + 2) * 4, ctx->stream));
   S_CUDA(cudaMemsetAsync(s.label_active, 0, K + 2, ctx->stream));
   S_CUDA(cudaMemsetAsync(s.estate, 0, 3 * T, ctx->stream));
@@ -692,8 +697,8 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
            flags + 12);
   {
     uint32_t* hf = (uint32_t*)ctx->pinned;
-    S_CUDA(cudaMemcpyAsync(hf, flags + 12, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    S_CUDA(cudaStreamSynchronize(ctx->stream));
+    S_TRY(small_d2h(ctx, hf, flags + 12, 4));
+    S_TRY(small_sync(ctx));
     if (hf[0] != 0) {
       set_error("simplify: a vertex has more than %d incident faces", S_VCAP);
       return done(IGN_ERR_UNSUPPORTED);
@@ -704,8 +709,8 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   {
     std::vector<uint32_t> af(K + 2, 0);
     for (uint64_t l = 1; l <= K; l++) af[l] = m->tri_off[l + 1] - m->tri_off[l];
-    S_CUDA(cudaMemcpyAsync(s.alive_faces, af.data(), (K + 2) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    S_CUDA(cudaStreamSynchronize(ctx->stream));
+    S_TRY(small_h2d(ctx, s.alive_faces, af.data(), (K + 2) * 4));
+    S_TRY(small_sync(ctx));
   }
 
   const double max_err2 = (double)max_error * (double)max_error;
@@ -719,8 +724,8 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
       S_CUDA(cudaMemsetAsync(flags + 8, 0, 8, ctx->stream));
       S_LAUNCH(k_simp_build_elist, blocks_for(3 * T, 256), 256, s, flags + 8);
       S_LAUNCH(k_simp_build_vlist, blocks_for(U, 256), 256, s, flags + 8);
-      S_CUDA(cudaMemcpyAsync(hflags + 8, flags + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
-      S_CUDA(cudaStreamSynchronize(ctx->stream));
+      S_TRY(small_d2h(ctx, hflags + 8, flags + 8, 8));
+      S_TRY(small_sync(ctx));
       s.ne = hflags[8];
       s.nv = hflags[9];
     }
@@ -735,8 +740,8 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
       const unsigned cg = blocks_for(s.nv / 16 + 1, 128);
       S_LAUNCH(k_simp_collapse, cg < 1184 ? cg : 1184, 128, s, max_err2, wlist, flags);
     }
-    S_CUDA(cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    S_CUDA(cudaStreamSynchronize(ctx->stream));
+    S_TRY(small_d2h(ctx, hflags, flags, 16));
+    S_TRY(small_sync(ctx));
     if (hflags[0] == 0) break;           // every label reached its target before this round
     if (hflags[1] == 0) { r++; break; }  // nothing collapsed or parked: fixed point
     // early stop (mirrored by the oracle): four consecutive rounds that each remove
@@ -760,11 +765,11 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, fflag, fscan, (int)T, ctx->stream));
   ctx->launches += 4;
   uint32_t last[4];
-  S_CUDA(cudaMemcpyAsync(&last[0], vscan + (U - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-  S_CUDA(cudaMemcpyAsync(&last[1], vflag + (U - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-  S_CUDA(cudaMemcpyAsync(&last[2], fscan + (T - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-  S_CUDA(cudaMemcpyAsync(&last[3], fflag + (T - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-  S_CUDA(cudaStreamSynchronize(ctx->stream));
+  S_TRY(small_d2h(ctx, &last[0], vscan + (U - 1), 4));
+  S_TRY(small_d2h(ctx, &last[1], vflag + (U - 1), 4));
+  S_TRY(small_d2h(ctx, &last[2], fscan + (T - 1), 4));
+  S_TRY(small_d2h(ctx, &last[3], fflag + (T - 1), 4));
+  S_TRY(small_sync(ctx));
   const uint32_t U2 = last[0] + last[1], T2 = last[2] + last[3];
   S_LAUNCH(k_simp_new_offsets, blocks_for(K + 2, 256), 256, d_vert_off, vscan, (uint32_t)(K + 2), U, U2,
            d_new_vert_off);
@@ -774,9 +779,9 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   float* pos_f = (float*)m->d_uniq_vkeys;
   S_LAUNCH(k_simp_compact_verts, blocks_for(U, 256), 256, s, vscan, pos_f);
   S_LAUNCH(k_simp_compact_faces, blocks_for(T, 256), 256, s, vscan, fscan, d_new_vert_off, m->d_faces);
-  S_CUDA(cudaMemcpyAsync(m->tri_off.data(), d_new_tri_off, (K + 2) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  S_CUDA(cudaMemcpyAsync(m->vert_off.data(), d_new_vert_off, (K + 2) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  S_CUDA(cudaStreamSynchronize(ctx->stream));
+  S_TRY(small_d2h(ctx, m->tri_off.data(), d_new_tri_off, (K + 2) * 4));
+  S_TRY(small_d2h(ctx, m->vert_off.data(), d_new_vert_off, (K + 2) * 4));
+  S_TRY(small_sync(ctx));
   m->U = U2;
   m->T = T2;
   m->d_pos_f = pos_f;
