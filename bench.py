@@ -206,6 +206,8 @@ def main():
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-cpu", action="store_true")
   ap.add_argument("--e2e-steps", type=int, default=2)
+  ap.add_argument("--e2e-shared-buffers", action="store_true",
+                  help="download the labels into the input host buffer (forced automatically when host RAM is tight)")
   ap.add_argument("--simplify", type=int, default=None, help="simplification factor (default 100)")
   ap.add_argument("--mesh-streams", type=int, default=8, help="concurrent MeshTask bodies per GPU")
   args = ap.parse_args()
@@ -343,6 +345,17 @@ def main():
     dist.destroy_process_group()
 
 
+def _mem_available():
+  try:
+    with open("/proc/meminfo") as f:
+      for line in f:
+        if line.startswith("MemAvailable:"):
+          return int(line.split()[1]) * 1024
+  except OSError:
+    pass
+  return None
+
+
 def run_e2e(ctx, pipe, args, dist, world):
   """Same metric through host buffers: every step copies the volume H2D from
   pinned memory, runs the pipeline and copies every product (mips, CCL labels,
@@ -350,16 +363,28 @@ def run_e2e(ctx, pipe, args, dist, world):
   from igneous_b200 import _shim
   n = pipe.n
   host_kind = "pinned (cudaHostAlloc)"
+  # host RAM guard: all local ranks keep input + products resident on the host.  When that
+  # does not fit comfortably, the label volume is downloaded into the input buffer (what
+  # in_place=True does in the reference) and the input is restored between steps, untimed.
+  out_bytes = sum(int(np.prod(s)) * 4 for s in pipe.mip_shapes) + n * pipe.ccl_out_dtype.itemsize
+  local_ranks = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+  avail = _mem_available()
+  shared = (avail is not None and (n * 4 + out_bytes) * local_ranks > 0.6 * avail
+            and pipe.ccl_out_dtype.itemsize == 4)
+  if args.e2e_shared_buffers:
+    shared = pipe.ccl_out_dtype.itemsize == 4
   try:
     host_in = ctx.pinned_empty(pipe.shape, np.uint32)
     host = {"mips": [ctx.pinned_empty(s, np.uint32) for s in pipe.mip_shapes],
-            "cc": ctx.pinned_empty(pipe.shape, pipe.ccl_out_dtype)}
+            "cc": (host_in.view(pipe.ccl_out_dtype) if shared
+                   else ctx.pinned_empty(pipe.shape, pipe.ccl_out_dtype))}
   except (MemoryError, _shim.IgneousB200Error):
-    # the host could not page-lock ~80 GB for this rank: fall back to pageable buffers
+    # the host could not page-lock the buffers for this rank: fall back to pageable memory
     host_kind = "pageable (pinned allocation failed)"
     host_in = np.empty(pipe.shape, dtype=np.uint32, order="F")
     host = {"mips": [np.empty(s, dtype=np.uint32, order="F") for s in pipe.mip_shapes],
-            "cc": np.empty(pipe.shape, dtype=pipe.ccl_out_dtype, order="F")}
+            "cc": (host_in.view(pipe.ccl_out_dtype) if shared
+                   else np.empty(pipe.shape, dtype=pipe.ccl_out_dtype, order="F"))}
   ctx.d2h(host_in, pipe.d_in)
   cap_v, cap_f = 1 << 22, 1 << 23
   ctx.sync()
@@ -394,16 +419,19 @@ def run_e2e(ctx, pipe, args, dist, world):
 
   one()  # warm-up (pinned pages touched, arena sized)
   ctx.sync()
-  if dist is not None:
-    dist.barrier()
-  t0 = time.perf_counter()
-  ctx.timer_start(4)
+  ms = 0.0
   for _ in range(steps):
+    if shared:  # the label download overwrote the input: restore it outside the timed region
+      ctx.d2h(host_in, pipe.d_in)
+      ctx.sync()
+    if dist is not None:
+      dist.barrier()
+    t0 = time.perf_counter()
+    ctx.timer_start(4)
     one()
-  ctx.timer_stop(4)
-  ms = ctx.timer_ms(4)
-  wall = (time.perf_counter() - t0) * 1e3
-  ms = max(ms, wall)  # host-side export work counts too
+    ctx.timer_stop(4)
+    ev = ctx.timer_ms(4)
+    ms += max(ev, (time.perf_counter() - t0) * 1e3)  # host-side export work counts too
   if dist is not None:
     import torch
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -413,7 +441,9 @@ def run_e2e(ctx, pipe, args, dist, world):
   d2h = sum(int(np.prod(s)) * 4 for s in pipe.mip_shapes) + n * pipe.ccl_out_dtype.itemsize + mesh_bytes[0]
   return {"value": n * world / (ms / steps * 1e-3) / 1e6, "unit": "Mvoxels/s",
           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": steps,
-          "ms_per_step": ms / steps, "host_memory": host_kind}
+          "ms_per_step": ms / steps, "host_memory": host_kind,
+          "host_buffers": ("input buffer reused for the label download, restored between steps outside "
+                           "the timed region" if shared else "separate input and output buffers")}
 
 
 if __name__ == "__main__":

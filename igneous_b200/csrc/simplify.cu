@@ -715,12 +715,14 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
 
   const double max_err2 = (double)max_error * (double)max_error;
   const int max_rounds = 400;
+  const int rebuild_every = getenv("IGN_SIMP_REBUILD") ? atoi(getenv("IGN_SIMP_REBUILD")) : 8;
+  const unsigned collapse_cap = getenv("IGN_SIMP_CAP") ? (unsigned)atoi(getenv("IGN_SIMP_CAP")) : 1184u;
   uint32_t* hflags = (uint32_t*)ctx->pinned;
   int r = 0, slow = 0;
   uint64_t cum_collapses = 0;
   for (; r < max_rounds; r++) {
     const uint32_t salt = (uint32_t)r * 0x9E3779B9u;
-    if (r % 8 == 0) {  // rebuild the compact work lists
+    if (r % rebuild_every == 0) {  // rebuild the compact work lists
       S_CUDA(cudaMemsetAsync(flags + 8, 0, 8, ctx->stream));
       S_LAUNCH(k_simp_build_elist, blocks_for(3 * T, 256), 256, s, flags + 8);
       S_LAUNCH(k_simp_build_vlist, blocks_for(U, 256), 256, s, flags + 8);
@@ -738,7 +740,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
       S_LAUNCH(k_simp_select, blocks_for(s.nv, 256), 256, s, salt, wlist, flags);
       // grid-stride over the device-side winner count: no host round trip in between
       const unsigned cg = blocks_for(s.nv / 16 + 1, 128);
-      S_LAUNCH(k_simp_collapse, cg < 1184 ? cg : 1184, 128, s, max_err2, wlist, flags);
+      S_LAUNCH(k_simp_collapse, cg < collapse_cap ? cg : collapse_cap, 128, s, max_err2, wlist, flags);
     }
     S_TRY(small_d2h(ctx, hflags, flags, 16));
     S_TRY(small_sync(ctx));
