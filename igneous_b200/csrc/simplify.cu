@@ -715,8 +715,10 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
 
   const double max_err2 = (double)max_error * (double)max_error;
   const int max_rounds = 400;
-  const int rebuild_every = getenv("IGN_SIMP_REBUILD") ? atoi(getenv("IGN_SIMP_REBUILD")) : 8;
-  const unsigned collapse_cap = getenv("IGN_SIMP_CAP") ? (unsigned)atoi(getenv("IGN_SIMP_CAP")) : 1184u;
+  // work-list rebuild period and collapse grid cap: measured on B200 (tools/time_simplify.py),
+  // 4 / 8 / 16 rounds -> 187.7 / 177.4 / 175.3 ms per 257^3 task; the grid cap has no effect
+  const int rebuild_every = 16;
+  const unsigned collapse_cap = 1184u;
   uint32_t* hflags = (uint32_t*)ctx->pinned;
   int r = 0, slow = 0;
   uint64_t cum_collapses = 0;
