@@ -827,14 +827,11 @@ static int ccl_core(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, uint32_
   const unsigned grid = (unsigned)ntiles;
   constexpr size_t smem = (TILE_VOX + CCL_WARPS * TASKS_PER_WARP) * sizeof(uint32_t);
   *overflow = false;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    IGN_CUDA(cudaFuncSetAttribute(k_ccl_local<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if constexpr (!R::thresholded)
-      IGN_CUDA(cudaFuncSetAttribute(k_ccl_local_fast<typename R::value_type>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // per device and cheap: set on every call (a process may drive several devices)
+  IGN_CUDA(cudaFuncSetAttribute(k_ccl_local<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if constexpr (!R::thresholded)
+    IGN_CUDA(cudaFuncSetAttribute(k_ccl_local_fast<typename R::value_type>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   IGN_CUDA(cudaMemsetAsync(s.counters, 0, 256, ctx->stream));
   bool fast = false;
   if constexpr (!R::thresholded) {  // raw labels (no threshold)

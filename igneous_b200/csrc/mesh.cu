@@ -22,6 +22,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
@@ -244,7 +245,8 @@ static int mesher_positions(ign_mesher* m, uint64_t first, uint64_t count, const
   return IGN_OK;
 }
 
-static bool g_tables_loaded[64] = {false};
+// one flag per device; set after the upload has completed (mesh streams of one device share it)
+static std::atomic<bool> g_tables_loaded[64];
 
 static int load_tables(ign_ctx* ctx) {
   if (ctx->device < 64 && g_tables_loaded[ctx->device]) return IGN_OK;

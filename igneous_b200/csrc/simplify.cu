@@ -638,14 +638,12 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
       !d_target || !s.label_active || !d_tri_off || !d_vert_off || !d_new_tri_off || !d_new_vert_off ||
       !flags || !tmp || !sorted_v || !sorted_h || !s.estate || !s.ecost || !s.vdirty || !s.elist ||
       !s.vlist || !wlist) {
-    // the plan above under-counted: grow once with slack and retry
     scratch_reset(ctx);
     set_error("scratch arena too small (simplify: %llu faces)", (unsigned long long)T);
     return IGN_ERR_NOMEM;
   }
   s.target = d_target;
   s.tri_off = d_tri_off;
-  int rc = IGN_OK;
   auto done = [&](int code) {
     scratch_reset(ctx);
     return code;
@@ -715,6 +713,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
 
   const double max_err2 = (double)max_error * (double)max_error;
   const int max_rounds = 400;
+  const bool trace = getenv("IGN_SIMP_TRACE") != nullptr;  // per-round progress on stderr
   // work-list rebuild period and collapse grid cap: measured on B200 (tools/time_simplify.py),
   // 4 / 8 / 16 rounds -> 187.7 / 177.4 / 175.3 ms per 257^3 task; the grid cap has no effect
   const int rebuild_every = 16;
@@ -753,7 +752,9 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
     cum_collapses += hflags[2];
     const uint64_t alive_total = T - 2 * cum_collapses;
     if ((uint64_t)hflags[2] * 1000 < alive_total) slow++; else slow = 0;
-    if (getenv("IGN_SIMP_TRACE")) fprintf(stderr, "round %d collapses %u alive %llu ne %u nv %u\n", r, hflags[2], (unsigned long long)alive_total, s.ne, s.nv);
+    if (trace)
+      fprintf(stderr, "round %d collapses %u alive %llu ne %u nv %u\n", r, hflags[2],
+              (unsigned long long)alive_total, s.ne, s.nv);
     if (slow >= 4) { r++; break; }
   }
   m->simp_rounds = r;
@@ -793,6 +794,5 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   m->present.clear();
   for (uint64_t l = 1; l <= K; l++)
     if (m->tri_off[l + 1] > m->tri_off[l]) m->present.push_back(m->ids[l - 1]);
-  (void)rc;
   return done(IGN_OK);
 }
