@@ -14,6 +14,8 @@
 // pooling pyramid once a thread owns the whole patch.
 // Generic path: one thread per output voxel, any extent (odd edges), sparse
 // mode, float32.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ign {
@@ -281,6 +283,103 @@ __global__ void __launch_bounds__(256)
   out[t] = acc;
 }
 
+// mode / average over fx x fy x fz blocks (factors 1 or 2 per axis), one thread per
+// output voxel -- the non-(2,2,1) factors of tinybrain.downsample_segmentation /
+// downsample_with_averaging (2x2x2 for --volumetric).  Rules: oracle/igneous_oracle.c
+// "Block pooling" (samples visited x fastest; planar factor with four samples left ->
+// COUNTLESS 2-D pick, otherwise highest count with ties to the earliest sample; averages
+// count the lone row/column/slice of an odd extent twice).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_block_mode(const T* __restrict__ in, uint64_t sx, uint64_t sy, uint64_t sz, uint32_t fx,
+                 uint32_t fy, uint32_t fz, int sparse, T* __restrict__ out) {
+  const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy, oz = (sz + fz - 1) / fz;
+  const uint64_t total = ox * oy * oz;
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const uint64_t x = t % ox, r = t / ox, y = r % oy, z = r / oy;
+  const uint64_t x0 = x * fx, y0 = y * fy, z0 = z * fz;
+  T v[8];
+  int n = 0;
+#pragma unroll
+  for (uint32_t dz = 0; dz < 2; dz++)
+#pragma unroll
+    for (uint32_t dy = 0; dy < 2; dy++)
+#pragma unroll
+      for (uint32_t dx = 0; dx < 2; dx++) {
+        if (dx < fx && dy < fy && dz < fz && x0 + dx < sx && y0 + dy < sy && z0 + dz < sz) {
+          const T s = in[((z0 + dz) * sy + (y0 + dy)) * sx + (x0 + dx)];
+          if (!sparse || s != 0) v[n++] = s;
+        }
+      }
+  T res = 0;
+  if (fx * fy * fz == 4 && n == 4) {
+    res = mode4(v[0], v[1], v[2], v[3]);
+  } else {
+    int best = 0;
+    for (int a = 0; a < n; a++) {
+      int ct = 0;
+      for (int b = 0; b < n; b++) ct += (v[b] == v[a]);
+      if (ct > best) {
+        best = ct;
+        res = v[a];
+      }
+    }
+  }
+  out[t] = res;
+}
+
+template <typename T, typename A>
+__global__ void __launch_bounds__(256)
+    k_block_avg(const T* __restrict__ in, uint64_t sx, uint64_t sy, uint64_t sz, uint32_t fx,
+                uint32_t fy, uint32_t fz, int rounding, T* __restrict__ out) {
+  const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy, oz = (sz + fz - 1) / fz;
+  const uint64_t total = ox * oy * oz;
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const uint64_t x = t % ox, r = t / ox, y = r % oy, z = r / oy;
+  A acc = 0;
+  for (uint32_t dz = 0; dz < fz; dz++)
+    for (uint32_t dy = 0; dy < fy; dy++)
+      for (uint32_t dx = 0; dx < fx; dx++) {
+        uint64_t xx = x * fx + dx, yy = y * fy + dy, zz = z * fz + dz;
+        xx = xx < sx ? xx : sx - 1;
+        yy = yy < sy ? yy : sy - 1;
+        zz = zz < sz ? zz : sz - 1;
+        acc += (A)in[(zz * sy + yy) * sx + xx];
+      }
+  const int shift = (fx == 2) + (fy == 2) + (fz == 2);
+  out[t] = (T)(shift ? render<A>(acc, shift, rounding) : acc);
+}
+
+__global__ void __launch_bounds__(256)
+    k_block_avg_f32(const float* __restrict__ in, uint64_t sx, uint64_t sy, uint64_t sz, uint32_t fx,
+                    uint32_t fy, uint32_t fz, float* __restrict__ out) {
+  const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy, oz = (sz + fz - 1) / fz;
+  const uint64_t total = ox * oy * oz;
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const uint64_t x = t % ox, r = t / ox, y = r % oy, z = r / oy;
+  float zs[2] = {0.0f, 0.0f};
+  for (uint32_t dz = 0; dz < fz; dz++) {
+    float ys[2] = {0.0f, 0.0f};
+    for (uint32_t dy = 0; dy < fy; dy++) {
+      float xs[2] = {0.0f, 0.0f};
+      for (uint32_t dx = 0; dx < fx; dx++) {
+        uint64_t xx = x * fx + dx, yy = y * fy + dy, zz = z * fz + dz;
+        xx = xx < sx ? xx : sx - 1;
+        yy = yy < sy ? yy : sy - 1;
+        zz = zz < sz ? zz : sz - 1;
+        xs[dx] = in[(zz * sy + yy) * sx + xx];
+      }
+      ys[dy] = (fx == 2) ? __fadd_rn(xs[0], xs[1]) : xs[0];
+    }
+    zs[dz] = (fy == 2) ? __fadd_rn(ys[0], ys[1]) : ys[0];
+  }
+  const float sum = (fz == 2) ? __fadd_rn(zs[0], zs[1]) : zs[0];
+  out[t] = __fmul_rn(sum, 1.0f / (float)(fx * fy * fz));
+}
+
 template <typename A>
 __global__ void __launch_bounds__(256)
     k_widen_from(const void* __restrict__ in, int dtype, uint64_t n, A* __restrict__ out) {
@@ -446,6 +545,12 @@ static int check_pool_args(const void* in, int dtype, uint64_t sx, uint64_t sy, 
   return IGN_OK;
 }
 
+// accumulator wide enough for eight samples
+template <typename T> struct BlockAcc { using type = uint32_t; };
+template <> struct BlockAcc<uint32_t> { using type = uint64_t; };
+
+// ops: 0 min, 1 max, 2 striding, 3 mode, 4 sparse mode, 5/6/7 average with
+// IGN_ROUND_FLOOR / HALF_UP / HALF_EVEN.  Every mip is computed from the previous one.
 template <typename T>
 static int select_pyramid(ign_ctx* ctx, const void* in, uint64_t sx, uint64_t sy, uint64_t sz, uint32_t fx,
                           uint32_t fy, uint32_t fz, int num_mips, int op, void* const* outs) {
@@ -453,8 +558,29 @@ static int select_pyramid(ign_ctx* ctx, const void* in, uint64_t sx, uint64_t sy
   for (int m = 0; m < num_mips; m++) {
     const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy, oz = (sz + fz - 1) / fz;
     const uint64_t total = ox * oy * oz;
-    if (total > 0)
-      IGN_LAUNCH(ctx, (k_pool_select<T>), blocks_for(total, 256), 256, 0, cur, sx, sy, sz, fx, fy, fz, op, (T*)outs[m]);
+    if (total > 0) {
+      const unsigned grid = blocks_for(total, 256);
+      if (op <= 2) {
+        IGN_LAUNCH(ctx, (k_pool_select<T>), grid, 256, 0, cur, sx, sy, sz, fx, fy, fz, op, (T*)outs[m]);
+      } else if (op <= 4) {
+        if constexpr (std::is_same<T, float>::value) {  // bit patterns: equality is all the mode needs
+          IGN_LAUNCH(ctx, (k_block_mode<uint32_t>), grid, 256, 0, (const uint32_t*)cur, sx, sy, sz, fx, fy, fz,
+                     op == 4, (uint32_t*)outs[m]);
+        } else {
+          IGN_LAUNCH(ctx, (k_block_mode<T>), grid, 256, 0, cur, sx, sy, sz, fx, fy, fz, op == 4, (T*)outs[m]);
+        }
+      } else {
+        if constexpr (std::is_same<T, float>::value) {
+          IGN_LAUNCH(ctx, k_block_avg_f32, grid, 256, 0, cur, sx, sy, sz, fx, fy, fz, (float*)outs[m]);
+        } else if constexpr (std::is_same<T, uint64_t>::value) {
+          set_error("averaging: uint64 images are not supported");
+          return IGN_ERR_UNSUPPORTED;
+        } else {
+          using A = typename BlockAcc<T>::type;
+          IGN_LAUNCH(ctx, (k_block_avg<T, A>), grid, 256, 0, cur, sx, sy, sz, fx, fy, fz, op - 5, (T*)outs[m]);
+        }
+      }
+    }
     cur = (const T*)outs[m];
     sx = ox; sy = oy; sz = oz;
   }
@@ -507,7 +633,8 @@ int ign_pool_select_dev(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, ui
   IGN_TRY(check_pool_args(in, dtype, sx, sy, sz, num_mips, outs));
   IGN_REQUIRE(fx >= 1 && fx <= 2 && fy >= 1 && fy <= 2 && fz >= 1 && fz <= 2, IGN_ERR_UNSUPPORTED,
               "pooling factors must be 1 or 2 per axis (got %u,%u,%u)", fx, fy, fz);
-  IGN_REQUIRE(op >= 0 && op <= 2, IGN_ERR_INVALID, "op must be 0 (min), 1 (max) or 2 (striding)");
+  IGN_REQUIRE(op >= 0 && op <= 7, IGN_ERR_INVALID,
+              "op must be 0 min, 1 max, 2 striding, 3 mode, 4 sparse mode or 5-7 average (floor / half-up / half-even)");
   switch (dtype) {
     case IGN_U8: return select_pyramid<uint8_t>(ctx, in, sx, sy, sz, fx, fy, fz, num_mips, op, outs);
     case IGN_U16: return select_pyramid<uint16_t>(ctx, in, sx, sy, sz, fx, fy, fz, num_mips, op, outs);

@@ -23,12 +23,9 @@ __all__ = ["downsample_segmentation", "downsample_with_averaging", "downsample_w
 DEFAULT_ROUNDING = _shim.ROUND_FLOOR
 
 
-def _check_factor(factor):
+def _is_221(factor):
   f = tuple(int(v) for v in factor)
-  if f[:3] != (2, 2, 1) or any(v != 1 for v in f[3:]):
-    raise NotImplementedError(
-      "igneous_b200 pooling implements factor (2,2,1) only (got %r); "
-      "2x2x2 / striding / min / max pooling are listed as next rows in DESIGN.md" % (factor,))
+  return f[:3] == (2, 2, 1) and all(v == 1 for v in f[3:])
 
 
 def _out_shapes(shape, num_mips):
@@ -41,7 +38,6 @@ def _out_shapes(shape, num_mips):
 
 
 def _pool(img, factor, num_mips, mode, flag, ctx):
-  _check_factor(factor)
   num_mips = int(num_mips)
   if num_mips < 1:
     return []
@@ -65,23 +61,34 @@ def _pool(img, factor, num_mips, mode, flag, ctx):
 
 
 def downsample_segmentation(img, factor, num_mips=1, sparse=False, ctx=None):
-  """2x2x1 mode pooling pyramid (COUNTLESS 2-D, recursive per mip)."""
+  """2x2x1 mode pooling pyramid (COUNTLESS 2-D, recursive per mip); other factors of
+  1 or 2 per axis (2x2x2 ...) use the generic block-mode kernel."""
+  if not _is_221(factor):
+    return _select(img, factor, num_mips, _OP_MODE_SPARSE if sparse else _OP_MODE, ctx)
   return _pool(img, factor, num_mips, True, bool(sparse), ctx)
 
 
 def downsample_with_averaging(img, factor, num_mips=1, sparse=False, ctx=None,
                               rounding=None):
-  """2x2x1 average pooling pyramid (exact sums in groups of four mips)."""
+  """2x2x1 average pooling pyramid (exact sums in groups of four mips); other factors
+  of 1 or 2 per axis (2x2x2 ...) use the generic block-average kernel, recursively."""
   if sparse:
     raise NotImplementedError("igneous_b200 averaging: sparse=True is not implemented")
-  return _pool(img, factor, num_mips, False,
-               DEFAULT_ROUNDING if rounding is None else rounding, ctx)
+  rounding = DEFAULT_ROUNDING if rounding is None else rounding
+  if not _is_221(factor):
+    if np.asarray(img).dtype == np.uint64:
+      raise NotImplementedError("igneous_b200 averaging: uint64 images are not supported")
+    return _select(img, factor, num_mips, _OP_AVG + int(rounding), ctx)
+  return _pool(img, factor, num_mips, False, rounding, ctx)
+
+
+_OP_MIN, _OP_MAX, _OP_STRIDE, _OP_MODE, _OP_MODE_SPARSE, _OP_AVG = 0, 1, 2, 3, 4, 5  # ign_pool_select ops
 
 
 def _select(img, factor, num_mips, op, ctx):
   f = tuple(int(v) for v in factor)
   if len(f) < 3 or any(v not in (1, 2) for v in f[:3]) or any(v != 1 for v in f[3:]):
-    raise NotImplementedError("igneous_b200 min/max/striding pooling: factors must be 1 or 2 per axis, got %r" % (factor,))
+    raise NotImplementedError("igneous_b200 pooling: factors must be 1 or 2 per axis, got %r" % (factor,))
   num_mips = int(num_mips)
   img = np.asarray(img)
   if num_mips < 1:
@@ -113,12 +120,12 @@ def _select(img, factor, num_mips, op, ctx):
 
 
 def downsample_with_min_pooling(img, factor, num_mips=1, ctx=None):
-  return _select(img, factor, num_mips, 0, ctx)
+  return _select(img, factor, num_mips, _OP_MIN, ctx)
 
 
 def downsample_with_max_pooling(img, factor, num_mips=1, ctx=None):
-  return _select(img, factor, num_mips, 1, ctx)
+  return _select(img, factor, num_mips, _OP_MAX, ctx)
 
 
 def downsample_with_striding(img, factor, num_mips=1, ctx=None):
-  return _select(img, factor, num_mips, 2, ctx)
+  return _select(img, factor, num_mips, _OP_STRIDE, ctx)

@@ -117,10 +117,17 @@ IGN_API int ign_pool_mode_2x2x1_dev(ign_ctx* ctx, const void* in, int dtype, uin
 IGN_API int ign_pool_avg_2x2x1_dev(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, uint64_t sy,
                            uint64_t sz, int num_mips, int rounding, void* const* outs);
 
-/* tinybrain.downsample_with_min_pooling / _max_pooling / _striding
- *   igneous/tasks/image/image.py:46-49,55 (reachable through TransferTask(downsample_method=...))
- * factors 1 or 2 per axis; op 0 = min, 1 = max, 2 = striding; partial edge blocks
- * reduce over the samples that exist.  [SURVEY 8(f) row 3, not on the headline path] */
+/* Block pooling with factors 1 or 2 per axis -- every tinybrain.downsample_* call other than
+ * the (2,2,1) mode / average pyramids above:
+ *   igneous/tasks/image/image.py:46-55 (downsample_method_to_fn: min / max / striding, and
+ *   mode / average with a non-(2,2,1) factor such as (2,2,2) for --volumetric)
+ * op: 0 min, 1 max, 2 striding (partial edge blocks reduce over the samples that exist);
+ *     3 mode, 4 sparse mode (zeros ignored): a planar factor with four samples left uses the
+ *       COUNTLESS 2-D pick, otherwise the highest count wins with ties to the earliest sample
+ *       (x fastest); 5 / 6 / 7 average rendered with IGN_ROUND_FLOOR / HALF_UP / HALF_EVEN
+ *       (the lone row / column / slice of an odd extent counts twice; u8, u16, u32, f32).
+ * Every mip is computed from the previous one.  Generic one-thread-per-output kernels.
+ * [SURVEY 8(f) row 3, not on the headline path] */
 IGN_API int ign_pool_select(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, uint64_t sy,
                             uint64_t sz, uint32_t fx, uint32_t fy, uint32_t fz, int num_mips, int op,
                             void* const* outs);

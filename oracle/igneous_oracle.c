@@ -204,6 +204,132 @@ int orc_avg_pool_2x2x1_f32(const float* in, uint64_t sx, uint64_t sy,
 }
 
 /* ------------------------------------------------------------------ */
+/* Block pooling with factors 1 or 2 per axis (the other                */
+/* tinybrain.downsample_* factors igneous can request: (2,2,2) for      */
+/* --volumetric, igneous_cli/cli.py; DownsampleMethods, types.py:6-12). */
+/* One level.  Samples of a block are visited x fastest, then y, then z.*/
+/*  mode  (sparse = zeros ignored; all zero -> 0):                      */
+/*    planar factor (fx*fy*fz == 4) and exactly four samples left:      */
+/*      the COUNTLESS 2-D pick of the 2x2x1 kernel, so that (2,2,1)     */
+/*      through this path equals orc_mode_pool_2x2x1;                   */
+/*    otherwise: the value with the highest count, ties -> the earliest */
+/*      sample (what replicate-the-edge + first-maximum gives).         */
+/*  average: sum over the block with the lone row/column/slice of an    */
+/*    odd extent counted twice (divisor stays fx*fy*fz), rendered with  */
+/*    the rounding enum of the 2x2x1 kernel.  Recursive per mip.        */
+/* PARITY UNPINNED: tie-break and edge rules are recalled, not pinned.  */
+/* ------------------------------------------------------------------ */
+#define DEF_BLOCK_MODE(T, NAME)                                              \
+  int NAME(const T* in, uint64_t sx, uint64_t sy, uint64_t sz, uint32_t fx,  \
+           uint32_t fy, uint32_t fz, int sparse, T* out) {                   \
+    if (fx < 1 || fx > 2 || fy < 1 || fy > 2 || fz < 1 || fz > 2)           \
+      return ORC_EINVAL;                                                     \
+    const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy,         \
+                   oz = (sz + fz - 1) / fz;                                  \
+    const int planar = (fx * fy * fz == 4);                                  \
+    for (uint64_t z = 0; z < oz; z++)                                        \
+      for (uint64_t y = 0; y < oy; y++)                                      \
+        for (uint64_t x = 0; x < ox; x++) {                                  \
+          T v[8];                                                            \
+          int n = 0;                                                         \
+          for (uint32_t dz = 0; dz < fz && z * fz + dz < sz; dz++)           \
+            for (uint32_t dy = 0; dy < fy && y * fy + dy < sy; dy++)         \
+              for (uint32_t dx = 0; dx < fx && x * fx + dx < sx; dx++) {     \
+                const T s = in[(x * fx + dx) +                               \
+                               sx * ((y * fy + dy) + sy * (z * fz + dz))];   \
+                if (!sparse || s != 0) v[n++] = s;                           \
+              }                                                              \
+          T r = 0;                                                           \
+          if (planar && n == 4) {                                            \
+            r = (v[0] == v[1] || v[0] == v[2]) ? v[0]                        \
+                : ((v[1] == v[2]) ? v[1] : v[3]);                            \
+          } else {                                                           \
+            int best = 0;                                                    \
+            for (int t = 0; t < n; t++) {                                    \
+              int ct = 0;                                                    \
+              for (int q = 0; q < n; q++) ct += (v[q] == v[t]);              \
+              if (ct > best) {                                               \
+                best = ct;                                                   \
+                r = v[t];                                                    \
+              }                                                              \
+            }                                                                \
+          }                                                                  \
+          out[x + ox * (y + oy * z)] = r;                                    \
+        }                                                                    \
+    return ORC_OK;                                                           \
+  }
+
+DEF_BLOCK_MODE(uint8_t, orc_block_mode_u8)
+DEF_BLOCK_MODE(uint16_t, orc_block_mode_u16)
+DEF_BLOCK_MODE(uint32_t, orc_block_mode_u32)
+DEF_BLOCK_MODE(uint64_t, orc_block_mode_u64)
+
+#define DEF_BLOCK_AVG(T, NAME)                                               \
+  int NAME(const T* in, uint64_t sx, uint64_t sy, uint64_t sz, uint32_t fx,  \
+           uint32_t fy, uint32_t fz, int rounding, T* out) {                 \
+    if (fx < 1 || fx > 2 || fy < 1 || fy > 2 || fz < 1 || fz > 2)           \
+      return ORC_EINVAL;                                                     \
+    const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy,         \
+                   oz = (sz + fz - 1) / fz;                                  \
+    const unsigned shift = (fx == 2) + (fy == 2) + (fz == 2);                \
+    for (uint64_t z = 0; z < oz; z++)                                        \
+      for (uint64_t y = 0; y < oy; y++)                                      \
+        for (uint64_t x = 0; x < ox; x++) {                                  \
+          uint64_t acc = 0;                                                  \
+          for (uint32_t dz = 0; dz < fz; dz++)                               \
+            for (uint32_t dy = 0; dy < fy; dy++)                             \
+              for (uint32_t dx = 0; dx < fx; dx++) {                         \
+                uint64_t xx = x * fx + dx, yy = y * fy + dy, zz = z * fz + dz; \
+                if (xx >= sx) xx = sx - 1;                                   \
+                if (yy >= sy) yy = sy - 1;                                   \
+                if (zz >= sz) zz = sz - 1;                                   \
+                acc += in[xx + sx * (yy + sy * zz)];                         \
+              }                                                              \
+          out[x + ox * (y + oy * z)] = (T)orc_render(acc, shift, rounding);  \
+        }                                                                    \
+    return ORC_OK;                                                           \
+  }
+
+DEF_BLOCK_AVG(uint8_t, orc_block_avg_u8)
+DEF_BLOCK_AVG(uint16_t, orc_block_avg_u16)
+DEF_BLOCK_AVG(uint32_t, orc_block_avg_u32)
+
+/* float32: pairwise sums in x, then y, then z (each a float add), times   */
+/* the exact reciprocal of the block size                                  */
+int orc_block_avg_f32(const float* in, uint64_t sx, uint64_t sy, uint64_t sz,
+                      uint32_t fx, uint32_t fy, uint32_t fz, int rounding,
+                      float* out) {
+  (void)rounding;
+  if (fx < 1 || fx > 2 || fy < 1 || fy > 2 || fz < 1 || fz > 2) return ORC_EINVAL;
+  const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy,
+                 oz = (sz + fz - 1) / fz;
+  const float scale = 1.0f / (float)(fx * fy * fz);
+  for (uint64_t z = 0; z < oz; z++)
+    for (uint64_t y = 0; y < oy; y++)
+      for (uint64_t x = 0; x < ox; x++) {
+        float zs[2] = {0.0f, 0.0f};
+        for (uint32_t dz = 0; dz < fz; dz++) {
+          float ys[2] = {0.0f, 0.0f};
+          for (uint32_t dy = 0; dy < fy; dy++) {
+            float xs[2] = {0.0f, 0.0f};
+            for (uint32_t dx = 0; dx < fx; dx++) {
+              uint64_t xx = x * fx + dx, yy = y * fy + dy, zz = z * fz + dz;
+              if (xx >= sx) xx = sx - 1;
+              if (yy >= sy) yy = sy - 1;
+              if (zz >= sz) zz = sz - 1;
+              xs[dx] = in[xx + sx * (yy + sy * zz)];
+            }
+            ys[dy] = (fx == 2) ? (float)(xs[0] + xs[1]) : xs[0];
+          }
+          zs[dz] = (fy == 2) ? (float)(ys[0] + ys[1]) : ys[0];
+        }
+        const float sum = (fz == 2) ? (float)(zs[0] + zs[1]) : zs[0];
+        out[x + ox * (y + oy * z)] = sum * scale;
+      }
+  return ORC_OK;
+}
+
+/* ------------------------------------------------------------------ */
 /* 6-connected multi-label CCL (cc3d.connected_components,             */
 /* connectivity=6; called at igneous/tasks/image/ccl.py:173,235,339).  */
 /* Two voxels are connected iff they are face adjacent and hold the    */

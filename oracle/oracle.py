@@ -58,8 +58,10 @@ def _ptr(a):
 # ---------------------------------------------------------------- pooling
 def downsample_segmentation(img, factor=(2, 2, 1), num_mips=1, sparse=False):
   """tinybrain.downsample_segmentation as called at
-  igneous/tasks/image/image.py:52-53,91 -- recursive 2x2x1 mode pooling."""
-  assert tuple(factor)[:3] == (2, 2, 1)
+  igneous/tasks/image/image.py:52-53,91 -- recursive 2x2x1 mode pooling; other
+  factors of 1 or 2 per axis (2x2x2 ...) go through the block rule."""
+  if tuple(int(v) for v in factor)[:3] != (2, 2, 1):
+    return _block_pool(img, factor, num_mips, "mode", int(bool(sparse)))
   img = np.asarray(img)
   four_d = img.ndim == 4
   chans = [img[..., c] for c in range(img.shape[3])] if four_d else [img]
@@ -84,8 +86,11 @@ def downsample_with_averaging(img, factor=(2, 2, 1), num_mips=1, sparse=False,
                               rounding=0):
   """tinybrain.downsample_with_averaging as called at
   igneous/tasks/image/image.py:50-51,91 -- 2x2x1 mean, exact sums in groups
-  of four mips, floor rendering (rounding=0; parity unpinned)."""
-  assert tuple(factor)[:3] == (2, 2, 1) and not sparse
+  of four mips, floor rendering (rounding=0; parity unpinned); other factors of
+  1 or 2 per axis are averaged block-wise, recursively per mip."""
+  assert not sparse
+  if tuple(int(v) for v in factor)[:3] != (2, 2, 1):
+    return _block_pool(img, factor, num_mips, "avg", int(rounding))
   img = np.asarray(img)
   four_d = img.ndim == 4
   chans = [img[..., c] for c in range(img.shape[3])] if four_d else [img]
@@ -105,6 +110,32 @@ def downsample_with_averaging(img, factor=(2, 2, 1), num_mips=1, sparse=False,
     assert rc == 0
     for m in range(num_mips):
       results[m].append(outs[m])
+  if four_d:
+    return [np.asfortranarray(np.stack(r, axis=3)) for r in results]
+  return [r[0] for r in results]
+
+
+def _block_pool(img, factor, num_mips, kind, flag):
+  """orc_block_mode_* / orc_block_avg_* applied recursively, per channel."""
+  f = tuple(int(v) for v in factor)[:3]
+  img = np.asarray(img)
+  four_d = img.ndim == 4
+  chans = [img[..., c] for c in range(img.shape[3])] if four_d else [img]
+  results = [[] for _ in range(num_mips)]
+  for ch in chans:
+    cur = _f3(ch)
+    suffix = "f32" if cur.dtype == np.float32 else _SUFFIX[cur.dtype]
+    if kind == "mode" and cur.dtype == np.float32:
+      cur, suffix = cur.view(np.uint32), "u32"
+    fn = getattr(lib(), "orc_block_%s_%s" % (kind, suffix))
+    for m in range(num_mips):
+      sx, sy, sz = cur.shape
+      out = np.zeros(tuple((s + ff - 1) // ff for s, ff in zip(cur.shape, f)), dtype=cur.dtype, order="F")
+      rc = fn(_ptr(cur), ctypes.c_uint64(sx), ctypes.c_uint64(sy), ctypes.c_uint64(sz),
+              ctypes.c_uint32(f[0]), ctypes.c_uint32(f[1]), ctypes.c_uint32(f[2]), ctypes.c_int(flag), _ptr(out))
+      assert rc == 0
+      results[m].append(out.view(ch.dtype) if ch.dtype == np.float32 else out)
+      cur = out
   if four_d:
     return [np.asfortranarray(np.stack(r, axis=3)) for r in results]
   return [r[0] for r in results]

@@ -237,3 +237,41 @@ def test_canonicalise_mesh_is_order_independent(oracle):
   v1, c1 = oracle.canonicalise_mesh(v, f)
   v2, c2 = oracle.canonicalise_mesh(v[perm], f2)
   assert np.array_equal(v1, v2) and np.array_equal(c1, c2)
+
+
+def test_block_pooling_rules(oracle):
+  """2x2x2 (and other 1/2 factors) mode / average: the restated rules on hand-made blocks."""
+  blk = lambda vals, dt=np.uint32: np.array(vals, dtype=dt).reshape(2, 2, 2, order="F")
+  mode = lambda a, **kw: int(oracle.downsample_segmentation(a, (2, 2, 2), **kw)[0][0, 0, 0])
+  assert mode(blk([1, 2, 3, 4, 5, 6, 7, 8])) == 1          # all distinct -> earliest
+  assert mode(blk([1, 2, 2, 1, 3, 3, 3, 4])) == 3          # plain majority
+  assert mode(blk([5, 6, 6, 5, 7, 7, 8, 9])) == 5          # 2-2-2 tie -> earliest sample
+  assert mode(blk([0, 0, 0, 0, 0, 9, 9, 4])) == 0          # dense counts zeros
+  assert mode(blk([0, 0, 0, 0, 0, 4, 9, 9]), sparse=True) == 9
+  assert mode(blk([0] * 8), sparse=True) == 0
+  avg = lambda a, r=0: int(oracle.downsample_with_averaging(a, (2, 2, 2), rounding=r)[0][0, 0, 0])
+  a = blk([1, 2, 3, 4, 5, 6, 7, 8], np.uint8)               # sum 36 -> 4.5
+  assert (avg(a, 0), avg(a, 1), avg(a, 2)) == (4, 5, 4)
+  assert avg(blk([255] * 8, np.uint8)) == 255
+  # odd extents: the lone slice counts twice (divisor stays 8)
+  odd = np.asfortranarray(np.arange(27, dtype=np.uint16).reshape(3, 3, 3, order="F"))
+  out = oracle.downsample_with_averaging(odd, (2, 2, 2))[0]
+  assert out.shape == (2, 2, 2) and out[1, 1, 1] == 26 and out[0, 0, 0] == (0 + 1 + 3 + 4 + 9 + 10 + 12 + 13) // 8
+  # (2,2,1) through the block rule equals the 2x2x1 kernel, dense and sparse
+  rng = np.random.default_rng(5)
+  vol = np.asfortranarray(rng.integers(0, 4, size=(21, 10, 3)).astype(np.uint16))
+  for sp in (0, 1):
+    a = oracle.downsample_segmentation(vol, (2, 2, 1), num_mips=2, sparse=bool(sp))
+    b = oracle._block_pool(vol, (2, 2, 1), 2, "mode", sp)
+    assert all(np.array_equal(p, q) for p, q in zip(a, b))
+  # invariants: constant volume stays constant; checker of 4^3 blocks subsamples exactly
+  const = np.full((9, 8, 7), 77, dtype=np.uint8, order="F")
+  for m in oracle.downsample_with_averaging(const, (2, 2, 2), num_mips=3) + \
+      oracle.downsample_segmentation(const, (2, 2, 2), num_mips=3):
+    assert (m == 77).all()
+  x, y, z = np.meshgrid(np.arange(16), np.arange(16), np.arange(16), indexing="ij")
+  checker = np.asfortranarray((1 + x // 4 + 4 * (y // 4) + 16 * (z // 4)).astype(np.uint32))
+  cur = checker
+  for m in oracle.downsample_segmentation(checker, (2, 2, 2), num_mips=2):
+    cur = cur[::2, ::2, ::2]
+    assert np.array_equal(m, cur)
