@@ -33,6 +33,22 @@ def test_downsample_task_config_c1(ctx, oracle, tmp_path):
   assert cv.provenance.processing[-1]["method"]["task"] == "DownsampleTask"
 
 
+def test_downsample_task_volumetric_factor(ctx, oracle, tmp_path):
+  """--volumetric: factor (2,2,2) mode pooling through DownsampleTask."""
+  import igneous_b200.task_creation as tc
+  from igneous_b200._compat import CloudVolume, LocalTaskQueue
+  seg = oracle.synth_seg((256, 256, 256), pitch=16, num_ids=64)[..., np.newaxis]
+  path = _layer(tmp_path, seg, "segmentation")
+  LocalTaskQueue(parallel=1).insert_all(tc.create_downsampling_tasks(path, mip=0, num_mips=2, factor=(2, 2, 2)))
+  cv = CloudVolume(path)
+  assert [list(map(int, cv.meta.volume_size(m))) for m in cv.available_mips] == \
+      [[256, 256, 256], [128, 128, 128], [64, 64, 64]]
+  want = oracle.downsample_segmentation(seg, (2, 2, 2, 1), num_mips=2)
+  for m in (1, 2):
+    cv.mip = m
+    assert np.array_equal(cv[cv.meta.bounds(m)], want[m - 1])
+
+
 @pytest.mark.parametrize("compress", [None, "gzip", "br"])
 def test_downsample_no_offset_average_pyramid(ctx, oracle, tmp_path, compress):
   """test/test_tasks.py:29-71: 4 average mips of a 1024x1024x128 uint8 image."""
