@@ -329,16 +329,26 @@ __global__ void __launch_bounds__(256)
   out[t] = res;
 }
 
+// acc / n with the rounding enum (n = number of non-zero samples of a sparse average)
+template <typename A>
+__device__ __forceinline__ A render_div(A acc, A n, int rounding) {
+  A q = acc / n;
+  const A rem2 = 2 * (acc - q * n);
+  if (rounding == IGN_ROUND_HALF_UP) q += (rem2 >= n);
+  else if (rounding == IGN_ROUND_HALF_EVEN) q += (rem2 > n || (rem2 == n && (q & 1)));
+  return q;
+}
+
 template <typename T, typename A>
 __global__ void __launch_bounds__(256)
     k_block_avg(const T* __restrict__ in, uint64_t sx, uint64_t sy, uint64_t sz, uint32_t fx,
-                uint32_t fy, uint32_t fz, int rounding, T* __restrict__ out) {
+                uint32_t fy, uint32_t fz, int rounding, int sparse, T* __restrict__ out) {
   const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy, oz = (sz + fz - 1) / fz;
   const uint64_t total = ox * oy * oz;
   const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (t >= total) return;
   const uint64_t x = t % ox, r = t / ox, y = r % oy, z = r / oy;
-  A acc = 0;
+  A acc = 0, nonzero = 0;
   for (uint32_t dz = 0; dz < fz; dz++)
     for (uint32_t dy = 0; dy < fy; dy++)
       for (uint32_t dx = 0; dx < fx; dx++) {
@@ -346,21 +356,28 @@ __global__ void __launch_bounds__(256)
         xx = xx < sx ? xx : sx - 1;
         yy = yy < sy ? yy : sy - 1;
         zz = zz < sz ? zz : sz - 1;
-        acc += (A)in[(zz * sy + yy) * sx + xx];
+        const A v = (A)in[(zz * sy + yy) * sx + xx];
+        acc += v;
+        nonzero += (v != 0);
       }
+  if (sparse) {  // mean of the non-zero samples
+    out[t] = (T)(nonzero ? render_div<A>(acc, nonzero, rounding) : A(0));
+    return;
+  }
   const int shift = (fx == 2) + (fy == 2) + (fz == 2);
   out[t] = (T)(shift ? render<A>(acc, shift, rounding) : acc);
 }
 
 __global__ void __launch_bounds__(256)
     k_block_avg_f32(const float* __restrict__ in, uint64_t sx, uint64_t sy, uint64_t sz, uint32_t fx,
-                    uint32_t fy, uint32_t fz, float* __restrict__ out) {
+                    uint32_t fy, uint32_t fz, int sparse, float* __restrict__ out) {
   const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy, oz = (sz + fz - 1) / fz;
   const uint64_t total = ox * oy * oz;
   const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (t >= total) return;
   const uint64_t x = t % ox, r = t / ox, y = r % oy, z = r / oy;
   float zs[2] = {0.0f, 0.0f};
+  int nonzero = 0;
   for (uint32_t dz = 0; dz < fz; dz++) {
     float ys[2] = {0.0f, 0.0f};
     for (uint32_t dy = 0; dy < fy; dy++) {
@@ -371,13 +388,15 @@ __global__ void __launch_bounds__(256)
         yy = yy < sy ? yy : sy - 1;
         zz = zz < sz ? zz : sz - 1;
         xs[dx] = in[(zz * sy + yy) * sx + xx];
+        nonzero += (xs[dx] != 0.0f);
       }
       ys[dy] = (fx == 2) ? __fadd_rn(xs[0], xs[1]) : xs[0];
     }
     zs[dz] = (fy == 2) ? __fadd_rn(ys[0], ys[1]) : ys[0];
   }
   const float sum = (fz == 2) ? __fadd_rn(zs[0], zs[1]) : zs[0];
-  out[t] = __fmul_rn(sum, 1.0f / (float)(fx * fy * fz));
+  if (sparse) out[t] = nonzero ? __fdiv_rn(sum, (float)nonzero) : 0.0f;
+  else out[t] = __fmul_rn(sum, 1.0f / (float)(fx * fy * fz));
 }
 
 template <typename A>
@@ -550,7 +569,8 @@ template <typename T> struct BlockAcc { using type = uint32_t; };
 template <> struct BlockAcc<uint32_t> { using type = uint64_t; };
 
 // ops: 0 min, 1 max, 2 striding, 3 mode, 4 sparse mode, 5/6/7 average with
-// IGN_ROUND_FLOOR / HALF_UP / HALF_EVEN.  Every mip is computed from the previous one.
+// IGN_ROUND_FLOOR / HALF_UP / HALF_EVEN, 8/9/10 sparse average (mean of the non-zero
+// samples) with the same roundings.  Every mip is computed from the previous one.
 template <typename T>
 static int select_pyramid(ign_ctx* ctx, const void* in, uint64_t sx, uint64_t sy, uint64_t sz, uint32_t fx,
                           uint32_t fy, uint32_t fz, int num_mips, int op, void* const* outs) {
@@ -571,13 +591,14 @@ static int select_pyramid(ign_ctx* ctx, const void* in, uint64_t sx, uint64_t sy
         }
       } else {
         if constexpr (std::is_same<T, float>::value) {
-          IGN_LAUNCH(ctx, k_block_avg_f32, grid, 256, 0, cur, sx, sy, sz, fx, fy, fz, (float*)outs[m]);
+          IGN_LAUNCH(ctx, k_block_avg_f32, grid, 256, 0, cur, sx, sy, sz, fx, fy, fz, op >= 8, (float*)outs[m]);
         } else if constexpr (std::is_same<T, uint64_t>::value) {
           set_error("averaging: uint64 images are not supported");
           return IGN_ERR_UNSUPPORTED;
         } else {
           using A = typename BlockAcc<T>::type;
-          IGN_LAUNCH(ctx, (k_block_avg<T, A>), grid, 256, 0, cur, sx, sy, sz, fx, fy, fz, op - 5, (T*)outs[m]);
+          IGN_LAUNCH(ctx, (k_block_avg<T, A>), grid, 256, 0, cur, sx, sy, sz, fx, fy, fz, (op - 5) % 3, op >= 8,
+                     (T*)outs[m]);
         }
       }
     }
@@ -633,8 +654,9 @@ int ign_pool_select_dev(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, ui
   IGN_TRY(check_pool_args(in, dtype, sx, sy, sz, num_mips, outs));
   IGN_REQUIRE(fx >= 1 && fx <= 2 && fy >= 1 && fy <= 2 && fz >= 1 && fz <= 2, IGN_ERR_UNSUPPORTED,
               "pooling factors must be 1 or 2 per axis (got %u,%u,%u)", fx, fy, fz);
-  IGN_REQUIRE(op >= 0 && op <= 7, IGN_ERR_INVALID,
-              "op must be 0 min, 1 max, 2 striding, 3 mode, 4 sparse mode or 5-7 average (floor / half-up / half-even)");
+  IGN_REQUIRE(op >= 0 && op <= 10, IGN_ERR_INVALID,
+              "op must be 0 min, 1 max, 2 striding, 3 mode, 4 sparse mode, 5-7 average or 8-10 sparse average "
+              "(floor / half-up / half-even)");
   switch (dtype) {
     case IGN_U8: return select_pyramid<uint8_t>(ctx, in, sx, sy, sz, fx, fy, fz, num_mips, op, outs);
     case IGN_U16: return select_pyramid<uint16_t>(ctx, in, sx, sy, sz, fx, fy, fz, num_mips, op, outs);

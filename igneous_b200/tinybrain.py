@@ -72,17 +72,17 @@ def downsample_with_averaging(img, factor, num_mips=1, sparse=False, ctx=None,
                               rounding=None):
   """2x2x1 average pooling pyramid (exact sums in groups of four mips); other factors
   of 1 or 2 per axis (2x2x2 ...) use the generic block-average kernel, recursively."""
-  if sparse:
-    raise NotImplementedError("igneous_b200 averaging: sparse=True is not implemented")
   rounding = DEFAULT_ROUNDING if rounding is None else rounding
-  if not _is_221(factor):
+  if sparse or not _is_221(factor):
     if np.asarray(img).dtype == np.uint64:
       raise NotImplementedError("igneous_b200 averaging: uint64 images are not supported")
-    return _select(img, factor, num_mips, _OP_AVG + int(rounding), ctx)
+    # sparse=True: mean of the non-zero samples (generic kernel for every factor)
+    return _select(img, factor, num_mips, (_OP_AVG_SPARSE if sparse else _OP_AVG) + int(rounding), ctx)
   return _pool(img, factor, num_mips, False, rounding, ctx)
 
 
-_OP_MIN, _OP_MAX, _OP_STRIDE, _OP_MODE, _OP_MODE_SPARSE, _OP_AVG = 0, 1, 2, 3, 4, 5  # ign_pool_select ops
+# ign_pool_select ops
+_OP_MIN, _OP_MAX, _OP_STRIDE, _OP_MODE, _OP_MODE_SPARSE, _OP_AVG, _OP_AVG_SPARSE = 0, 1, 2, 3, 4, 5, 8
 
 
 def _select(img, factor, num_mips, op, ctx):

@@ -125,7 +125,9 @@ IGN_API int ign_pool_avg_2x2x1_dev(ign_ctx* ctx, const void* in, int dtype, uint
  *     3 mode, 4 sparse mode (zeros ignored): a planar factor with four samples left uses the
  *       COUNTLESS 2-D pick, otherwise the highest count wins with ties to the earliest sample
  *       (x fastest); 5 / 6 / 7 average rendered with IGN_ROUND_FLOOR / HALF_UP / HALF_EVEN
- *       (the lone row / column / slice of an odd extent counts twice; u8, u16, u32, f32).
+ *       (the lone row / column / slice of an odd extent counts twice; u8, u16, u32, f32);
+ *     8 / 9 / 10 sparse average = mean of the non-zero samples (0 if there are none), same
+ *       roundings (tinybrain.downsample_with_averaging(sparse=True)).
  * Every mip is computed from the previous one.  Generic one-thread-per-output kernels.
  * [SURVEY 8(f) row 3, not on the headline path] */
 IGN_API int ign_pool_select(ign_ctx* ctx, const void* in, int dtype, uint64_t sx, uint64_t sy,

@@ -217,6 +217,8 @@ int orc_avg_pool_2x2x1_f32(const float* in, uint64_t sx, uint64_t sy,
 /*  average: sum over the block with the lone row/column/slice of an    */
 /*    odd extent counted twice (divisor stays fx*fy*fz), rendered with  */
 /*    the rounding enum of the 2x2x1 kernel.  Recursive per mip.        */
+/*    sparse: mean of the non-zero samples (replicated edge samples     */
+/*    included), 0 when there are none.                                 */
 /* PARITY UNPINNED: tie-break and edge rules are recalled, not pinned.  */
 /* ------------------------------------------------------------------ */
 #define DEF_BLOCK_MODE(T, NAME)                                              \
@@ -264,18 +266,28 @@ DEF_BLOCK_MODE(uint16_t, orc_block_mode_u16)
 DEF_BLOCK_MODE(uint32_t, orc_block_mode_u32)
 DEF_BLOCK_MODE(uint64_t, orc_block_mode_u64)
 
+static uint64_t orc_render_div(uint64_t acc, uint64_t n, int rounding) {
+  if (n == 0) return 0;
+  uint64_t q = acc / n;
+  const uint64_t rem2 = 2 * (acc - q * n);
+  if (rounding == 1) q += (rem2 >= n);
+  else if (rounding == 2) q += (rem2 > n || (rem2 == n && (q & 1)));
+  return q;
+}
+
 #define DEF_BLOCK_AVG(T, NAME)                                               \
   int NAME(const T* in, uint64_t sx, uint64_t sy, uint64_t sz, uint32_t fx,  \
-           uint32_t fy, uint32_t fz, int rounding, T* out) {                 \
+           uint32_t fy, uint32_t fz, int flag, T* out) {                     \
     if (fx < 1 || fx > 2 || fy < 1 || fy > 2 || fz < 1 || fz > 2)           \
       return ORC_EINVAL;                                                     \
+    const int rounding = flag % 3, sparse = flag >= 3;                       \
     const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy,         \
                    oz = (sz + fz - 1) / fz;                                  \
     const unsigned shift = (fx == 2) + (fy == 2) + (fz == 2);                \
     for (uint64_t z = 0; z < oz; z++)                                        \
       for (uint64_t y = 0; y < oy; y++)                                      \
         for (uint64_t x = 0; x < ox; x++) {                                  \
-          uint64_t acc = 0;                                                  \
+          uint64_t acc = 0, nonzero = 0;                                     \
           for (uint32_t dz = 0; dz < fz; dz++)                               \
             for (uint32_t dy = 0; dy < fy; dy++)                             \
               for (uint32_t dx = 0; dx < fx; dx++) {                         \
@@ -284,8 +296,11 @@ DEF_BLOCK_MODE(uint64_t, orc_block_mode_u64)
                 if (yy >= sy) yy = sy - 1;                                   \
                 if (zz >= sz) zz = sz - 1;                                   \
                 acc += in[xx + sx * (yy + sy * zz)];                         \
+                nonzero += (in[xx + sx * (yy + sy * zz)] != 0);              \
               }                                                              \
-          out[x + ox * (y + oy * z)] = (T)orc_render(acc, shift, rounding);  \
+          out[x + ox * (y + oy * z)] =                                       \
+              sparse ? (T)orc_render_div(acc, nonzero, rounding)             \
+                     : (T)orc_render(acc, shift, rounding);                  \
         }                                                                    \
     return ORC_OK;                                                           \
   }
@@ -297,9 +312,9 @@ DEF_BLOCK_AVG(uint32_t, orc_block_avg_u32)
 /* float32: pairwise sums in x, then y, then z (each a float add), times   */
 /* the exact reciprocal of the block size                                  */
 int orc_block_avg_f32(const float* in, uint64_t sx, uint64_t sy, uint64_t sz,
-                      uint32_t fx, uint32_t fy, uint32_t fz, int rounding,
+                      uint32_t fx, uint32_t fy, uint32_t fz, int flag,
                       float* out) {
-  (void)rounding;
+  const int sparse = flag >= 3;
   if (fx < 1 || fx > 2 || fy < 1 || fy > 2 || fz < 1 || fz > 2) return ORC_EINVAL;
   const uint64_t ox = (sx + fx - 1) / fx, oy = (sy + fy - 1) / fy,
                  oz = (sz + fz - 1) / fz;
@@ -308,6 +323,7 @@ int orc_block_avg_f32(const float* in, uint64_t sx, uint64_t sy, uint64_t sz,
     for (uint64_t y = 0; y < oy; y++)
       for (uint64_t x = 0; x < ox; x++) {
         float zs[2] = {0.0f, 0.0f};
+        int nonzero = 0;
         for (uint32_t dz = 0; dz < fz; dz++) {
           float ys[2] = {0.0f, 0.0f};
           for (uint32_t dy = 0; dy < fy; dy++) {
@@ -318,13 +334,15 @@ int orc_block_avg_f32(const float* in, uint64_t sx, uint64_t sy, uint64_t sz,
               if (yy >= sy) yy = sy - 1;
               if (zz >= sz) zz = sz - 1;
               xs[dx] = in[xx + sx * (yy + sy * zz)];
+              nonzero += (xs[dx] != 0.0f);
             }
             ys[dy] = (fx == 2) ? (float)(xs[0] + xs[1]) : xs[0];
           }
           zs[dz] = (fy == 2) ? (float)(ys[0] + ys[1]) : ys[0];
         }
         const float sum = (fz == 2) ? (float)(zs[0] + zs[1]) : zs[0];
-        out[x + ox * (y + oy * z)] = sum * scale;
+        if (sparse) out[x + ox * (y + oy * z)] = nonzero ? sum / (float)nonzero : 0.0f;
+        else out[x + ox * (y + oy * z)] = sum * scale;
       }
   return ORC_OK;
 }

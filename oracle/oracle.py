@@ -88,7 +88,8 @@ def downsample_with_averaging(img, factor=(2, 2, 1), num_mips=1, sparse=False,
   igneous/tasks/image/image.py:50-51,91 -- 2x2x1 mean, exact sums in groups
   of four mips, floor rendering (rounding=0; parity unpinned); other factors of
   1 or 2 per axis are averaged block-wise, recursively per mip."""
-  assert not sparse
+  if sparse:  # mean of the non-zero samples, any factor
+    return _block_pool(img, factor, num_mips, "avg", int(rounding) + 3)
   if tuple(int(v) for v in factor)[:3] != (2, 2, 1):
     return _block_pool(img, factor, num_mips, "avg", int(rounding))
   img = np.asarray(img)

@@ -275,3 +275,11 @@ def test_block_pooling_rules(oracle):
   for m in oracle.downsample_segmentation(checker, (2, 2, 2), num_mips=2):
     cur = cur[::2, ::2, ::2]
     assert np.array_equal(m, cur)
+  # sparse average: mean of the non-zero samples
+  sp = lambda a, r=0: int(oracle.downsample_with_averaging(a, (2, 2, 2), sparse=True, rounding=r)[0][0, 0, 0])
+  b = blk([0, 0, 0, 0, 0, 10, 11, 14], np.uint8)             # 35 / 3 = 11.67
+  assert (sp(b, 0), sp(b, 1), sp(b, 2)) == (11, 12, 12)
+  assert sp(blk([0] * 8, np.uint8)) == 0
+  assert sp(blk([0, 0, 0, 0, 0, 0, 7, 8], np.uint8), 2) == 8  # 7.5 -> even
+  q = np.array([[0, 5], [6, 0]], dtype=np.uint16).reshape(2, 2, 1, order="F")
+  assert int(oracle.downsample_with_averaging(q, (2, 2, 1), sparse=True)[0][0, 0, 0]) == 5

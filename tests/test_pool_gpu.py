@@ -215,3 +215,23 @@ def test_block_pooling_4d_and_221_consistency(ctx, oracle):
   generic = tinybrain._select(vol, (2, 2, 1), 2, tinybrain._OP_MODE, None)
   for g, w in zip(generic, tuned):
     assert np.array_equal(g, w)
+
+
+@pytest.mark.parametrize("factor", [(2, 2, 1), (2, 2, 2)])
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.float32])
+@pytest.mark.parametrize("rounding", [0, 1, 2])
+def test_sparse_average_pooling(ctx, oracle, factor, dtype, rounding):
+  """downsample_with_averaging(sparse=True): mean of the non-zero samples."""
+  from igneous_b200 import tinybrain
+  rng = np.random.default_rng(10)
+  for shape in ((37, 22, 9), (16, 16, 4)):
+    if dtype == np.float32:
+      img = rng.random(shape).astype(np.float32)
+    else:
+      img = rng.integers(1, np.iinfo(dtype).max, size=shape, endpoint=True).astype(dtype)
+    img[rng.random(shape) < 0.6] = 0
+    img = np.asfortranarray(img)
+    got = tinybrain.downsample_with_averaging(img, factor, num_mips=3, sparse=True, rounding=rounding)
+    want = oracle.downsample_with_averaging(img, factor, num_mips=3, sparse=True, rounding=rounding)
+    for g, w in zip(got, want):
+      assert g.shape == w.shape and g.dtype == w.dtype and np.array_equal(g, w)
