@@ -283,3 +283,93 @@ def test_block_pooling_rules(oracle):
   assert sp(blk([0, 0, 0, 0, 0, 0, 7, 8], np.uint8), 2) == 8  # 7.5 -> even
   q = np.array([[0, 5], [6, 0]], dtype=np.uint16).reshape(2, 2, 1, order="F")
   assert int(oracle.downsample_with_averaging(q, (2, 2, 1), sparse=True)[0][0, 0, 0]) == 5
+
+
+# ------------------------------------------------------------------ simplifier
+def _edge_use(faces):
+  e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]]).astype(np.int64)
+  e.sort(axis=1)
+  _, counts = np.unique(e, axis=0, return_counts=True)
+  return counts
+
+
+def _signed_volume(v, f):
+  a, b, c = (v[f[:, k]].astype(np.float64) for k in range(3))
+  return float(np.einsum("ij,ij->i", a, np.cross(b, c)).sum() / 6.0)
+
+
+def test_simplify_box_stays_closed_genus0(oracle):
+  """The reference's own mesh test volume (test/test_tasks.py:413-415): simplification keeps
+  the surface closed, manifold, genus 0 and outward oriented, moves no vertex further than the
+  error bound allows and reaches the face target or a fixed point."""
+  labels = np.zeros((64, 64, 64), dtype=np.uint32, order="F")
+  labels[1:-1, 1:-1, 1:-1] = 7
+  tl, tv = oracle.marching_cubes(labels)
+  W = oracle.WeldedMeshes(tl, tv)
+  v0, f0 = W.get(7)
+  out, rounds = oracle.simplify_welded(W, resolution=(1, 1, 1), reduction_factor=100, max_error=40.0)
+  v, f = out[7]
+  assert len(f0) == 46124 and len(v0) == 23064
+  assert 0 < rounds <= 400
+  assert len(f) <= len(f0) // 20                      # heavily decimated (flat faces collapse freely)
+  assert (_edge_use(f) == 2).all()                    # closed 2-manifold edges
+  assert len(v) - len(f) * 3 // 2 + len(f) == 2       # Euler characteristic of a sphere
+  assert f.max() == len(v) - 1 and len(np.unique(f)) == len(v)
+  vol0, vol = _signed_volume(v0, f0), _signed_volume(v, f)
+  assert vol0 > 0 and vol > 0 and abs(vol - vol0) / vol0 < 0.02
+  lo, hi = v.min(axis=0), v.max(axis=0)
+  assert np.all(lo >= v0.min(axis=0) - 1e-3) and np.all(hi <= v0.max(axis=0) + 1e-3)
+
+
+def test_simplify_is_deterministic_and_label_order_free(oracle):
+  """Same input -> same output; a label's result does not depend on which other labels
+  share the task (keys are label-local)."""
+  rng = np.random.default_rng(3)
+  seg = oracle.synth_seg((48, 40, 36), pitch=16, num_ids=6).astype(np.uint32)
+  tl, tv = oracle.marching_cubes(seg)
+  W = oracle.WeldedMeshes(tl, tv)
+  a, ra = oracle.simplify_welded(W, resolution=(16, 16, 40), reduction_factor=10, max_error=40.0)
+  b, rb = oracle.simplify_welded(W, resolution=(16, 16, 40), reduction_factor=10, max_error=40.0)
+  assert ra == rb and a.keys() == b.keys()
+  for k in a:
+    assert np.array_equal(a[k][0], b[k][0]) and np.array_equal(a[k][1], b[k][1])
+  # one label alone: relabel everything else to background
+  lab = int(W.labels[len(W.labels) // 2])
+  only = np.where(seg == lab, seg, 0).astype(np.uint32)
+  tl1, tv1 = oracle.marching_cubes(only)
+  W1 = oracle.WeldedMeshes(tl1, tv1)
+  c, _ = oracle.simplify_welded(W1, resolution=(16, 16, 40), reduction_factor=10, max_error=40.0)
+  assert np.array_equal(c[lab][0], a[lab][0]) and np.array_equal(c[lab][1], a[lab][1])
+  del rng
+
+
+def test_simplify_locks_open_boundaries_and_respects_zero_error(oracle):
+  """A label cut by the task border is an open surface: its boundary vertices (edges used once)
+  must survive untouched so that neighbouring tasks stitch; max_error=0 only removes
+  zero-cost (coplanar) geometry, so the enclosed volume is exactly preserved."""
+  labels = np.zeros((24, 24, 24), dtype=np.uint32, order="F")
+  labels[4:20, 4:20, :] = 3                       # a bar that leaves the block through both z faces
+  tl, tv = oracle.marching_cubes(labels)
+  W = oracle.WeldedMeshes(tl, tv)
+  v0, f0 = W.get(3)
+  e = np.concatenate([f0[:, [0, 1]], f0[:, [1, 2]], f0[:, [2, 0]]]).astype(np.int64)
+  e.sort(axis=1)
+  ue, cnt = np.unique(e, axis=0, return_counts=True)
+  boundary = np.unique(ue[cnt == 1])
+  assert len(boundary) > 0
+  out, _ = oracle.simplify_welded(W, reduction_factor=100, max_error=40.0)
+  v, f = out[3]
+  assert len(f) < len(f0) // 4
+  have = {tuple(p) for p in np.round(v * 2).astype(np.int64)}
+  assert all(tuple(p) in have for p in np.round(v0[boundary] * 2).astype(np.int64))
+  assert (_edge_use(f) <= 2).all() and (_edge_use(f) == 1).sum() == (cnt == 1).sum()
+  # zero error budget on a closed box: only coplanar collapses, volume exactly kept
+  box = np.zeros((20, 20, 20), dtype=np.uint32, order="F")
+  box[2:-2, 2:-2, 2:-2] = 9
+  tlb, tvb = oracle.marching_cubes(box)
+  Wb = oracle.WeldedMeshes(tlb, tvb)
+  vb0, fb0 = Wb.get(9)
+  outb, _ = oracle.simplify_welded(Wb, reduction_factor=100, max_error=0.0)
+  vb, fb = outb[9]
+  assert len(fb) < len(fb0) and (_edge_use(fb) == 2).all()
+  assert abs(_signed_volume(vb, fb) - _signed_volume(vb0, fb0)) < 1e-6 * abs(_signed_volume(vb0, fb0))
