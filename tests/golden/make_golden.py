@@ -36,6 +36,18 @@ def main():
     dust40=dust, renumber=ren, mesh_label=np.uint64(lab), mesh_vertices=v, mesh_faces=f,
     simp_vertices=simp[lab][0], simp_faces=simp[lab][1], n_triangles=np.uint64(len(tl)))
   print("wrote", os.path.join(HERE, "hotpath_small.npz"))
+  # block pooling (factors 1 or 2 per axis other than (2,2,1)), SURVEY 8(f) row 3
+  blocks = {}
+  for name, arrs in (("mode222", O.downsample_segmentation(seg, (2, 2, 2), num_mips=2)),
+                     ("smode222", O.downsample_segmentation(seg, (2, 2, 2), num_mips=2, sparse=True)),
+                     ("mode122", O.downsample_segmentation(seg, (1, 2, 2), num_mips=2)),
+                     ("avg222", O.downsample_with_averaging(img, (2, 2, 2), num_mips=2)),
+                     ("savg221", O.downsample_with_averaging(np.where(img > 128, img, 0).astype(np.uint8), (2, 2, 1),
+                                                            num_mips=2, sparse=True))):
+    for k, a in enumerate(arrs):
+      blocks["%s_%d" % (name, k + 1)] = a
+  np.savez_compressed(os.path.join(HERE, "pooling_blocks.npz"), **blocks)
+  print("wrote", os.path.join(HERE, "pooling_blocks.npz"))
 
 
 if __name__ == "__main__":

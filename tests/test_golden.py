@@ -28,6 +28,20 @@ def test_oracle_reproduces_golden(oracle):
   assert np.array_equal(sv, G["simp_vertices"]) and np.array_equal(sf, G["simp_faces"])
 
 
+def test_oracle_reproduces_block_pooling_golden(oracle):
+  B = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pooling_blocks.npz"))
+  seg, img = G["seg"], G["img"]
+  runs = {"mode222": oracle.downsample_segmentation(seg, (2, 2, 2), num_mips=2),
+          "smode222": oracle.downsample_segmentation(seg, (2, 2, 2), num_mips=2, sparse=True),
+          "mode122": oracle.downsample_segmentation(seg, (1, 2, 2), num_mips=2),
+          "avg222": oracle.downsample_with_averaging(img, (2, 2, 2), num_mips=2),
+          "savg221": oracle.downsample_with_averaging(np.where(img > 128, img, 0).astype(np.uint8), (2, 2, 1),
+                                                      num_mips=2, sparse=True)}
+  for name, arrs in runs.items():
+    for k, a in enumerate(arrs):
+      assert np.array_equal(a, B["%s_%d" % (name, k + 1)]), name
+
+
 @pytest.mark.gpu
 def test_cuda_reproduces_golden(ctx):
   from igneous_b200 import tinybrain, cc3d, fastremap, zmesh
