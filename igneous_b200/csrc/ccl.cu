@@ -485,6 +485,288 @@ __global__ void __launch_bounds__(CCL_THREADS)
   else local_tile_fast<T, false>(in, sx, sy, sz, t, L, tasks, parent, cand, cand_cap, counters);
 }
 
+// --------------------------------------- L (v2, experimental): 4 voxels per lane
+// Same results as k_ccl_local_fast.  k_ccl_local_fast is issue bound (137 warp
+// instructions per 32-voxel sub-word, profiles/r01_ccl_local_fast_full_512_raw.csv);
+// this variant cuts the instruction count per voxel:
+//   * a lane owns FOUR consecutive voxels (one 128-bit load for u32): compares stay
+//     per voxel, but shuffles, ballots, address arithmetic and shared-memory traffic
+//     are paid once per 128 voxels instead of once per 32;
+//   * ONE pass over the labels: the y neighbour row is the row the warp read just
+//     before (registers) for 3 of its 4 rows, and the y / z union tasks are queued
+//     while the run starts are written (a task only needs indices, not the parents);
+//     they are executed after the barrier as before.
+// Requires full tiles and sx % 4 == 0 (vector loads); everything else takes the
+// existing paths.  NOT ENABLED BY DEFAULT (IGN_CCL_V2=1): written at the end of
+// round 1 without GPU time left to validate it; tests/test_ccl_gpu.py covers it
+// through the environment switch.
+template <typename T>
+struct Vec4Load;
+template <>
+struct Vec4Load<uint8_t> {
+  static __device__ __forceinline__ void ld(const uint8_t* p, uint8_t (&a)[4]) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+    a[0] = (uint8_t)(w & 0xFFu); a[1] = (uint8_t)((w >> 8) & 0xFFu);
+    a[2] = (uint8_t)((w >> 16) & 0xFFu); a[3] = (uint8_t)(w >> 24);
+  }
+};
+template <>
+struct Vec4Load<uint16_t> {
+  static __device__ __forceinline__ void ld(const uint16_t* p, uint16_t (&a)[4]) {
+    const uint2 w = *reinterpret_cast<const uint2*>(p);
+    a[0] = (uint16_t)(w.x & 0xFFFFu); a[1] = (uint16_t)(w.x >> 16);
+    a[2] = (uint16_t)(w.y & 0xFFFFu); a[3] = (uint16_t)(w.y >> 16);
+  }
+};
+template <>
+struct Vec4Load<uint32_t> {
+  static __device__ __forceinline__ void ld(const uint32_t* p, uint32_t (&a)[4]) {
+    const uint4 w = *reinterpret_cast<const uint4*>(p);
+    a[0] = w.x; a[1] = w.y; a[2] = w.z; a[3] = w.w;
+  }
+};
+template <>
+struct Vec4Load<uint64_t> {
+  static __device__ __forceinline__ void ld(const uint64_t* p, uint64_t (&a)[4]) {
+    const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(p);
+    const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(p + 2);
+    a[0] = w0.x; a[1] = w0.y; a[2] = w1.x; a[3] = w1.y;
+  }
+};
+
+constexpr int QUAD = 128;                 // voxels a warp covers per step (4 per lane)
+constexpr int QUADS = TILE_X / QUAD;      // 2
+static_assert(ROWS_PER_WARP == 4 && TILE_Y == 8 && QUADS == 2, "local_tile_v2 row ownership");
+
+template <typename T>
+__device__ __forceinline__ void local_tile_v2(const T* __restrict__ in, uint32_t sx, uint32_t sy,
+                                              const TilePos& t, uint32_t* L, uint32_t* tasks,
+                                              uint32_t* __restrict__ parent, uint32_t* __restrict__ cand,
+                                              uint32_t cand_cap, uint32_t* counters) {
+  const uint32_t sxy = sx * sy;
+  const uint32_t ltmask = (1u << t.lane) - 1u;  // lanes < mine
+  const uint32_t tile_g0 = (t.Z0 * sy + t.Y0) * sx + t.X0;
+  // a warp owns 4 consecutive y rows of one z slice of the tile
+  const uint32_t lz = t.warp >> 1, ly0 = (t.warp & 1u) * ROWS_PER_WARP;
+  uint32_t* q = tasks + t.warp * TASKS_PER_WARP;
+  uint32_t nq = 0;
+  bool overflow = false;
+
+  // ---- pass 1: run starts + queued y / z union tasks
+  T prev[QUADS][4];  // the row this warp handled before (y neighbour of the next one)
+#pragma unroll
+  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+    const uint32_t ly = ly0 + rr, r = lz * TILE_Y + ly;
+    const T* row = in + (tile_g0 + lz * sxy + ly * sx + 4 * t.lane);
+    uint32_t carry = 0;   // local index of the last run start seen in this row
+    T prev_last = 0;      // last voxel of the previous quad (0 never equals a foreground label)
+    uint32_t cprev = 0;   // bit 0 / 1: y / z connection of the previous quad's last voxel
+#pragma unroll
+    for (int qd = 0; qd < QUADS; qd++) {
+      T a[4], y[4], z[4];
+      Vec4Load<T>::ld(row + QUAD * qd, a);
+      if (rr > 0) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) y[j] = prev[qd][j];
+      } else if (ly > 0) {
+        Vec4Load<T>::ld(row + QUAD * qd - sx, y);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) y[j] = 0;
+      }
+      if (lz > 0) {
+        Vec4Load<T>::ld(row + QUAD * qd - sxy, z);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) z[j] = 0;
+      }
+      T left = shfl_up1(a[3]);
+      if (t.lane == 0) left = prev_last;
+      bool nzv[4], same[4], st[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        nzv[j] = a[j] != 0;
+        same[j] = nzv[j] && (a[j] == (j == 0 ? left : a[j - 1]));
+        st[j] = nzv[j] && !same[j];
+      }
+      const uint32_t base = r * TILE_X + QUAD * qd + 4 * t.lane;  // local index of a[0]
+      const bool has = st[0] || st[1] || st[2] || st[3];
+      const uint32_t last_local = base + (st[3] ? 3u : (st[2] ? 2u : (st[1] ? 1u : 0u)));
+      const uint32_t m_has = __ballot_sync(FULL, has);
+      const uint32_t below = m_has & ltmask;
+      uint32_t incoming = __shfl_sync(FULL, last_local, below ? (31 - __clz(below)) : 0);
+      if (!below) incoming = carry;
+      uint32_t c[4];
+      c[0] = st[0] ? base : incoming;
+#pragma unroll
+      for (int j = 1; j < 4; j++) c[j] = st[j] ? (base + j) : c[j - 1];
+      uint4 o;
+      o.x = nzv[0] ? c[0] : CCL_BG;
+      o.y = nzv[1] ? c[1] : CCL_BG;
+      o.z = nzv[2] ? c[2] : CCL_BG;
+      o.w = nzv[3] ? c[3] : CCL_BG;
+      *reinterpret_cast<uint4*>(L + base) = o;
+      if (m_has) carry = __shfl_sync(FULL, last_local, 31 - __clz(m_has));
+      prev_last = shfl_idx(a[3], 31);
+
+      // y / z connections: a union is needed where the connection starts or the x-run breaks
+      bool cy[4], cz[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        cy[j] = nzv[j] && (a[j] == y[j]);
+        cz[j] = nzv[j] && (a[j] == z[j]);
+      }
+      const uint32_t pk = (cy[3] ? 1u : 0u) | (cz[3] ? 2u : 0u);
+      uint32_t pl = __shfl_up_sync(FULL, pk, 1);
+      if (t.lane == 0) pl = cprev;
+      cprev = __shfl_sync(FULL, pk, 31);
+      uint32_t ty = 0, tz = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const bool py = (j == 0) ? ((pl & 1u) != 0) : cy[j - 1];
+        const bool pz = (j == 0) ? ((pl & 2u) != 0) : cz[j - 1];
+        if (cy[j] && !(same[j] && py)) ty |= 1u << j;
+        if (cz[j] && !(same[j] && pz)) tz |= 1u << j;
+      }
+#pragma unroll
+      for (int dir = 0; dir < 2; dir++) {
+        const uint32_t nib = dir ? tz : ty;
+        if (!__any_sync(FULL, nib != 0)) continue;
+        const uint32_t delta = dir ? (uint32_t)(TILE_X * TILE_Y) : (uint32_t)TILE_X;
+        const uint32_t m0 = __ballot_sync(FULL, nib & 1u), m1 = __ballot_sync(FULL, nib & 2u),
+                       m2 = __ballot_sync(FULL, nib & 4u), m3 = __ballot_sync(FULL, nib & 8u);
+        const uint32_t total = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+        if (overflow || nq + total > (uint32_t)TASKS_PER_WARP) {
+          overflow = true;  // queue full before the barrier: the classic pass below redoes everything
+          continue;
+        }
+        uint32_t off = nq + __popc(m0 & ltmask) + __popc(m1 & ltmask) + __popc(m2 & ltmask) + __popc(m3 & ltmask);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (nib & (1u << j)) q[off++] = (c[j] << 16) | (base + j - delta);
+        nq += total;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) prev[qd][j] = a[j];
+    }
+  }
+  const int any_overflow = __syncthreads_or(overflow ? 1 : 0);
+
+  // ---- pass 2: execute the queued unions 32 wide on the shared-memory union-find
+  auto flush = [&]() {
+    __syncwarp();
+    for (uint32_t i = t.lane; i < nq; i += 32) {
+      const uint32_t ab = q[i];
+      sm_union(L, ab >> 16, ab & 0xFFFFu);
+    }
+    __syncwarp();
+    nq = 0;
+  };
+  if (any_overflow) {
+    // rare (more than TASKS_PER_WARP tasks in 4 rows): drop the queues and redo the y / z
+    // unions the classic way, 32 voxels at a time with a flush whenever the queue fills
+    nq = 0;
+    const uint32_t lemask = 0xFFFFFFFFu >> (31 - t.lane);
+#pragma unroll 1
+    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+      const uint32_t ly = ly0 + rr, r = lz * TILE_Y + ly;
+      if (ly == 0 && lz == 0) continue;
+      const T* p = in + (tile_g0 + lz * sxy + ly * sx + t.lane);
+      T prev_last = 0;
+      uint32_t cy_prev = 0, cz_prev = 0;
+#pragma unroll 1
+      for (int k = 0; k < SUBW; k++) {
+        const T v = p[32 * k];
+        const T vy = (ly > 0) ? *(p + 32 * k - sx) : (T)0;
+        const T vz = (lz > 0) ? *(p + 32 * k - sxy) : (T)0;
+        const T vl = shfl_up1(v);
+        const T v0 = shfl_idx(v, 0);
+        const bool cont = (k > 0) && (v0 != 0) && (v0 == prev_last);
+        const bool nz = v != 0;
+        const bool sm = (t.lane > 0) ? (v == vl) : cont;
+        const uint32_t m_same = __ballot_sync(FULL, nz && sm);
+        const uint32_t m_cy = __ballot_sync(FULL, nz && (v == vy));
+        const uint32_t m_cz = __ballot_sync(FULL, nz && (v == vz));
+        const uint32_t t_y = m_cy & ~(m_same & ((m_cy << 1) | cy_prev));
+        const uint32_t t_z = m_cz & ~(m_same & ((m_cz << 1) | cz_prev));
+        if (t_y | t_z) {
+          const uint32_t ny = __popc(t_y), nz_ = __popc(t_z);
+          if (nq + ny + nz_ > (uint32_t)TASKS_PER_WARP) flush();
+          if (((t_y | t_z) >> t.lane) & 1u) {
+            const uint32_t li = r * TILE_X + 32 * k + t.lane;
+            const uint32_t node = ((volatile uint32_t*)L)[li];
+            if ((t_y >> t.lane) & 1u) q[nq + __popc(t_y & (lemask >> 1))] = (node << 16) | (li - TILE_X);
+            if ((t_z >> t.lane) & 1u) q[nq + ny + __popc(t_z & (lemask >> 1))] = (node << 16) | (li - TILE_X * TILE_Y);
+          }
+          nq += ny + nz_;
+        }
+        prev_last = shfl_idx(v, 31);
+        cy_prev = m_cy >> 31;
+        cz_prev = m_cz >> 31;
+      }
+    }
+  }
+  flush();
+  __syncthreads();
+
+  // ---- pass 3: flatten, translate to global indices, log local roots (4 voxels per lane)
+#pragma unroll 1
+  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
+    const uint32_t ly = ly0 + rr, r = lz * TILE_Y + ly;
+    uint32_t* out = parent + (tile_g0 + lz * sxy + ly * sx + 4 * t.lane);
+#pragma unroll
+    for (int qd = 0; qd < QUADS; qd++) {
+      const uint32_t base = r * TILE_X + QUAD * qd + 4 * t.lane;
+      const uint4 P = *reinterpret_cast<const uint4*>(L + base);
+      const uint32_t p0[4] = {P.x, P.y, P.z, P.w};
+      uint32_t cur[4], nxt[4];
+      bool bgv[4], more = false;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        bgv[j] = (p0[j] == CCL_BG);
+        cur[j] = bgv[j] ? (base + j) : p0[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) nxt[j] = L[cur[j]];
+#pragma unroll
+      for (int j = 0; j < 4; j++) more |= (!bgv[j] && nxt[j] != cur[j]);
+      if (__any_sync(FULL, more)) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          while (!bgv[j] && nxt[j] != cur[j]) {
+            cur[j] = nxt[j];
+            nxt[j] = L[cur[j]];
+          }
+      }
+      uint32_t g[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        g[j] = bgv[j] ? CCL_BG : (tile_g0 + (cur[j] >> 11) * sxy + ((cur[j] >> 8) & 7u) * sx + (cur[j] & 255u));
+      *reinterpret_cast<uint4*>(out + QUAD * qd) = make_uint4(g[0], g[1], g[2], g[3]);
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (!bgv[j] && p0[j] == base + j) {  // tile-local root: log it as a root candidate
+          const uint32_t pos = atomicAdd(&counters[0], 1u);
+          if (pos < cand_cap) cand[pos] = g[j];
+          else counters[1] = 1;
+        }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CCL_THREADS)
+    k_ccl_local_v2(const T* __restrict__ in, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t ntx,
+                   uint32_t nty, uint32_t* __restrict__ parent, uint32_t* __restrict__ cand,
+                   uint32_t cand_cap, uint32_t* counters) {
+  extern __shared__ __align__(16) uint32_t Lv2[];
+  uint32_t* tasks = Lv2 + TILE_VOX;
+  const TilePos t = tile_pos(ntx, nty);
+  const bool full = (t.X0 + TILE_X <= sx) && (t.Y0 + TILE_Y <= sy) && (t.Z0 + TILE_Z <= sz);
+  if (full) local_tile_v2<T>(in, sx, sy, t, Lv2, tasks, parent, cand, cand_cap, counters);
+  else local_tile_fast<T, false>(in, sx, sy, sz, t, Lv2, tasks, parent, cand, cand_cap, counters);
+}
+
 // ------------------------------------------------- G: merges across tile faces
 // Flat mapping over the voxel pairs that straddle a tile face, one 32-voxel
 // sub-word per warp (y and z faces) or 32 rows per warp (x faces), so that the
@@ -836,9 +1118,18 @@ static int ccl_core(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, uint32_
   bool fast = false;
   if constexpr (!R::thresholded) {  // raw labels (no threshold)
     fast = (rd.rx & rd.ry & rd.rz) == 0xFFFFFFFFu && getenv("IGN_CCL_GENERIC") == nullptr;
-    if (fast)
+    // experimental 4-voxels-per-lane kernel: opt-in until it has been validated on a GPU
+    const bool v2 = fast && getenv("IGN_CCL_V2") != nullptr && (sx % 4 == 0) &&
+                    ((uintptr_t)rd.in % 16 == 0) && ((uintptr_t)s.parent % 16 == 0);
+    if (v2) {
+      IGN_CUDA(cudaFuncSetAttribute(k_ccl_local_v2<typename R::value_type>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local_v2<typename R::value_type>), grid, CCL_THREADS, smem,
+                      rd.in, sx, sy, sz, ntx, nty, s.parent, s.cand, s.cap, s.counters);
+    } else if (fast) {
       IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local_fast<typename R::value_type>), grid, CCL_THREADS, smem,
                       rd.in, sx, sy, sz, ntx, nty, s.parent, s.cand, s.cap, s.counters);
+    }
   }
   if (!fast)
     IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local<R>), grid, CCL_THREADS, smem, rd, sx, sy, sz, ntx, nty,
