@@ -538,9 +538,11 @@ constexpr int QUAD = 128;                 // voxels a warp covers per step (4 pe
 constexpr int QUADS = TILE_X / QUAD;      // 2
 static_assert(ROWS_PER_WARP == 4 && TILE_Y == 8 && QUADS == 2, "local_tile_v2 row ownership");
 
+constexpr int STARTS_PER_WARP = 128;      // run starts a warp can list for the compression pass
+
 template <typename T>
 __device__ __forceinline__ void local_tile_v2(const T* __restrict__ in, uint32_t sx, uint32_t sy,
-                                              const TilePos& t, uint32_t* L, uint32_t* tasks,
+                                              const TilePos& t, uint32_t* L, uint32_t* tasks, uint32_t* starts,
                                               uint32_t* __restrict__ parent, uint32_t* __restrict__ cand,
                                               uint32_t cand_cap, uint32_t* counters) {
   const uint32_t sxy = sx * sy;
@@ -549,10 +551,11 @@ __device__ __forceinline__ void local_tile_v2(const T* __restrict__ in, uint32_t
   // a warp owns 4 consecutive y rows of one z slice of the tile
   const uint32_t lz = t.warp >> 1, ly0 = (t.warp & 1u) * ROWS_PER_WARP;
   uint32_t* q = tasks + t.warp * TASKS_PER_WARP;
-  uint32_t nq = 0;
-  bool overflow = false;
+  uint32_t* sq = starts + t.warp * STARTS_PER_WARP;
+  uint32_t nq = 0, ns = 0;
+  bool overflow = false, soverflow = false;
 
-  // ---- pass 1: run starts + queued y / z union tasks
+  // ---- pass 1: run starts + queued y / z union tasks + list of run starts
   T prev[QUADS][4];  // the row this warp handled before (y neighbour of the next one)
 #pragma unroll
   for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
@@ -628,23 +631,41 @@ __device__ __forceinline__ void local_tile_v2(const T* __restrict__ in, uint32_t
         if (cy[j] && !(same[j] && py)) ty |= 1u << j;
         if (cz[j] && !(same[j] && pz)) tz |= 1u << j;
       }
-#pragma unroll
-      for (int dir = 0; dir < 2; dir++) {
-        const uint32_t nib = dir ? tz : ty;
-        if (!__any_sync(FULL, nib != 0)) continue;
-        const uint32_t delta = dir ? (uint32_t)(TILE_X * TILE_Y) : (uint32_t)TILE_X;
-        const uint32_t m0 = __ballot_sync(FULL, nib & 1u), m1 = __ballot_sync(FULL, nib & 2u),
-                       m2 = __ballot_sync(FULL, nib & 4u), m3 = __ballot_sync(FULL, nib & 8u);
-        const uint32_t total = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-        if (overflow || nq + total > (uint32_t)TASKS_PER_WARP) {
-          overflow = true;  // queue full before the barrier: the classic pass below redoes everything
-          continue;
+      // slots for this quad's tasks (low half-word) and run starts (high half-word): only the
+      // few lanes that hold any take part in the reservation
+      const uint32_t stn = (st[0] ? 1u : 0u) | (st[1] ? 2u : 0u) | (st[2] ? 4u : 0u) | (st[3] ? 8u : 0u);
+      const uint32_t cnt = (uint32_t)(__popc(ty) + __popc(tz)) | ((uint32_t)__popc(stn) << 16);
+      const uint32_t m_t = __ballot_sync(FULL, cnt != 0);
+      if (m_t) {
+        uint32_t off = 0, total = 0;
+        for (uint32_t m = m_t; m; m &= m - 1) {
+          const int src = __ffs(m) - 1;
+          const uint32_t k = __shfl_sync(FULL, cnt, src);
+          if ((int)t.lane > src) off += k;
+          total += k;
         }
-        uint32_t off = nq + __popc(m0 & ltmask) + __popc(m1 & ltmask) + __popc(m2 & ltmask) + __popc(m3 & ltmask);
+        const uint32_t tt = total & 0xFFFFu, ts = total >> 16;
+        // a full queue before the barrier: the classic pass below redoes every union
+        if (nq + tt > (uint32_t)TASKS_PER_WARP) overflow = true;
+        // a full start list: pass 3 falls back to chasing every voxel
+        if (ns + ts > (uint32_t)STARTS_PER_WARP) soverflow = true;
+        if (!overflow) {
+          uint32_t w = nq + (off & 0xFFFFu);
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (nib & (1u << j)) q[off++] = (c[j] << 16) | (base + j - delta);
-        nq += total;
+          for (int j = 0; j < 4; j++)
+            if (ty & (1u << j)) q[w++] = (c[j] << 16) | (base + j - (uint32_t)TILE_X);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (tz & (1u << j)) q[w++] = (c[j] << 16) | (base + j - (uint32_t)(TILE_X * TILE_Y));
+          nq += tt;
+        }
+        if (!soverflow) {
+          uint32_t w = ns + (off >> 16);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (stn & (1u << j)) sq[w++] = base + j;
+          ns += ts;
+        }
       }
 #pragma unroll
       for (int j = 0; j < 4; j++) prev[qd][j] = a[j];
@@ -707,9 +728,25 @@ __device__ __forceinline__ void local_tile_v2(const T* __restrict__ in, uint32_t
     }
   }
   flush();
-  __syncthreads();
+  const int any_soverflow = __syncthreads_or(soverflow ? 1 : 0);
 
-  // ---- pass 3: flatten, translate to global indices, log local roots (4 voxels per lane)
+  // ---- pass 2b: point every run start at its root.  Every node of a parent chain is a run
+  // start (only roots are hooked, and a root is the first voxel of its run), so afterwards
+  // any voxel reaches its root in ONE hop: parent entry -> L[entry].
+  if (!any_soverflow) {
+    for (uint32_t i = t.lane; i < ns; i += 32) {
+      const uint32_t s0 = sq[i];
+      uint32_t rt = s0, pp = ((volatile uint32_t*)L)[rt];
+      while (pp != rt) {
+        rt = pp;
+        pp = ((volatile uint32_t*)L)[rt];
+      }
+      ((volatile uint32_t*)L)[s0] = rt;
+    }
+    __syncthreads();
+  }
+
+  // ---- pass 3: translate to global indices, log local roots (4 voxels per lane)
 #pragma unroll 1
   for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
     const uint32_t ly = ly0 + rr, r = lz * TILE_Y + ly;
@@ -728,15 +765,20 @@ __device__ __forceinline__ void local_tile_v2(const T* __restrict__ in, uint32_t
       }
 #pragma unroll
       for (int j = 0; j < 4; j++) nxt[j] = L[cur[j]];
+      if (!any_soverflow) {  // compressed: the entry's parent is the root
 #pragma unroll
-      for (int j = 0; j < 4; j++) more |= (!bgv[j] && nxt[j] != cur[j]);
-      if (__any_sync(FULL, more)) {
+        for (int j = 0; j < 4; j++) cur[j] = bgv[j] ? cur[j] : nxt[j];
+      } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          while (!bgv[j] && nxt[j] != cur[j]) {
-            cur[j] = nxt[j];
-            nxt[j] = L[cur[j]];
-          }
+        for (int j = 0; j < 4; j++) more |= (!bgv[j] && nxt[j] != cur[j]);
+        if (__any_sync(FULL, more)) {
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            while (!bgv[j] && nxt[j] != cur[j]) {
+              cur[j] = nxt[j];
+              nxt[j] = L[cur[j]];
+            }
+        }
       }
       uint32_t g[4];
 #pragma unroll
@@ -761,9 +803,10 @@ __global__ void __launch_bounds__(CCL_THREADS)
                    uint32_t cand_cap, uint32_t* counters) {
   extern __shared__ __align__(16) uint32_t Lv2[];
   uint32_t* tasks = Lv2 + TILE_VOX;
+  uint32_t* starts = tasks + CCL_WARPS * TASKS_PER_WARP;
   const TilePos t = tile_pos(ntx, nty);
   const bool full = (t.X0 + TILE_X <= sx) && (t.Y0 + TILE_Y <= sy) && (t.Z0 + TILE_Z <= sz);
-  if (full) local_tile_v2<T>(in, sx, sy, t, Lv2, tasks, parent, cand, cand_cap, counters);
+  if (full) local_tile_v2<T>(in, sx, sy, t, Lv2, tasks, starts, parent, cand, cand_cap, counters);
   else local_tile_fast<T, false>(in, sx, sy, sz, t, Lv2, tasks, parent, cand, cand_cap, counters);
 }
 
@@ -1122,9 +1165,10 @@ static int ccl_core(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, uint32_
     const bool v2 = fast && getenv("IGN_CCL_V2") != nullptr && (sx % 4 == 0) &&
                     ((uintptr_t)rd.in % 16 == 0) && ((uintptr_t)s.parent % 16 == 0);
     if (v2) {
+      constexpr size_t smem2 = smem + (size_t)CCL_WARPS * STARTS_PER_WARP * sizeof(uint32_t);
       IGN_CUDA(cudaFuncSetAttribute(k_ccl_local_v2<typename R::value_type>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local_v2<typename R::value_type>), grid, CCL_THREADS, smem,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local_v2<typename R::value_type>), grid, CCL_THREADS, smem2,
                       rd.in, sx, sy, sz, ntx, nty, s.parent, s.cand, s.cap, s.counters);
     } else if (fast) {
       IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local_fast<typename R::value_type>), grid, CCL_THREADS, smem,

@@ -54,15 +54,15 @@ def union(L, a, b):
   L[a] = b
 
 
-def run_tile(tile, tasks_cap=TASKS_PER_WARP):
+def run_tile(tile, tasks_cap=TASKS_PER_WARP, starts_cap=128):
   """tile: [256, 8, 8] labels (x, y, z).  Returns parent (local root index or BG) per voxel
   and whether the overflow path was taken."""
   lin = lambda x, y, z: (z * TILE_Y + y) * TILE_X + x
   L = np.zeros(TILE_X * TILE_Y * TILE_Z, dtype=np.int64)
-  queues, overflow_any = [], False
+  queues, start_lists, overflow_any, soverflow_any = [], [], False, False
   for warp in range(16):
     lz, ly0 = warp >> 1, (warp & 1) * 4
-    q, overflow = [], False
+    q, sq, overflow, soverflow = [], [], False, False
     prev = [None, None]
     for rr in range(4):
       ly = ly0 + rr
@@ -115,28 +115,52 @@ def run_tile(tile, tasks_cap=TASKS_PER_WARP):
           pz = (pl & 2) != 0 if j == 0 else cz[j - 1]
           ty |= (cy[j] & ~(same[j] & py)).astype(np.int64) << j
           tz |= (cz[j] & ~(same[j] & pz)).astype(np.int64) << j
-        for direction, nib in ((0, ty), (1, tz)):
-          if not (nib != 0).any():
-            continue
-          delta = TILE_X * TILE_Y if direction else TILE_X
-          m = [ballot(nib & (1 << j)) for j in range(4)]
-          total = sum(popc(x) for x in m)
-          if overflow or len(q) + total > tasks_cap:
+        stn = sum(st[j].astype(np.int64) << j for j in range(4))
+        cnt = np.array([popc(ty[l]) + popc(tz[l]) for l in range(32)]) | (np.array([popc(stn[l]) for l in range(32)]) << 16)
+        m_t = ballot(cnt != 0)
+        if m_t:
+          off = np.zeros(32, dtype=np.int64)
+          total = 0
+          m = m_t
+          while m:
+            src = (m & -m).bit_length() - 1
+            k = int(cnt[src])
+            off[LANES > src] += k
+            total += k
+            m &= m - 1
+          tt, ts = total & 0xFFFF, total >> 16
+          if len(q) + tt > tasks_cap:
             overflow = True
-            continue
-          slots = [None] * total
-          for l in range(32):
-            off = sum(popc(x & ((1 << l) - 1)) for x in m)
-            for j in range(4):
-              if nib[l] & (1 << j):
-                assert slots[off] is None
-                slots[off] = (int(c[j][l]), int(base[l] + j - delta))
-                off += 1
-          assert all(s is not None for s in slots)
-          q.extend(slots)
+          if len(sq) + ts > starts_cap:
+            soverflow = True
+          if not overflow:
+            slots = [None] * tt
+            for l in range(32):
+              w = int(off[l] & 0xFFFF)
+              for nib, delta in ((ty, TILE_X), (tz, TILE_X * TILE_Y)):
+                for j in range(4):
+                  if nib[l] & (1 << j):
+                    assert slots[w] is None
+                    slots[w] = (int(c[j][l]), int(base[l] + j - delta))
+                    w += 1
+            assert all(x is not None for x in slots)
+            q.extend(slots)
+          if not soverflow:
+            slots = [None] * ts
+            for l in range(32):
+              w = int(off[l] >> 16)
+              for j in range(4):
+                if stn[l] & (1 << j):
+                  assert slots[w] is None
+                  slots[w] = int(base[l] + j)
+                  w += 1
+            assert all(x is not None for x in slots)
+            sq.extend(slots)
         prev[qd] = a
     queues.append(q)
+    start_lists.append(sq)
     overflow_any |= overflow
+    soverflow_any |= soverflow
   if overflow_any:  # classic pass: every y / z adjacency (a superset of the needed unions)
     for zz in range(TILE_Z):
       for yy in range(TILE_Y):
@@ -154,9 +178,22 @@ def run_tile(tile, tasks_cap=TASKS_PER_WARP):
         assert L[a_] != BG and L[b_] != BG
         union(L, a_, b_)
   out = np.full(L.shape, BG, dtype=np.int64)
-  for i in range(len(L)):
-    if L[i] != BG:
-      out[i] = find(L, i)
+  if not soverflow_any:  # pass 2b: run starts -> roots, then ONE hop per voxel
+    listed = [x for sq in start_lists for x in sq]
+    assert len(listed) == len(set(listed))
+    for s0 in listed:
+      rt = s0
+      while L[rt] != rt:
+        rt = L[rt]
+      L[s0] = rt
+    for i in range(len(L)):
+      if L[i] != BG:
+        out[i] = L[L[i]]
+        assert L[out[i]] == out[i], "single hop did not reach a root"
+  else:
+    for i in range(len(L)):
+      if L[i] != BG:
+        out[i] = find(L, i)
   return out, overflow_any
 
 
