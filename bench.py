@@ -24,7 +24,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
-METRIC = "Mvoxels/s (downsample 2 mips + CCL + mesh) on uint32 segmentation"
+def _baseline_metric():
+  """The metric string of BASELINE.json (the bench line must name exactly that metric)."""
+  fallback = "Mvoxels/s on 2048\u00b3 uint32 seg (downsample+CCL+mesh) @1/2/4/8 B200; % HBM roofline"
+  try:
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "BASELINE.json")) as f:
+      return json.load(f).get("metric", fallback)
+  except (OSError, ValueError):
+    return fallback
+
+
+METRIC = _baseline_metric()
 RESOLUTION = (16, 16, 40)
 PITCH, NUM_IDS = 64, 1 << 20
 
