@@ -506,6 +506,257 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ---------------------------------------------------------------- batched gathers
+// Opt-in variants (IGN_SIMP_BATCH=1) of the three latency-bound ring walkers.  The serial
+// versions above chase node -> alive flag -> vertex ids -> positions one ring entry at a
+// time (k_simp_collapse: 19-21 % issue-active, profiles/r01_simp_round_metrics.csv); here
+// the loads of S_B ring entries are issued together before anything depends on them.
+// Only the order of LOADS changes: every comparison, every floating-point operation and
+// every store happens in the same order on the same values, so results are bit-identical
+// to the serial kernels (and to oracle/igneous_oracle.c::orc_simplify).
+constexpr int S_B = 8;
+
+// s_ring + the vertex ids of every collected face (3 per face, the flip test reuses them)
+__device__ bool s_ring_b(const Simp& s, uint32_t w, uint32_t* faces, uint32_t* fverts, uint32_t* nbr,
+                         int* nf, int* nn) {
+  *nf = 0;
+  *nn = 0;
+  const uint32_t* lw = s.vf + (uint64_t)w * S_VCAP;
+  const uint32_t cw = s.vn[w];
+  for (uint32_t j0 = 0; j0 < cw; j0 += S_B) {
+    uint32_t h[S_B], fv[S_B][3];
+    uint8_t al[S_B];
+#pragma unroll
+    for (int i = 0; i < S_B; i++) h[i] = (j0 + i < cw) ? lw[j0 + i] : S_NONE;
+#pragma unroll
+    for (int i = 0; i < S_B; i++) al[i] = (h[i] != S_NONE) ? s.falive[h[i] / 3] : (uint8_t)0;
+#pragma unroll
+    for (int i = 0; i < S_B; i++) {
+      const uint32_t* p = s.face + 3 * (uint64_t)((al[i] ? h[i] : 0u) / 3);  // dead entry: any valid face
+      fv[i][0] = p[0];
+      fv[i][1] = p[1];
+      fv[i][2] = p[2];
+    }
+#pragma unroll
+    for (int i = 0; i < S_B; i++) {
+      if (!al[i]) continue;
+      if (*nf >= S_MAXV) return false;
+      faces[*nf] = h[i] / 3;
+      fverts[3 * *nf + 0] = fv[i][0];
+      fverts[3 * *nf + 1] = fv[i][1];
+      fverts[3 * *nf + 2] = fv[i][2];
+      (*nf)++;
+      for (int k = 0; k < 3; k++) {
+        const uint32_t x = fv[i][k];
+        if (x == w) continue;
+        bool seen = false;
+        for (int j = 0; j < *nn; j++) seen |= (nbr[j] == x);
+        if (!seen) {
+          if (*nn >= S_MAXV) return false;
+          nbr[(*nn)++] = x;
+        }
+      }
+    }
+  }
+  return true;
+}
+
+__device__ void s_evaluate_b(const Simp& s, uint32_t u, uint32_t v, double max_err2, SEval* e) {
+  s_cost(s, u, v, max_err2, e);
+  if (!e->valid) return;
+  e->valid = false;
+  const double* best = e->p;
+  uint32_t fu[S_MAXV], fv[S_MAXV], nu[S_MAXV], nv[S_MAXV], xu[3 * S_MAXV], xv[3 * S_MAXV];
+  int nfu, nfv, nnu, nnv;
+  if (!s_ring_b(s, u, fu, xu, nu, &nfu, &nnu)) return;
+  if (!s_ring_b(s, v, fv, xv, nv, &nfv, &nnv)) return;
+  int common = 0;
+  for (int i = 0; i < nnu; i++)
+    for (int j = 0; j < nnv; j++) common += (nu[i] == nv[j]);
+  int shared = 0;
+  for (int i = 0; i < nfu; i++)
+    for (int j = 0; j < nfv; j++) shared += (fu[i] == fv[j]);
+  if (shared != 2 || common != 2) return;
+  for (int pass = 0; pass < 2; pass++) {
+    const uint32_t* xl = pass ? xv : xu;
+    const int n = pass ? nfv : nfu;
+    const uint32_t w = pass ? v : u, other = pass ? u : v;
+    for (int i0 = 0; i0 < n; i0 += 2) {  // positions of two faces (18 doubles) per batch
+      double pos[2][3][3];
+      uint32_t ids[2][3];
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        const int i = (i0 + b < n) ? (i0 + b) : i0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) ids[b][k] = xl[3 * i + k];
+      }
+#pragma unroll
+      for (int b = 0; b < 2; b++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const double* p = s.pos + 3 * (uint64_t)ids[b][k];
+          pos[b][k][0] = p[0];
+          pos[b][k][1] = p[1];
+          pos[b][k][2] = p[2];
+        }
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        if (i0 + b >= n) continue;
+        const uint32_t* fx = ids[b];
+        if (fx[0] == other || fx[1] == other || fx[2] == other) continue;
+        const double* P[3];
+        const double* N[3];
+        for (int k = 0; k < 3; k++) {
+          P[k] = pos[b][k];
+          N[k] = (fx[k] == w) ? best : P[k];
+        }
+        const double ax = P[1][0] - P[0][0], ay = P[1][1] - P[0][1], az = P[1][2] - P[0][2];
+        const double bx = P[2][0] - P[0][0], by = P[2][1] - P[0][1], bz = P[2][2] - P[0][2];
+        const double n0x = ay * bz - az * by, n0y = az * bx - ax * bz, n0z = ax * by - ay * bx;
+        const double cx = N[1][0] - N[0][0], cy = N[1][1] - N[0][1], cz = N[1][2] - N[0][2];
+        const double dx = N[2][0] - N[0][0], dy = N[2][1] - N[0][1], dz = N[2][2] - N[0][2];
+        const double n1x = cy * dz - cz * dy, n1y = cz * dx - cx * dz, n1z = cx * dy - cy * dx;
+        const double dot = n0x * n1x + n0y * n1y + n0z * n1z;
+        if (!(dot > 0.0)) return;
+      }
+    }
+  }
+  e->valid = true;
+}
+
+__global__ void __launch_bounds__(256) k_simp_key2_b(Simp s) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= s.nv) return;
+  const uint32_t w = s.vlist[i];
+  s.vdirty[w] = 0;
+  if (!s.valive[w]) {
+    s.key2[w] = S_KEYMAX;
+    return;
+  }
+  unsigned long long m = s.key1[w];
+  const uint32_t* lw = s.vf + (uint64_t)w * S_VCAP;
+  const uint32_t cw = s.vn[w];
+  for (uint32_t j0 = 0; j0 < cw; j0 += S_B) {
+    uint32_t h[S_B], fv[S_B][3];
+    uint8_t al[S_B];
+#pragma unroll
+    for (int b = 0; b < S_B; b++) h[b] = (j0 + b < cw) ? lw[j0 + b] : S_NONE;
+#pragma unroll
+    for (int b = 0; b < S_B; b++) al[b] = (h[b] != S_NONE) ? s.falive[h[b] / 3] : (uint8_t)0;
+#pragma unroll
+    for (int b = 0; b < S_B; b++) {
+      const uint32_t* p = s.face + 3 * (uint64_t)((al[b] ? h[b] : 0u) / 3);
+      fv[b][0] = al[b] ? p[0] : w;  // dead entry: w itself (its key1 is already in m)
+      fv[b][1] = al[b] ? p[1] : w;
+      fv[b][2] = al[b] ? p[2] : w;
+    }
+#pragma unroll
+    for (int b = 0; b < S_B; b++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const unsigned long long kk = s.key1[fv[b][k]];
+        if (kk < m) m = kk;
+      }
+  }
+  s.key2[w] = m;
+}
+
+__global__ void __launch_bounds__(128)
+    k_simp_collapse_b(Simp s, double max_err2, const uint32_t* __restrict__ wlist, uint32_t* flags) {
+  const uint32_t nw = flags[3];
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nw;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t h = wlist[i];
+    const uint32_t f = h / 3, c = h % 3;
+    const uint32_t u = s.face[3 * (uint64_t)f + c], v = s.face[3 * (uint64_t)f + (c + 1) % 3];
+    SEval e;
+    s_evaluate_b(s, u, v, max_err2, &e);
+    if (!e.valid) {
+      s.estate[h] = 1;
+      flags[1] = 1;
+      continue;
+    }
+    const uint32_t k = e.keep, rm = e.remove;
+    s.pos[3 * (uint64_t)k + 0] = e.p[0];
+    s.pos[3 * (uint64_t)k + 1] = e.p[1];
+    s.pos[3 * (uint64_t)k + 2] = e.p[2];
+    {
+      double qk[10], qr[10];
+#pragma unroll
+      for (int q = 0; q < 10; q++) {
+        qk[q] = s.Q[10 * (uint64_t)k + q];
+        qr[q] = s.Q[10 * (uint64_t)rm + q];
+      }
+#pragma unroll
+      for (int q = 0; q < 10; q++) s.Q[10 * (uint64_t)k + q] = qk[q] + qr[q];
+    }
+    uint32_t* lk = s.vf + (uint64_t)k * S_VCAP;
+    const uint32_t* lr = s.vf + (uint64_t)rm * S_VCAP;
+    const uint32_t ck = s.vn[k], cr = s.vn[rm];
+    // faces of rm: those that also hold k die, the others get k in rm's corner
+    for (uint32_t j0 = 0; j0 < cr; j0 += S_B) {
+      uint32_t hh[S_B], fx[S_B][3];
+      uint8_t al[S_B];
+#pragma unroll
+      for (int b = 0; b < S_B; b++) hh[b] = (j0 + b < cr) ? lr[j0 + b] : S_NONE;
+#pragma unroll
+      for (int b = 0; b < S_B; b++) al[b] = (hh[b] != S_NONE) ? s.falive[hh[b] / 3] : (uint8_t)0;
+#pragma unroll
+      for (int b = 0; b < S_B; b++) {
+        const uint32_t* p = s.face + 3 * (uint64_t)((al[b] ? hh[b] : 0u) / 3);
+        fx[b][0] = p[0];
+        fx[b][1] = p[1];
+        fx[b][2] = p[2];
+      }
+#pragma unroll
+      for (int b = 0; b < S_B; b++) {
+        if (!al[b]) continue;
+        const uint32_t g = hh[b] / 3;
+        if (fx[b][0] == k || fx[b][1] == k || fx[b][2] == k) {
+          s.falive[g] = 0;
+          atomicSub(&s.alive_faces[s.flabel[g]], 1u);
+        } else {
+          s.face[3 * (uint64_t)g + hh[b] % 3] = k;
+        }
+      }
+    }
+    // k's new ring = alive entries of k's array (compacted in place) ++ alive entries of rm's
+    uint32_t nk = 0;
+    for (int pass = 0; pass < 2; pass++) {
+      const uint32_t* src = pass ? lr : lk;
+      const uint32_t cnt = pass ? cr : ck;
+      for (uint32_t j0 = 0; j0 < cnt; j0 += S_B) {
+        uint32_t hh[S_B], fx[S_B][3];
+        uint8_t al[S_B];
+#pragma unroll
+        for (int b = 0; b < S_B; b++) hh[b] = (j0 + b < cnt) ? src[j0 + b] : S_NONE;
+#pragma unroll
+        for (int b = 0; b < S_B; b++) al[b] = (hh[b] != S_NONE) ? s.falive[hh[b] / 3] : (uint8_t)0;
+#pragma unroll
+        for (int b = 0; b < S_B; b++) {
+          const uint32_t* p = s.face + 3 * (uint64_t)((al[b] ? hh[b] : 0u) / 3);
+          fx[b][0] = p[0];
+          fx[b][1] = p[1];
+          fx[b][2] = p[2];
+        }
+#pragma unroll
+        for (int b = 0; b < S_B; b++) {
+          if (!al[b]) continue;
+          lk[nk++] = hh[b];
+          s.vdirty[fx[b][0]] = 1;
+          s.vdirty[fx[b][1]] = 1;
+          s.vdirty[fx[b][2]] = 1;
+        }
+      }
+    }
+    s.vn[k] = nk;
+    s.vdirty[k] = 1;
+    s.valive[rm] = 0;
+    flags[1] = 1;
+    atomicAdd(&flags[2], 1u);
+  }
+}
+
 __global__ void __launch_bounds__(256)
     k_simp_flags_u32(const uint8_t* __restrict__ a, uint64_t n, uint32_t* __restrict__ out) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -714,6 +965,8 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   const double max_err2 = (double)max_error * (double)max_error;
   const int max_rounds = 400;
   const bool trace = getenv("IGN_SIMP_TRACE") != nullptr;  // per-round progress on stderr
+  // batched-gather ring walkers: same results, opt-in until validated on a GPU
+  const bool batch = getenv("IGN_SIMP_BATCH") != nullptr;
   // work-list rebuild period and collapse grid cap: measured on B200 (tools/time_simplify.py),
   // 4 / 8 / 16 rounds -> 187.7 / 177.4 / 175.3 ms per 257^3 task; the grid cap has no effect
   const int rebuild_every = 16;
@@ -737,11 +990,13 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
     S_LAUNCH(k_simp_round_begin, blocks_for(nb, 256), 256, s, (uint32_t)K, flags);
     if (s.ne) S_LAUNCH(k_simp_edge_keys, blocks_for(s.ne, 128), 128, s, max_err2, salt);
     if (s.nv) {
-      S_LAUNCH(k_simp_key2, blocks_for(s.nv, 256), 256, s);
+      if (batch) S_LAUNCH(k_simp_key2_b, blocks_for(s.nv, 256), 256, s);
+      else S_LAUNCH(k_simp_key2, blocks_for(s.nv, 256), 256, s);
       S_LAUNCH(k_simp_select, blocks_for(s.nv, 256), 256, s, salt, wlist, flags);
       // grid-stride over the device-side winner count: no host round trip in between
       const unsigned cg = blocks_for(s.nv / 16 + 1, 128);
-      S_LAUNCH(k_simp_collapse, cg < collapse_cap ? cg : collapse_cap, 128, s, max_err2, wlist, flags);
+      if (batch) S_LAUNCH(k_simp_collapse_b, cg < collapse_cap ? cg : collapse_cap, 128, s, max_err2, wlist, flags);
+      else S_LAUNCH(k_simp_collapse, cg < collapse_cap ? cg : collapse_cap, 128, s, max_err2, wlist, flags);
     }
     S_TRY(small_d2h(ctx, hflags, flags, 16));
     S_TRY(small_sync(ctx));
