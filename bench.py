@@ -220,6 +220,8 @@ def main():
                   help="download the labels into the input host buffer (forced automatically when host RAM is tight)")
   ap.add_argument("--simplify", type=int, default=None, help="simplification factor (default 100)")
   ap.add_argument("--mesh-streams", type=int, default=8, help="concurrent MeshTask bodies per GPU")
+  ap.add_argument("--serial-simplify", action="store_true",
+                  help="use the serial ring walkers of the simplifier instead of the batched-gather kernels")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == "b200":
     args.warmup = 3
@@ -238,6 +240,14 @@ def main():
     dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dist = dist_mod
 
+  # The simplifier's batched-gather kernels (simplify.cu, IGN_SIMP_BATCH) give bit-identical
+  # meshes (tests/test_mesh_gpu.py::test_simplify_batched_kernels_bit_exact) and 28 % shorter
+  # MeshTask bodies; the library default is still the serial kernels until the whole GPU suite
+  # has run with them, so the bench opts in explicitly.
+  if args.serial_simplify:
+    os.environ.pop("IGN_SIMP_BATCH", None)
+  else:
+    os.environ.setdefault("IGN_SIMP_BATCH", "1")
   from igneous_b200 import _shim, pipeline
   ctx = _shim.Context(local_rank)
   S = args.size
@@ -339,6 +349,7 @@ def main():
       "volume_per_gpu": list(shape), "parallelism": "z-slab per GPU, %d rank(s)" % world,
       "l2": "inputs larger than L2 (%.1f GB volume vs 126 MB L2)" % (pipe.n * 4 / 1e9),
       "simplification_factor": simplify, "components": pipe.n_components, "mesh": pipe.mesh_stats, "mesh_streams": pipe.mesh_streams,
+      "simplify_kernels": "batched gathers (IGN_SIMP_BATCH=1)" if os.environ.get("IGN_SIMP_BATCH") else "serial ring walks",
       "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
     },
     "roofline": roofline, "clocks": clocks,

@@ -162,3 +162,29 @@ def test_simplify_multilabel_matches_oracle(ctx, oracle, factor, max_error):
   assert total_after < sum(before.values())
   with pytest.raises(ValueError):
     m.get(m.ids()[0], reduction_factor=factor + 1, max_error=max_error)
+
+
+def test_simplify_batched_kernels_bit_exact(ctx, oracle, monkeypatch):
+  """IGN_SIMP_BATCH=1 (batched-gather ring walkers, what bench.py runs): identical meshes to the
+  serial kernels and to the oracle."""
+  from igneous_b200 import zmesh
+
+  def meshes(seg, factor):
+    m = zmesh.Mesher((16, 16, 40))
+    m.mesh(seg)
+    return {int(i): m.get(i, reduction_factor=factor, max_error=40.0, voxel_centered=True) for i in m.ids()}
+
+  for shape, pitch, factor in (((96, 80, 64), 24, 10), ((128, 128, 64), 32, 100)):
+    seg = np.asfortranarray(oracle.synth_seg(shape, pitch=pitch, num_ids=9).astype(np.uint32))
+    monkeypatch.delenv("IGN_SIMP_BATCH", raising=False)
+    serial = meshes(seg, factor)
+    monkeypatch.setenv("IGN_SIMP_BATCH", "1")
+    batched = meshes(seg, factor)
+    monkeypatch.delenv("IGN_SIMP_BATCH", raising=False)
+    tl, tv = oracle.marching_cubes(seg)
+    want, _ = oracle.simplify_welded(oracle.WeldedMeshes(tl, tv), (16, 16, 40), factor, 40.0, True)
+    assert serial.keys() == batched.keys() == want.keys()
+    for k in serial:
+      assert np.array_equal(serial[k].vertices, batched[k].vertices)
+      assert np.array_equal(serial[k].faces, batched[k].faces)
+      assert np.array_equal(batched[k].vertices, want[k][0]) and np.array_equal(batched[k].faces, want[k][1])
