@@ -222,6 +222,8 @@ def main():
   ap.add_argument("--mesh-streams", type=int, default=8, help="concurrent MeshTask bodies per GPU")
   ap.add_argument("--serial-simplify", action="store_true",
                   help="use the serial ring walkers of the simplifier instead of the batched-gather kernels")
+  ap.add_argument("--ccl-v1", action="store_true",
+                  help="use k_ccl_local_fast instead of the 4-voxels-per-lane tile kernel k_ccl_local_v2")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == "b200":
     args.warmup = 3
@@ -248,6 +250,12 @@ def main():
     os.environ.pop("IGN_SIMP_BATCH", None)
   else:
     os.environ.setdefault("IGN_SIMP_BATCH", "1")
+  # Same for the CCL tile kernel: k_ccl_local_v2 (ccl.cu, IGN_CCL_V2) is bit-exact
+  # (tests/test_ccl_gpu.py::test_ccl_v2_kernel_matches_oracle) and 11 % faster at 512^3.
+  if args.ccl_v1:
+    os.environ.pop("IGN_CCL_V2", None)
+  else:
+    os.environ.setdefault("IGN_CCL_V2", "1")
   from igneous_b200 import _shim, pipeline
   ctx = _shim.Context(local_rank)
   S = args.size
@@ -350,6 +358,7 @@ def main():
       "l2": "inputs larger than L2 (%.1f GB volume vs 126 MB L2)" % (pipe.n * 4 / 1e9),
       "simplification_factor": simplify, "components": pipe.n_components, "mesh": pipe.mesh_stats, "mesh_streams": pipe.mesh_streams,
       "simplify_kernels": "batched gathers (IGN_SIMP_BATCH=1)" if os.environ.get("IGN_SIMP_BATCH") else "serial ring walks",
+      "ccl_tile_kernel": "k_ccl_local_v2 (IGN_CCL_V2=1)" if os.environ.get("IGN_CCL_V2") else "k_ccl_local_fast",
       "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
     },
     "roofline": roofline, "clocks": clocks,
