@@ -332,7 +332,8 @@ def main():
     # dram__bytes_read+write of this kernel from the ncu --set full capture in
     # profiles/r01_ccl_local_fast_full_512_raw.csv: 7.657 B/voxel (537+491 MB at 512^3), scaled per launch
     "traffic": (7.657 * pipe.n / dom_launches) if dominant == "ccl_local" else None,
-    "traffic_source": "ncu capture at 512^3 scaled by voxels per launch (profiles/r01_ccl_local_fast_full_512_raw.csv)",
+    "traffic_source": "ncu capture at 512^3 scaled by voxels per launch (profiles/%s; both tile kernels move 7.65 B/voxel)"
+                      % ("r01_ccl_local_v2_full_512_raw.csv" if os.environ.get("IGN_CCL_V2") else "r01_ccl_local_fast_full_512_raw.csv"),
     "peak_source": peak_src,
     "algorithmic_bytes_per_voxel": alg[dominant],
     "avg_launch_ms": dom_ms / dom_launches, "launches_per_step": dom_launches,
