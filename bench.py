@@ -400,10 +400,21 @@ def run_e2e(ctx, pipe, args, dist, world):
   out_bytes = sum(int(np.prod(s)) * 4 for s in pipe.mip_shapes) + n * pipe.ccl_out_dtype.itemsize
   local_ranks = int(os.environ.get("LOCAL_WORLD_SIZE", world))
   avail = _mem_available()
+  if dist is not None:  # every rank must take the same decisions below: agree on the smallest reading
+    import torch
+    t = torch.tensor([float(avail) if avail is not None else -1.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    avail = int(t.item()) if t.item() >= 0 else None
   shared = (avail is not None and (n * 4 + out_bytes) * local_ranks > 0.6 * avail
             and pipe.ccl_out_dtype.itemsize == 4)
   if args.e2e_shared_buffers:
     shared = pipe.ccl_out_dtype.itemsize == 4
+  need = (n * 4 + (out_bytes - n * pipe.ccl_out_dtype.itemsize if shared else out_bytes)) * local_ranks
+  if avail is not None and need > 0.85 * avail:
+    # never drive the host out of memory: report the leg as not measurable on this box
+    return {"value": None, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+            "skipped": "host buffers for %d local rank(s) need %.0f GB, %.0f GB of host RAM available"
+                       % (local_ranks, need / 1e9, avail / 1e9)}
   try:
     host_in = ctx.pinned_empty(pipe.shape, np.uint32)
     host = {"mips": [ctx.pinned_empty(s, np.uint32) for s in pipe.mip_shapes],
