@@ -521,3 +521,42 @@ def synth_tiled(shape, seed):
   dataset per (seed), generated by the C synthesiser."""
   return synth_seg(shape, pitch=64, num_ids=1 << 20, seed=0,
                    offset=(0, 0, (seed % 100000) * shape[2]))
+
+
+# ------------------------------------------------- compressed_segmentation codec
+def cseg_encode(labels, block_size=(8, 8, 8)):
+  """Precomputed `compressed_segmentation` encoding of a [x,y,z,(c)] uint32 / uint64 chunk
+  (what CloudVolume does on the host before uploading a segmentation
+  chunk).  Returns the file as a uint32 array."""
+  arr = np.asarray(labels)
+  if arr.ndim == 3:
+    arr = arr[..., np.newaxis]
+  assert arr.ndim == 4 and arr.dtype in (np.uint32, np.uint64)
+  arr = np.asfortranarray(arr)
+  fn = getattr(lib(), "orc_cseg_encode_" + _SUFFIX[arr.dtype])
+  fn.restype = ctypes.c_int64
+  args = (_ptr(arr), ctypes.c_uint64(arr.shape[0]), ctypes.c_uint64(arr.shape[1]), ctypes.c_uint64(arr.shape[2]),
+          ctypes.c_uint64(arr.shape[3]), ctypes.c_uint32(block_size[0]), ctypes.c_uint32(block_size[1]),
+          ctypes.c_uint32(block_size[2]))
+  need = fn(*args, None, ctypes.c_uint64(0))
+  assert need > 0
+  out = np.zeros(need, dtype=np.uint32)
+  got = fn(*args, _ptr(out), ctypes.c_uint64(need))
+  assert got == need
+  return out
+
+
+def cseg_decode(words, shape, dtype, block_size=(8, 8, 8)):
+  """Inverse of cseg_encode (accepts any conforming stream): returns the [x,y,z,c] chunk."""
+  words = np.ascontiguousarray(words, dtype=np.uint32)
+  shape = tuple(int(s) for s in shape)
+  if len(shape) == 3:
+    shape = shape + (1,)
+  out = np.zeros(shape, dtype=dtype, order="F")
+  fn = getattr(lib(), "orc_cseg_decode_" + _SUFFIX[np.dtype(dtype)])
+  rc = fn(_ptr(words), ctypes.c_uint64(len(words)), ctypes.c_uint64(shape[0]), ctypes.c_uint64(shape[1]),
+          ctypes.c_uint64(shape[2]), ctypes.c_uint64(shape[3]), ctypes.c_uint32(block_size[0]),
+          ctypes.c_uint32(block_size[1]), ctypes.c_uint32(block_size[2]), _ptr(out))
+  if rc != 0:
+    raise ValueError("malformed compressed_segmentation stream")
+  return out

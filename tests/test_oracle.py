@@ -373,3 +373,51 @@ def test_simplify_locks_open_boundaries_and_respects_zero_error(oracle):
   vb, fb = outb[9]
   assert len(fb) < len(fb0) and (_edge_use(fb) == 2).all()
   assert abs(_signed_volume(vb, fb) - _signed_volume(vb0, fb0)) < 1e-6 * abs(_signed_volume(vb0, fb0))
+
+
+# ------------------------------------------------- compressed_segmentation codec
+def test_cseg_format_kats(oracle):
+  """Hand-checked streams of the compressed_segmentation layout: offsets are
+  u32 words relative to the channel start, header = [table offset | bits << 24, indices offset]."""
+  one = np.full((8, 8, 8), 7, dtype=np.uint32, order="F")
+  # single value: 0 bits, no index words, the table follows the header directly
+  assert oracle.cseg_encode(one).tolist() == [1, 2 | (0 << 24), 2, 7]
+  two = one.copy()
+  two[0, 0, 0] = 9
+  w = oracle.cseg_encode(two)
+  # 1 bit per voxel: 512 bits = 16 index words at offset 2, sorted table [7, 9] at offset 18
+  assert len(w) == 1 + 2 + 16 + 2
+  assert w[1] == (18 | (1 << 24)) and w[2] == 2
+  assert w[3] == 1 and not w[4:19].any() and w[19:].tolist() == [7, 9]
+  # uint64 labels: the table holds (low, high) word pairs
+  big = np.full((8, 8, 8), (5 << 32) | 3, dtype=np.uint64, order="F")
+  assert oracle.cseg_encode(big).tolist() == [1, 2, 2, 3, 5]
+  # two blocks with the same label set share one table; voxel (1,0,0) of block 1 is bit 1
+  pair = np.full((16, 8, 8), 4, dtype=np.uint32, order="F")
+  pair[0, 0, 0] = 6
+  pair[9, 0, 0] = 6
+  w = oracle.cseg_encode(pair)
+  t0, t1 = w[1] & 0xFFFFFF, w[3] & 0xFFFFFF
+  assert t0 == t1 and (w[1] >> 24) == 1 and (w[3] >> 24) == 1
+  assert w[1 + w[2]] == 1 and w[1 + w[4]] == 2
+  assert len(w) == 1 + 4 + 16 + 2 + 16
+
+
+@pytest.mark.parametrize("dtype", [np.uint32, np.uint64])
+def test_cseg_roundtrip(oracle, dtype):
+  rng = np.random.default_rng(12)
+  vols = [oracle.synth_seg((64, 64, 64), pitch=16, num_ids=300).astype(dtype),
+          rng.integers(0, 1 << 20, size=(17, 9, 5)).astype(dtype),            # ragged edges, 16/32-bit indices
+          rng.integers(0, 3, size=(8, 8, 8, 3)).astype(dtype),                 # three channels, 2-bit indices
+          np.zeros((5, 5, 5), dtype=dtype)]
+  if dtype == np.uint64:
+    vols[0] = vols[0] + np.uint64(1 << 40)
+  for v in vols:
+    for bs in ((8, 8, 8), (4, 4, 2)):
+      w = oracle.cseg_encode(v, bs)
+      back = oracle.cseg_decode(w, v.shape, dtype, bs)
+      assert np.array_equal(back.reshape(v.shape), v)
+  # the real segmentation compresses: 64^3 u32 = 262144 words raw
+  assert len(oracle.cseg_encode(vols[0])) < 64 ** 3 // 3
+  with pytest.raises(ValueError):
+    oracle.cseg_decode(np.array([1, 0xFF000000, 2], dtype=np.uint32), (8, 8, 8), dtype)
