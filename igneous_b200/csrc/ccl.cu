@@ -815,6 +815,45 @@ __global__ void __launch_bounds__(CCL_THREADS)
   else local_tile_fast<T, false>(in, sx, sy, sz, t, Lv2, tasks, parent, cand, cand_cap, counters);
 }
 
+// ------------------------------ L / G2 on 256 x 8 x 4 tiles (experiment, IGN_CCL_V2=3)
+// k_ccl_local_v2 is no longer issue bound: two 512-thread CTAs per SM spend a large share
+// of their time in block barriers and in the latency-bound shared-memory union phase
+// (DESIGN.md section 8).  The same device code runs unchanged on half-height tiles with
+// 256 threads (a warp still owns 4 consecutive y rows of one z slice): 40 KB of shared
+// memory and 16 K registers per CTA let 4-5 CTAs in different phases share an SM, at the
+// price of twice as many z faces to merge.  NOT VALIDATED ON A GPU YET (written after the
+// round's GPU budget was spent); nothing selects it unless IGN_CCL_V2=3 is set.
+constexpr int TILE_Z_S = 4;
+constexpr int TILE_VOX_S = TILE_X * TILE_Y * TILE_Z_S;
+constexpr int CCL_THREADS_S = 256;
+constexpr int CCL_WARPS_S = CCL_THREADS_S / 32;
+static_assert(TILE_Y * TILE_Z_S / CCL_WARPS_S == ROWS_PER_WARP, "small tiles keep 4 rows per warp");
+
+__device__ __forceinline__ TilePos tile_pos_s(uint32_t ntx, uint32_t nty) {
+  TilePos t;
+  const uint32_t b = blockIdx.x;
+  t.X0 = (b % ntx) * TILE_X;
+  t.Y0 = ((b / ntx) % nty) * TILE_Y;
+  t.Z0 = (b / (ntx * nty)) * TILE_Z_S;
+  t.warp = threadIdx.x >> 5;
+  t.lane = threadIdx.x & 31;
+  return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CCL_THREADS_S)
+    k_ccl_local_v3(const T* __restrict__ in, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t ntx,
+                   uint32_t nty, uint32_t* __restrict__ parent, uint32_t* __restrict__ cand,
+                   uint32_t cand_cap, uint32_t* counters) {
+  extern __shared__ __align__(16) uint32_t Lv3[];
+  uint32_t* tasks = Lv3 + TILE_VOX_S;
+  uint32_t* starts = tasks + CCL_WARPS_S * TASKS_PER_WARP;
+  const TilePos t = tile_pos_s(ntx, nty);
+  const bool full = (t.X0 + TILE_X <= sx) && (t.Y0 + TILE_Y <= sy) && (t.Z0 + TILE_Z_S <= sz);
+  if (full) local_tile_v2<T>(in, sx, sy, t, Lv3, tasks, starts, parent, cand, cand_cap, counters);
+  else local_tile_fast<T, false>(in, sx, sy, sz, t, Lv3, tasks, parent, cand, cand_cap, counters);
+}
+
 // ------------------------------------------------- G: merges across tile faces
 // Flat mapping over the voxel pairs that straddle a tile face, one 32-voxel
 // sub-word per warp (y and z faces) or 32 rows per warp (x faces), so that the
@@ -928,6 +967,55 @@ __global__ void __launch_bounds__(256)
   }
   if (t.X0 > 0) {  // x face: one voxel pair per tile row
     for (uint32_t r = threadIdx.x; r < TILE_ROWS; r += blockDim.x) {
+      const uint32_t y = t.Y0 + (r % TILE_Y), z = t.Z0 + (r / TILE_Y);
+      if (y >= sy || z >= sz) continue;
+      const uint32_t idx = (z * sy + y) * sx + t.X0;
+      const V a = rd.at(idx, t.X0, y, z);
+      if (a != 0 && a == rd.at(idx - 1, t.X0 - 1, y, z)) merge_emit(set, parent, parent[idx], parent[idx - 1]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < MERGE_SLOTS; i += blockDim.x) {
+    const unsigned long long key = set[i];
+    if (key != 0xFFFFFFFFFFFFFFFFull) uf_union(parent, (uint32_t)(key >> 32), (uint32_t)(key & 0xFFFFFFFFu));
+  }
+}
+
+// G2 for the 256 x 8 x 4 tiles of k_ccl_local_v3: y faces have TILE_Z_S rows, z faces TILE_Y
+template <typename R>
+__global__ void __launch_bounds__(256)
+    k_ccl_merge_tiles_s(R rd, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t ntx, uint32_t nty,
+                        uint32_t* parent) {
+  using V = typename R::V;
+  __shared__ unsigned long long set[MERGE_SLOTS];
+  for (int i = threadIdx.x; i < MERGE_SLOTS; i += blockDim.x) set[i] = 0xFFFFFFFFFFFFFFFFull;
+  __syncthreads();
+  const TilePos t = tile_pos_s(ntx, nty);
+  const uint32_t sxy = sx * sy;
+  const uint32_t nwarps = blockDim.x >> 5;
+  constexpr uint32_t Y_ITEMS = TILE_Z_S * SUBW, Z_ITEMS = TILE_Y * SUBW;
+  for (uint32_t item = t.warp; item < Y_ITEMS + Z_ITEMS; item += nwarps) {
+    const uint32_t face = item < Y_ITEMS ? 0u : 1u;  // 0: y face (ly = 0), 1: z face (lz = 0)
+    const uint32_t it = face == 0 ? item : item - Y_ITEMS;
+    const uint32_t rowi = it / SUBW, k = it % SUBW;
+    const uint32_t ly = face == 0 ? 0 : rowi, lz = face == 0 ? rowi : 0;
+    const uint32_t y = t.Y0 + ly, z = t.Z0 + lz;
+    if (y >= sy || z >= sz) continue;
+    if (face == 0 ? (y == 0) : (z == 0)) continue;
+    const uint32_t stride = face == 0 ? sx : sxy;
+    const uint32_t x = t.X0 + 32 * k + t.lane;
+    const bool inb = x < sx;
+    const uint32_t idx = (z * sy + y) * sx + x;
+    const V v = inb ? rd.at(idx, x, y, z) : (V)0;
+    const V vn = inb ? (face == 0 ? rd.at(idx - sx, x, y - 1, z) : rd.at(idx - sxy, x, y, z - 1)) : (V)0;
+    const V vl = shfl_up1(v);
+    const bool same_left = (t.lane > 0) && (v == vl);
+    const bool c = (v != 0) && (v == vn);
+    const bool c_l = __shfl_up_sync(FULL, (int)c, 1) != 0;
+    if (c && !(same_left && c_l)) merge_emit(set, parent, parent[idx], parent[idx - stride]);
+  }
+  if (t.X0 > 0) {  // x face: one voxel pair per tile row
+    for (uint32_t r = threadIdx.x; r < (uint32_t)(TILE_Y * TILE_Z_S); r += blockDim.x) {
       const uint32_t y = t.Y0 + (r % TILE_Y), z = t.Z0 + (r / TILE_Y);
       if (y >= sy || z >= sz) continue;
       const uint32_t idx = (z * sy + y) * sx + t.X0;
@@ -1149,8 +1237,17 @@ static uint32_t default_cap(uint64_t n) {
 template <typename R>
 static int ccl_core(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, uint32_t sz,
                     CclScratch& s, uint32_t* n_roots, bool* overflow) {
+  // IGN_CCL_V2=3: the half-height tile experiment (k_ccl_local_v3 / k_ccl_merge_tiles_s)
+  bool small = false;
+  if constexpr (!R::thresholded) {
+    const char* e = getenv("IGN_CCL_V2");
+    small = e != nullptr && e[0] == '3' && (rd.rx & rd.ry & rd.rz) == 0xFFFFFFFFu &&
+            getenv("IGN_CCL_GENERIC") == nullptr && getenv("IGN_CCL_FLATMERGE") == nullptr && (sx % 4 == 0) &&
+            ((uintptr_t)rd.in % 16 == 0) && ((uintptr_t)s.parent % 16 == 0);
+  }
+  const uint32_t tile_z = small ? (uint32_t)TILE_Z_S : (uint32_t)TILE_Z;
   const uint32_t ntx = (sx + TILE_X - 1) / TILE_X, nty = (sy + TILE_Y - 1) / TILE_Y,
-                 ntz = (sz + TILE_Z - 1) / TILE_Z;
+                 ntz = (sz + tile_z - 1) / tile_z;
   const uint64_t n = (uint64_t)sx * sy * sz;
   const uint64_t ntiles = (uint64_t)ntx * nty * ntz;
   IGN_REQUIRE(ntiles < 0x7FFFFFFFull, IGN_ERR_OVERFLOW, "too many CCL tiles");
@@ -1169,7 +1266,11 @@ static int ccl_core(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, uint32_
     // experimental 4-voxels-per-lane kernel: opt-in until it has been validated on a GPU
     const bool v2 = fast && getenv("IGN_CCL_V2") != nullptr && (sx % 4 == 0) &&
                     ((uintptr_t)rd.in % 16 == 0) && ((uintptr_t)s.parent % 16 == 0);
-    if (v2) {
+    if (small) {
+      constexpr size_t smem3 = (size_t)(TILE_VOX_S + CCL_WARPS_S * (TASKS_PER_WARP + STARTS_PER_WARP)) * sizeof(uint32_t);
+      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local_v3<typename R::value_type>), grid, CCL_THREADS_S, smem3,
+                      rd.in, sx, sy, sz, ntx, nty, s.parent, s.cand, s.cap, s.counters);
+    } else if (v2) {
       constexpr size_t smem2 = smem + (size_t)CCL_WARPS * STARTS_PER_WARP * sizeof(uint32_t);
       IGN_CUDA(cudaFuncSetAttribute(k_ccl_local_v2<typename R::value_type>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
@@ -1184,7 +1285,10 @@ static int ccl_core(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, uint32_
     IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local<R>), grid, CCL_THREADS, smem, rd, sx, sy, sz, ntx, nty,
                     s.parent, s.cand, s.cap, s.counters);
   if (ntiles > 1) {
-    if (getenv("IGN_CCL_FLATMERGE") == nullptr) {
+    if (small) {
+      if constexpr (!R::thresholded)
+        IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, (k_ccl_merge_tiles_s<R>), grid, 256, 0, rd, sx, sy, sz, ntx, nty, s.parent);
+    } else if (getenv("IGN_CCL_FLATMERGE") == nullptr) {
       IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, (k_ccl_merge_tiles<R>), grid, 256, 0, rd, sx, sy, sz, ntx, nty, s.parent);
     } else {
       const uint32_t w32 = (sx + 31) / 32;
