@@ -113,15 +113,52 @@ def oracle_pipeline(seg, simplify=100):
 
 
 _WORKER = {}
+REF_CHUNK = (256, 256, 64)
 
 
-def _oracle_worker_init(counter, shape):
-  """Each pool worker synthesises its own chunk of the dataset ONCE (outside any timed region)."""
+def host_cores():
+  """Cores this process may actually use: the affinity mask clipped by the cgroup CPU quota
+  (os.cpu_count() reports the whole node even inside a small lease)."""
+  try:
+    n = len(os.sched_getaffinity(0))
+  except (AttributeError, OSError):
+    n = os.cpu_count() or 1
+  quota = None
+  try:
+    with open("/sys/fs/cgroup/cpu.max") as f:  # cgroup v2
+      q, per = f.read().split()[:2]
+      if q != "max":
+        quota = float(q) / float(per)
+  except (OSError, ValueError):
+    try:
+      with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f1, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f2:
+        q, per = float(f1.read()), float(f2.read())
+        if q > 0:
+          quota = q / per
+    except (OSError, ValueError):
+      pass
+  if quota is not None:
+    n = max(1, min(n, int(quota + 0.5)))
+  return n
+
+
+def ref_chunk_offset(index, size):
+  """Chunk `index` of the REF_CHUNK grid over the size^3 bench volume (x fastest, as
+  FinelyDividedTaskIterator enumerates tasks, igneous/task_creation/common.py:91-98)."""
+  gx, gy, gz = (max(1, size // c) for c in REF_CHUNK)
+  index %= gx * gy * gz
+  return ((index % gx) * REF_CHUNK[0], ((index // gx) % gy) * REF_CHUNK[1], (index // (gx * gy)) * REF_CHUNK[2])
+
+
+def _oracle_worker_init(counter, size):
+  """Each pool worker synthesises its own chunk of the bench volume ONCE (outside any timed region)."""
   from oracle import oracle as O
   with counter.get_lock():
     wid = counter.value
     counter.value += 1
-  _WORKER["seg"] = O.synth_tiled(shape, wid)
+  # spread the workers' chunks over the volume (stride 37 is coprime with the chunk grid)
+  _WORKER["seg"] = O.synth_seg(REF_CHUNK, pitch=PITCH, num_ids=NUM_IDS, seed=0,
+                               offset=ref_chunk_offset(wid * 37, size))
   O.lib()
 
 
@@ -134,22 +171,25 @@ def _oracle_worker(_):
 def run_reference_arm(args):
   """--impl reference: the reference's CPU implementation of the path.  The
   reference's own kernels (tinybrain / cc3d / zmesh wheels) are absent from
-  this image, so this times the C oracle port on all host cores (one chunk
-  worker per core, spawn, as igneous_cli/cli.py:915-933 does).  Every worker
-  holds one chunk of the synthetic dataset; a step = every worker runs the
-  pipeline once on its chunk."""
+  this image, so this times the C oracle port on the host cores this process may
+  use (one chunk worker per core, spawn, as igneous_cli/cli.py:915-933 does).  Every
+  worker holds one 256x256x64 chunk cut from the SAME synthetic volume the GPU arm
+  processes; a step = every worker runs the pipeline once on its chunk."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
   import multiprocessing as mp
   from oracle import oracle as O
   O.build()
-  cores = os.cpu_count() or 1
-  shape = (256, 256, 64)  # ~14 s per step on a 128-thread host under full contention
+  cores = host_cores()
   ctx = mp.get_context("spawn")
+  # one chunk alone on an otherwise idle host: the reference's real per-worker speed
+  _oracle_worker_init(ctx.Value("i", 0), args.size)
+  _oracle_worker(0)
+  alone = min(_oracle_worker(0)[1] for _ in range(2))
   counter = ctx.Value("i", 0)
   times, per_chunk = [], []
-  with ctx.Pool(cores, initializer=_oracle_worker_init, initargs=(counter, shape)) as pool:
+  with ctx.Pool(cores, initializer=_oracle_worker_init, initargs=(counter, args.size)) as pool:
     pool.map(_oracle_worker, range(cores), chunksize=1)  # untimed: all workers initialised and warm
     for it in range(args.warmup + args.steps):
       t = time.perf_counter()
@@ -161,16 +201,20 @@ def run_reference_arm(args):
   vox = sum(t[0] for t in times)
   sec = sum(t[1] for t in times)
   value = vox / sec / 1e6
+  shape = REF_CHUNK
   line = {
     "impl": "reference", "metric": METRIC, "value": value, "unit": "Mvoxels/s", "n_gpus": args.gpus,
     "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(len(times), 1),
     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
     "data": "synthetic", "gpu_launches": 0,
-    "config": {"workload": "oracle port of the igneous CPU path: per step %d chunks of %dx%dx%d uint32 "
-                           "(one per host core, jittered-Voronoi pitch 64): mode pool 2 mips + 6-connected CCL + "
-                           "marching cubes / weld / quadric simplification x100 at mip 2" % ((cores,) + shape),
-               "chunk": list(shape), "simplification_factor": 100,
-               "seconds_per_chunk_median": float(np.median(per_chunk)) if per_chunk else None},
+    "config": {"workload": "oracle port of the igneous CPU path on %dx%dx%d uint32 chunks cut from the %d^3 "
+                           "jittered-Voronoi bench volume (pitch 64), one chunk per usable host core (%d) per step: "
+                           "mode pool 2 mips + 6-connected CCL + marching cubes / weld / quadric simplification "
+                           "x100 at mip 2" % (shape + (args.size, cores)),
+               "chunk": list(shape), "simplification_factor": 100, "cores_used": cores,
+               "os_cpu_count": os.cpu_count(),
+               "seconds_per_chunk_alone": alone,
+               "seconds_per_chunk_contended_median": float(np.median(per_chunk)) if per_chunk else None},
     "cpu_baseline": {"value": value, "unit": "Mvoxels/s", "cores": cores, "kind": "port",
                      "sample": "%d x %dx%dx%d chunks per step, %d steps" % ((cores,) + shape + (args.steps,))},
     "e2e": {"value": value, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -6,33 +6,45 @@
 // blackout_non_face_rails :103-124, `+= label_offset`, `[labels==0] = 0`
 // :174-175) into the same kernels.
 //
-// Algorithm (two-level run-based union-find, union by minimum voxel index):
-//   L  local  : a CTA owns a 256x8x8 voxel tile.  Warps walk tile rows as 8
-//               sub-words of 32 voxels (one voxel per lane: every global access
-//               is a coalesced 128 B line for any row pitch -- igneous's own
-//               task shape is 513^3).  Ballots over "differs from my left
-//               neighbour" find the x-runs; y / z adjacencies between runs are
-//               queued per warp and resolved 32 at a time on a union-find held
-//               in SHARED memory; every voxel then stores the global index of
-//               its tile-local root (dense 4 B/voxel write) and local roots are
-//               logged as root candidates.  k_ccl_local_fast (raw labels) /
-//               k_ccl_local (threshold_image + rails fused in the reader).
-//   G  merge  : one CTA per tile gathers the (local root, local root) pairs that
-//               meet across the tile's low x / y / z faces in a shared-memory
-//               hash set and unites the unique pairs with an atomicMin
-//               union-find in global memory (path halving).  k_ccl_merge_tiles.
-//   R  roots  : candidates that are still their own parent are the component
-//               minima; sorted, their rank+1 is cc3d's id (first voxel in
-//               raster order); it is written back into the root's entry, flagged.
-//   F  label  : every voxel chases parent links to a flagged root (8 independent
-//               chases per lane), optionally through a lookup table (dust,
-//               multi-slab and multi-GPU relabelling), and writes u16/u32/u64.
-// HBM traffic: in (L) + 4 (L) + face rows (G) + 4 + out (F) ~ in + 8 + out
-// bytes/voxel (measured 7.65 B/voxel for L with u32 input); algorithmic bytes
-// (cc3d contract) = in + out.
-#include <cub/device/device_radix_sort.cuh>
+// Algorithm: union-find over x-RUNS described by per-voxel BIT MASKS.  Voxels
+// are touched by two streaming passes only (A reads them once, C writes them
+// once); everything in between works on 0.625 bytes per voxel of masks and on
+// one u32 per run (a run = maximal x-segment of equal non-zero labels; typical
+// segmentation has ~40 voxels per run).
+//
+//   A  masks   k_ccl_masks: persistent CTAs stage (128+halo) x 9 x 9 voxel tiles
+//              in shared memory -- one cp.async.bulk.tensor.3d (TMA) per tile into
+//              a double buffer, completion on an mbarrier, out-of-volume halo
+//              zero-filled by the copy engine, so the compute loop has no address
+//              arithmetic and no bounds predicates (volumes whose row pitch is
+//              not a multiple of 16 bytes -- igneous's own 513^3 task shape --
+//              take a cooperative-load fill of the same tile).  Per 32-voxel
+//              word four ballots: S run starts (v != 0 && v != left), Z non-zero,
+//              Ey / Ez equal to the y-1 / z-1 neighbour.  threshold_image and
+//              blackout_non_face_rails are applied to the staged tile in place.
+//      scan    exclusive sum of popc(S): the id of the first run starting in each
+//              word.  Run ids therefore follow voxel raster order.
+//   B  tiles   k_ccl_tiles: a CTA owns all words of 8 x 8 rows; the runs of the tile
+//              are united along y and z on a union-find in SHARED memory (one
+//              union per stretch of Ey / Ez in which neither row starts a new run),
+//              then every run's parent (global run id of its tile root) is written.
+//      merge   k_ccl_merge: the rows on tile faces do the same unions on the global
+//              parent array (atomicMin union-find, path halving).
+//   R  roots   flatten, then an exclusive scan over (parent[r] == r): roots are run
+//              ids in raster order, so the scan IS cc3d's numbering (rank of the
+//              component's first voxel); no sort.
+//   C  expand  k_ccl_expand: label of voxel = label[run base of its word +
+//              popc(S below it) - 1], 0 where Z is clear; optional offset /
+//              lookup table (dust, multi-GPU relabelling); u16 / u32 / u64.
+// HBM traffic ~ in + 0.625 (A) + ~0.6 (B, R: masks + runs) + 0.25 + out (C)
+// bytes/voxel; algorithmic bytes (cc3d contract) = in + out.
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+#include <cuda.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <type_traits>
 #include <vector>
@@ -41,25 +53,23 @@
 
 namespace ign {
 
-constexpr uint32_t CCL_BG = 0xFFFFFFFFu;
-constexpr uint32_t CCL_FLAG = 0x80000000u;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 // ----------------------------------------------------------------- reader
-// How a voxel value is obtained: raw label, or threshold_image() -> {0,1};
-// rails of the +1 overlap shell are blacked out on the fly.
+// How a voxel value becomes a label: raw, or threshold_image() -> {0,1}; the
+// rails of the +1 overlap shell are blacked out (ccl.py:103-124).
 template <typename T, bool THR>
 struct Reader {
-  using V = std::conditional_t<THR, uint32_t, T>;
   using value_type = T;
   static constexpr bool thresholded = THR;
   const T* in;
   double gte, lte;
   int use_gte, use_lte;
   uint32_t rx, ry, rz;  // rail coordinates (0xFFFFFFFF = none)
-  __device__ __forceinline__ V at(uint32_t idx, uint32_t x, uint32_t y, uint32_t z) const {
-    const T raw = in[idx];
-    V v;
+  __host__ __device__ __forceinline__ bool has_rails() const { return (rx & ry & rz) != 0xFFFFFFFFu; }
+  // label stored back in the staged tile (type T: 0 / 1 when thresholded)
+  __device__ __forceinline__ T label(T raw, uint32_t x, uint32_t y, uint32_t z) const {
+    T v = raw;
     if constexpr (THR) {
       bool ok = true;
       if constexpr (std::is_same<T, float>::value) {
@@ -69,23 +79,16 @@ struct Reader {
         if (use_gte) ok = ok && ((double)raw >= gte);
         if (use_lte) ok = ok && ((double)raw <= lte);
       }
-      v = ok ? 1u : 0u;
-    } else {
-      v = raw;
+      v = ok ? (T)1 : (T)0;
     }
     const int on = (int)(x == rx) + (int)(y == ry) + (int)(z == rz);
-    if (on >= 2) v = 0;
+    if (on >= 2) v = (T)0;
     return v;
   }
 };
 
-template <typename V>
-__device__ __forceinline__ V shfl_up1(V v) {
-  if constexpr (sizeof(V) <= 4) return (V)__shfl_up_sync(FULL, (uint32_t)v, 1);
-  else return (V)__shfl_up_sync(FULL, (unsigned long long)v, 1);
-}
-
 // ------------------------------------------------------------- union-find
+// works on shared and on global memory (generic pointers)
 __device__ __forceinline__ uint32_t uf_find(volatile uint32_t* P, uint32_t i) {
   uint32_t cur = i, p = P[cur];
   while (p != cur) {
@@ -113,1220 +116,765 @@ __device__ __forceinline__ void uf_union(uint32_t* P, uint32_t a, uint32_t b) {
   }
 }
 
-// ------------------------------------------------------------------ tiling
-// A CTA owns a TILE_X x TILE_Y x TILE_Z voxel tile; a warp walks whole tile
-// rows as SUBW sub-words of 32 voxels (one voxel per lane per sub-word, so all
-// global accesses are 128 B coalesced whatever the row pitch -- igneous's own
-// task shape is 513^3 -- and SUBW independent loads are in flight per lane).
-constexpr int TILE_X = 256, TILE_Y = 8, TILE_Z = 8;
-constexpr int SUBW = TILE_X / 32;             // sub-words per tile row
-constexpr int TILE_ROWS = TILE_Y * TILE_Z;    // 64
-constexpr int TILE_VOX = TILE_X * TILE_ROWS;  // 16384 -> 64 KB of u32 parents
-constexpr int CCL_THREADS = 512;
-constexpr int CCL_WARPS = CCL_THREADS / 32;
-constexpr int ROWS_PER_WARP = TILE_ROWS / CCL_WARPS;  // 4
-constexpr int TASKS_PER_WARP = 128;
-static_assert(TILE_X == 256 && TILE_Y == 8, "k_ccl_local_fast decodes local indices with shifts");           // queued (a<<16|b) union tasks, 14-bit local indices
+// ---------------------------------------------------------------- TMA / mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 
-struct TilePos {
-  uint32_t X0, Y0, Z0, warp, lane;
+// ------------------------------------------------------------------ pass A
+// tile of the mask kernel: MT_BX x MT_BY x bz voxels (+1 halo row / plane on the low
+// side, +16 bytes of halo on the low x side: TMA boxes are multiples of 16 bytes)
+constexpr int MT_BX = 128, MT_BY = 8;
+constexpr int MT_THREADS = 256;
+template <typename T> struct MaskTile {
+  static constexpr int BZ = sizeof(T) == 8 ? 4 : 8;
+  static constexpr int HX = 16 / (int)sizeof(T);
+  static constexpr int PITCH = MT_BX + HX;             // elements per tile row
+  static constexpr int ROWS = (MT_BY + 1) * (BZ + 1);  // rows incl. halo
+  static constexpr int ELEMS = PITCH * ROWS;
+  static constexpr size_t BYTES = ((size_t)ELEMS * sizeof(T) + 127) / 128 * 128;
 };
 
-__device__ __forceinline__ TilePos tile_pos(uint32_t ntx, uint32_t nty) {
-  TilePos t;
-  const uint32_t b = blockIdx.x;
-  t.X0 = (b % ntx) * TILE_X;
-  t.Y0 = ((b / ntx) % nty) * TILE_Y;
-  t.Z0 = (b / (ntx * nty)) * TILE_Z;
-  t.warp = threadIdx.x >> 5;
-  t.lane = threadIdx.x & 31;
-  return t;
+struct MaskArgs {
+  uint32_t sx, sy, sz, wpr;
+  uint32_t ntx, nty, ntz, nby, nbz;  // tiles per axis; 8x8 blocks of (y,z) tile columns
+  uint32_t ncols;                    // padded number of (y,z) columns = nby*nbz*64
+  uint32_t *S, *Z, *Ey, *Ez;
+};
+
+// tile index -> tile coordinates (x fastest, then 8x8 blocks of (y,z) columns so that
+// the halo rows / planes a tile re-reads are still in L2); false = padding, skip
+__device__ __forceinline__ bool mask_tile_coords(const MaskArgs& a, uint64_t t, uint32_t* tx, uint32_t* ty,
+                                                 uint32_t* tz) {
+  *tx = (uint32_t)(t % a.ntx);
+  const uint32_t c = (uint32_t)(t / a.ntx);
+  const uint32_t b = c >> 6, r = c & 63u;
+  *ty = (b % a.nby) * 8 + (r & 7u);
+  *tz = (b / a.nby) * 8 + (r >> 3);
+  return *ty < a.nty && *tz < a.ntz;
 }
 
-__device__ __forceinline__ uint32_t seg_start_lane(uint32_t sm, uint32_t lane) {
-  return 31 - __clz(sm & (0xFFFFFFFFu >> (31 - lane)));
-}
+template <typename T, bool THR, bool TMA>
+__global__ void __launch_bounds__(MT_THREADS)
+    k_ccl_masks(const __grid_constant__ CUtensorMap tmap, const Reader<T, THR> rd, const MaskArgs a) {
+  using MT = MaskTile<T>;
+  extern __shared__ __align__(128) unsigned char mt_smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  T* buf[2] = {(T*)mt_smem, (T*)(mt_smem + MT::BYTES)};
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint64_t ntiles = (uint64_t)a.ntx * a.ncols;
+  const bool transform = THR || rd.has_rails();
 
-// shared-memory union-find (same algorithm as the global one)
-__device__ __forceinline__ uint32_t sm_find(volatile uint32_t* L, uint32_t i) {
-  uint32_t cur = i, p = L[cur];
-  while (p != cur) {
-    const uint32_t gp = L[p];
-    if (gp != p) L[cur] = gp;
-    cur = p;
-    p = gp;
-  }
-  return cur;
-}
-__device__ __forceinline__ void sm_union(uint32_t* L, uint32_t a, uint32_t b) {
-  while (true) {
-    a = sm_find(L, a);
-    b = sm_find(L, b);
-    if (a == b) return;
-    if (a < b) {
-      const uint32_t t = a;
-      a = b;
-      b = t;
-    }
-    const uint32_t old = atomicMin(&L[a], b);
-    if (old == a) return;
-    a = old;
-  }
-}
-
-// -------------------------------------------------------- L: tile-local CCL
-// Resolves every tile completely in shared memory and writes, for each voxel,
-// the GLOBAL linear index of its tile-local root (background -> BG).  Local
-// roots are logged as root candidates.
-template <typename R>
-__global__ void __launch_bounds__(CCL_THREADS)
-    k_ccl_local(R rd, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t ntx, uint32_t nty,
-                uint32_t* __restrict__ parent, uint32_t* __restrict__ cand, uint32_t cand_cap,
-                uint32_t* counters) {
-  extern __shared__ uint32_t L[];
-  uint32_t* tasks = L + TILE_VOX;
-  using V = typename R::V;
-  const TilePos t = tile_pos(ntx, nty);
-
-  // step 1: segment starts
-#pragma unroll 1
-  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
-    const uint32_t r = t.warp * ROWS_PER_WARP + rr;
-    const uint32_t y = t.Y0 + (r % TILE_Y), z = t.Z0 + (r / TILE_Y);
-    const bool rowok = (y < sy) && (z < sz);
-    const uint32_t rowbase = (z * sy + y) * sx;
-    V v[SUBW];
-#pragma unroll
-    for (int k = 0; k < SUBW; k++) {
-      const uint32_t x = t.X0 + 32 * k + t.lane;
-      v[k] = (rowok && x < sx) ? rd.at(rowbase + x, x, y, z) : (V)0;
-    }
-#pragma unroll
-    for (int k = 0; k < SUBW; k++) {
-      const V vl = shfl_up1(v[k]);
-      const bool start = (v[k] != 0) && (t.lane == 0 || vl != v[k]);
-      const uint32_t sm = __ballot_sync(FULL, start);
-      const uint32_t li = r * TILE_X + 32 * k + t.lane;
-      L[li] = (v[k] != 0) ? (r * TILE_X + 32 * k + seg_start_lane(sm, t.lane)) : CCL_BG;
-    }
-  }
-  __syncthreads();
-
-  // step 2: unions inside the tile.  Union tasks (a,b) are queued per warp in
-  // shared memory and executed 32 at a time: the dependent-load chains of one
-  // sub-word's unions would otherwise run back to back on a single lane.
-  uint32_t* q = tasks + t.warp * TASKS_PER_WARP;
-  uint32_t nq = 0;
-  auto flush = [&]() {
-    __syncwarp();
-    for (uint32_t i = t.lane; i < nq; i += 32) {
-      const uint32_t ab = q[i];
-      sm_union(L, ab >> 16, ab & 0xFFFFu);
-    }
-    __syncwarp();
-    nq = 0;
+  uint32_t tx = 0, ty = 0, tz = 0;
+  auto advance = [&](uint64_t from) {  // first valid tile index >= from in this CTA's stride class
+    uint64_t q = from;
+    while (q < ntiles && !mask_tile_coords(a, q, &tx, &ty, &tz)) q += gridDim.x;
+    return q;
   };
-#pragma unroll 1
-  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
-    const uint32_t r = t.warp * ROWS_PER_WARP + rr;
-    const uint32_t ly = r % TILE_Y, lz = r / TILE_Y;
-    const uint32_t y = t.Y0 + ly, z = t.Z0 + lz;
-    if (!((y < sy) && (z < sz))) continue;
-    const uint32_t rowbase = (z * sy + y) * sx;
-    const uint32_t sxy = sx * sy;
-    V v[SUBW], vy[SUBW], vz[SUBW];
-#pragma unroll
-    for (int k = 0; k < SUBW; k++) {
-      const uint32_t x = t.X0 + 32 * k + t.lane;
-      const bool inb = x < sx;
-      v[k] = inb ? rd.at(rowbase + x, x, y, z) : (V)0;
-      vy[k] = (inb && ly > 0) ? rd.at(rowbase + x - sx, x, y - 1, z) : (V)0;
-      vz[k] = (inb && lz > 0) ? rd.at(rowbase + x - sxy, x, y, z - 1) : (V)0;
-    }
-    V prev_last = 0;
-#pragma unroll
-    for (int k = 0; k < SUBW; k++) {
-      const V vl = shfl_up1(v[k]);
-      const bool same_left = (t.lane > 0) && (v[k] == vl);
-      const bool start = (v[k] != 0) && !same_left;
-      const uint32_t sm = __ballot_sync(FULL, start);
-      const bool cy = (v[k] != 0) && (v[k] == vy[k]);
-      const bool cz = (v[k] != 0) && (v[k] == vz[k]);
-      const bool cy_l = __shfl_up_sync(FULL, (int)cy, 1) != 0;
-      const bool cz_l = __shfl_up_sync(FULL, (int)cz, 1) != 0;
-      const bool tx = (t.lane == 0) && (k > 0) && (v[k] != 0) && (v[k] == prev_last);
-      const bool ty = cy && !(same_left && cy_l);
-      const bool tz = cz && !(same_left && cz_l);
-      const uint32_t li = r * TILE_X + 32 * k + t.lane;
-      const uint32_t node = r * TILE_X + 32 * k + seg_start_lane(sm | 1u, t.lane);
-      const uint32_t my = __ballot_sync(FULL, ty), mz = __ballot_sync(FULL, tz);
-      const uint32_t mx = __ballot_sync(FULL, tx);
-      const uint32_t below = (1u << t.lane) - 1u;
-      if (nq + __popc(my) + __popc(mz) + __popc(mx) > TASKS_PER_WARP) flush();
-      if (tx) q[nq] = (li << 16) | (li - 1);
-      uint32_t o = nq + __popc(mx);
-      if (ty) q[o + __popc(my & below)] = (node << 16) | (li - TILE_X);
-      o += __popc(my);
-      if (tz) q[o + __popc(mz & below)] = (node << 16) | (li - TILE_X * TILE_Y);
-      nq = o + __popc(mz);
-      if constexpr (sizeof(V) <= 4) prev_last = (V)__shfl_sync(FULL, (uint32_t)v[k], 31);
-      else prev_last = (V)__shfl_sync(FULL, (unsigned long long)v[k], 31);
-    }
-  }
-  flush();
-  __syncthreads();
-
-  // step 3: flatten, translate to global indices, log local roots
-#pragma unroll 1
-  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
-    const uint32_t r = t.warp * ROWS_PER_WARP + rr;
-    const uint32_t y = t.Y0 + (r % TILE_Y), z = t.Z0 + (r / TILE_Y);
-    if (!((y < sy) && (z < sz))) continue;
-    const uint32_t rowbase = (z * sy + y) * sx;
-#pragma unroll
-    for (int k = 0; k < SUBW; k++) {
-      const uint32_t x = t.X0 + 32 * k + t.lane;
-      const uint32_t li = r * TILE_X + 32 * k + t.lane;
-      uint32_t p = L[li];
-      bool is_root = false;
-      uint32_t g = CCL_BG;
-      if (p != CCL_BG) {
-        is_root = (p == li);
-        uint32_t cur = p;
-        while (true) {  // read-only chase: no writer after the barrier
-          const uint32_t q = L[cur];
-          if (q == cur) break;
-          cur = q;
-        }
-        const uint32_t rr2 = cur / TILE_X, lx = cur % TILE_X;
-        g = ((t.Z0 + rr2 / TILE_Y) * sy + (t.Y0 + rr2 % TILE_Y)) * sx + t.X0 + lx;
-      }
-      if (x < sx) parent[rowbase + x] = g;
-      const uint32_t cm = __ballot_sync(FULL, is_root);
-      if (cm) {
-        const int leader = __ffs(cm) - 1;
-        uint32_t base = 0;
-        if ((int)t.lane == leader) base = atomicAdd(&counters[0], (uint32_t)__popc(cm));
-        base = __shfl_sync(FULL, base, leader);
-        if (is_root) {
-          const uint32_t pos = base + __popc(cm & ((1u << t.lane) - 1u));
-          if (pos < cand_cap) cand[pos] = g;
-          else counters[1] = 1;
-        }
-      }
-    }
-  }
-}
-
-// ------------------------------------------------ L (fast path): plain labels
-// Same algorithm and same results as k_ccl_local, specialised for the common
-// case (raw labels, no threshold, no rails): loads are pointer + immediate
-// offset, interior tiles carry no bounds predicates, per-lane flags are derived
-// from warp-uniform ballot masks, and x-runs continue across the 32-voxel
-// sub-words of a tile row (no x-boundary unions inside a tile).  The generic
-// kernel above was issue bound: 27 % IMAD + 20 % ISETP of 221 warp
-// instructions per sub-word (profiles/r01_ccl_local_full_512_raw.csv).
-template <typename T>
-__device__ __forceinline__ T shfl_idx(T v, int src) {
-  if constexpr (sizeof(T) <= 4) return (T)__shfl_sync(FULL, (uint32_t)v, src);
-  else return (T)__shfl_sync(FULL, (unsigned long long)v, src);
-}
-
-template <typename T, bool FULLTILE>
-__device__ __forceinline__ void local_tile_fast(const T* __restrict__ in, uint32_t sx, uint32_t sy,
-                                                uint32_t sz, const TilePos& t, uint32_t* L,
-                                                uint32_t* tasks, uint32_t* __restrict__ parent,
-                                                uint32_t* __restrict__ cand, uint32_t cand_cap,
-                                                uint32_t* counters) {
-  const uint32_t sxy = sx * sy;
-  const uint32_t lemask = 0xFFFFFFFFu >> (31 - t.lane);  // lanes <= mine
-  const uint32_t ltmask = lemask >> 1;                   // lanes <  mine
-  const uint32_t tile_g0 = (t.Z0 * sy + t.Y0) * sx + t.X0;
-
-  // ---- phase 1: segment starts (runs continue across sub-words of the row)
-#pragma unroll 1
-  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
-    const uint32_t r = t.warp * ROWS_PER_WARP + rr;
-    const uint32_t ly = r % TILE_Y, lz = r / TILE_Y;
-    const bool rowok = FULLTILE || ((t.Y0 + ly < sy) && (t.Z0 + lz < sz));
-    const T* p = in + (tile_g0 + lz * sxy + ly * sx + t.lane);
-    T v[SUBW];
-#pragma unroll
-    for (int k = 0; k < SUBW; k++)
-      v[k] = (FULLTILE || (rowok && (t.X0 + 32 * k + t.lane < sx))) ? p[32 * k] : (T)0;
-    uint32_t carry = 0;
-    T prev_last = 0;
-#pragma unroll
-    for (int k = 0; k < SUBW; k++) {
-      const T vl = shfl_up1(v[k]);
-      const T v0 = shfl_idx(v[k], 0);
-      const bool cont = (k > 0) && (v0 != 0) && (v0 == prev_last);
-      const bool nz = v[k] != 0;
-      const bool same = (t.lane > 0) ? (v[k] == vl) : cont;
-      const uint32_t m_start = __ballot_sync(FULL, nz && !same);
-      const uint32_t below = m_start & lemask;
-      const uint32_t base = r * TILE_X + 32 * k;
-      const uint32_t start = below ? (base + 31 - __clz(below)) : carry;
-      L[base + t.lane] = nz ? start : CCL_BG;
-      if (m_start) carry = base + 31 - __clz(m_start);
-      prev_last = shfl_idx(v[k], 31);
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 2: y / z unions, queued per warp and executed 32 wide
-  uint32_t* q = tasks + t.warp * TASKS_PER_WARP;
-  uint32_t nq = 0;
-  auto flush = [&]() {
-    __syncwarp();
-    for (uint32_t i = t.lane; i < nq; i += 32) {
-      const uint32_t ab = q[i];
-      sm_union(L, ab >> 16, ab & 0xFFFFu);
-    }
-    __syncwarp();
-    nq = 0;
-  };
-#pragma unroll 1
-  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
-    const uint32_t r = t.warp * ROWS_PER_WARP + rr;
-    const uint32_t ly = r % TILE_Y, lz = r / TILE_Y;
-    if (!FULLTILE && !((t.Y0 + ly < sy) && (t.Z0 + lz < sz))) continue;
-    if (ly == 0 && lz == 0) continue;  // no in-tile neighbour below: nothing to unite
-    const T* p = in + (tile_g0 + lz * sxy + ly * sx + t.lane);
-    T v[SUBW], vy[SUBW], vz[SUBW];
-#pragma unroll
-    for (int k = 0; k < SUBW; k++) {
-      const bool inb = FULLTILE || (t.X0 + 32 * k + t.lane < sx);
-      v[k] = inb ? p[32 * k] : (T)0;
-      vy[k] = (inb && ly > 0) ? *(p + 32 * k - sx) : (T)0;
-      vz[k] = (inb && lz > 0) ? *(p + 32 * k - sxy) : (T)0;
-    }
-    T prev_last = 0;
-    uint32_t cy_prev = 0, cz_prev = 0;  // bit 31 of the previous sub-word's masks
-#pragma unroll
-    for (int k = 0; k < SUBW; k++) {
-      const T vl = shfl_up1(v[k]);
-      const T v0 = shfl_idx(v[k], 0);
-      const bool cont = (k > 0) && (v0 != 0) && (v0 == prev_last);
-      const bool nz = v[k] != 0;
-      const bool same = (t.lane > 0) ? (v[k] == vl) : cont;
-      const uint32_t m_same = __ballot_sync(FULL, nz && same);
-      const uint32_t m_cy = __ballot_sync(FULL, nz && (v[k] == vy[k]));
-      const uint32_t m_cz = __ballot_sync(FULL, nz && (v[k] == vz[k]));
-      // a union is needed where the connection starts or the x-run breaks
-      const uint32_t t_y = m_cy & ~(m_same & ((m_cy << 1) | cy_prev));
-      const uint32_t t_z = m_cz & ~(m_same & ((m_cz << 1) | cz_prev));
-      const uint32_t both = t_y | t_z;
-      if (both) {
-        const uint32_t ny = __popc(t_y), nz_ = __popc(t_z);
-        if (nq + ny + nz_ > TASKS_PER_WARP) flush();
-        if ((both >> t.lane) & 1u) {
-          const uint32_t li = r * TILE_X + 32 * k + t.lane;
-          // any member of my run's set represents it: the entry written in phase 1
-          // (or an ancestor another warp's path halving put there meanwhile)
-          const uint32_t node = ((volatile uint32_t*)L)[li];
-          if ((t_y >> t.lane) & 1u) q[nq + __popc(t_y & ltmask)] = (node << 16) | (li - TILE_X);
-          if ((t_z >> t.lane) & 1u) q[nq + ny + __popc(t_z & ltmask)] = (node << 16) | (li - TILE_X * TILE_Y);
-        }
-        nq += ny + nz_;
-      }
-      prev_last = shfl_idx(v[k], 31);
-      cy_prev = m_cy >> 31;
-      cz_prev = m_cz >> 31;
-    }
-  }
-  flush();
-  __syncthreads();
-
-  // ---- phase 3: flatten, translate to global indices, log local roots
-#pragma unroll 1
-  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
-    const uint32_t r = t.warp * ROWS_PER_WARP + rr;
-    const uint32_t ly = r % TILE_Y, lz = r / TILE_Y;
-    if (!FULLTILE && !((t.Y0 + ly < sy) && (t.Z0 + lz < sz))) continue;
-    uint32_t* out = parent + (tile_g0 + lz * sxy + ly * sx + t.lane);
-#pragma unroll
-    for (int k = 0; k < SUBW; k++) {
-      const uint32_t li = r * TILE_X + 32 * k + t.lane;
-      const uint32_t p0 = L[li];
-      const bool bgv = (p0 == CCL_BG);
-      // two unrolled hops cover almost every voxel after path halving (voxel -> run
-      // start -> root); the loop only runs for the rare deeper chains
-      uint32_t cur = bgv ? li : p0;
-      uint32_t nxt = L[cur];
-      if (__any_sync(FULL, !bgv && nxt != cur)) {
-        while (!bgv && nxt != cur) {
-          cur = nxt;
-          nxt = L[cur];
-        }
-      }
-      const uint32_t rr2 = cur >> 8;  // TILE_X == 256
-      const uint32_t g = bgv ? CCL_BG : (tile_g0 + (rr2 >> 3) * sxy + (rr2 & 7) * sx + (cur & 255));
-      if (FULLTILE || (t.X0 + 32 * k + t.lane < sx)) out[32 * k] = g;
-      if (!bgv && p0 == li) {  // tile-local root (a handful per tile): log it as a root candidate
-        const uint32_t pos = atomicAdd(&counters[0], 1u);
-        if (pos < cand_cap) cand[pos] = g;
-        else counters[1] = 1;
-      }
-    }
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(CCL_THREADS)
-    k_ccl_local_fast(const T* __restrict__ in, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t ntx,
-                     uint32_t nty, uint32_t* __restrict__ parent, uint32_t* __restrict__ cand,
-                     uint32_t cand_cap, uint32_t* counters) {
-  extern __shared__ uint32_t L[];
-  uint32_t* tasks = L + TILE_VOX;
-  const TilePos t = tile_pos(ntx, nty);
-  const bool full = (t.X0 + TILE_X <= sx) && (t.Y0 + TILE_Y <= sy) && (t.Z0 + TILE_Z <= sz);
-  if (full) local_tile_fast<T, true>(in, sx, sy, sz, t, L, tasks, parent, cand, cand_cap, counters);
-  else local_tile_fast<T, false>(in, sx, sy, sz, t, L, tasks, parent, cand, cand_cap, counters);
-}
-
-// --------------------------------------- L (v2, experimental): 4 voxels per lane
-// Same results as k_ccl_local_fast.  k_ccl_local_fast is issue bound (137 warp
-// instructions per 32-voxel sub-word, profiles/r01_ccl_local_fast_full_512_raw.csv);
-// this variant cuts the instruction count per voxel:
-//   * a lane owns FOUR consecutive voxels (one 128-bit load for u32): compares stay
-//     per voxel, but shuffles, ballots, address arithmetic and shared-memory traffic
-//     are paid once per 128 voxels instead of once per 32;
-//   * ONE pass over the labels: the y neighbour row is the row the warp read just
-//     before (registers) for 3 of its 4 rows, and the y / z union tasks are queued
-//     while the run starts are written (a task only needs indices, not the parents);
-//     they are executed after the barrier as before.
-//   * the run starts are listed, pointed at their roots after the unions, and every
-//     voxel then reaches its root with a single shared-memory hop (no chase loop).
-// Requires full tiles and sx % 4 == 0 (vector loads); everything else takes the
-// existing paths.  OPT-IN (IGN_CCL_V2=1): validated bit-exact on a B200 for u8 / u16 /
-// u32 / u64 including partial tiles and the overflow paths (tools/check_ccl_v2.py,
-// tests/test_ccl_gpu.py::test_ccl_v2_kernel_matches_oracle;
-// tools/model_ccl_v2.py is a lane-level numpy model of the mask arithmetic) and 11 %
-// faster than k_ccl_local_fast at 512^3, but the full GPU suite and the bench have not
-// been run with it yet, so the default stays k_ccl_local_fast.
-template <typename T>
-struct Vec4Load;
-template <>
-struct Vec4Load<uint8_t> {
-  static __device__ __forceinline__ void ld(const uint8_t* p, uint8_t (&a)[4]) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
-    a[0] = (uint8_t)(w & 0xFFu); a[1] = (uint8_t)((w >> 8) & 0xFFu);
-    a[2] = (uint8_t)((w >> 16) & 0xFFu); a[3] = (uint8_t)(w >> 24);
-  }
-};
-template <>
-struct Vec4Load<uint16_t> {
-  static __device__ __forceinline__ void ld(const uint16_t* p, uint16_t (&a)[4]) {
-    const uint2 w = *reinterpret_cast<const uint2*>(p);
-    a[0] = (uint16_t)(w.x & 0xFFFFu); a[1] = (uint16_t)(w.x >> 16);
-    a[2] = (uint16_t)(w.y & 0xFFFFu); a[3] = (uint16_t)(w.y >> 16);
-  }
-};
-template <>
-struct Vec4Load<uint32_t> {
-  static __device__ __forceinline__ void ld(const uint32_t* p, uint32_t (&a)[4]) {
-    const uint4 w = *reinterpret_cast<const uint4*>(p);
-    a[0] = w.x; a[1] = w.y; a[2] = w.z; a[3] = w.w;
-  }
-};
-template <>
-struct Vec4Load<uint64_t> {
-  static __device__ __forceinline__ void ld(const uint64_t* p, uint64_t (&a)[4]) {
-    const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(p);
-    const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(p + 2);
-    a[0] = w0.x; a[1] = w0.y; a[2] = w1.x; a[3] = w1.y;
-  }
-};
-
-constexpr int QUAD = 128;                 // voxels a warp covers per step (4 per lane)
-constexpr int QUADS = TILE_X / QUAD;      // 2
-static_assert(ROWS_PER_WARP == 4 && TILE_Y == 8 && QUADS == 2, "local_tile_v2 row ownership");
-
-constexpr int STARTS_PER_WARP = 128;      // run starts a warp can list for the compression pass
-
-template <typename T>
-__device__ __forceinline__ void local_tile_v2(const T* __restrict__ in, uint32_t sx, uint32_t sy,
-                                              const TilePos& t, uint32_t* L, uint32_t* tasks, uint32_t* starts,
-                                              uint32_t* __restrict__ parent, uint32_t* __restrict__ cand,
-                                              uint32_t cand_cap, uint32_t* counters) {
-  const uint32_t sxy = sx * sy;
-  const uint32_t ltmask = (1u << t.lane) - 1u;  // lanes < mine
-  const uint32_t tile_g0 = (t.Z0 * sy + t.Y0) * sx + t.X0;
-  // a warp owns 4 consecutive y rows of one z slice of the tile
-  const uint32_t lz = t.warp >> 1, ly0 = (t.warp & 1u) * ROWS_PER_WARP;
-  uint32_t* q = tasks + t.warp * TASKS_PER_WARP;
-  uint32_t* sq = starts + t.warp * STARTS_PER_WARP;
-  uint32_t nq = 0, ns = 0;
-  bool overflow = false, soverflow = false;
-
-  // ---- pass 1: run starts + queued y / z union tasks + list of run starts
-  T prev[QUADS][4];  // the row this warp handled before (y neighbour of the next one)
-#pragma unroll
-  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
-    const uint32_t ly = ly0 + rr, r = lz * TILE_Y + ly;
-    const T* row = in + (tile_g0 + lz * sxy + ly * sx + 4 * t.lane);
-    uint32_t carry = 0;   // local index of the last run start seen in this row
-    T prev_last = 0;      // last voxel of the previous quad (0 never equals a foreground label)
-    uint32_t cprev = 0;   // bit 0 / 1: y / z connection of the previous quad's last voxel
-#pragma unroll
-    for (int qd = 0; qd < QUADS; qd++) {
-      T a[4], y[4], z[4];
-      Vec4Load<T>::ld(row + QUAD * qd, a);
-      if (rr > 0) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) y[j] = prev[qd][j];
-      } else if (ly > 0) {
-        Vec4Load<T>::ld(row + QUAD * qd - sx, y);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; j++) y[j] = 0;
-      }
-      if (lz > 0) {
-        Vec4Load<T>::ld(row + QUAD * qd - sxy, z);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; j++) z[j] = 0;
-      }
-      T left = shfl_up1(a[3]);
-      if (t.lane == 0) left = prev_last;
-      bool nzv[4], same[4], st[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        nzv[j] = a[j] != 0;
-        same[j] = nzv[j] && (a[j] == (j == 0 ? left : a[j - 1]));
-        st[j] = nzv[j] && !same[j];
-      }
-      const uint32_t base = r * TILE_X + QUAD * qd + 4 * t.lane;  // local index of a[0]
-      const bool has = st[0] || st[1] || st[2] || st[3];
-      const uint32_t last_local = base + (st[3] ? 3u : (st[2] ? 2u : (st[1] ? 1u : 0u)));
-      const uint32_t m_has = __ballot_sync(FULL, has);
-      const uint32_t below = m_has & ltmask;
-      uint32_t incoming = __shfl_sync(FULL, last_local, below ? (31 - __clz(below)) : 0);
-      if (!below) incoming = carry;
-      uint32_t c[4];
-      c[0] = st[0] ? base : incoming;
-#pragma unroll
-      for (int j = 1; j < 4; j++) c[j] = st[j] ? (base + j) : c[j - 1];
-      uint4 o;
-      o.x = nzv[0] ? c[0] : CCL_BG;
-      o.y = nzv[1] ? c[1] : CCL_BG;
-      o.z = nzv[2] ? c[2] : CCL_BG;
-      o.w = nzv[3] ? c[3] : CCL_BG;
-      *reinterpret_cast<uint4*>(L + base) = o;
-      if (m_has) carry = __shfl_sync(FULL, last_local, 31 - __clz(m_has));
-      prev_last = shfl_idx(a[3], 31);
-
-      // y / z connections: a union is needed where the connection starts or the x-run breaks
-      bool cy[4], cz[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        cy[j] = nzv[j] && (a[j] == y[j]);
-        cz[j] = nzv[j] && (a[j] == z[j]);
-      }
-      const uint32_t pk = (cy[3] ? 1u : 0u) | (cz[3] ? 2u : 0u);
-      uint32_t pl = __shfl_up_sync(FULL, pk, 1);
-      if (t.lane == 0) pl = cprev;
-      cprev = __shfl_sync(FULL, pk, 31);
-      uint32_t ty = 0, tz = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const bool py = (j == 0) ? ((pl & 1u) != 0) : cy[j - 1];
-        const bool pz = (j == 0) ? ((pl & 2u) != 0) : cz[j - 1];
-        if (cy[j] && !(same[j] && py)) ty |= 1u << j;
-        if (cz[j] && !(same[j] && pz)) tz |= 1u << j;
-      }
-      // slots for this quad's tasks (low half-word) and run starts (high half-word): only the
-      // few lanes that hold any take part in the reservation
-      const uint32_t stn = (st[0] ? 1u : 0u) | (st[1] ? 2u : 0u) | (st[2] ? 4u : 0u) | (st[3] ? 8u : 0u);
-      const uint32_t cnt = (uint32_t)(__popc(ty) + __popc(tz)) | ((uint32_t)__popc(stn) << 16);
-      const uint32_t m_t = __ballot_sync(FULL, cnt != 0);
-      if (m_t) {
-        uint32_t off = 0, total = 0;
-        for (uint32_t m = m_t; m; m &= m - 1) {
-          const int src = __ffs(m) - 1;
-          const uint32_t k = __shfl_sync(FULL, cnt, src);
-          if ((int)t.lane > src) off += k;
-          total += k;
-        }
-        const uint32_t tt = total & 0xFFFFu, ts = total >> 16;
-        // a full queue before the barrier: the classic pass below redoes every union
-        if (nq + tt > (uint32_t)TASKS_PER_WARP) overflow = true;
-        // a full start list: pass 3 falls back to chasing every voxel
-        if (ns + ts > (uint32_t)STARTS_PER_WARP) soverflow = true;
-        if (!overflow) {
-          uint32_t w = nq + (off & 0xFFFFu);
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (ty & (1u << j)) q[w++] = (c[j] << 16) | (base + j - (uint32_t)TILE_X);
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (tz & (1u << j)) q[w++] = (c[j] << 16) | (base + j - (uint32_t)(TILE_X * TILE_Y));
-          nq += tt;
-        }
-        if (!soverflow) {
-          uint32_t w = ns + (off >> 16);
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (stn & (1u << j)) sq[w++] = base + j;
-          ns += ts;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; j++) prev[qd][j] = a[j];
-    }
-  }
-  const int any_overflow = __syncthreads_or(overflow ? 1 : 0);
-
-  // ---- pass 2: execute the queued unions 32 wide on the shared-memory union-find
-  auto flush = [&]() {
-    __syncwarp();
-    for (uint32_t i = t.lane; i < nq; i += 32) {
-      const uint32_t ab = q[i];
-      sm_union(L, ab >> 16, ab & 0xFFFFu);
-    }
-    __syncwarp();
-    nq = 0;
-  };
-  if (any_overflow) {
-    // rare (more than TASKS_PER_WARP tasks in 4 rows): drop the queues and redo the y / z
-    // unions the classic way, 32 voxels at a time with a flush whenever the queue fills
-    nq = 0;
-    const uint32_t lemask = 0xFFFFFFFFu >> (31 - t.lane);
-#pragma unroll 1
-    for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
-      const uint32_t ly = ly0 + rr, r = lz * TILE_Y + ly;
-      if (ly == 0 && lz == 0) continue;
-      const T* p = in + (tile_g0 + lz * sxy + ly * sx + t.lane);
-      T prev_last = 0;
-      uint32_t cy_prev = 0, cz_prev = 0;
-#pragma unroll 1
-      for (int k = 0; k < SUBW; k++) {
-        const T v = p[32 * k];
-        const T vy = (ly > 0) ? *(p + 32 * k - sx) : (T)0;
-        const T vz = (lz > 0) ? *(p + 32 * k - sxy) : (T)0;
-        const T vl = shfl_up1(v);
-        const T v0 = shfl_idx(v, 0);
-        const bool cont = (k > 0) && (v0 != 0) && (v0 == prev_last);
-        const bool nz = v != 0;
-        const bool sm = (t.lane > 0) ? (v == vl) : cont;
-        const uint32_t m_same = __ballot_sync(FULL, nz && sm);
-        const uint32_t m_cy = __ballot_sync(FULL, nz && (v == vy));
-        const uint32_t m_cz = __ballot_sync(FULL, nz && (v == vz));
-        const uint32_t t_y = m_cy & ~(m_same & ((m_cy << 1) | cy_prev));
-        const uint32_t t_z = m_cz & ~(m_same & ((m_cz << 1) | cz_prev));
-        if (t_y | t_z) {
-          const uint32_t ny = __popc(t_y), nz_ = __popc(t_z);
-          if (nq + ny + nz_ > (uint32_t)TASKS_PER_WARP) flush();
-          if (((t_y | t_z) >> t.lane) & 1u) {
-            const uint32_t li = r * TILE_X + 32 * k + t.lane;
-            const uint32_t node = ((volatile uint32_t*)L)[li];
-            if ((t_y >> t.lane) & 1u) q[nq + __popc(t_y & (lemask >> 1))] = (node << 16) | (li - TILE_X);
-            if ((t_z >> t.lane) & 1u) q[nq + ny + __popc(t_z & (lemask >> 1))] = (node << 16) | (li - TILE_X * TILE_Y);
-          }
-          nq += ny + nz_;
-        }
-        prev_last = shfl_idx(v, 31);
-        cy_prev = m_cy >> 31;
-        cz_prev = m_cz >> 31;
-      }
-    }
-  }
-  flush();
-  const int any_soverflow = __syncthreads_or(soverflow ? 1 : 0);
-
-  // ---- pass 2b: point every run start at its root.  Every node of a parent chain is a run
-  // start (only roots are hooked, and a root is the first voxel of its run), so afterwards
-  // any voxel reaches its root in ONE hop: parent entry -> L[entry].
-  if (!any_soverflow) {
-    for (uint32_t i = t.lane; i < ns; i += 32) {
-      const uint32_t s0 = sq[i];
-      uint32_t rt = s0, pp = ((volatile uint32_t*)L)[rt];
-      while (pp != rt) {
-        rt = pp;
-        pp = ((volatile uint32_t*)L)[rt];
-      }
-      ((volatile uint32_t*)L)[s0] = rt;
+  uint64_t t = advance(blockIdx.x);
+  if constexpr (TMA) {
+    if (tid == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (tid == 0 && t < ntiles) {
+      mbar_expect_tx(&bars[0], (uint32_t)(MT::ELEMS * sizeof(T)));
+      tma_load_3d(buf[0], &tmap, &bars[0], (int)(tx * MT_BX) - MT::HX, (int)(ty * MT_BY) - 1, (int)(tz * MT::BZ) - 1);
+    }
   }
-
-  // ---- pass 3: translate to global indices, log local roots (4 voxels per lane)
-#pragma unroll 1
-  for (int rr = 0; rr < ROWS_PER_WARP; rr++) {
-    const uint32_t ly = ly0 + rr, r = lz * TILE_Y + ly;
-    uint32_t* out = parent + (tile_g0 + lz * sxy + ly * sx + 4 * t.lane);
-#pragma unroll
-    for (int qd = 0; qd < QUADS; qd++) {
-      const uint32_t base = r * TILE_X + QUAD * qd + 4 * t.lane;
-      const uint4 P = *reinterpret_cast<const uint4*>(L + base);
-      const uint32_t p0[4] = {P.x, P.y, P.z, P.w};
-      uint32_t cur[4], nxt[4];
-      bool bgv[4], more = false;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        bgv[j] = (p0[j] == CCL_BG);
-        cur[j] = bgv[j] ? (base + j) : p0[j];
+  uint32_t it = 0;
+  while (t < ntiles) {
+    const uint32_t cur = it & 1u;
+    const uint32_t x0 = tx * MT_BX, y0 = ty * MT_BY, z0 = tz * MT::BZ;
+    // next tile of this CTA (its coordinates replace tx/ty/tz from here on)
+    const uint64_t tn = advance(t + gridDim.x);
+    T* tile = buf[cur];
+    if constexpr (TMA) {
+      if (tid == 0 && tn < ntiles) {  // the other buffer was released by the barrier that ended the previous iteration
+        mbar_expect_tx(&bars[cur ^ 1u], (uint32_t)(MT::ELEMS * sizeof(T)));
+        tma_load_3d(buf[cur ^ 1u], &tmap, &bars[cur ^ 1u], (int)(tx * MT_BX) - MT::HX, (int)(ty * MT_BY) - 1,
+                    (int)(tz * MT::BZ) - 1);
       }
-#pragma unroll
-      for (int j = 0; j < 4; j++) nxt[j] = L[cur[j]];
-      if (!any_soverflow) {  // compressed: the entry's parent is the root
-#pragma unroll
-        for (int j = 0; j < 4; j++) cur[j] = bgv[j] ? cur[j] : nxt[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; j++) more |= (!bgv[j] && nxt[j] != cur[j]);
-        if (__any_sync(FULL, more)) {
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            while (!bgv[j] && nxt[j] != cur[j]) {
-              cur[j] = nxt[j];
-              nxt[j] = L[cur[j]];
-            }
+      mbar_wait(&bars[cur], (it >> 1) & 1u);
+    } else {
+      // cooperative fill (row pitch not 16-byte aligned): a warp per tile row, zero outside the volume
+      for (uint32_t r = warp; r < (uint32_t)MT::ROWS; r += MT_THREADS / 32) {
+        const uint32_t iy = r % (MT_BY + 1), iz = r / (MT_BY + 1);
+        const int64_t gy = (int64_t)y0 + iy - 1, gz = (int64_t)z0 + iz - 1;
+        const bool rok = gy >= 0 && gz >= 0 && gy < (int64_t)a.sy && gz < (int64_t)a.sz;
+        const T* src = rd.in + ((uint64_t)(rok ? gz : 0) * a.sy + (uint64_t)(rok ? gy : 0)) * a.sx;
+        for (uint32_t ix = MT::HX - 1 + lane; ix < (uint32_t)MT::PITCH; ix += 32) {
+          const int64_t gx = (int64_t)x0 + ix - MT::HX;
+          tile[r * MT::PITCH + ix] = (rok && gx >= 0 && gx < (int64_t)a.sx) ? src[gx] : (T)0;
         }
       }
-      uint32_t g[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        g[j] = bgv[j] ? CCL_BG : (tile_g0 + (cur[j] >> 11) * sxy + ((cur[j] >> 8) & 7u) * sx + (cur[j] & 255u));
-      *reinterpret_cast<uint4*>(out + QUAD * qd) = make_uint4(g[0], g[1], g[2], g[3]);
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (!bgv[j] && p0[j] == base + j) {  // tile-local root: log it as a root candidate
-          const uint32_t pos = atomicAdd(&counters[0], 1u);
-          if (pos < cand_cap) cand[pos] = g[j];
-          else counters[1] = 1;
+      __syncthreads();
+    }
+    if (transform) {  // threshold_image / rails on the staged tile, in place
+      for (uint32_t r = warp; r < (uint32_t)MT::ROWS; r += MT_THREADS / 32) {
+        const uint32_t iy = r % (MT_BY + 1), iz = r / (MT_BY + 1);
+        const uint32_t gy = y0 + iy - 1, gz = z0 + iz - 1;  // wraps to huge values in the low halo: out of range
+        const bool rok = gy < a.sy && gz < a.sz;
+        for (uint32_t ix = MT::HX - 1 + lane; ix < (uint32_t)MT::PITCH; ix += 32) {
+          const uint32_t gx = x0 + ix - MT::HX;
+          const T raw = tile[r * MT::PITCH + ix];
+          tile[r * MT::PITCH + ix] = (rok && gx < a.sx) ? rd.label(raw, gx, gy, gz) : (T)0;
         }
+      }
+      if constexpr (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
+    // ---- masks: warp w owns plane w % BZ; with BZ = 4 the two warps of a plane split its rows
+    {
+      constexpr int WPP = (MT_THREADS / 32) / MT::BZ;  // warps per plane
+      constexpr int RPW = MT_BY / WPP;                 // rows per warp
+      const uint32_t iz = warp % MT::BZ + 1;
+      const uint32_t ry0 = (warp / MT::BZ) * RPW;
+      const uint32_t gz = z0 + iz - 1;
+      if (gz < a.sz) {
+#pragma unroll 2
+        for (uint32_t k = 0; k < (uint32_t)RPW; k++) {
+          const uint32_t iy = ry0 + k + 1, gy = y0 + iy - 1;
+          if (gy >= a.sy) break;
+          const T* row = tile + ((size_t)iz * (MT_BY + 1) + iy) * MT::PITCH + MT::HX;
+          const T* rup = row - MT::PITCH;
+          const T* rbk = row - (size_t)(MT_BY + 1) * MT::PITCH;
+          uint32_t mS = 0, mZ = 0, mY = 0, mB = 0;
+#pragma unroll
+          for (uint32_t xw = 0; xw < MT_BX / 32; xw++) {
+            const uint32_t ix = xw * 32 + lane;
+            const T v = row[ix], left = row[(int)ix - 1], up = rup[ix], back = rbk[ix];
+            const bool nz = v != (T)0;
+            const uint32_t bS = __ballot_sync(FULL, nz && v != left);
+            const uint32_t bZ = __ballot_sync(FULL, nz);
+            const uint32_t bY = __ballot_sync(FULL, nz && v == up);
+            const uint32_t bB = __ballot_sync(FULL, nz && v == back);
+            if (lane == xw) { mS = bS; mZ = bZ; mY = bY; mB = bB; }
+          }
+          const uint32_t w0 = x0 / 32;
+          if (lane < MT_BX / 32 && w0 + lane < a.wpr) {
+            const uint64_t wi = ((uint64_t)gz * a.sy + gy) * a.wpr + w0 + lane;
+            a.S[wi] = mS; a.Z[wi] = mZ; a.Ey[wi] = mY; a.Ez[wi] = mB;
+          }
+        }
+      }
+    }
+    __syncthreads();  // tile consumed: its buffer may be refilled
+    t = tn;
+    it++;
+  }
+}
+
+// ------------------------------------------------------------------ pass B
+constexpr int TB_WMAX = 4096;    // words of a tile (all words of TY x TZ rows)
+constexpr int TB_RCAP = 12288;   // runs of a tile resolved in shared memory
+constexpr int TB_THREADS = 256;
+
+struct TileArgs {
+  uint32_t sx, sy, sz, wpr, TY, TZ, nty, ntz;
+  const uint32_t *S, *Ey, *Ez, *rbase;
+  uint32_t* parent;
+};
+
+__device__ __forceinline__ uint32_t mask_le(uint32_t p) { return 0xFFFFFFFFu >> (31u - p); }
+
+// unions of one word against the same word of a neighbour row: one union per stretch of
+// E in which neither row starts a new run.  base / nbase: id of the first run that starts
+// in the word (own row / neighbour row).
+template <typename UNION>
+__device__ __forceinline__ void word_unions(uint32_t E, uint32_t Eprev_bit31, uint32_t S, uint32_t Sn, uint32_t base,
+                                            uint32_t nbase, UNION&& unite) {
+  uint32_t cand = E & (S | Sn | ~((E << 1) | Eprev_bit31));
+  while (cand) {
+    const uint32_t p = __ffs(cand) - 1;
+    cand &= cand - 1;
+    const uint32_t le = mask_le(p);
+    unite(base + __popc(S & le) - 1, nbase + __popc(Sn & le) - 1);
+  }
+}
+
+__global__ void __launch_bounds__(TB_THREADS) k_ccl_tiles(const TileArgs a) {
+  extern __shared__ __align__(16) uint32_t tb_smem[];
+  uint32_t* sS = tb_smem;
+  uint32_t* sEy = sS + TB_WMAX;
+  uint32_t* sEz = sEy + TB_WMAX;
+  uint32_t* par = sEz + TB_WMAX;                 // [TB_RCAP]
+  uint16_t* lbase = (uint16_t*)(par + TB_RCAP);  // [TB_WMAX]
+  __shared__ uint32_t warp_sums[TB_THREADS / 32];
+  __shared__ uint32_t total_runs;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t ty = blockIdx.x % a.nty, tz = blockIdx.x / a.nty;
+  const uint32_t y0 = ty * a.TY, z0 = tz * a.TZ;
+  const uint32_t ny = min(a.TY, a.sy - y0), nz = min(a.TZ, a.sz - z0);
+  const uint32_t wpr = a.wpr, rowsw = ny * wpr, W = rowsw * nz;
+  auto gword = [&](uint32_t lw) -> uint64_t {  // local word -> global word
+    const uint32_t lz = lw / rowsw, r = lw - lz * rowsw;
+    return ((uint64_t)(z0 + lz) * a.sy + y0) * wpr + r;
+  };
+  // ---- load the masks (the ny rows of one plane are contiguous words)
+  for (uint32_t lw = tid; lw < W; lw += TB_THREADS) {
+    const uint64_t g = gword(lw);
+    sS[lw] = a.S[g];
+    sEy[lw] = a.Ey[g];
+    sEz[lw] = a.Ez[g];
+  }
+  __syncthreads();
+  // ---- local run numbering: exclusive scan of popc(S) over the tile's words
+  constexpr int WPT = TB_WMAX / TB_THREADS;  // 16 consecutive words per thread
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int k = 0; k < WPT; k++) {
+    const uint32_t lw = tid * WPT + k;
+    if (lw < W) cnt += __popc(sS[lw]);
+  }
+  uint32_t inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(FULL, inc, d);
+    if ((int)lane >= d) inc += o;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (uint32_t w = 0; w < warp; w++) woff += warp_sums[w];
+  if (tid == TB_THREADS - 1) total_runs = woff + inc;
+  uint32_t run = woff + inc - cnt;
+  __syncthreads();
+  const uint32_t RL = total_runs;
+  const bool fits = RL <= (uint32_t)TB_RCAP;
+  if (fits) {
+#pragma unroll
+    for (int k = 0; k < WPT; k++) {
+      const uint32_t lw = tid * WPT + k;
+      if (lw < W) {
+        lbase[lw] = (uint16_t)run;
+        run += __popc(sS[lw]);
+      }
+    }
+    for (uint32_t i = tid; i < RL; i += TB_THREADS) par[i] = i;
+  } else {
+    // too many runs for shared memory (noise-like data): unions go to the global array
+    for (uint32_t lw = tid; lw < W; lw += TB_THREADS) {
+      const uint32_t b = a.rbase[gword(lw)], c = __popc(sS[lw]);
+      for (uint32_t k = 0; k < c; k++) a.parent[b + k] = b + k;
+    }
+  }
+  __syncthreads();
+  // ---- unions along y and z inside the tile
+  for (uint32_t lw = tid; lw < W; lw += TB_THREADS) {
+    const uint32_t lz = lw / rowsw, r = lw - lz * rowsw, ly = r / wpr, xw = r - ly * wpr;
+    const uint32_t S = sS[lw];
+    const uint32_t ey = ly > 0 ? sEy[lw] : 0u, ez = lz > 0 ? sEz[lw] : 0u;
+    if (!(ey | ez)) continue;
+    if (fits) {
+      const uint32_t base = lbase[lw];
+      auto un = [&](uint32_t x, uint32_t y) { uf_union(par, x, y); };
+      if (ey) word_unions(ey, xw > 0 ? sEy[lw - 1] >> 31 : 0u, S, sS[lw - wpr], base, (uint32_t)lbase[lw - wpr], un);
+      if (ez) word_unions(ez, xw > 0 ? sEz[lw - 1] >> 31 : 0u, S, sS[lw - rowsw], base, (uint32_t)lbase[lw - rowsw], un);
+    } else {
+      const uint32_t base = a.rbase[gword(lw)];
+      auto un = [&](uint32_t x, uint32_t y) { uf_union(a.parent, x, y); };
+      if (ey) word_unions(ey, xw > 0 ? sEy[lw - 1] >> 31 : 0u, S, sS[lw - wpr], base, a.rbase[gword(lw - wpr)], un);
+      if (ez) word_unions(ez, xw > 0 ? sEz[lw - 1] >> 31 : 0u, S, sS[lw - rowsw], base, a.rbase[gword(lw - rowsw)], un);
+    }
+  }
+  if (!fits) return;
+  __syncthreads();
+  // ---- every run's parent = global id of its tile root
+  for (uint32_t lw = tid; lw < W; lw += TB_THREADS) {
+    const uint32_t c = __popc(sS[lw]);
+    if (c == 0) continue;
+    const uint32_t lb = lbase[lw], gb = a.rbase[gword(lw)];
+    for (uint32_t k = 0; k < c; k++) {
+      const uint32_t root = uf_find(par, lb + k);
+      uint32_t groot = gb + k;
+      if (root != lb + k) {
+        // word of the root: the last word whose lbase <= root (words without starts share
+        // the lbase of the next word with starts and come before it)
+        uint32_t lo = 0, hi = lw;  // the root is never after lw (it is the minimum)
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi + 1) >> 1;
+          if (lbase[mid] <= root) lo = mid;
+          else hi = mid - 1;
+        }
+        groot = a.rbase[gword(lo)] + (root - lbase[lo]);
+      }
+      a.parent[gb + k] = groot;
     }
   }
 }
 
+// rows on tile faces: the same unions on the global parent array
+struct MergeArgs {
+  uint32_t sx, sy, sz, wpr, TY, TZ, nty, ntz;
+  uint64_t words_y, words_z;  // work items of the y-face rows / z-face rows
+  const uint32_t *S, *Ey, *Ez, *rbase;
+  uint32_t* parent;
+};
+
+__global__ void __launch_bounds__(256) k_ccl_merge(const MergeArgs a) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= a.words_y + a.words_z) return;
+  uint32_t y, z, xw;
+  bool ydir;
+  if (i < a.words_y) {  // rows y = k*TY (k >= 1), every z
+    ydir = true;
+    xw = (uint32_t)(i % a.wpr);
+    const uint64_t r = i / a.wpr;
+    y = ((uint32_t)(r % (a.nty - 1)) + 1) * a.TY;
+    z = (uint32_t)(r / (a.nty - 1));
+  } else {  // rows of planes z = k*TZ (k >= 1), every y
+    ydir = false;
+    const uint64_t j = i - a.words_y;
+    xw = (uint32_t)(j % a.wpr);
+    const uint64_t r = j / a.wpr;
+    y = (uint32_t)(r % a.sy);
+    z = ((uint32_t)(r / a.sy) + 1) * a.TZ;
+  }
+  const uint64_t g = ((uint64_t)z * a.sy + y) * a.wpr + xw;
+  const uint32_t E = ydir ? a.Ey[g] : a.Ez[g];
+  if (!E) return;
+  const uint64_t gn = ydir ? g - a.wpr : g - (uint64_t)a.sy * a.wpr;
+  const uint32_t prev = xw > 0 ? ((ydir ? a.Ey[g - 1] : a.Ez[g - 1]) >> 31) : 0u;
+  auto un = [&](uint32_t x, uint32_t yv) { uf_union(a.parent, x, yv); };
+  word_unions(E, prev, a.S[g], a.S[gn], a.rbase[g], a.rbase[gn], un);
+}
+
+// ------------------------------------------------------------------ runs
+__global__ void __launch_bounds__(256) k_ccl_flatten(uint32_t* parent, uint32_t R) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  volatile uint32_t* P = parent;
+  uint32_t cur = r, p = P[cur];
+  while (p != cur) {
+    cur = p;
+    p = P[cur];
+  }
+  P[r] = cur;
+}
+
+struct IsRootOp {
+  const uint32_t* parent;
+  __host__ __device__ __forceinline__ uint32_t operator()(uint32_t r) const { return parent[r] == r ? 1u : 0u; }
+};
+struct PopcOp {
+  __host__ __device__ __forceinline__ uint32_t operator()(uint32_t w) const {
+#ifdef __CUDA_ARCH__
+    return __popc(w);
+#else
+    return (uint32_t)__builtin_popcount(w);
+#endif
+  }
+};
+
+// parent[r] (flattened) -> label of the run: rank of its root + 1
+__global__ void __launch_bounds__(256)
+    k_ccl_runlabel(uint32_t* parent, const uint32_t* __restrict__ rank, uint32_t R) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  parent[r] = rank[parent[r]] + 1;
+}
+__global__ void __launch_bounds__(256)
+    k_ccl_relabel_runs(uint32_t* label, uint32_t R, const uint32_t* __restrict__ lut) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R) label[r] = lut[label[r]];
+}
+
+// ------------------------------------------------------------------ pass C
+struct ExpandArgs {
+  uint32_t sx, wpr;
+  uint64_t rows;    // sy * sz
+  uint64_t offset;  // added to every non-zero label
+  const uint32_t *S, *Z, *rbase, *label;
+};
+
+// a lane owns 4 consecutive voxels (one vector store); a warp covers 4 words
+template <typename OUT>
+__global__ void __launch_bounds__(256) k_ccl_expand4(const ExpandArgs a, OUT* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t groups = (a.wpr + 3) / 4;  // 128-voxel groups per row
+  const uint64_t gi = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  if (gi >= a.rows * groups) return;
+  const uint64_t row = gi / groups;
+  const uint32_t g = (uint32_t)(gi - row * groups);
+  const uint32_t xw = g * 4 + (lane >> 3);
+  const uint32_t x = xw * 32 + (lane & 7u) * 4;
+  if (xw >= a.wpr || x >= a.sx) return;  // sx % 4 == 0: a quad is all in or all out
+  const uint64_t wi = row * a.wpr + xw;
+  const uint32_t S = a.S[wi], Z = a.Z[wi], rb = a.rbase[wi];
+  const uint32_t b0 = (lane & 7u) * 4;
+  OUT v[4];
+  uint32_t last_idx = 0xFFFFFFFFu, last_lab = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint32_t b = b0 + j;
+    OUT o = 0;
+    if ((Z >> b) & 1u) {
+      const uint32_t idx = rb + __popc(S & mask_le(b)) - 1;
+      if (idx != last_idx) {
+        last_idx = idx;
+        last_lab = a.label[idx];
+      }
+      o = last_lab ? (OUT)(last_lab + a.offset) : (OUT)0;
+    }
+    v[j] = o;
+  }
+  OUT* dst = out + row * a.sx + x;
+  if constexpr (sizeof(OUT) == 2) {
+    *(uint2*)dst = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
+  } else if constexpr (sizeof(OUT) == 4) {
+    st_stream(dst, make_uint4((uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2], (uint32_t)v[3]));
+  } else {
+    st_stream(dst, make_uint4((uint32_t)v[0], (uint32_t)((uint64_t)v[0] >> 32), (uint32_t)v[1], (uint32_t)((uint64_t)v[1] >> 32)));
+    st_stream(dst + 2, make_uint4((uint32_t)v[2], (uint32_t)((uint64_t)v[2] >> 32), (uint32_t)v[3], (uint32_t)((uint64_t)v[3] >> 32)));
+  }
+}
+
+// any row pitch: a lane owns one voxel
+template <typename OUT>
+__global__ void __launch_bounds__(256) k_ccl_expand1(const ExpandArgs a, OUT* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t wi = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  if (wi >= a.rows * a.wpr) return;
+  const uint64_t row = wi / a.wpr;
+  const uint32_t xw = (uint32_t)(wi - row * a.wpr);
+  const uint32_t x = xw * 32 + lane;
+  if (x >= a.sx) return;
+  const uint32_t S = a.S[wi], Z = a.Z[wi];
+  OUT o = 0;
+  if ((Z >> lane) & 1u) {
+    const uint32_t l = a.label[a.rbase[wi] + __popc(S & mask_le(lane)) - 1];
+    o = l ? (OUT)(l + a.offset) : (OUT)0;
+  }
+  out[row * a.sx + x] = o;
+}
+
+// one z-plane: voxel values widened to u64 and run labels (multi-GPU face exchange)
 template <typename T>
-__global__ void __launch_bounds__(CCL_THREADS)
-    k_ccl_local_v2(const T* __restrict__ in, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t ntx,
-                   uint32_t nty, uint32_t* __restrict__ parent, uint32_t* __restrict__ cand,
-                   uint32_t cand_cap, uint32_t* counters) {
-  extern __shared__ __align__(16) uint32_t Lv2[];
-  uint32_t* tasks = Lv2 + TILE_VOX;
-  uint32_t* starts = tasks + CCL_WARPS * TASKS_PER_WARP;
-  const TilePos t = tile_pos(ntx, nty);
-  const bool full = (t.X0 + TILE_X <= sx) && (t.Y0 + TILE_Y <= sy) && (t.Z0 + TILE_Z <= sz);
-  if (full) local_tile_v2<T>(in, sx, sy, t, Lv2, tasks, starts, parent, cand, cand_cap, counters);
-  else local_tile_fast<T, false>(in, sx, sy, sz, t, Lv2, tasks, parent, cand, cand_cap, counters);
-}
-
-// ------------------------------ L / G2 on 256 x 8 x 4 tiles (experiment, IGN_CCL_V2=3)
-// k_ccl_local_v2 is no longer issue bound: two 512-thread CTAs per SM spend a large share
-// of their time in block barriers and in the latency-bound shared-memory union phase
-// (DESIGN.md section 8).  The same device code runs unchanged on half-height tiles with
-// 256 threads (a warp still owns 4 consecutive y rows of one z slice): 40 KB of shared
-// memory and 16 K registers per CTA let 4-5 CTAs in different phases share an SM, at the
-// price of twice as many z faces to merge.  NOT VALIDATED ON A GPU YET (written after the
-// round's GPU budget was spent); nothing selects it unless IGN_CCL_V2=3 is set.
-constexpr int TILE_Z_S = 4;
-constexpr int TILE_VOX_S = TILE_X * TILE_Y * TILE_Z_S;
-constexpr int CCL_THREADS_S = 256;
-constexpr int CCL_WARPS_S = CCL_THREADS_S / 32;
-static_assert(TILE_Y * TILE_Z_S / CCL_WARPS_S == ROWS_PER_WARP, "small tiles keep 4 rows per warp");
-
-__device__ __forceinline__ TilePos tile_pos_s(uint32_t ntx, uint32_t nty) {
-  TilePos t;
-  const uint32_t b = blockIdx.x;
-  t.X0 = (b % ntx) * TILE_X;
-  t.Y0 = ((b / ntx) % nty) * TILE_Y;
-  t.Z0 = (b / (ntx * nty)) * TILE_Z_S;
-  t.warp = threadIdx.x >> 5;
-  t.lane = threadIdx.x & 31;
-  return t;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(CCL_THREADS_S)
-    k_ccl_local_v3(const T* __restrict__ in, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t ntx,
-                   uint32_t nty, uint32_t* __restrict__ parent, uint32_t* __restrict__ cand,
-                   uint32_t cand_cap, uint32_t* counters) {
-  extern __shared__ __align__(16) uint32_t Lv3[];
-  uint32_t* tasks = Lv3 + TILE_VOX_S;
-  uint32_t* starts = tasks + CCL_WARPS_S * TASKS_PER_WARP;
-  const TilePos t = tile_pos_s(ntx, nty);
-  const bool full = (t.X0 + TILE_X <= sx) && (t.Y0 + TILE_Y <= sy) && (t.Z0 + TILE_Z_S <= sz);
-  if (full) local_tile_v2<T>(in, sx, sy, t, Lv3, tasks, starts, parent, cand, cand_cap, counters);
-  else local_tile_fast<T, false>(in, sx, sy, sz, t, Lv3, tasks, parent, cand, cand_cap, counters);
-}
-
-// ------------------------------------------------- G: merges across tile faces
-// Flat mapping over the voxel pairs that straddle a tile face, one 32-voxel
-// sub-word per warp (y and z faces) or 32 rows per warp (x faces), so that the
-// dependent global-memory chains of the unions are hidden by warp parallelism.
-template <typename R>
 __global__ void __launch_bounds__(256)
-    k_ccl_merge(R rd, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t nfy, uint32_t nfz,
-                uint32_t nfx, uint64_t items_y, uint64_t items_z, uint64_t items_x,
-                uint32_t* parent) {
-  using V = typename R::V;
-  const uint64_t wid = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t w32 = (sx + 31) / 32;
-  const uint32_t sxy = sx * sy;
-  if (wid < items_y + items_z) {
-    uint32_t x0, y, z, stride;
-    if (wid < items_y) {  // (k32, z, fy)
-      x0 = (uint32_t)(wid % w32) * 32;
-      const uint64_t r = wid / w32;
-      z = (uint32_t)(r % sz);
-      y = ((uint32_t)(r / sz) + 1) * TILE_Y;
-      stride = sx;
-    } else {  // (k32, y, fz)
-      const uint64_t w2 = wid - items_y;
-      x0 = (uint32_t)(w2 % w32) * 32;
-      const uint64_t r = w2 / w32;
-      y = (uint32_t)(r % sy);
-      z = ((uint32_t)(r / sy) + 1) * TILE_Z;
-      stride = sxy;
-    }
-    const uint32_t x = x0 + lane;
-    const bool inb = x < sx;
-    const uint32_t idx = (z * sy + y) * sx + x;
-    const V v = inb ? rd.at(idx, x, y, z) : (V)0;
-    const V vn = inb ? ((stride == sx) ? rd.at(idx - sx, x, y - 1, z) : rd.at(idx - sxy, x, y, z - 1))
-                     : (V)0;
-    const V vl = shfl_up1(v);
-    // a 32-voxel sub-word may straddle a tile x face: segments break there too,
-    // which only costs a redundant union.
-    const bool same_left = (lane > 0) && (v == vl);
-    const bool c = (v != 0) && (v == vn);
-    const bool c_l = __shfl_up_sync(FULL, (int)c, 1) != 0;
-    if (c && !(same_left && c_l)) uf_union(parent, idx, idx - stride);
-  } else if (wid < items_y + items_z + items_x) {  // (row block of 32, fx)
-    const uint64_t w2 = wid - items_y - items_z;
-    const uint64_t nrows = (uint64_t)sy * sz;
-    const uint64_t rb = (nrows + 31) / 32;
-    const uint32_t fx = (uint32_t)(w2 / rb) + 1;
-    const uint64_t row = (w2 % rb) * 32 + lane;
-    if (row < nrows) {
-      const uint32_t x = fx * TILE_X;
-      const uint32_t y = (uint32_t)(row % sy), z = (uint32_t)(row / sy);
-      const uint32_t idx = (uint32_t)row * sx + x;
-      const V a = rd.at(idx, x, y, z);
-      if (a != 0 && a == rd.at(idx - 1, x - 1, y, z)) uf_union(parent, idx, idx - 1);
-    }
-  }
-  (void)nfy; (void)nfz; (void)nfx;
+    k_ccl_plane(const T* __restrict__ in, const ExpandArgs a, uint64_t z, uint32_t sy, uint64_t* __restrict__ values,
+                uint32_t* __restrict__ labels) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t np = (uint64_t)a.sx * sy;
+  if (i >= np) return;
+  const uint32_t y = (uint32_t)(i / a.sx), x = (uint32_t)(i - (uint64_t)y * a.sx);
+  const uint64_t row = z * sy + y;
+  const uint64_t wi = row * a.wpr + (x >> 5);
+  const uint32_t b = x & 31u;
+  values[i] = (uint64_t)in[row * a.sx + x];
+  uint32_t l = 0;
+  if ((a.Z[wi] >> b) & 1u) l = a.label[a.rbase[wi] + __popc(a.S[wi] & mask_le(b)) - 1];
+  labels[i] = l;
 }
 
-// ----------------------------------------- G2: face merges, deduplicated per tile
-// One CTA per tile handles the tile's low y / z / x faces.  Along a face the same
-// pair of tile-local components meets in up to 64 sub-words; instead of running
-// a global union-find for each meeting, the (local root A, local root B) pairs
-// are first collected in a shared-memory hash set and only the unique pairs are
-// united in global memory.
-constexpr int MERGE_SLOTS = 1024;  // power of two, 8 KB of u64
-
-__device__ __forceinline__ void merge_emit(unsigned long long* set, uint32_t* parent, uint32_t a,
-                                           uint32_t b) {
-  const unsigned long long key = ((unsigned long long)a << 32) | b;
-  uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 54) & (MERGE_SLOTS - 1);
-  for (int probe = 0; probe < 16; probe++) {
-    const unsigned long long cur = atomicCAS(&set[h], 0xFFFFFFFFFFFFFFFFull, key);
-    if (cur == 0xFFFFFFFFFFFFFFFFull || cur == key) return;
-    h = (h + 1) & (MERGE_SLOTS - 1);
+// ------------------------------------------------------------------- dust
+// voxels per component: every x-segment of a run inside a word adds its length once
+__global__ void __launch_bounds__(256) k_ccl_count(const ExpandArgs a, uint32_t* __restrict__ counts) {
+  const uint64_t wi = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (wi >= a.rows * a.wpr) return;
+  const uint32_t S = a.S[wi], Z = a.Z[wi];
+  if (!Z) return;
+  const uint32_t rb = a.rbase[wi];
+  // segment heads: a start, or a non-zero voxel at bit 0 (run continuing from the previous word)
+  uint32_t heads = S | (Z & 1u);
+  while (heads) {
+    const uint32_t p = __ffs(heads) - 1;
+    heads &= heads - 1;
+    // the segment ends before the next start or the next zero voxel
+    const uint32_t stop = (p == 31) ? 0u : ((S | ~Z) & ~mask_le(p));
+    const uint32_t q = stop ? (uint32_t)(__ffs(stop) - 1) : 32u;
+    const uint32_t l = a.label[rb + __popc(S & mask_le(p)) - 1];
+    atomicAdd(&counts[l], q - p);
   }
-  uf_union(parent, a, b);  // table crowded: unite directly
 }
 
-template <typename R>
 __global__ void __launch_bounds__(256)
-    k_ccl_merge_tiles(R rd, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t ntx, uint32_t nty,
-                      uint32_t* parent) {
-  using V = typename R::V;
-  __shared__ unsigned long long set[MERGE_SLOTS];
-  for (int i = threadIdx.x; i < MERGE_SLOTS; i += blockDim.x) set[i] = 0xFFFFFFFFFFFFFFFFull;
-  __syncthreads();
-  const TilePos t = tile_pos(ntx, nty);
-  const uint32_t sxy = sx * sy;
-  const uint32_t nwarps = blockDim.x >> 5;
-  // faces as (row list, neighbour stride): y face = rows (ly=0, lz=0..7); z face = rows (lz=0, ly=0..7)
-  for (uint32_t item = t.warp; item < 2 * TILE_Y * SUBW; item += nwarps) {
-    const uint32_t face = item / (TILE_Y * SUBW);      // 0: y face, 1: z face
-    const uint32_t rowi = (item / SUBW) % TILE_Y, k = item % SUBW;
-    const uint32_t ly = face == 0 ? 0 : rowi, lz = face == 0 ? rowi : 0;
-    const uint32_t y = t.Y0 + ly, z = t.Z0 + lz;
-    if (y >= sy || z >= sz) continue;
-    if (face == 0 ? (y == 0) : (z == 0)) continue;
-    const uint32_t stride = face == 0 ? sx : sxy;
-    const uint32_t x = t.X0 + 32 * k + t.lane;
-    const bool inb = x < sx;
-    const uint32_t idx = (z * sy + y) * sx + x;
-    const V v = inb ? rd.at(idx, x, y, z) : (V)0;
-    const V vn = inb ? (face == 0 ? rd.at(idx - sx, x, y - 1, z) : rd.at(idx - sxy, x, y, z - 1)) : (V)0;
-    const V vl = shfl_up1(v);
-    const bool same_left = (t.lane > 0) && (v == vl);
-    const bool c = (v != 0) && (v == vn);
-    const bool c_l = __shfl_up_sync(FULL, (int)c, 1) != 0;
-    if (c && !(same_left && c_l)) merge_emit(set, parent, parent[idx], parent[idx - stride]);
-  }
-  if (t.X0 > 0) {  // x face: one voxel pair per tile row
-    for (uint32_t r = threadIdx.x; r < TILE_ROWS; r += blockDim.x) {
-      const uint32_t y = t.Y0 + (r % TILE_Y), z = t.Z0 + (r / TILE_Y);
-      if (y >= sy || z >= sz) continue;
-      const uint32_t idx = (z * sy + y) * sx + t.X0;
-      const V a = rd.at(idx, t.X0, y, z);
-      if (a != 0 && a == rd.at(idx - 1, t.X0 - 1, y, z)) merge_emit(set, parent, parent[idx], parent[idx - 1]);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < MERGE_SLOTS; i += blockDim.x) {
-    const unsigned long long key = set[i];
-    if (key != 0xFFFFFFFFFFFFFFFFull) uf_union(parent, (uint32_t)(key >> 32), (uint32_t)(key & 0xFFFFFFFFu));
-  }
-}
-
-// G2 for the 256 x 8 x 4 tiles of k_ccl_local_v3: y faces have TILE_Z_S rows, z faces TILE_Y
-template <typename R>
-__global__ void __launch_bounds__(256)
-    k_ccl_merge_tiles_s(R rd, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t ntx, uint32_t nty,
-                        uint32_t* parent) {
-  using V = typename R::V;
-  __shared__ unsigned long long set[MERGE_SLOTS];
-  for (int i = threadIdx.x; i < MERGE_SLOTS; i += blockDim.x) set[i] = 0xFFFFFFFFFFFFFFFFull;
-  __syncthreads();
-  const TilePos t = tile_pos_s(ntx, nty);
-  const uint32_t sxy = sx * sy;
-  const uint32_t nwarps = blockDim.x >> 5;
-  constexpr uint32_t Y_ITEMS = TILE_Z_S * SUBW, Z_ITEMS = TILE_Y * SUBW;
-  for (uint32_t item = t.warp; item < Y_ITEMS + Z_ITEMS; item += nwarps) {
-    const uint32_t face = item < Y_ITEMS ? 0u : 1u;  // 0: y face (ly = 0), 1: z face (lz = 0)
-    const uint32_t it = face == 0 ? item : item - Y_ITEMS;
-    const uint32_t rowi = it / SUBW, k = it % SUBW;
-    const uint32_t ly = face == 0 ? 0 : rowi, lz = face == 0 ? rowi : 0;
-    const uint32_t y = t.Y0 + ly, z = t.Z0 + lz;
-    if (y >= sy || z >= sz) continue;
-    if (face == 0 ? (y == 0) : (z == 0)) continue;
-    const uint32_t stride = face == 0 ? sx : sxy;
-    const uint32_t x = t.X0 + 32 * k + t.lane;
-    const bool inb = x < sx;
-    const uint32_t idx = (z * sy + y) * sx + x;
-    const V v = inb ? rd.at(idx, x, y, z) : (V)0;
-    const V vn = inb ? (face == 0 ? rd.at(idx - sx, x, y - 1, z) : rd.at(idx - sxy, x, y, z - 1)) : (V)0;
-    const V vl = shfl_up1(v);
-    const bool same_left = (t.lane > 0) && (v == vl);
-    const bool c = (v != 0) && (v == vn);
-    const bool c_l = __shfl_up_sync(FULL, (int)c, 1) != 0;
-    if (c && !(same_left && c_l)) merge_emit(set, parent, parent[idx], parent[idx - stride]);
-  }
-  if (t.X0 > 0) {  // x face: one voxel pair per tile row
-    for (uint32_t r = threadIdx.x; r < (uint32_t)(TILE_Y * TILE_Z_S); r += blockDim.x) {
-      const uint32_t y = t.Y0 + (r % TILE_Y), z = t.Z0 + (r / TILE_Y);
-      if (y >= sy || z >= sz) continue;
-      const uint32_t idx = (z * sy + y) * sx + t.X0;
-      const V a = rd.at(idx, t.X0, y, z);
-      if (a != 0 && a == rd.at(idx - 1, t.X0 - 1, y, z)) merge_emit(set, parent, parent[idx], parent[idx - 1]);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < MERGE_SLOTS; i += blockDim.x) {
-    const unsigned long long key = set[i];
-    if (key != 0xFFFFFFFFFFFFFFFFull) uf_union(parent, (uint32_t)(key >> 32), (uint32_t)(key & 0xFFFFFFFFu));
-  }
-}
-
-// -------------------------------------------------------------------- roots
-__global__ void __launch_bounds__(256)
-    k_ccl_roots(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ cand,
-                uint32_t ncand, uint32_t* __restrict__ roots, uint32_t* counters) {
+    k_dust_flags(const uint32_t* __restrict__ counts, uint32_t n, uint64_t threshold, uint32_t* __restrict__ keep) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n + 1) keep[i] = (i >= 1 && i <= n && (uint64_t)counts[i] >= threshold) ? 1u : 0u;
+}
+
+// keep[] (0/1) and its exclusive scan -> lut: old label -> new label (0 = removed)
+__global__ void __launch_bounds__(256)
+    k_dust_lut(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ scan, uint32_t n,
+               uint32_t* __restrict__ lut) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n) lut[i] = keep[i] ? scan[i] + 1 : 0u;
+}
+
+// cc3d.dust(in_place=True): zero the voxels of removed components in the input array
+template <typename T>
+__global__ void __launch_bounds__(256) k_dust_apply(const ExpandArgs a, T* __restrict__ labels) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t wi = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  if (wi >= a.rows * a.wpr) return;
+  const uint64_t row = wi / a.wpr;
+  const uint32_t xw = (uint32_t)(wi - row * a.wpr);
+  const uint32_t x = xw * 32 + lane;
+  if (x >= a.sx) return;
+  const uint32_t S = a.S[wi], Z = a.Z[wi];
+  if (!((Z >> lane) & 1u)) return;
+  if (a.label[a.rbase[wi] + __popc(S & mask_le(lane)) - 1] == 0) labels[row * a.sx + x] = (T)0;
+}
+
+// equivalence pairs between two facing planes (same x,y; adjacent z)
+__global__ void __launch_bounds__(256)
+    k_ccl_link(const uint64_t* __restrict__ va, const uint32_t* __restrict__ la, uint64_t offa,
+               const uint64_t* __restrict__ vb, const uint32_t* __restrict__ lb, uint64_t offb,
+               uint64_t nplane, uint64_t* __restrict__ pairs, uint32_t cap, uint32_t* counters) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31;
-  bool is_root = false;
-  uint32_t c = 0;
-  if (i < ncand) {
-    c = cand[i];
-    is_root = (parent[c] == c);
+  bool emit = false;
+  uint64_t a = 0, b = 0;
+  if (i < nplane) {
+    const uint64_t v = va[i];
+    if (v != 0 && v == vb[i]) {
+      a = offa + la[i];
+      b = offb + lb[i];
+      // runs of the same pair along x are emitted once
+      emit = !(i > 0 && la[i - 1] == la[i] && lb[i - 1] == lb[i] && va[i - 1] == v && vb[i - 1] == v);
+    }
   }
-  const uint32_t m = __ballot_sync(FULL, is_root);
+  const uint32_t m = __ballot_sync(FULL, emit);
   if (m) {
     const int leader = __ffs(m) - 1;
     uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(&counters[2], (uint32_t)__popc(m));
+    if ((int)lane == leader) base = atomicAdd(&counters[0], (uint32_t)__popc(m));
     base = __shfl_sync(FULL, base, leader);
-    if (is_root) roots[base + __popc(m & ((1u << lane) - 1u))] = c;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-    k_ccl_rank(uint32_t* __restrict__ parent, const uint32_t* __restrict__ roots_sorted,
-               uint32_t nroots) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nroots) parent[roots_sorted[i]] = CCL_FLAG | (i + 1);
-}
-
-// ------------------------------------------------------------------ F label
-// flat mapping: a warp owns ROWCHUNK = 256 consecutive voxels of one row
-struct ChunkPos {
-  uint32_t lane, rowbase, x0;
-  bool ok;
-};
-__device__ __forceinline__ ChunkPos chunk_pos(uint32_t sx, uint32_t cpr, uint64_t nchunks) {
-  ChunkPos c;
-  const uint64_t wid = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-  c.ok = wid < nchunks;
-  c.lane = threadIdx.x & 31;
-  const uint32_t row = (uint32_t)(wid / cpr);
-  c.x0 = (uint32_t)(wid % cpr) * TILE_X;
-  c.rowbase = row * sx;
-  return c;
-}
-
-// rank (1..N) of the component of a voxel whose parent entry is e; BG -> BG
-__device__ __forceinline__ uint32_t chase(const uint32_t* __restrict__ parent, uint32_t e) {
-  while (!(e & CCL_FLAG)) e = parent[e];
-  return e;
-}
-
-template <typename OUT>
-__global__ void __launch_bounds__(256)
-    k_ccl_label(const uint32_t* __restrict__ parent, uint32_t sx, uint32_t cpr, uint64_t nchunks,
-                uint64_t offset, const uint32_t* __restrict__ rank_map, OUT* __restrict__ out) {
-  const ChunkPos c = chunk_pos(sx, cpr, nchunks);
-  if (!c.ok) return;
-  uint32_t e[SUBW];
-#pragma unroll
-  for (int k = 0; k < SUBW; k++) {
-    const uint32_t x = c.x0 + 32 * k + c.lane;
-    e[k] = (x < sx) ? parent[c.rowbase + x] : CCL_BG;
-  }
-#pragma unroll
-  for (int k = 0; k < SUBW; k++) e[k] = chase(parent, e[k]);
-#pragma unroll
-  for (int k = 0; k < SUBW; k++) {
-    const uint32_t x = c.x0 + 32 * k + c.lane;
-    uint32_t label = (e[k] == CCL_BG) ? 0u : (e[k] & ~CCL_FLAG);
-    if (rank_map != nullptr && label != 0) label = rank_map[label];  // dust: 0 = removed
-    if (x < sx) out[c.rowbase + x] = (label == 0) ? (OUT)0 : (OUT)((uint64_t)label + offset);
-  }
-}
-
-// component sizes: one atomicAdd per run of equal ids inside a sub-word
-__global__ void __launch_bounds__(256)
-    k_ccl_count(const uint32_t* __restrict__ parent, uint32_t sx, uint32_t cpr, uint64_t nchunks,
-                uint32_t* __restrict__ counts) {
-  const ChunkPos c = chunk_pos(sx, cpr, nchunks);
-  if (!c.ok) return;
-#pragma unroll 1
-  for (int k = 0; k < SUBW; k++) {
-    const uint32_t x = c.x0 + 32 * k + c.lane;
-    const uint32_t e = chase(parent, (x < sx) ? parent[c.rowbase + x] : CCL_BG);
-    const bool bg = (e == CCL_BG);
-    const uint32_t label = bg ? 0u : (e & ~CCL_FLAG);
-    const uint32_t ll = __shfl_up_sync(FULL, label, 1);
-    const bool head = !bg && (c.lane == 0 || ll != label);
-    const uint32_t hm = __ballot_sync(FULL, head || bg);
-    if (head) {
-      const uint32_t above = (c.lane == 31) ? 0u : (hm & ~((2u << c.lane) - 1u));
-      const uint32_t end = above ? (uint32_t)(__ffs(above) - 1) : 32u;
-      atomicAdd(&counts[label], end - c.lane);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-    k_dust_flags(const uint32_t* __restrict__ counts, uint32_t n, uint64_t threshold,
-                 uint32_t* __restrict__ keep) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= n && i > 0) keep[i] = ((uint64_t)counts[i] >= threshold) ? 1u : 0u;
-  if (i == 0) keep[0] = 0;
-}
-
-// single-block inclusive scan: component counts are tiny next to voxel counts
-__global__ void __launch_bounds__(1024)
-    k_scan_keep(const uint32_t* __restrict__ keep, uint32_t n_plus1, uint32_t* __restrict__ rank_map,
-                uint32_t* __restrict__ total) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < n_plus1; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t k = (i < n_plus1) ? keep[i] : 0;
-    uint32_t v = k;
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(FULL, v, d);
-      if ((threadIdx.x & 31) >= d) v += t;
-    }
-    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      uint32_t s = warp_sums[threadIdx.x];
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, s, d);
-        if (threadIdx.x >= d) s += t;
+    if (emit) {
+      const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+      if (pos < cap) {
+        pairs[2 * (uint64_t)pos] = a;
+        pairs[2 * (uint64_t)pos + 1] = b;
       }
-      warp_sums[threadIdx.x] = s;
     }
-    __syncthreads();
-    const uint32_t prev_warps = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0;
-    const uint32_t incl = carry + prev_warps + v;
-    if (i < n_plus1) rank_map[i] = k ? incl : 0;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = carry;
-}
-
-// in-place dust on the caller's labels: zero voxels of removed components
-template <typename T>
-__global__ void __launch_bounds__(256)
-    k_dust_apply(const uint32_t* __restrict__ parent, uint32_t sx, uint32_t cpr, uint64_t nchunks,
-                 const uint32_t* __restrict__ keep, T* __restrict__ labels) {
-  const ChunkPos c = chunk_pos(sx, cpr, nchunks);
-  if (!c.ok) return;
-#pragma unroll
-  for (int k = 0; k < SUBW; k++) {
-    const uint32_t x = c.x0 + 32 * k + c.lane;
-    if (x >= sx) continue;
-    const uint32_t e = chase(parent, parent[c.rowbase + x]);
-    if (e != CCL_BG && keep[e & ~CCL_FLAG] == 0) labels[c.rowbase + x] = 0;
   }
 }
 
 // ------------------------------------------------------------- host driver
-struct CclScratch {
-  uint32_t* parent;
-  uint32_t* cand;
-  uint32_t* roots;
-  uint32_t* roots_sorted;
-  uint32_t* counters;  // [0] ncand [1] overflow [2] nroots [3] kept
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+template <typename T> static CUtensorMapDataType tmap_dtype() {
+  if (std::is_same<T, float>::value) return CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  switch (sizeof(T)) {
+    case 1: return CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    case 2: return CU_TENSOR_MAP_DATA_TYPE_UINT16;
+    case 4: return CU_TENSOR_MAP_DATA_TYPE_UINT32;
+    default: return CU_TENSOR_MAP_DATA_TYPE_UINT64;
+  }
+}
+
+// the structure of one CCL call, all device pointers inside the scratch arena
+struct CclPlan {
+  uint32_t sx, sy, sz, wpr;
+  uint64_t n, W;  // voxels, words
+  uint32_t *S, *Z, *Ey, *Ez, *rbase;
+  uint32_t R;       // runs
+  uint32_t* label;  // [R+1]: parent during the build, then the label of every run
+  uint32_t* rank;   // [R+1] scratch of the build
+  uint32_t ncomp;
   void* cub_tmp;
   size_t cub_bytes;
-  uint32_t cap;
+  ExpandArgs expand_args(uint64_t offset) const {
+    ExpandArgs e;
+    e.sx = sx; e.wpr = wpr; e.rows = (uint64_t)sy * sz; e.offset = offset;
+    e.S = S; e.Z = Z; e.rbase = rbase; e.label = label;
+    return e;
+  }
 };
 
-static size_t ccl_cub_bytes(uint32_t cap) {
-  size_t b = 0;
-  cub::DeviceRadixSort::SortKeys(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)cap);
-  return b;
-}
-
-static size_t ccl_scratch_bytes(uint64_t n, uint32_t cap) {
-  return align_up(n * 4, 256) + 3 * align_up((size_t)cap * 4, 256) + 256 + align_up(ccl_cub_bytes(cap), 256) + 4096;
-}
-
-static int ccl_take(ign_ctx* ctx, uint64_t n, uint32_t cap, CclScratch& s,
-                    uint32_t* ext_parent = nullptr) {
-  s.cap = cap;
-  s.parent = ext_parent ? ext_parent : (uint32_t*)scratch_take(ctx, n * 4);
-  s.cand = (uint32_t*)scratch_take(ctx, (size_t)cap * 4);
-  s.roots = (uint32_t*)scratch_take(ctx, (size_t)cap * 4);
-  s.roots_sorted = (uint32_t*)scratch_take(ctx, (size_t)cap * 4);
-  s.counters = (uint32_t*)scratch_take(ctx, 256);
-  s.cub_bytes = ccl_cub_bytes(cap);
-  s.cub_tmp = scratch_take(ctx, s.cub_bytes);
-  IGN_REQUIRE(s.parent && s.cand && s.roots && s.roots_sorted && s.counters && s.cub_tmp,
-              IGN_ERR_NOMEM, "CCL scratch arena too small");
+static int check_ccl_dims(uint64_t sx, uint64_t sy, uint64_t sz) {
+  IGN_REQUIRE(sx > 0 && sy > 0 && sz > 0, IGN_ERR_INVALID, "empty volume");
+  IGN_REQUIRE(sx < (1ull << 31) && sy < (1ull << 31) && sz < (1ull << 31), IGN_ERR_OVERFLOW, "CCL extent too large");
+  const uint64_t wpr = (sx + 31) / 32;
+  IGN_REQUIRE(wpr <= (uint64_t)TB_WMAX, IGN_ERR_OVERFLOW, "CCL rows longer than %d voxels are not supported", TB_WMAX * 32);
+  IGN_REQUIRE(sy * sz < (1ull << 40) && wpr * sy * sz < 0x7FFFFFF0ull, IGN_ERR_OVERFLOW,
+              "CCL volume of %llu voxels exceeds the 2^36 voxel limit; split it into tasks (igneous uses 512^3)",
+              (unsigned long long)(sx * sy * sz));
   return IGN_OK;
 }
 
-static uint32_t default_cap(uint64_t n) {
-  uint64_t c = n / 8 + 4096;
-  return (uint32_t)c;
+static size_t ccl_cub_bytes(uint64_t items) {
+  size_t b = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)items);
+  return b + 256;
 }
+// arena bytes of a CCL with W mask words whose runs fit rcap
+static size_t ccl_scratch_bytes(uint64_t W, uint64_t rcap) {
+  const uint64_t items = (W + 1 > rcap + 1 ? W + 1 : rcap + 1);
+  return 5 * align_up((W + 2) * 4, 256) + 2 * align_up((rcap + 2) * 4, 256) + align_up(ccl_cub_bytes(items), 256) + 8192;
+}
+static uint64_t default_rcap(uint64_t n) { return n / 8 + 4096; }
 
-// runs A1, A2, roots, sort, rank.  On return parent[] holds flagged roots and
-// *n_roots the number of components.  *overflow set if the candidate buffer
-// was too small (nothing else valid then).
+// Pass A .. run labels.  On success plan.label[r] = component id (1..ncomp, cc3d numbering)
+// of every run and plan.ncomp is on the host.  `rcap` = run capacity reserved in the arena;
+// *need_rcap > rcap on return means the volume has more runs (nothing else is valid).
 template <typename R>
-static int ccl_core(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, uint32_t sz,
-                    CclScratch& s, uint32_t* n_roots, bool* overflow) {
-  // IGN_CCL_V2=3: the half-height tile experiment (k_ccl_local_v3 / k_ccl_merge_tiles_s)
-  bool small = false;
-  if constexpr (!R::thresholded) {
-    const char* e = getenv("IGN_CCL_V2");
-    small = e != nullptr && e[0] == '3' && (rd.rx & rd.ry & rd.rz) == 0xFFFFFFFFu &&
-            getenv("IGN_CCL_GENERIC") == nullptr && getenv("IGN_CCL_FLATMERGE") == nullptr && (sx % 4 == 0) &&
-            ((uintptr_t)rd.in % 16 == 0) && ((uintptr_t)s.parent % 16 == 0);
+static int ccl_structure(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, uint32_t sz, uint64_t rcap,
+                         CclPlan& p, uint64_t* need_rcap) {
+  using T = typename R::value_type;
+  using MT = MaskTile<T>;
+  p.sx = sx; p.sy = sy; p.sz = sz;
+  p.wpr = (sx + 31) / 32;
+  p.n = (uint64_t)sx * sy * sz;
+  p.W = (uint64_t)p.wpr * sy * sz;
+  p.R = 0;
+  p.ncomp = 0;
+  const uint64_t W = p.W;
+  p.S = (uint32_t*)scratch_take(ctx, (W + 2) * 4);
+  p.Z = (uint32_t*)scratch_take(ctx, (W + 2) * 4);
+  p.Ey = (uint32_t*)scratch_take(ctx, (W + 2) * 4);
+  p.Ez = (uint32_t*)scratch_take(ctx, (W + 2) * 4);
+  p.rbase = (uint32_t*)scratch_take(ctx, (W + 2) * 4);
+  p.label = (uint32_t*)scratch_take(ctx, (rcap + 2) * 4);
+  p.rank = (uint32_t*)scratch_take(ctx, (rcap + 2) * 4);
+  const uint64_t items = (W + 1 > rcap + 1 ? W + 1 : rcap + 1);
+  p.cub_bytes = ccl_cub_bytes(items);
+  p.cub_tmp = scratch_take(ctx, p.cub_bytes);
+  IGN_REQUIRE(p.S && p.Z && p.Ey && p.Ez && p.rbase && p.label && p.rank && p.cub_tmp, IGN_ERR_NOMEM,
+              "CCL scratch arena too small");
+  *need_rcap = 0;
+
+  // ---- pass A
+  MaskArgs ma;
+  ma.sx = sx; ma.sy = sy; ma.sz = sz; ma.wpr = p.wpr;
+  ma.ntx = (sx + MT_BX - 1) / MT_BX;
+  ma.nty = (sy + MT_BY - 1) / MT_BY;
+  ma.ntz = (sz + MT::BZ - 1) / MT::BZ;
+  ma.nby = (ma.nty + 7) / 8;
+  ma.nbz = (ma.ntz + 7) / 8;
+  ma.ncols = ma.nby * ma.nbz * 64;
+  ma.S = p.S; ma.Z = p.Z; ma.Ey = p.Ey; ma.Ez = p.Ez;
+  const uint64_t ntiles = (uint64_t)ma.ntx * ma.ncols;
+  const size_t es = sizeof(T);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  const bool use_tma = ((uint64_t)sx * es) % 16 == 0 && ((uintptr_t)rd.in % 16) == 0 && getenv("IGN_CCL_NO_TMA") == nullptr;
+  if (use_tma) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    IGN_REQUIRE(enc != nullptr, IGN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[3] = {sx, sy, sz};
+    const cuuint64_t gstr[2] = {(cuuint64_t)sx * es, (cuuint64_t)sx * sy * es};
+    const cuuint32_t box[3] = {(cuuint32_t)MT::PITCH, MT_BY + 1, (cuuint32_t)MT::BZ + 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tmap, tmap_dtype<T>(), 3, (void*)rd.in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IGN_REQUIRE(r == CUDA_SUCCESS, IGN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %ux%ux%u", (int)r, sx, sy, sz);
   }
-  const uint32_t tile_z = small ? (uint32_t)TILE_Z_S : (uint32_t)TILE_Z;
-  const uint32_t ntx = (sx + TILE_X - 1) / TILE_X, nty = (sy + TILE_Y - 1) / TILE_Y,
-                 ntz = (sz + tile_z - 1) / tile_z;
-  const uint64_t n = (uint64_t)sx * sy * sz;
-  const uint64_t ntiles = (uint64_t)ntx * nty * ntz;
-  IGN_REQUIRE(ntiles < 0x7FFFFFFFull, IGN_ERR_OVERFLOW, "too many CCL tiles");
-  const unsigned grid = (unsigned)ntiles;
-  constexpr size_t smem = (TILE_VOX + CCL_WARPS * TASKS_PER_WARP) * sizeof(uint32_t);
-  *overflow = false;
-  // per device and cheap: set on every call (a process may drive several devices)
-  IGN_CUDA(cudaFuncSetAttribute(k_ccl_local<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if constexpr (!R::thresholded)
-    IGN_CUDA(cudaFuncSetAttribute(k_ccl_local_fast<typename R::value_type>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  IGN_CUDA(cudaMemsetAsync(s.counters, 0, 256, ctx->stream));
-  bool fast = false;
-  if constexpr (!R::thresholded) {  // raw labels (no threshold)
-    fast = (rd.rx & rd.ry & rd.rz) == 0xFFFFFFFFu && getenv("IGN_CCL_GENERIC") == nullptr;
-    // experimental 4-voxels-per-lane kernel: opt-in until it has been validated on a GPU
-    const bool v2 = fast && getenv("IGN_CCL_V2") != nullptr && (sx % 4 == 0) &&
-                    ((uintptr_t)rd.in % 16 == 0) && ((uintptr_t)s.parent % 16 == 0);
-    if (small) {
-      constexpr size_t smem3 = (size_t)(TILE_VOX_S + CCL_WARPS_S * (TASKS_PER_WARP + STARTS_PER_WARP)) * sizeof(uint32_t);
-      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local_v3<typename R::value_type>), grid, CCL_THREADS_S, smem3,
-                      rd.in, sx, sy, sz, ntx, nty, s.parent, s.cand, s.cap, s.counters);
-    } else if (v2) {
-      constexpr size_t smem2 = smem + (size_t)CCL_WARPS * STARTS_PER_WARP * sizeof(uint32_t);
-      IGN_CUDA(cudaFuncSetAttribute(k_ccl_local_v2<typename R::value_type>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local_v2<typename R::value_type>), grid, CCL_THREADS, smem2,
-                      rd.in, sx, sy, sz, ntx, nty, s.parent, s.cand, s.cap, s.counters);
-    } else if (fast) {
-      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local_fast<typename R::value_type>), grid, CCL_THREADS, smem,
-                      rd.in, sx, sy, sz, ntx, nty, s.parent, s.cand, s.cap, s.counters);
-    }
-  }
-  if (!fast)
-    IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_local<R>), grid, CCL_THREADS, smem, rd, sx, sy, sz, ntx, nty,
-                    s.parent, s.cand, s.cap, s.counters);
-  if (ntiles > 1) {
-    if (small) {
-      if constexpr (!R::thresholded)
-        IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, (k_ccl_merge_tiles_s<R>), grid, 256, 0, rd, sx, sy, sz, ntx, nty, s.parent);
-    } else if (getenv("IGN_CCL_FLATMERGE") == nullptr) {
-      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, (k_ccl_merge_tiles<R>), grid, 256, 0, rd, sx, sy, sz, ntx, nty, s.parent);
+  {
+    const size_t smem = 2 * MT::BYTES;
+    const unsigned per_sm = (unsigned)(200 * 1024 / (smem + 1024));
+    const uint64_t cap = (uint64_t)ctx->sm_count * (per_sm ? per_sm : 1);
+    const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+    IGN_CUDA(cudaMemsetAsync(p.S + W, 0, 8, ctx->stream));  // sentinel words S[W], S[W+1]
+    if (use_tma) {
+      IGN_CUDA(cudaFuncSetAttribute(k_ccl_masks<T, R::thresholded, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_masks<T, R::thresholded, true>), grid, MT_THREADS, smem, tmap, rd, ma);
     } else {
-      const uint32_t w32 = (sx + 31) / 32;
-      const uint64_t items_y = (uint64_t)(nty - 1) * sz * w32;
-      const uint64_t items_z = (uint64_t)(ntz - 1) * sy * w32;
-      const uint64_t items_x = (uint64_t)(ntx - 1) * (((uint64_t)sy * sz + 31) / 32);
-      const uint64_t items = items_y + items_z + items_x;
-      if (items > 0)
-        IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, (k_ccl_merge<R>), blocks_for(items * 32, 256), 256, 0, rd, sx, sy, sz, nty - 1,
-                   ntz - 1, ntx - 1, items_y, items_z, items_x, s.parent);
+      IGN_CUDA(cudaFuncSetAttribute(k_ccl_masks<T, R::thresholded, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_masks<T, R::thresholded, false>), grid, MT_THREADS, smem, tmap, rd, ma);
     }
   }
-  uint32_t* h = (uint32_t*)ctx->pinned;
-  IGN_CUDA(cudaMemcpyAsync(h, s.counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  IGN_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (h[1] != 0 || h[0] > s.cap) {
-    *overflow = true;
+  // ---- run ids: exclusive scan of popc(S) over W+1 words (rbase[W] = number of runs)
+  {
+    auto it = thrust::make_transform_iterator((const uint32_t*)p.S, PopcOp());
+    size_t tb = p.cub_bytes;
+    IGN_CUDA(cub::DeviceScan::ExclusiveSum(p.cub_tmp, tb, it, p.rbase, (int)(W + 1), ctx->stream));
+    ctx->launches += 2;
+  }
+  uint32_t hR = 0;
+  IGN_TRY(small_d2h(ctx, &hR, p.rbase + W, 4));
+  IGN_TRY(small_sync(ctx));
+  p.R = hR;
+  if ((uint64_t)hR > rcap) {
+    *need_rcap = hR;
     return IGN_OK;
   }
-  const uint32_t ncand = h[0];
-  uint32_t nroots = 0;
-  if (ncand > 0) {
-    IGN_LAUNCH(ctx, k_ccl_roots, blocks_for(ncand, 256), 256, 0, s.parent, s.cand, ncand, s.roots,
-               s.counters);
-    IGN_CUDA(cudaMemcpyAsync(h, s.counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    IGN_CUDA(cudaStreamSynchronize(ctx->stream));
-    nroots = h[2];
+  if (hR == 0) return IGN_OK;
+  const uint32_t Rn = hR;
+  // ---- pass B: tiles, then the rows on tile faces
+  uint32_t TY = 8;
+  while (TY > 1 && (uint64_t)p.wpr * TY * TY > (uint64_t)TB_WMAX) TY >>= 1;
+  TileArgs ta;
+  ta.sx = sx; ta.sy = sy; ta.sz = sz; ta.wpr = p.wpr; ta.TY = TY; ta.TZ = TY;
+  ta.nty = (sy + TY - 1) / TY;
+  ta.ntz = (sz + TY - 1) / TY;
+  ta.S = p.S; ta.Ey = p.Ey; ta.Ez = p.Ez; ta.rbase = p.rbase; ta.parent = p.label;
+  {
+    const size_t smem = (size_t)3 * TB_WMAX * 4 + (size_t)TB_RCAP * 4 + (size_t)(TB_WMAX + 2) * 2;
+    IGN_CUDA(cudaFuncSetAttribute(k_ccl_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IGN_REQUIRE((uint64_t)ta.nty * ta.ntz < 0x7FFFFFFFull, IGN_ERR_OVERFLOW, "too many CCL tiles");
+    IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, k_ccl_tiles, ta.nty * ta.ntz, TB_THREADS, smem, ta);
   }
-  if (nroots > 0) {
-    int end_bit = 1;
-    while (end_bit < 32 && (1ull << end_bit) < n) end_bit++;
-    size_t tb = s.cub_bytes;
-    IGN_CUDA(cub::DeviceRadixSort::SortKeys(s.cub_tmp, tb, s.roots, s.roots_sorted, (int)nroots, 0,
-                                            end_bit, ctx->stream));
-    ctx->launches += 2;  // cub radix sort: library kernels, counted conservatively
-    IGN_LAUNCH(ctx, k_ccl_rank, blocks_for(nroots, 256), 256, 0, s.parent, s.roots_sorted, nroots);
+  if (ta.nty > 1 || ta.ntz > 1) {
+    MergeArgs me;
+    me.sx = sx; me.sy = sy; me.sz = sz; me.wpr = p.wpr; me.TY = TY; me.TZ = TY; me.nty = ta.nty; me.ntz = ta.ntz;
+    me.words_y = (uint64_t)(ta.nty - 1) * sz * p.wpr;
+    me.words_z = (uint64_t)(ta.ntz - 1) * sy * p.wpr;
+    me.S = p.S; me.Ey = p.Ey; me.Ez = p.Ez; me.rbase = p.rbase; me.parent = p.label;
+    const uint64_t mitems = me.words_y + me.words_z;
+    IGN_REQUIRE(mitems / 256 < 0x7FFFFFFFull, IGN_ERR_OVERFLOW, "too many CCL face words");
+    IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, k_ccl_merge, blocks_for(mitems, 256), 256, 0, me);
   }
-  *n_roots = nroots;
+  // ---- roots: flatten, rank = exclusive scan over (parent[r] == r), labels
+  IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, k_ccl_flatten, blocks_for(Rn, 256), 256, 0, p.label, Rn);
+  IGN_CUDA(cudaMemsetAsync(p.label + Rn, 0xFF, 4, ctx->stream));  // sentinel: not a root
+  {
+    IsRootOp op;
+    op.parent = p.label;
+    auto it = thrust::make_transform_iterator(thrust::counting_iterator<uint32_t>(0), op);
+    size_t tb = p.cub_bytes;
+    IGN_CUDA(cub::DeviceScan::ExclusiveSum(p.cub_tmp, tb, it, p.rank, (int)(Rn + 1), ctx->stream));
+    ctx->launches += 2;
+  }
+  uint32_t hN = 0;
+  IGN_TRY(small_d2h(ctx, &hN, p.rank + Rn, 4));
+  IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, k_ccl_runlabel, blocks_for(Rn, 256), 256, 0, p.label, p.rank, Rn);
+  IGN_TRY(small_sync(ctx));
+  p.ncomp = hN;
   return IGN_OK;
 }
 
@@ -1340,32 +888,27 @@ static Reader<T, false> plain_reader(const void* in) {
   return r;
 }
 
-static int check_ccl_dims(uint64_t sx, uint64_t sy, uint64_t sz) {
-  IGN_REQUIRE(sx > 0 && sy > 0 && sz > 0, IGN_ERR_INVALID, "empty volume");
-  IGN_REQUIRE(sx * sy * sz <= 0x7FFFFFF0ull, IGN_ERR_OVERFLOW,
-              "CCL chunk of %llu voxels exceeds the 2^31 voxel limit of 32-bit provisional labels; "
-              "split the volume into tasks (igneous uses 512^3)",
-              (unsigned long long)(sx * sy * sz));
-  return IGN_OK;
-}
-
-static int launch_label(ign_ctx* ctx, const CclScratch& s, uint32_t sx, uint32_t sy, uint32_t sz,
-                        uint64_t offset, const uint32_t* rank_map, void* out, int out_dtype,
-                        uint64_t max_label) {
-  const uint32_t wpr = (sx + TILE_X - 1) / TILE_X;
-  const uint64_t nwords = (uint64_t)wpr * sy * sz;
-  const unsigned grid = blocks_for(nwords * 32, 256);
+static int launch_expand(ign_ctx* ctx, const CclPlan& p, uint64_t offset, void* out, int out_dtype,
+                         uint64_t max_label) {
+  const ExpandArgs e = p.expand_args(offset);
+  const bool vec = (p.sx % 4 == 0) && ((uintptr_t)out % 16 == 0);
+  const uint64_t warps = vec ? e.rows * ((p.wpr + 3) / 4) : e.rows * p.wpr;
+  IGN_REQUIRE(warps * 32 / 256 < 0x7FFFFFFFull, IGN_ERR_OVERFLOW, "CCL expand grid too large");
+  const unsigned grid = blocks_for(warps * 32, 256);
   switch (out_dtype) {
     case IGN_U16:
       IGN_REQUIRE(max_label + offset <= 0xFFFFull, IGN_ERR_OVERFLOW, "%llu labels do not fit uint16", (unsigned long long)max_label);
-      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LABEL, (k_ccl_label<uint16_t>), grid, 256, 0, s.parent, sx, wpr, nwords, offset, rank_map, (uint16_t*)out);
+      if (vec) IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LABEL, (k_ccl_expand4<uint16_t>), grid, 256, 0, e, (uint16_t*)out);
+      else IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LABEL, (k_ccl_expand1<uint16_t>), grid, 256, 0, e, (uint16_t*)out);
       break;
     case IGN_U32:
       IGN_REQUIRE(max_label + offset <= 0xFFFFFFFFull, IGN_ERR_OVERFLOW, "labels do not fit uint32");
-      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LABEL, (k_ccl_label<uint32_t>), grid, 256, 0, s.parent, sx, wpr, nwords, offset, rank_map, (uint32_t*)out);
+      if (vec) IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LABEL, (k_ccl_expand4<uint32_t>), grid, 256, 0, e, (uint32_t*)out);
+      else IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LABEL, (k_ccl_expand1<uint32_t>), grid, 256, 0, e, (uint32_t*)out);
       break;
     case IGN_U64:
-      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LABEL, (k_ccl_label<uint64_t>), grid, 256, 0, s.parent, sx, wpr, nwords, offset, rank_map, (uint64_t*)out);
+      if (vec) IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LABEL, (k_ccl_expand4<uint64_t>), grid, 256, 0, e, (uint64_t*)out);
+      else IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LABEL, (k_ccl_expand1<uint64_t>), grid, 256, 0, e, (uint64_t*)out);
       break;
     default:
       set_error("CCL out_dtype must be u16/u32/u64 (got %d)", out_dtype);
@@ -1374,29 +917,33 @@ static int launch_label(ign_ctx* ctx, const CclScratch& s, uint32_t sx, uint32_t
   return IGN_OK;
 }
 
-// dust on the component structure held in s.parent: builds keep/rank maps.
-// returns device pointers (inside the arena) and the number of kept components.
-static int dust_maps(ign_ctx* ctx, const CclScratch& s, uint32_t sx, uint32_t sy, uint32_t sz,
-                     uint32_t nroots, uint64_t threshold, uint32_t** keep_out,
-                     uint32_t** rank_map_out, uint32_t* kept) {
-  const uint32_t wpr = (sx + TILE_X - 1) / TILE_X;
-  const uint64_t nwords = (uint64_t)wpr * sy * sz;
-  const unsigned grid = blocks_for(nwords * 32, 256);
-  const size_t bytes = ((size_t)nroots + 1) * 4;
+// dust on the run labels of p: components with fewer than `threshold` voxels get label 0,
+// the others are renumbered 1..kept in the same order.
+static int dust_runs(ign_ctx* ctx, CclPlan& p, uint64_t threshold, uint32_t* kept) {
+  const uint32_t N = p.ncomp;
+  *kept = N;
+  if (N == 0 || p.R == 0) return IGN_OK;
+  const size_t bytes = ((size_t)N + 2) * 4;
   uint32_t* counts = (uint32_t*)scratch_take(ctx, bytes);
   uint32_t* keep = (uint32_t*)scratch_take(ctx, bytes);
-  uint32_t* rank_map = (uint32_t*)scratch_take(ctx, bytes);
-  IGN_REQUIRE(counts && keep && rank_map, IGN_ERR_NOMEM, "scratch arena too small for dust maps");
+  uint32_t* scan = (uint32_t*)scratch_take(ctx, bytes);
+  uint32_t* lut = (uint32_t*)scratch_take(ctx, bytes);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(N + 2));
+  void* tmp = scratch_take(ctx, tb + 256);
+  IGN_REQUIRE(counts && keep && scan && lut && tmp, IGN_ERR_NOMEM, "scratch arena too small for dust maps");
   IGN_CUDA(cudaMemsetAsync(counts, 0, bytes, ctx->stream));
-  IGN_LAUNCH(ctx, k_ccl_count, grid, 256, 0, s.parent, sx, wpr, nwords, counts);
-  IGN_LAUNCH(ctx, k_dust_flags, blocks_for(nroots + 1, 256), 256, 0, counts, nroots, threshold, keep);
-  IGN_LAUNCH(ctx, k_scan_keep, 1, 1024, 0, keep, nroots + 1, rank_map, s.counters + 3);
-  uint32_t* h = (uint32_t*)ctx->pinned;
-  IGN_CUDA(cudaMemcpyAsync(h, s.counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  IGN_CUDA(cudaStreamSynchronize(ctx->stream));
-  *kept = h[3];
-  *keep_out = keep;
-  *rank_map_out = rank_map;
+  const ExpandArgs e = p.expand_args(0);
+  IGN_LAUNCH(ctx, k_ccl_count, blocks_for(p.W, 256), 256, 0, e, counts);
+  IGN_LAUNCH(ctx, k_dust_flags, blocks_for((uint64_t)N + 2, 256), 256, 0, counts, N, threshold, keep);
+  IGN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, keep, scan, (int)(N + 2), ctx->stream));
+  ctx->launches += 2;
+  IGN_LAUNCH(ctx, k_dust_lut, blocks_for((uint64_t)N + 1, 256), 256, 0, keep, scan, N, lut);
+  IGN_LAUNCH(ctx, k_ccl_relabel_runs, blocks_for(p.R, 256), 256, 0, p.label, p.R, lut);
+  uint32_t h = 0;
+  IGN_TRY(small_d2h(ctx, &h, scan + (N + 1), 4));  // keep[N+1] is 0: scan[N+1] = number kept
+  IGN_TRY(small_sync(ctx));
+  *kept = h;
   return IGN_OK;
 }
 
@@ -1406,49 +953,48 @@ static int ccl_run(ign_ctx* ctx, const R& rd, uint64_t sx, uint64_t sy, uint64_t
                    uint64_t dust_threshold, uint64_t offset, void* out, int out_dtype,
                    TL* dust_labels_inplace, uint64_t* n_components) {
   IGN_TRY(check_ccl_dims(sx, sy, sz));
-  const uint64_t n = sx * sy * sz;
+  const uint64_t n = sx * sy * sz, W = ((sx + 31) / 32) * sy * sz;
   const bool own_arena = (ctx->scratch_used == 0);
-  uint32_t cap = default_cap(n);
+  uint64_t rcap = default_rcap(n);
   for (int attempt = 0; attempt < 2; attempt++) {
     const size_t keep_used = ctx->scratch_used;
-    const size_t need = ccl_scratch_bytes(n, cap) + 3 * ((size_t)cap + 1) * 4 + 1024;
-    if (own_arena) IGN_TRY(scratch_reserve(ctx, need));
-    CclScratch s;
-    IGN_TRY(ccl_take(ctx, n, cap, s));
-    uint32_t nroots = 0;
-    bool overflow = false;
-    int rc = ccl_core(ctx, rd, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, s, &nroots, &overflow);
-    if (rc != IGN_OK) {
+    auto fail = [&](int rc) {
       ctx->scratch_used = keep_used;
       return rc;
+    };
+    if (own_arena) {
+      const int rc = scratch_reserve(ctx, ccl_scratch_bytes(W, rcap) + 6 * (rcap + 4) * 4 + 65536);
+      if (rc != IGN_OK) return fail(rc);
     }
-    if (overflow) {
+    CclPlan p;
+    uint64_t need = 0;
+    int rc = ccl_structure(ctx, rd, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, rcap, p, &need);
+    if (rc != IGN_OK) return fail(rc);
+    if (need > rcap) {
       ctx->scratch_used = keep_used;
-      IGN_REQUIRE(attempt == 0, IGN_ERR_OVERFLOW,
-                  "CCL candidate buffer overflow (more than %u isolated segments)", cap);
-      cap = (uint32_t)n + 1024;  // worst case: every voxel its own component
+      IGN_REQUIRE(attempt == 0, IGN_ERR_NOMEM, "CCL: %llu runs do not fit the scratch arena", (unsigned long long)need);
+      rcap = need + 16;
       continue;
     }
-    uint32_t* rank_map = nullptr;
-    uint32_t* keep = nullptr;
-    uint32_t kept = nroots;
-    if (dust_threshold > 0 && nroots > 0) {
-      rc = dust_maps(ctx, s, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, nroots, dust_threshold, &keep, &rank_map, &kept);
-      if (rc != IGN_OK) {
-        ctx->scratch_used = keep_used;
-        return rc;
-      }
+    uint32_t kept = p.ncomp;
+    if (dust_threshold > 0 && p.ncomp > 0) {
+      rc = dust_runs(ctx, p, dust_threshold, &kept);
+      if (rc != IGN_OK) return fail(rc);
     }
-    if (dust_labels_inplace != nullptr && keep != nullptr) {
-      const uint32_t wpr = ((uint32_t)sx + TILE_X - 1) / TILE_X;
-      const uint64_t nwords = (uint64_t)wpr * sy * sz;
-      IGN_LAUNCH(ctx, (k_dust_apply<TL>), blocks_for(nwords * 32, 256), 256, 0, s.parent, (uint32_t)sx, wpr, nwords, keep, dust_labels_inplace);
+    if (dust_labels_inplace != nullptr && dust_threshold > 0 && p.R > 0) {
+      const ExpandArgs e = p.expand_args(0);
+      IGN_LAUNCH(ctx, (k_dust_apply<TL>), blocks_for(p.W * 32, 256), 256, 0, e, dust_labels_inplace);
     }
     if (out != nullptr) {
-      rc = launch_label(ctx, s, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, offset, rank_map, out, out_dtype, kept);
-      if (rc != IGN_OK) {
-        ctx->scratch_used = keep_used;
-        return rc;
+      if (p.R == 0) {
+        cudaError_t e = cudaMemsetAsync(out, 0, n * dtype_size(out_dtype), ctx->stream);
+        if (e != cudaSuccess) {
+          set_error("CCL: memset failed: %s", cudaGetErrorString(e));
+          return fail(IGN_ERR_CUDA);
+        }
+      } else {
+        rc = launch_expand(ctx, p, offset, out, out_dtype, kept);
+        if (rc != IGN_OK) return fail(rc);
       }
     }
     if (n_components) *n_components = kept;
@@ -1487,96 +1033,57 @@ static int ccl_task_typed(ign_ctx* ctx, const void* in, uint64_t sx, uint64_t sy
   }
 }
 
-
-// ------------------------------------------------------ multi-slab building blocks
-// (igneous/tasks/image/ccl.py passes 1-4 without the file exchange: slabs are
-// disjoint in z, linked through their facing planes.)
-
-// structure only (phases L, G, roots, rank) into a caller-owned parent array
-template <typename R>
-static int ccl_build(ign_ctx* ctx, const R& rd, uint64_t sx, uint64_t sy, uint64_t sz,
-                     uint32_t* parent, uint64_t* n_local) {
-  IGN_TRY(check_ccl_dims(sx, sy, sz));
-  const uint64_t n = sx * sy * sz;
-  const bool own_arena = (ctx->scratch_used == 0);
-  uint32_t cap = default_cap(n);
-  for (int attempt = 0; attempt < 2; attempt++) {
-    const size_t keep_used = ctx->scratch_used;
-    if (own_arena) IGN_TRY(scratch_reserve(ctx, ccl_scratch_bytes(0, cap) + 4096));
-    CclScratch s;
-    int rc = ccl_take(ctx, n, cap, s, parent);
-    if (rc != IGN_OK) {
-      ctx->scratch_used = keep_used;
-      return rc;
-    }
-    uint32_t nroots = 0;
-    bool overflow = false;
-    rc = ccl_core(ctx, rd, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, s, &nroots, &overflow);
-    ctx->scratch_used = keep_used;
-    if (rc != IGN_OK) return rc;
-    if (overflow) {
-      IGN_REQUIRE(attempt == 0, IGN_ERR_OVERFLOW, "CCL candidate buffer overflow");
-      cap = (uint32_t)n + 1024;
-      continue;
-    }
-    *n_local = nroots;
-    return IGN_OK;
-  }
-  return IGN_ERR_OVERFLOW;
-}
-
-// one z-plane of a slab: voxel values widened to u64 and local component ids
-template <typename T>
-__global__ void __launch_bounds__(256)
-    k_ccl_plane(const T* __restrict__ in, const uint32_t* __restrict__ parent, uint64_t plane_base,
-                uint64_t nplane, const uint32_t* __restrict__ lut, uint64_t* __restrict__ values,
-                uint32_t* __restrict__ labels) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= nplane) return;
-  values[i] = (uint64_t)in[plane_base + i];
-  const uint32_t e = chase(parent, parent[plane_base + i]);
-  uint32_t l = (e == CCL_BG) ? 0u : (e & ~CCL_FLAG);
-  if (lut != nullptr && l != 0) l = lut[l];
-  labels[i] = l;
-}
-
-// equivalence pairs between two facing planes (same x,y; adjacent z)
-__global__ void __launch_bounds__(256)
-    k_ccl_link(const uint64_t* __restrict__ va, const uint32_t* __restrict__ la, uint64_t offa,
-               const uint64_t* __restrict__ vb, const uint32_t* __restrict__ lb, uint64_t offb,
-               uint64_t nplane, uint64_t* __restrict__ pairs, uint32_t cap, uint32_t* counters) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const uint32_t lane = threadIdx.x & 31;
-  bool emit = false;
-  uint64_t a = 0, b = 0;
-  if (i < nplane) {
-    const uint64_t v = va[i];
-    if (v != 0 && v == vb[i]) {
-      a = offa + la[i];
-      b = offb + lb[i];
-      // runs of the same pair along x are emitted once
-      emit = !(i > 0 && la[i - 1] == la[i] && lb[i - 1] == lb[i] && va[i - 1] == v && vb[i - 1] == v);
-    }
-  }
-  const uint32_t m = __ballot_sync(FULL, emit);
-  if (m) {
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(&counters[0], (uint32_t)__popc(m));
-    base = __shfl_sync(FULL, base, leader);
-    if (emit) {
-      const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-      if (pos < cap) {
-        pairs[2 * (uint64_t)pos] = a;
-        pairs[2 * (uint64_t)pos + 1] = b;
-      }
-    }
-  }
-}
-
 }  // namespace ign
 
 using namespace ign;
+
+// ---------------------------------------------------------------- volume CCL
+// begin / finish are split so that a multi-GPU run can exchange the outer planes of
+// every rank's volume in between (ONE all-gather) and fold the global relabelling into
+// the run labels before the single expansion pass.
+struct ign_ccl_volume {
+  ign_ctx* ctx;
+  const void* in;
+  int in_dtype;
+  CclPlan plan;
+  uint64_t n_local;
+};
+
+template <typename T>
+static int volume_begin_typed(ign_ctx* ctx, ign_ccl_volume* v, uint64_t sx, uint64_t sy, uint64_t sz,
+                              uint64_t* first_values, uint32_t* first_labels, uint64_t* last_values,
+                              uint32_t* last_labels) {
+  const uint64_t n = sx * sy * sz, W = ((sx + 31) / 32) * sy * sz;
+  uint64_t rcap = default_rcap(n);
+  for (int attempt = 0; attempt < 2; attempt++) {
+    scratch_reset(ctx);
+    IGN_TRY(scratch_reserve(ctx, ccl_scratch_bytes(W, rcap) + (rcap + 64) * 4 + 65536));
+    uint64_t need = 0;
+    IGN_TRY(ccl_structure(ctx, plain_reader<T>(v->in), (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, rcap, v->plan, &need));
+    if (need > rcap) {
+      IGN_REQUIRE(attempt == 0, IGN_ERR_NOMEM, "CCL: %llu runs do not fit the scratch arena", (unsigned long long)need);
+      rcap = need + 16;
+      continue;
+    }
+    break;
+  }
+  v->n_local = v->plan.ncomp;
+  if (first_values && first_labels && last_values && last_labels) {
+    const uint64_t np = sx * sy;
+    const ExpandArgs e = v->plan.expand_args(0);
+    if (v->plan.R == 0) {
+      IGN_CUDA(cudaMemsetAsync(first_labels, 0, np * 4, ctx->stream));
+      IGN_CUDA(cudaMemsetAsync(last_labels, 0, np * 4, ctx->stream));
+      IGN_CUDA(cudaMemsetAsync(first_values, 0, np * 8, ctx->stream));
+      IGN_CUDA(cudaMemsetAsync(last_values, 0, np * 8, ctx->stream));
+    } else {
+      IGN_LAUNCH(ctx, (k_ccl_plane<T>), blocks_for(np, 256), 256, 0, (const T*)v->in, e, (uint64_t)0, (uint32_t)sy, first_values, first_labels);
+      IGN_LAUNCH(ctx, (k_ccl_plane<T>), blocks_for(np, 256), 256, 0, (const T*)v->in, e, (uint64_t)(sz - 1), (uint32_t)sy, last_values, last_labels);
+    }
+    IGN_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return IGN_OK;
+}
 
 extern "C" {
 
@@ -1634,10 +1141,10 @@ int ign_ccl6(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t s
   IGN_TRY(check_ccl_dims(sx, sy, sz));
   const int es = dtype_size(in_dtype), os = dtype_size(out_dtype);
   IGN_REQUIRE(es > 0 && os > 0, IGN_ERR_UNSUPPORTED, "unsupported dtype");
-  const uint64_t n = sx * sy * sz;
+  const uint64_t n = sx * sy * sz, W = ((sx + 31) / 32) * sy * sz;
   scratch_reset(ctx);
-  const uint32_t cap = (uint32_t)n + 1024;  // host path: size for the worst case once
-  IGN_TRY(scratch_reserve(ctx, align_up(n * es, 256) + align_up(n * os, 256) + ccl_scratch_bytes(n, cap) + 3 * ((size_t)cap + 1) * 4 + 8192));
+  const uint64_t rcap = n + 16;  // host path: size for the worst case once
+  IGN_TRY(scratch_reserve(ctx, align_up(n * es, 256) + align_up(n * os, 256) + ccl_scratch_bytes(W, rcap) + 6 * (rcap + 4) * 4 + 65536));
   void* d_in = scratch_take(ctx, n * es);
   void* d_out = scratch_take(ctx, n * os);
   IGN_CUDA(cudaMemcpyAsync(d_in, in, n * es, cudaMemcpyHostToDevice, ctx->stream));
@@ -1662,10 +1169,10 @@ int ign_dust(ign_ctx* ctx, void* labels, int dtype, uint64_t sx, uint64_t sy, ui
   IGN_TRY(check_ccl_dims(sx, sy, sz));
   const int es = dtype_size(dtype);
   IGN_REQUIRE(es > 0 && dtype != IGN_F32, IGN_ERR_UNSUPPORTED, "unsupported dtype");
-  const uint64_t n = sx * sy * sz;
+  const uint64_t n = sx * sy * sz, W = ((sx + 31) / 32) * sy * sz;
   scratch_reset(ctx);
-  const uint32_t cap = (uint32_t)n + 1024;
-  IGN_TRY(scratch_reserve(ctx, align_up(n * es, 256) + ccl_scratch_bytes(n, cap) + 3 * ((size_t)cap + 1) * 4 + 8192));
+  const uint64_t rcap = n + 16;
+  IGN_TRY(scratch_reserve(ctx, align_up(n * es, 256) + ccl_scratch_bytes(W, rcap) + 6 * (rcap + 4) * 4 + 65536));
   void* d = scratch_take(ctx, n * es);
   IGN_CUDA(cudaMemcpyAsync(d, labels, n * es, cudaMemcpyHostToDevice, ctx->stream));
   int rc = ign_dust_dev(ctx, d, dtype, sx, sy, sz, threshold);
@@ -1681,53 +1188,6 @@ int ign_dust(ign_ctx* ctx, void* labels, int dtype, uint64_t sx, uint64_t sy, ui
   return rc;
 }
 
-
-// ------------------------------------------------------------ multi-slab API
-int ign_ccl6_build_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
-                       uint64_t sz, uint32_t* work, uint64_t* n_local) {
-  IGN_TRY(activate(ctx));
-  IGN_REQUIRE(in && work && n_local, IGN_ERR_INVALID, "null argument");
-  switch (in_dtype) {
-    case IGN_U8: return ccl_build(ctx, plain_reader<uint8_t>(in), sx, sy, sz, work, n_local);
-    case IGN_U16: return ccl_build(ctx, plain_reader<uint16_t>(in), sx, sy, sz, work, n_local);
-    case IGN_U32: return ccl_build(ctx, plain_reader<uint32_t>(in), sx, sy, sz, work, n_local);
-    case IGN_U64: return ccl_build(ctx, plain_reader<uint64_t>(in), sx, sy, sz, work, n_local);
-  }
-  set_error("CCL build: unsupported input dtype %d", in_dtype);
-  return IGN_ERR_UNSUPPORTED;
-}
-
-static int ccl_plane(ign_ctx* ctx, const void* in, int in_dtype, const uint32_t* work, uint64_t sx,
-                     uint64_t sy, uint64_t sz, uint64_t z, const uint32_t* lut, uint64_t* values,
-                     uint32_t* labels);
-
-int ign_ccl6_plane_dev(ign_ctx* ctx, const void* in, int in_dtype, const uint32_t* work, uint64_t sx,
-                       uint64_t sy, uint64_t sz, uint64_t z, uint64_t* values, uint32_t* labels) {
-  return ccl_plane(ctx, in, in_dtype, work, sx, sy, sz, z, nullptr, values, labels);
-}
-
-static int ccl_plane(ign_ctx* ctx, const void* in, int in_dtype, const uint32_t* work, uint64_t sx,
-                     uint64_t sy, uint64_t sz, uint64_t z, const uint32_t* lut, uint64_t* values,
-                     uint32_t* labels) {
-  IGN_TRY(activate(ctx));
-  IGN_REQUIRE(in && work && values && labels && z < sz, IGN_ERR_INVALID, "bad plane argument");
-  const uint64_t np = sx * sy, base = z * np;
-  const unsigned g = blocks_for(np, 256);
-  switch (in_dtype) {
-    case IGN_U8: IGN_LAUNCH(ctx, (k_ccl_plane<uint8_t>), g, 256, 0, (const uint8_t*)in, work, base, np, lut, values, labels); break;
-    case IGN_U16: IGN_LAUNCH(ctx, (k_ccl_plane<uint16_t>), g, 256, 0, (const uint16_t*)in, work, base, np, lut, values, labels); break;
-    case IGN_U32: IGN_LAUNCH(ctx, (k_ccl_plane<uint32_t>), g, 256, 0, (const uint32_t*)in, work, base, np, lut, values, labels); break;
-    case IGN_U64: IGN_LAUNCH(ctx, (k_ccl_plane<uint64_t>), g, 256, 0, (const uint64_t*)in, work, base, np, lut, values, labels); break;
-    default: set_error("CCL plane: unsupported input dtype %d", in_dtype); return IGN_ERR_UNSUPPORTED;
-  }
-  return IGN_OK;
-}
-
-// device address of the pair list written by the last ign_ccl6_link_dev call on
-// this thread; valid until the next arena allocation at the same bump position
-static thread_local uint64_t* g_last_link_pairs = nullptr;
-static uint64_t* link_pairs_dev(ign_ctx*) { return g_last_link_pairs; }
-
 int ign_ccl6_link_dev(ign_ctx* ctx, const uint64_t* values_a, const uint32_t* labels_a,
                       uint64_t offset_a, const uint64_t* values_b, const uint32_t* labels_b,
                       uint64_t offset_b, uint64_t n_plane, uint64_t* pairs_host, uint64_t capacity,
@@ -1742,7 +1202,6 @@ int ign_ccl6_link_dev(ign_ctx* ctx, const uint64_t* values_a, const uint32_t* la
   if (own) IGN_TRY(scratch_reserve(ctx, (size_t)cap * 16 + 8192));
   uint64_t* d_pairs = (uint64_t*)scratch_take(ctx, (size_t)cap * 16);
   uint32_t* counters = (uint32_t*)scratch_take(ctx, 256);
-  g_last_link_pairs = d_pairs;
   if (!d_pairs || !counters) {
     ctx->scratch_used = keep;
     set_error("scratch arena too small (CCL link)");
@@ -1800,34 +1259,6 @@ int ign_ccl6_solve(const uint64_t* pairs, uint64_t n_pairs, uint64_t total, uint
   return IGN_OK;
 }
 
-int ign_ccl6_label_dev(ign_ctx* ctx, const uint32_t* work, uint64_t sx, uint64_t sy, uint64_t sz,
-                       const uint32_t* lut_dev, uint64_t offset, void* out, int out_dtype,
-                       uint64_t max_label) {
-  IGN_TRY(activate(ctx));
-  IGN_REQUIRE(work && out, IGN_ERR_INVALID, "null argument");
-  IGN_TRY(check_ccl_dims(sx, sy, sz));
-  CclScratch s;
-  s.parent = const_cast<uint32_t*>(work);
-  return launch_label(ctx, s, (uint32_t)sx, (uint32_t)sy, (uint32_t)sz, offset, lut_dev, out, out_dtype, max_label);
-}
-
-// ---------------------------------------------------------------- volume CCL
-// z-slabs of <= 2^30 voxels are resolved independently, linked through their
-// facing planes, solved on the host and labelled once through the composed
-// lookup table.  begin/finish are split so that a multi-GPU run can exchange the
-// outer planes of every rank's volume in between (ONE all-gather) and fold the
-// global relabelling into the same single label pass.
-struct ign_ccl_volume {
-  ign_ctx* ctx;
-  const void* in;
-  int in_dtype;
-  uint64_t sx, sy, sz, slab_sz, nslabs;
-  uint32_t* work;
-  std::vector<uint64_t> nloc, off;   // per slab component counts / offsets
-  std::vector<uint32_t> local_lut;   // provisional slab id -> volume-local id (1..n_local)
-  uint64_t n_local;
-};
-
 int ign_ccl6_volume_abort(ign_ccl_volume* v) {
   if (!v) return IGN_OK;
   scratch_reset(v->ctx);
@@ -1836,145 +1267,83 @@ int ign_ccl6_volume_abort(ign_ccl_volume* v) {
 }
 
 int ign_ccl6_volume_begin_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
-                              uint64_t sz, uint64_t max_slab_voxels, uint64_t* first_values,
-                              uint32_t* first_labels, uint64_t* last_values, uint32_t* last_labels,
-                              ign_ccl_volume** out, uint64_t* n_local) {
+                              uint64_t sz, uint64_t* first_values, uint32_t* first_labels,
+                              uint64_t* last_values, uint32_t* last_labels, ign_ccl_volume** out,
+                              uint64_t* n_local) {
   IGN_TRY(activate(ctx));
   IGN_REQUIRE(in && out && n_local, IGN_ERR_INVALID, "null argument");
   *out = nullptr;
-  IGN_REQUIRE(sx > 0 && sy > 0 && sz > 0, IGN_ERR_INVALID, "empty volume");
-  const int es = dtype_size(in_dtype);
-  IGN_REQUIRE(es > 0 && in_dtype != IGN_F32, IGN_ERR_UNSUPPORTED, "unsupported dtype");
-  const uint64_t np = sx * sy;
-  if (max_slab_voxels == 0 || max_slab_voxels > 0x40000000ull) max_slab_voxels = 0x40000000ull;
-  IGN_REQUIRE(np <= max_slab_voxels, IGN_ERR_OVERFLOW, "one z-plane exceeds the slab limit");
+  IGN_TRY(check_ccl_dims(sx, sy, sz));
   IGN_REQUIRE(ctx->scratch_used == 0, IGN_ERR_INVALID, "volume CCL must own the scratch arena");
   ign_ccl_volume* v = new ign_ccl_volume();
   v->ctx = ctx;
   v->in = in;
   v->in_dtype = in_dtype;
-  v->sx = sx; v->sy = sy; v->sz = sz;
-  v->slab_sz = max_slab_voxels / np;
-  v->nslabs = (sz + v->slab_sz - 1) / v->slab_sz;
-  const uint64_t n = np * sz, slab_sz = v->slab_sz, nslabs = v->nslabs;
-  const uint64_t slab_vox = np * (slab_sz < sz ? slab_sz : sz);
-  const uint32_t cap = (uint32_t)slab_vox + 1024;
-  const size_t need = align_up(n * 4, 256) + ccl_scratch_bytes(0, cap) + 2 * (align_up(np * 8, 256) + align_up(np * 4, 256)) +
-                      2 * align_up(np * 16, 256) + 2 * align_up((n / 8 + 4096) * 4, 256) + (4 << 20);
-  int rc = scratch_reserve(ctx, need);
-  if (rc != IGN_OK) { delete v; return rc; }
-  uint32_t* work = v->work = (uint32_t*)scratch_take(ctx, n * 4);
-  uint64_t* va = (uint64_t*)scratch_take(ctx, np * 8);
-  uint64_t* vb = (uint64_t*)scratch_take(ctx, np * 8);
-  uint32_t* la = (uint32_t*)scratch_take(ctx, np * 4);
-  uint32_t* lb = (uint32_t*)scratch_take(ctx, np * 4);
-  if (!work || !va || !vb || !la || !lb) {
-    set_error("scratch arena too small (volume CCL)");
-    ign_ccl6_volume_abort(v);
-    return IGN_ERR_NOMEM;
-  }
-  v->nloc.assign(nslabs, 0);
-  v->off.assign(nslabs + 1, 0);
-  for (uint64_t s = 0; s < nslabs && rc == IGN_OK; s++) {
-    const uint64_t z0 = s * slab_sz, zs = (z0 + slab_sz <= sz) ? slab_sz : sz - z0;
-    rc = ign_ccl6_build_dev(ctx, (const char*)in + z0 * np * es, in_dtype, sx, sy, zs, work + z0 * np, &v->nloc[s]);
-    v->off[s + 1] = v->off[s] + v->nloc[s];
-  }
-  const uint64_t total = v->off[nslabs];
-  std::vector<uint64_t> pairs;
-  for (uint64_t s = 0; s + 1 < nslabs && rc == IGN_OK; s++) {
-    const uint64_t z0 = s * slab_sz, z1 = (s + 1) * slab_sz;
-    const uint64_t zs1 = (z1 + slab_sz <= sz) ? slab_sz : sz - z1;
-    rc = ign_ccl6_plane_dev(ctx, (const char*)in + z0 * np * es, in_dtype, work + z0 * np, sx, sy, slab_sz, slab_sz - 1, va, la);
-    if (rc == IGN_OK) rc = ign_ccl6_plane_dev(ctx, (const char*)in + z1 * np * es, in_dtype, work + z1 * np, sx, sy, zs1, 0, vb, lb);
-    if (rc != IGN_OK) break;
-    uint64_t cnt = 0;
-    rc = ign_ccl6_link_dev(ctx, va, la, v->off[s], vb, lb, v->off[s + 1], np, nullptr, 0, &cnt);
-    if (rc != IGN_OK) break;
-    if (cnt) {
-      const size_t at = pairs.size();
-      pairs.resize(at + 2 * cnt);
-      cudaError_t e = cudaMemcpy(pairs.data() + at, link_pairs_dev(ctx), cnt * 16, cudaMemcpyDeviceToHost);
-      if (e != cudaSuccess) {
-        set_error("volume CCL: pairs D2H: %s", cudaGetErrorString(e));
-        rc = IGN_ERR_CUDA;
-      }
-    }
-  }
-  if (rc == IGN_OK) {
-    v->local_lut.assign(total + 1, 0);
-    if (nslabs > 1) {
-      rc = ign_ccl6_solve(pairs.data(), pairs.size() / 2, total, v->local_lut.data(), &v->n_local);
-    } else {
-      for (uint64_t i = 0; i <= total; i++) v->local_lut[i] = (uint32_t)i;
-      v->n_local = total;
-    }
-  }
-  // outer planes with volume-local ids, for a caller that links several volumes
-  if (rc == IGN_OK && first_values && first_labels && last_values && last_labels) {
-    uint32_t* d_lut = (uint32_t*)scratch_take(ctx, (total + 1) * 4);
-    if (!d_lut) {
-      set_error("scratch arena too small for the relabel table (%llu components)", (unsigned long long)total);
-      rc = IGN_ERR_NOMEM;
-    } else {
-      cudaError_t e = cudaMemcpyAsync(d_lut, v->local_lut.data(), (total + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
-      if (e != cudaSuccess) { set_error("volume CCL: lut H2D: %s", cudaGetErrorString(e)); rc = IGN_ERR_CUDA; }
-      const uint64_t zl = (nslabs - 1) * slab_sz, zsl = sz - zl;
-      if (rc == IGN_OK) rc = ccl_plane(ctx, in, in_dtype, work, sx, sy, (slab_sz < sz ? slab_sz : sz), 0, d_lut + v->off[0], first_values, first_labels);
-      if (rc == IGN_OK) rc = ccl_plane(ctx, (const char*)in + zl * np * es, in_dtype, work + zl * np, sx, sy, zsl, zsl - 1, d_lut + v->off[nslabs - 1], last_values, last_labels);
-      if (rc == IGN_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error("volume CCL: sync failed"); rc = IGN_ERR_CUDA; }
-    }
+  int rc;
+  switch (in_dtype) {
+    case IGN_U8: rc = volume_begin_typed<uint8_t>(ctx, v, sx, sy, sz, first_values, first_labels, last_values, last_labels); break;
+    case IGN_U16: rc = volume_begin_typed<uint16_t>(ctx, v, sx, sy, sz, first_values, first_labels, last_values, last_labels); break;
+    case IGN_U32: rc = volume_begin_typed<uint32_t>(ctx, v, sx, sy, sz, first_values, first_labels, last_values, last_labels); break;
+    case IGN_U64: rc = volume_begin_typed<uint64_t>(ctx, v, sx, sy, sz, first_values, first_labels, last_values, last_labels); break;
+    default: set_error("volume CCL: unsupported input dtype %d", in_dtype); rc = IGN_ERR_UNSUPPORTED;
   }
   if (rc != IGN_OK) {
     ign_ccl6_volume_abort(v);
     return rc;
   }
-  // the arena stays held (work[] lives in it) until finish/abort; later
-  // allocations of this call sequence bump above the structure
+  // the arena stays held (the masks and run labels live in it) until finish / abort
   *n_local = v->n_local;
   *out = v;
   return IGN_OK;
 }
 
-// global_lut: NULL, or [n_local+1] volume-local id -> final id (from the caller's
-// cross-volume solve).  Labels every slab once and releases the arena.
+// global_lut: NULL, or HOST table [n_local+1] volume-local id -> final id (from the caller's
+// cross-volume solve).  Expands the labels once and releases the arena.
 int ign_ccl6_volume_finish_dev(ign_ccl_volume* v, const uint32_t* global_lut, uint64_t max_label,
                                void* out, int out_dtype) {
   IGN_REQUIRE(v && out, IGN_ERR_INVALID, "null argument");
   ign_ctx* ctx = v->ctx;
   IGN_TRY(activate(ctx));
-  const int os = dtype_size(out_dtype);
-  const uint64_t np = v->sx * v->sy, total = v->off[v->nslabs];
+  CclPlan& p = v->plan;
   int rc = IGN_OK;
-  uint32_t* d_lut = nullptr;
-  std::vector<uint32_t> composed;
-  const uint32_t* lut_host = nullptr;
-  if (global_lut) {
-    composed.resize(total + 1);
-    for (uint64_t i = 0; i <= total; i++) composed[i] = global_lut[v->local_lut[i]];
-    lut_host = composed.data();
-  } else if (v->nslabs > 1) {
-    lut_host = v->local_lut.data();
-    max_label = v->n_local;
-  } else {
-    max_label = v->n_local;
-  }
-  if (os <= 0) { set_error("unsupported out dtype"); rc = IGN_ERR_UNSUPPORTED; }
-  if (rc == IGN_OK && lut_host) {
-    d_lut = (uint32_t*)scratch_take(ctx, (total + 1) * 4);
-    if (!d_lut) {
-      set_error("scratch arena too small for the relabel table (%llu components)", (unsigned long long)total);
-      rc = IGN_ERR_NOMEM;
-    } else {
-      cudaError_t e = cudaMemcpyAsync(d_lut, lut_host, (total + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // host table is a temporary
-      if (e != cudaSuccess) { set_error("volume CCL: lut H2D: %s", cudaGetErrorString(e)); rc = IGN_ERR_CUDA; }
+  if (!global_lut) max_label = v->n_local;
+  if (p.R == 0) {
+    const uint64_t n = (uint64_t)p.sx * p.sy * p.sz;
+    if (dtype_size(out_dtype) <= 0) {
+      set_error("unsupported out dtype");
+      rc = IGN_ERR_UNSUPPORTED;
+    } else if (cudaMemsetAsync(out, 0, n * dtype_size(out_dtype), ctx->stream) != cudaSuccess) {
+      set_error("volume CCL: memset failed");
+      rc = IGN_ERR_CUDA;
     }
-  }
-  for (uint64_t s = 0; s < v->nslabs && rc == IGN_OK; s++) {
-    const uint64_t z0 = s * v->slab_sz, zs = (z0 + v->slab_sz <= v->sz) ? v->slab_sz : v->sz - z0;
-    rc = ign_ccl6_label_dev(ctx, v->work + z0 * np, v->sx, v->sy, zs, d_lut ? d_lut + v->off[s] : nullptr, 0,
-                            (char*)out + z0 * np * os, out_dtype, max_label);
+  } else {
+    if (global_lut) {
+      uint32_t* d_lut = (uint32_t*)scratch_take(ctx, (v->n_local + 1) * 4);
+      if (!d_lut) {
+        set_error("scratch arena too small for the relabel table (%llu components)", (unsigned long long)v->n_local);
+        rc = IGN_ERR_NOMEM;
+      } else {
+        cudaError_t e = cudaMemcpyAsync(d_lut, global_lut, (v->n_local + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+          set_error("volume CCL: lut H2D: %s", cudaGetErrorString(e));
+          rc = IGN_ERR_CUDA;
+        }
+        if (rc == IGN_OK) {
+          k_ccl_relabel_runs<<<blocks_for(p.R, 256), 256, 0, ctx->stream>>>(p.label, p.R, d_lut);
+          ctx->launches++;
+          if (cudaGetLastError() != cudaSuccess) {
+            set_error("volume CCL: relabel launch failed");
+            rc = IGN_ERR_CUDA;
+          }
+        }
+        // the host table may be a temporary of the caller
+        if (rc == IGN_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+          set_error("volume CCL: sync failed");
+          rc = IGN_ERR_CUDA;
+        }
+      }
+    }
+    if (rc == IGN_OK) rc = launch_expand(ctx, p, 0, out, out_dtype, max_label);
   }
   scratch_reset(ctx);
   delete v;
@@ -1982,13 +1351,11 @@ int ign_ccl6_volume_finish_dev(ign_ccl_volume* v, const uint32_t* global_lut, ui
 }
 
 int ign_ccl6_volume_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
-                        uint64_t sz, void* out, int out_dtype, uint64_t max_slab_voxels,
-                        uint64_t* n_components) {
+                        uint64_t sz, void* out, int out_dtype, uint64_t* n_components) {
   IGN_REQUIRE(in && out, IGN_ERR_INVALID, "null buffer");
   ign_ccl_volume* v = nullptr;
   uint64_t n = 0;
-  IGN_TRY(ign_ccl6_volume_begin_dev(ctx, in, in_dtype, sx, sy, sz, max_slab_voxels, nullptr, nullptr, nullptr,
-                                    nullptr, &v, &n));
+  IGN_TRY(ign_ccl6_volume_begin_dev(ctx, in, in_dtype, sx, sy, sz, nullptr, nullptr, nullptr, nullptr, &v, &n));
   IGN_TRY(ign_ccl6_volume_finish_dev(v, nullptr, n, out, out_dtype));
   if (n_components) *n_components = n;
   return IGN_OK;

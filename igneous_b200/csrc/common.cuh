@@ -86,7 +86,7 @@ struct ign_ctx {
 };
 
 enum { IGN_PROF_CCL_LOCAL = 0, IGN_PROF_CCL_MERGE = 1, IGN_PROF_CCL_LABEL = 2, IGN_PROF_POOL = 3,
-       IGN_PROF_MC = 4, IGN_PROF_CLASSES = 8 };
+       IGN_PROF_MC = 4, IGN_PROF_SIMP = 5, IGN_PROF_CLASSES = 8 };
 
 namespace ign {
 

@@ -9,18 +9,22 @@
 //           face order), boundary vertices locked (chunk borders must stitch),
 //           per-vertex incident-face arrays (half-edge nodes, fixed capacity,
 //           merged and compacted on collapse).
-//   round   E  one thread per half-edge: the half-edge with u < v of every edge
-//              of a label still above its face target computes the cheap
-//              quadric cost (min over {u, v, midpoint} of p^T (Qu+Qv) p) and,
-//              if cost <= max_error^2, posts a (float cost, hashed label-local
+//   round   E  every edge of a label still above its face target computes the cheap
+//              quadric cost (min over {u, v, midpoint} of p^T (Qu+Qv) p) and, if
+//              cost <= max_error^2, posts a (float cost, hashed label-local
 //              half-edge id) key to both endpoints (atomicMin);
-//           K2 one thread per vertex: minimum key over its 1-ring;
+//           K2 per vertex: minimum key over its 1-ring;
 //           C  an edge WINS iff its key is the minimum of both endpoints'
 //              rings -> winners never touch each other's faces or vertices
 //              and are processed concurrently: a winner collapses iff the
 //              link condition holds and no incident face flips, otherwise it
 //              is parked until one of its endpoints' rings changes.
+//   stop    per label: faces <= target, or a round without winners, or four
+//           consecutive rounds that each remove < 0.2% of the label's faces.
 //   compact scans renumber surviving vertices / faces per label.
+//
+// Labels are independent, so all rounds of one label run inside ONE CTA with the
+// label's topology in shared memory (k_simp_labels below).
 //
 // All arithmetic is double precision WITHOUT fused multiply-add (this file is
 // compiled with -fmad=false) so that oracle/igneous_oracle.c::orc_simplify
@@ -30,11 +34,13 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+#include <type_traits>
+
 #include "mesher.h"
 
 namespace ign {
 
-constexpr uint32_t S_NONE = 0xFFFFFFFFu;
 constexpr uint64_t S_KEYMAX = 0xFFFFFFFFFFFFFFFFull;
 constexpr int S_MAXV = 32;
 constexpr int S_VCAP = 64;  // two rings of < S_MAXV alive faces always fit after a collapse
@@ -53,18 +59,7 @@ struct Simp {
   // enumeration is a set of independent loads instead of a linked-list pointer chase
   uint32_t* vf;   // [U * S_VCAP]
   uint32_t* vn;   // [U] entries in use (dead faces are skipped, compacted when the vertex is kept)
-  unsigned long long *key1, *key2;
-  uint32_t* alive_faces;   // [K+2]
-  const uint32_t* target;  // [K+2]
-  uint8_t* label_active;   // [K+2]
-  const uint32_t* tri_off; // [K+2] first face of each label: keys use label-local half-edge ids
-  uint8_t* estate;  // [3T] see k_simp_edge_keys
-  float* ecost;     // [3T] cached float cost of state 2
-  uint8_t* vdirty;  // [U] ring changed by a collapse of the previous round
-  // compacted work lists (rebuilt every few rounds; pure work skipping)
-  uint32_t* elist;  // candidate half-edges
-  uint32_t* vlist;  // alive vertices of active labels
-  uint32_t ne, nv;
+  const uint32_t* tri_off;  // [K+2] first face of each label
 };
 
 __device__ __forceinline__ uint32_t s_mix(uint32_t x) {
@@ -103,119 +98,12 @@ __device__ int s_twins(const Simp& s, uint32_t f, uint32_t u, uint32_t v, uint32
   return cnt;
 }
 
-__device__ bool s_ring(const Simp& s, uint32_t w, uint32_t* faces, uint32_t* nbr, int* nf, int* nn) {
-  *nf = 0;
-  *nn = 0;
-  const uint32_t* lw = s.vf + (uint64_t)w * S_VCAP;
-  const uint32_t cw = s.vn[w];
-  for (uint32_t j = 0; j < cw; j++) {
-    const uint32_t h = lw[j];
-    const uint32_t g = h / 3;
-    if (!s.falive[g]) continue;
-    if (*nf >= S_MAXV) return false;
-    faces[(*nf)++] = g;
-    const uint32_t* fv = s.face + 3 * (uint64_t)g;
-    for (int k = 0; k < 3; k++) {
-      const uint32_t x = fv[k];
-      if (x == w) continue;
-      bool seen = false;
-      for (int j = 0; j < *nn; j++) seen |= (nbr[j] == x);
-      if (!seen) {
-        if (*nn >= S_MAXV) return false;
-        nbr[(*nn)++] = x;
-      }
-    }
-  }
-  return true;
-}
-
 struct SEval {
   bool valid;
   double cost;
   uint32_t keep, remove;
   double p[3];
 };
-
-// cheap part: placement and quadric cost (no ring walks)
-__device__ void s_cost(const Simp& s, uint32_t u, uint32_t v, double max_err2, SEval* e) {
-  e->valid = false;
-  if (s.vbound[u] && s.vbound[v]) return;
-  double q[10];
-  for (int i = 0; i < 10; i++) q[i] = s.Q[10 * (uint64_t)u + i] + s.Q[10 * (uint64_t)v + i];
-  const double* pu = s.pos + 3 * (uint64_t)u;
-  const double* pv = s.pos + 3 * (uint64_t)v;
-  double best[3], cost;
-  if (s.vbound[u]) {
-    e->keep = u;
-    e->remove = v;
-    best[0] = pu[0]; best[1] = pu[1]; best[2] = pu[2];
-    cost = s_qeval(q, best);
-  } else if (s.vbound[v]) {
-    e->keep = v;
-    e->remove = u;
-    best[0] = pv[0]; best[1] = pv[1]; best[2] = pv[2];
-    cost = s_qeval(q, best);
-  } else {
-    e->keep = u < v ? u : v;
-    e->remove = u < v ? v : u;
-    const double* pk = s.pos + 3 * (uint64_t)e->keep;
-    const double* pr = s.pos + 3 * (uint64_t)e->remove;
-    double mid[3] = {(pk[0] + pr[0]) * 0.5, (pk[1] + pr[1]) * 0.5, (pk[2] + pr[2]) * 0.5};
-    const double ck = s_qeval(q, pk), cr = s_qeval(q, pr), cm = s_qeval(q, mid);
-    cost = ck;
-    best[0] = pk[0]; best[1] = pk[1]; best[2] = pk[2];
-    if (cr < cost) { cost = cr; best[0] = pr[0]; best[1] = pr[1]; best[2] = pr[2]; }
-    if (cm < cost) { cost = cm; best[0] = mid[0]; best[1] = mid[1]; best[2] = mid[2]; }
-  }
-  if (cost < 0.0) cost = 0.0;
-  if (!(cost <= max_err2)) return;
-  e->valid = true;
-  e->cost = cost;
-  e->p[0] = best[0]; e->p[1] = best[1]; e->p[2] = best[2];
-}
-
-// full validation of a round winner: link condition + no face flips
-__device__ void s_evaluate(const Simp& s, uint32_t u, uint32_t v, double max_err2, SEval* e) {
-  s_cost(s, u, v, max_err2, e);
-  if (!e->valid) return;
-  e->valid = false;
-  const double* best = e->p;
-  uint32_t fu[S_MAXV], fv[S_MAXV], nu[S_MAXV], nv[S_MAXV];
-  int nfu, nfv, nnu, nnv;
-  if (!s_ring(s, u, fu, nu, &nfu, &nnu)) return;
-  if (!s_ring(s, v, fv, nv, &nfv, &nnv)) return;
-  int common = 0;
-  for (int i = 0; i < nnu; i++)
-    for (int j = 0; j < nnv; j++) common += (nu[i] == nv[j]);
-  int shared = 0;
-  for (int i = 0; i < nfu; i++)
-    for (int j = 0; j < nfv; j++) shared += (fu[i] == fv[j]);
-  if (shared != 2 || common != 2) return;
-  for (int pass = 0; pass < 2; pass++) {
-    const uint32_t* fl = pass ? fv : fu;
-    const int n = pass ? nfv : nfu;
-    const uint32_t w = pass ? v : u, other = pass ? u : v;
-    for (int i = 0; i < n; i++) {
-      const uint32_t* fx = s.face + 3 * (uint64_t)fl[i];
-      if (fx[0] == other || fx[1] == other || fx[2] == other) continue;
-      const double* P[3];
-      const double* N[3];
-      for (int k = 0; k < 3; k++) {
-        P[k] = s.pos + 3 * (uint64_t)fx[k];
-        N[k] = (fx[k] == w) ? best : P[k];
-      }
-      const double ax = P[1][0] - P[0][0], ay = P[1][1] - P[0][1], az = P[1][2] - P[0][2];
-      const double bx = P[2][0] - P[0][0], by = P[2][1] - P[0][1], bz = P[2][2] - P[0][2];
-      const double n0x = ay * bz - az * by, n0y = az * bx - ax * bz, n0z = ax * by - ay * bx;
-      const double cx = N[1][0] - N[0][0], cy = N[1][1] - N[0][1], cz = N[1][2] - N[0][2];
-      const double dx = N[2][0] - N[0][0], dy = N[2][1] - N[0][1], dz = N[2][2] - N[0][2];
-      const double n1x = cy * dz - cz * dy, n1y = cz * dx - cx * dz, n1z = cx * dy - cy * dx;
-      const double dot = n0x * n1x + n0y * n1y + n0z * n1z;
-      if (!(dot > 0.0)) return;
-    }
-  }
-  e->valid = true;
-}
 
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(256)
@@ -319,441 +207,509 @@ __global__ void __launch_bounds__(256) k_simp_boundary(Simp s) {
   }
 }
 
-// work-list construction (warp-aggregated append; order is irrelevant)
-__device__ __forceinline__ void s_append(bool take, uint32_t value, uint32_t* list, uint32_t* counter) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t m = __ballot_sync(0xFFFFFFFFu, take);
-  if (!m) return;
-  const int leader = __ffs(m) - 1;
-  uint32_t base = 0;
-  if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
-  base = __shfl_sync(0xFFFFFFFFu, base, leader);
-  if (take) list[base + __popc(m & ((1u << lane) - 1u))] = value;
-}
+// ------------------------------------------------------------------ per-label rounds
+// One CTA owns one label for ALL of its rounds (labels are independent: keys use
+// label-local half-edge ids and the stop rules are per label).  The topology of the
+// label -- faces as label-local vertex ids (u16 SoA), one state byte per face (alive bit
+// + a 2-bit memo per half-edge), one flag byte per vertex, the 64-bit round keys and the
+// ring lists of the round's winners -- lives in SHARED MEMORY for the whole run; only the
+// double-precision data that a round touches sparsely (positions, quadrics, cached float
+// costs) stays in global memory (L2).  A round is a handful of __syncthreads() phases
+// instead of five launches and a host round trip:
+//
+//   P1  key1[v] = MAX                                         (vertex parallel)
+//   P2  every canonical half-edge (u < v) of an alive face posts its key to both
+//       endpoints with a shared-memory atomicMin; the float cost is memoised until an
+//       endpoint's ring changes (DIRTY)                       (face parallel)
+//   P3  a vertex LOSEs if a face neighbour holds a smaller key1 (== key2 test of the
+//       round formulation: key2[w] == key1[w] <=> !LOSE[w])   (face parallel)
+//   P4  a vertex a WINs iff its key's half-edge starts at a, both endpoints hold that
+//       key and neither LOSEs                                 (vertex parallel)
+//   E1  the faces that touch a winner's endpoints append themselves to the winner's
+//       two ring lists                                        (face parallel)
+//   E2  one WARP per winner: link condition by ballots / shuffles over the ring lists,
+//       one face flip test per lane, then the collapse itself  (warp parallel)
+//
+// Labels that do not fit (or have more than 65535 faces / vertices) run the same code
+// on the whole-task arrays in global memory (SM = false).
+constexpr uint32_t VF_ALIVE = 1, VF_BOUND = 2, VF_DIRTY = 4, VF_LOSE = 8, VF_WIN = 16, VF_END = 32;
+constexpr int SL_THREADS = 1024;
+constexpr int SL_WCAP = 128;  // winners validated per batch (a round runs as many batches as it needs)
 
-__global__ void __launch_bounds__(256) k_simp_build_elist(Simp s, uint32_t* counters) {
-  const uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  bool take = false;
-  if (h < 3 * s.T) {
-    const uint32_t f = (uint32_t)(h / 3), c = (uint32_t)(h % 3);
-    // every half-edge of an alive face of an active label: faces only die and labels
-    // only deactivate, so the list stays a superset between rebuilds (u<v can flip
-    // when a collapse renames a vertex, so that filter stays in the edge pass)
-    (void)c;
-    take = s.falive[f] && s.alive_faces[s.flabel[f]] > s.target[s.flabel[f]];
-  }
-  s_append(take, (uint32_t)h, s.elist, &counters[0]);
-}
+struct SlArgs {
+  double* pos;            // 3U
+  double* Q;              // 10U
+  uint32_t* face;         // 3T global vertex ids
+  uint8_t* falive;        // T   (out)
+  uint8_t* valive;        // U   (out)
+  const uint8_t* vbound;  // U
+  float* ecost;           // 3T  memoised float cost per half-edge
+  unsigned long long* key1;  // U   (global-memory class only)
+  uint8_t* fstate;        // T   (global-memory class only)
+  uint8_t* vflag;         // U   (global-memory class only)
+  const uint32_t* tri_off;   // [K+2]
+  const uint32_t* vert_off;  // [K+2]
+  const uint32_t* target;    // [K+2]
+  const uint32_t* order;     // [K] dense labels, largest first
+  uint32_t K;
+  uint32_t* counters;  // [0] next work item  [1] max rounds  [2] labels run in shared memory  [3] in global memory
+  double max_err2;
+  int max_rounds;
+  uint32_t smem_bytes;  // dynamic shared memory of the launch
+};
 
-__global__ void __launch_bounds__(256) k_simp_build_vlist(Simp s, uint32_t* counters) {
-  const uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  bool take = false;
-  if (v < s.U && s.valive[v]) {
-    const uint32_t l = s.flabel[s.vf[(uint64_t)v * S_VCAP] / 3];
-    take = s.alive_faces[l] > s.target[l];
-  }
-  s_append(take, (uint32_t)v, s.vlist, &counters[1]);
-}
+struct SlWin {
+  uint32_t u, v, h, cnt[2];
+};
 
-__global__ void __launch_bounds__(256)
-    k_simp_round_begin(Simp s, uint32_t K, uint32_t* flags /* [0] any label active, [1] progress, [2] collapses */) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i < s.nv) s.key1[s.vlist[i]] = S_KEYMAX;
-  if (i >= 1 && i <= K) {
-    const bool a = s.alive_faces[i] > s.target[i];
-    s.label_active[i] = a ? 1 : 0;
-    if (a) flags[0] = 1;
-  }
-}
+struct SlShared {
+  uint32_t work, alive, progress, ncol, nslot, stop, slow, pad;
+  SlWin win[SL_WCAP];
+};
 
-__global__ void __launch_bounds__(128) k_simp_edge_keys(Simp s, double max_err2, uint32_t salt) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= s.ne) return;
-  const uint32_t h = s.elist[i];
-  const uint32_t f = (uint32_t)(h / 3), c = (uint32_t)(h % 3);
-  if (!s.falive[f] || !s.label_active[s.flabel[f]]) return;
-  const uint32_t u = s.face[3 * (uint64_t)f + c], v = s.face[3 * (uint64_t)f + (c + 1) % 3];
-  if (!(u < v)) return;  // one key per edge
-  // estate: 0 unknown, 1 parked (won a round, failed validation), 2 cost cached in
-  // ecost, 3 known to exceed max_error.  Any cached state is dropped when one of the
-  // endpoints' rings changed in the previous round (pure memoisation).
-  uint8_t st = s.estate[h];
-  if (st != 0 && (s.vdirty[u] || s.vdirty[v])) st = 0;
-  if (st == 1 || st == 3) return;
-  float cf;
-  if (st == 2) {
-    cf = s.ecost[h];
+template <bool SM>
+struct SlLab {
+  typedef typename std::conditional<SM, uint16_t, uint32_t>::type idx_t;
+  uint32_t T, U, tbase, vbase, target;
+  idx_t *fc0, *fc1, *fc2;  // SM: label-local ids, SoA in shared memory
+  uint32_t* gface;         // !SM: AoS global ids in place
+  uint8_t* fstate;         // bit 7 alive, bits 2c..2c+1 memo of half-edge c
+  uint8_t* vflag;
+  unsigned long long* key1;
+  idx_t* ring;  // [SL_WCAP][2][S_MAXV] face ids
+};
+
+template <bool SM>
+__device__ __forceinline__ uint32_t sl_fget(const SlLab<SM>& L, uint32_t f, int c) {
+  if (SM) return c == 0 ? L.fc0[f] : (c == 1 ? L.fc1[f] : L.fc2[f]);
+  return L.gface[3 * (uint64_t)f + c] - L.vbase;
+}
+template <bool SM>
+__device__ __forceinline__ void sl_fset(const SlLab<SM>& L, uint32_t f, int c, uint32_t x) {
+  typedef typename SlLab<SM>::idx_t idx_t;
+  if (SM) {
+    if (c == 0) L.fc0[f] = (idx_t)x;
+    else if (c == 1) L.fc1[f] = (idx_t)x;
+    else L.fc2[f] = (idx_t)x;
   } else {
-    SEval e;
-    s_cost(s, u, v, max_err2, &e);
-    if (!e.valid) {
-      s.estate[h] = 3;
-      return;
-    }
-    cf = __double2float_rn(e.cost);
-    s.ecost[h] = cf;
-    s.estate[h] = 2;
-  }
-  const unsigned long long key = ((unsigned long long)__float_as_uint(cf) << 32) |
-                                 s_mix(((uint32_t)h - 3 * s.tri_off[s.flabel[f]]) ^ salt);
-  atomicMin(&s.key1[u], key);
-  atomicMin(&s.key1[v], key);
-}
-
-__global__ void __launch_bounds__(256) k_simp_key2(Simp s) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= s.nv) return;
-  const uint32_t w = s.vlist[i];
-  s.vdirty[w] = 0;  // consumed by this round's edge pass; the collapse pass sets it again
-  if (!s.valive[w]) {
-    s.key2[w] = S_KEYMAX;
-    return;
-  }
-  unsigned long long m = s.key1[w];
-  const uint32_t* lw = s.vf + (uint64_t)w * S_VCAP;
-  const uint32_t cw = s.vn[w];
-  for (uint32_t j = 0; j < cw; j++) {
-    const uint32_t g = lw[j] / 3;
-    if (!s.falive[g]) continue;
-    for (int k = 0; k < 3; k++) {
-      const unsigned long long kk = s.key1[s.face[3 * (uint64_t)g + k]];
-      if (kk < m) m = kk;
-    }
-  }
-  s.key2[w] = m;
-}
-
-// winners of the round -> dense list (one winner per ~50 vertices: processing
-// them in place would leave one active lane per warp)
-__global__ void __launch_bounds__(256)
-    k_simp_select(Simp s, uint32_t salt, uint32_t* wlist, uint32_t* counters) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  bool win = false;
-  uint32_t h = 0;
-  if (i < s.nv) {
-    const uint32_t a = s.vlist[i];
-    const unsigned long long key = s.key1[a];
-    if (s.valive[a] && key != S_KEYMAX) {
-      // the key holds a label-local half-edge id; a's label is that of any of its faces
-      const uint32_t hl = s_unmix((uint32_t)(key & 0xFFFFFFFFu)) ^ salt;
-      h = hl + 3 * s.tri_off[s.flabel[s.vf[(uint64_t)a * S_VCAP] / 3]];
-      const uint32_t f = h / 3, c = h % 3;
-      const uint32_t u = s.face[3 * (uint64_t)f + c], v = s.face[3 * (uint64_t)f + (c + 1) % 3];
-      win = (a == u) && s.key2[u] == key && s.key2[v] == key;
-    }
-  }
-  s_append(win, h, wlist, &counters[3]);
-}
-
-__global__ void __launch_bounds__(128)
-    k_simp_collapse(Simp s, double max_err2, const uint32_t* __restrict__ wlist, uint32_t* flags) {
-  const uint32_t nw = flags[3];  // written by k_simp_select (stream ordered)
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nw;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t h = wlist[i];
-    const uint32_t f = h / 3, c = h % 3;
-    const uint32_t u = s.face[3 * (uint64_t)f + c], v = s.face[3 * (uint64_t)f + (c + 1) % 3];
-    SEval e;
-    s_evaluate(s, u, v, max_err2, &e);
-    if (!e.valid) {  // park the edge until one of its endpoints' rings changes
-      s.estate[h] = 1;
-      flags[1] = 1;
-      continue;
-    }
-    const uint32_t k = e.keep, rm = e.remove;
-    s.pos[3 * (uint64_t)k + 0] = e.p[0];
-    s.pos[3 * (uint64_t)k + 1] = e.p[1];
-    s.pos[3 * (uint64_t)k + 2] = e.p[2];
-    for (int q = 0; q < 10; q++)
-      s.Q[10 * (uint64_t)k + q] = s.Q[10 * (uint64_t)k + q] + s.Q[10 * (uint64_t)rm + q];
-    uint32_t* lk = s.vf + (uint64_t)k * S_VCAP;
-    const uint32_t* lr = s.vf + (uint64_t)rm * S_VCAP;
-    const uint32_t ck = s.vn[k], cr = s.vn[rm];
-    for (uint32_t j = 0; j < cr; j++) {
-      const uint32_t hh = lr[j];
-      const uint32_t g = hh / 3;
-      if (!s.falive[g]) continue;
-      uint32_t* fv = s.face + 3 * (uint64_t)g;
-      if (fv[0] == k || fv[1] == k || fv[2] == k) {
-        s.falive[g] = 0;
-        atomicSub(&s.alive_faces[s.flabel[g]], 1u);
-      } else {
-        fv[hh % 3] = k;
-      }
-    }
-    // k's new ring = alive entries of k's array (compacted in place) ++ alive entries of
-    // rm's.  Both rings had < S_MAXV alive faces (validated), so S_VCAP entries suffice.
-    // Only this thread touches k and rm this round.
-    uint32_t nk = 0;
-    for (int pass = 0; pass < 2; pass++) {
-      const uint32_t* src = pass ? lr : lk;
-      const uint32_t cnt = pass ? cr : ck;
-      for (uint32_t j = 0; j < cnt; j++) {
-        const uint32_t hh = src[j];
-        if (!s.falive[hh / 3]) continue;
-        lk[nk++] = hh;
-        const uint32_t* fv = s.face + 3 * (uint64_t)(hh / 3);
-        s.vdirty[fv[0]] = 1;
-        s.vdirty[fv[1]] = 1;
-        s.vdirty[fv[2]] = 1;
-      }
-    }
-    s.vn[k] = nk;
-    s.vdirty[k] = 1;
-    s.valive[rm] = 0;
-    flags[1] = 1;
-    atomicAdd(&flags[2], 1u);
+    L.gface[3 * (uint64_t)f + c] = x + L.vbase;
   }
 }
-
-// ---------------------------------------------------------------- batched gathers
-// Opt-in variants (IGN_SIMP_BATCH=1) of the three latency-bound ring walkers.  The serial
-// versions above chase node -> alive flag -> vertex ids -> positions one ring entry at a
-// time (k_simp_collapse: 19-21 % issue-active, profiles/r01_simp_round_metrics.csv); here
-// the loads of S_B ring entries are issued together before anything depends on them.
-// Only the order of LOADS changes: every comparison, every floating-point operation and
-// every store happens in the same order on the same values, so results are bit-identical
-// to the serial kernels (and to oracle/igneous_oracle.c::orc_simplify).
-constexpr int S_B = 8;
-
-// s_ring + the vertex ids of every collected face (3 per face, the flip test reuses them)
-__device__ bool s_ring_b(const Simp& s, uint32_t w, uint32_t* faces, uint32_t* fverts, uint32_t* nbr,
-                         int* nf, int* nn) {
-  *nf = 0;
-  *nn = 0;
-  const uint32_t* lw = s.vf + (uint64_t)w * S_VCAP;
-  const uint32_t cw = s.vn[w];
-  for (uint32_t j0 = 0; j0 < cw; j0 += S_B) {
-    uint32_t h[S_B], fv[S_B][3];
-    uint8_t al[S_B];
-#pragma unroll
-    for (int i = 0; i < S_B; i++) h[i] = (j0 + i < cw) ? lw[j0 + i] : S_NONE;
-#pragma unroll
-    for (int i = 0; i < S_B; i++) al[i] = (h[i] != S_NONE) ? s.falive[h[i] / 3] : (uint8_t)0;
-#pragma unroll
-    for (int i = 0; i < S_B; i++) {
-      const uint32_t* p = s.face + 3 * (uint64_t)((al[i] ? h[i] : 0u) / 3);  // dead entry: any valid face
-      fv[i][0] = p[0];
-      fv[i][1] = p[1];
-      fv[i][2] = p[2];
-    }
-#pragma unroll
-    for (int i = 0; i < S_B; i++) {
-      if (!al[i]) continue;
-      if (*nf >= S_MAXV) return false;
-      faces[*nf] = h[i] / 3;
-      fverts[3 * *nf + 0] = fv[i][0];
-      fverts[3 * *nf + 1] = fv[i][1];
-      fverts[3 * *nf + 2] = fv[i][2];
-      (*nf)++;
-      for (int k = 0; k < 3; k++) {
-        const uint32_t x = fv[i][k];
-        if (x == w) continue;
-        bool seen = false;
-        for (int j = 0; j < *nn; j++) seen |= (nbr[j] == x);
-        if (!seen) {
-          if (*nn >= S_MAXV) return false;
-          nbr[(*nn)++] = x;
-        }
-      }
-    }
-  }
-  return true;
+// flag bytes are modified with word atomics whenever two threads may touch the same word
+__device__ __forceinline__ void sl_vor(uint8_t* vflag, uint32_t v, uint32_t bits) {
+  const uintptr_t a = (uintptr_t)(vflag + v);
+  if ((*(volatile uint8_t*)a & bits) == bits) return;
+  atomicOr((uint32_t*)(a & ~(uintptr_t)3), bits << (8 * (a & 3)));
+}
+__device__ __forceinline__ void sl_vclear(uint8_t* vflag, uint32_t v, uint32_t bits) {
+  const uintptr_t a = (uintptr_t)(vflag + v);
+  atomicAnd((uint32_t*)(a & ~(uintptr_t)3), ~(bits << (8 * (a & 3))));
 }
 
-__device__ void s_evaluate_b(const Simp& s, uint32_t u, uint32_t v, double max_err2, SEval* e) {
-  s_cost(s, u, v, max_err2, e);
-  if (!e->valid) return;
+// s_cost on label-local ids (same arithmetic, same order)
+template <bool SM>
+__device__ void sl_cost(const SlArgs& A, const SlLab<SM>& L, uint32_t u, uint32_t v, SEval* e) {
   e->valid = false;
-  const double* best = e->p;
-  uint32_t fu[S_MAXV], fv[S_MAXV], nu[S_MAXV], nv[S_MAXV], xu[3 * S_MAXV], xv[3 * S_MAXV];
-  int nfu, nfv, nnu, nnv;
-  if (!s_ring_b(s, u, fu, xu, nu, &nfu, &nnu)) return;
-  if (!s_ring_b(s, v, fv, xv, nv, &nfv, &nnv)) return;
-  int common = 0;
-  for (int i = 0; i < nnu; i++)
-    for (int j = 0; j < nnv; j++) common += (nu[i] == nv[j]);
-  int shared = 0;
-  for (int i = 0; i < nfu; i++)
-    for (int j = 0; j < nfv; j++) shared += (fu[i] == fv[j]);
-  if (shared != 2 || common != 2) return;
-  for (int pass = 0; pass < 2; pass++) {
-    const uint32_t* xl = pass ? xv : xu;
-    const int n = pass ? nfv : nfu;
-    const uint32_t w = pass ? v : u, other = pass ? u : v;
-    for (int i0 = 0; i0 < n; i0 += 2) {  // positions of two faces (18 doubles) per batch
-      double pos[2][3][3];
-      uint32_t ids[2][3];
+  const bool bu = L.vflag[u] & VF_BOUND, bv = L.vflag[v] & VF_BOUND;
+  if (bu && bv) return;
+  const double* Qu = A.Q + 10 * (uint64_t)(L.vbase + u);
+  const double* Qv = A.Q + 10 * (uint64_t)(L.vbase + v);
+  double q[10];
 #pragma unroll
-      for (int b = 0; b < 2; b++) {
-        const int i = (i0 + b < n) ? (i0 + b) : i0;
-#pragma unroll
-        for (int k = 0; k < 3; k++) ids[b][k] = xl[3 * i + k];
-      }
-#pragma unroll
-      for (int b = 0; b < 2; b++)
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const double* p = s.pos + 3 * (uint64_t)ids[b][k];
-          pos[b][k][0] = p[0];
-          pos[b][k][1] = p[1];
-          pos[b][k][2] = p[2];
-        }
-#pragma unroll
-      for (int b = 0; b < 2; b++) {
-        if (i0 + b >= n) continue;
-        const uint32_t* fx = ids[b];
-        if (fx[0] == other || fx[1] == other || fx[2] == other) continue;
-        const double* P[3];
-        const double* N[3];
-        for (int k = 0; k < 3; k++) {
-          P[k] = pos[b][k];
-          N[k] = (fx[k] == w) ? best : P[k];
-        }
-        const double ax = P[1][0] - P[0][0], ay = P[1][1] - P[0][1], az = P[1][2] - P[0][2];
-        const double bx = P[2][0] - P[0][0], by = P[2][1] - P[0][1], bz = P[2][2] - P[0][2];
-        const double n0x = ay * bz - az * by, n0y = az * bx - ax * bz, n0z = ax * by - ay * bx;
-        const double cx = N[1][0] - N[0][0], cy = N[1][1] - N[0][1], cz = N[1][2] - N[0][2];
-        const double dx = N[2][0] - N[0][0], dy = N[2][1] - N[0][1], dz = N[2][2] - N[0][2];
-        const double n1x = cy * dz - cz * dy, n1y = cz * dx - cx * dz, n1z = cx * dy - cy * dx;
-        const double dot = n0x * n1x + n0y * n1y + n0z * n1z;
-        if (!(dot > 0.0)) return;
-      }
-    }
+  for (int i = 0; i < 10; i++) q[i] = Qu[i] + Qv[i];
+  const double* pu = A.pos + 3 * (uint64_t)(L.vbase + u);
+  const double* pv = A.pos + 3 * (uint64_t)(L.vbase + v);
+  double best[3], cost;
+  if (bu) {
+    e->keep = u;
+    e->remove = v;
+    best[0] = pu[0]; best[1] = pu[1]; best[2] = pu[2];
+    cost = s_qeval(q, best);
+  } else if (bv) {
+    e->keep = v;
+    e->remove = u;
+    best[0] = pv[0]; best[1] = pv[1]; best[2] = pv[2];
+    cost = s_qeval(q, best);
+  } else {
+    e->keep = u < v ? u : v;
+    e->remove = u < v ? v : u;
+    const double* pk = u < v ? pu : pv;
+    const double* pr = u < v ? pv : pu;
+    const double pk0 = pk[0], pk1 = pk[1], pk2 = pk[2], pr0 = pr[0], pr1 = pr[1], pr2 = pr[2];
+    double kk[3] = {pk0, pk1, pk2}, rr[3] = {pr0, pr1, pr2};
+    double mid[3] = {(pk0 + pr0) * 0.5, (pk1 + pr1) * 0.5, (pk2 + pr2) * 0.5};
+    const double ck = s_qeval(q, kk), cr = s_qeval(q, rr), cm = s_qeval(q, mid);
+    cost = ck;
+    best[0] = pk0; best[1] = pk1; best[2] = pk2;
+    if (cr < cost) { cost = cr; best[0] = pr0; best[1] = pr1; best[2] = pr2; }
+    if (cm < cost) { cost = cm; best[0] = mid[0]; best[1] = mid[1]; best[2] = mid[2]; }
   }
+  if (cost < 0.0) cost = 0.0;
+  if (!(cost <= A.max_err2)) return;
   e->valid = true;
+  e->cost = cost;
+  e->p[0] = best[0]; e->p[1] = best[1]; e->p[2] = best[2];
 }
 
-__global__ void __launch_bounds__(256) k_simp_key2_b(Simp s) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= s.nv) return;
-  const uint32_t w = s.vlist[i];
-  s.vdirty[w] = 0;
-  if (!s.valive[w]) {
-    s.key2[w] = S_KEYMAX;
-    return;
+// does face (a0,a1,a2) flip when vertex w moves to `best`?  (s_evaluate's test)
+template <bool SM>
+__device__ __forceinline__ bool sl_flips(const SlArgs& A, const SlLab<SM>& L, const uint32_t* a, uint32_t w,
+                                         const double* best) {
+  double P[3][3], N[3][3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double* p = A.pos + 3 * (uint64_t)(L.vbase + a[k]);
+    P[k][0] = p[0]; P[k][1] = p[1]; P[k][2] = p[2];
   }
-  unsigned long long m = s.key1[w];
-  const uint32_t* lw = s.vf + (uint64_t)w * S_VCAP;
-  const uint32_t cw = s.vn[w];
-  for (uint32_t j0 = 0; j0 < cw; j0 += S_B) {
-    uint32_t h[S_B], fv[S_B][3];
-    uint8_t al[S_B];
 #pragma unroll
-    for (int b = 0; b < S_B; b++) h[b] = (j0 + b < cw) ? lw[j0 + b] : S_NONE;
-#pragma unroll
-    for (int b = 0; b < S_B; b++) al[b] = (h[b] != S_NONE) ? s.falive[h[b] / 3] : (uint8_t)0;
-#pragma unroll
-    for (int b = 0; b < S_B; b++) {
-      const uint32_t* p = s.face + 3 * (uint64_t)((al[b] ? h[b] : 0u) / 3);
-      fv[b][0] = al[b] ? p[0] : w;  // dead entry: w itself (its key1 is already in m)
-      fv[b][1] = al[b] ? p[1] : w;
-      fv[b][2] = al[b] ? p[2] : w;
-    }
-#pragma unroll
-    for (int b = 0; b < S_B; b++)
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const unsigned long long kk = s.key1[fv[b][k]];
-        if (kk < m) m = kk;
-      }
+  for (int k = 0; k < 3; k++) {
+    const bool mv = (a[k] == w);
+    N[k][0] = mv ? best[0] : P[k][0];
+    N[k][1] = mv ? best[1] : P[k][1];
+    N[k][2] = mv ? best[2] : P[k][2];
   }
-  s.key2[w] = m;
+  const double ax = P[1][0] - P[0][0], ay = P[1][1] - P[0][1], az = P[1][2] - P[0][2];
+  const double bx = P[2][0] - P[0][0], by = P[2][1] - P[0][1], bz = P[2][2] - P[0][2];
+  const double n0x = ay * bz - az * by, n0y = az * bx - ax * bz, n0z = ax * by - ay * bx;
+  const double cx = N[1][0] - N[0][0], cy = N[1][1] - N[0][1], cz = N[1][2] - N[0][2];
+  const double dx = N[2][0] - N[0][0], dy = N[2][1] - N[0][1], dz = N[2][2] - N[0][2];
+  const double n1x = cy * dz - cz * dy, n1y = cz * dx - cx * dz, n1z = cx * dy - cy * dx;
+  const double dot = n0x * n1x + n0y * n1y + n0z * n1z;
+  return !(dot > 0.0);
 }
 
-__global__ void __launch_bounds__(128)
-    k_simp_collapse_b(Simp s, double max_err2, const uint32_t* __restrict__ wlist, uint32_t* flags) {
-  const uint32_t nw = flags[3];
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nw;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t h = wlist[i];
-    const uint32_t f = h / 3, c = h % 3;
-    const uint32_t u = s.face[3 * (uint64_t)f + c], v = s.face[3 * (uint64_t)f + (c + 1) % 3];
-    SEval e;
-    s_evaluate_b(s, u, v, max_err2, &e);
-    if (!e.valid) {
-      s.estate[h] = 1;
-      flags[1] = 1;
-      continue;
+// the two corners of a ring face other than w, in cyclic order after w
+__device__ __forceinline__ void sl_others(const uint32_t* a, uint32_t w, uint32_t* o1, uint32_t* o2) {
+  if (a[0] == w) { *o1 = a[1]; *o2 = a[2]; }
+  else if (a[1] == w) { *o1 = a[2]; *o2 = a[0]; }
+  else { *o1 = a[0]; *o2 = a[1]; }
+}
+
+// distinct values among the (x1, x2) of the first n lanes; f1 / f2 flag the first occurrences
+__device__ __forceinline__ uint32_t sl_distinct(uint32_t x1, uint32_t x2, uint32_t n, uint32_t lane, bool* f1,
+                                                bool* f2) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const bool have = lane < n;
+  const uint32_t m1 = __match_any_sync(FULL, x1);
+  const uint32_t m2 = __match_any_sync(FULL, x2);
+  *f1 = have && ((int)lane == __ffs(m1) - 1);
+  bool in1 = false;
+  for (uint32_t j = 0; j < n; j++) in1 |= (__shfl_sync(FULL, x1, j) == x2);
+  *f2 = have && ((int)lane == __ffs(m2) - 1) && !in1;
+  return __popc(__ballot_sync(FULL, *f1)) + __popc(__ballot_sync(FULL, *f2));
+}
+
+template <bool SM>
+__device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t tid = threadIdx.x, NT = blockDim.x, lane = tid & 31u, warp = tid >> 5, NW = NT >> 5;
+  const uint32_t T = L.T, U = L.U;
+  // ---- load the label
+  for (uint32_t f = tid; f < T; f += NT) {
+    if (SM) {
+      const uint32_t* g = A.face + 3 * (uint64_t)(L.tbase + f);
+      sl_fset<SM>(L, f, 0, g[0] - L.vbase);
+      sl_fset<SM>(L, f, 1, g[1] - L.vbase);
+      sl_fset<SM>(L, f, 2, g[2] - L.vbase);
     }
-    const uint32_t k = e.keep, rm = e.remove;
-    s.pos[3 * (uint64_t)k + 0] = e.p[0];
-    s.pos[3 * (uint64_t)k + 1] = e.p[1];
-    s.pos[3 * (uint64_t)k + 2] = e.p[2];
-    {
-      double qk[10], qr[10];
-#pragma unroll
-      for (int q = 0; q < 10; q++) {
-        qk[q] = s.Q[10 * (uint64_t)k + q];
-        qr[q] = s.Q[10 * (uint64_t)rm + q];
-      }
-#pragma unroll
-      for (int q = 0; q < 10; q++) s.Q[10 * (uint64_t)k + q] = qk[q] + qr[q];
+    L.fstate[f] = 0x80;
+  }
+  for (uint32_t v = tid; v < U; v += NT) L.vflag[v] = (uint8_t)(VF_ALIVE | (A.vbound[L.vbase + v] ? VF_BOUND : 0u));
+  if (tid == 0) {
+    sh.alive = T;
+    sh.slow = 0;
+    sh.stop = 0;
+  }
+  __syncthreads();
+
+  int r = 0;
+  for (; r < A.max_rounds; r++) {
+    if (sh.alive <= L.target) break;  // reached the target before this round
+    const uint32_t salt = (uint32_t)r * 0x9E3779B9u;
+    // ---- P1
+    for (uint32_t v = tid; v < U; v += NT) {
+      L.key1[v] = S_KEYMAX;
+      const uint8_t b = L.vflag[v];
+      if (b & VF_LOSE) L.vflag[v] = (uint8_t)(b & ~VF_LOSE);
     }
-    uint32_t* lk = s.vf + (uint64_t)k * S_VCAP;
-    const uint32_t* lr = s.vf + (uint64_t)rm * S_VCAP;
-    const uint32_t ck = s.vn[k], cr = s.vn[rm];
-    // faces of rm: those that also hold k die, the others get k in rm's corner
-    for (uint32_t j0 = 0; j0 < cr; j0 += S_B) {
-      uint32_t hh[S_B], fx[S_B][3];
-      uint8_t al[S_B];
+    if (tid == 0) {
+      sh.progress = 0;
+      sh.ncol = 0;
+    }
+    __syncthreads();
+    // ---- P2: keys of the canonical half-edges
+    for (uint32_t f = tid; f < T; f += NT) {
+      const uint32_t st = L.fstate[f];
+      if (!(st & 0x80u)) continue;
+      uint32_t a[3] = {sl_fget<SM>(L, f, 0), sl_fget<SM>(L, f, 1), sl_fget<SM>(L, f, 2)};
+      uint32_t nst = st;
 #pragma unroll
-      for (int b = 0; b < S_B; b++) hh[b] = (j0 + b < cr) ? lr[j0 + b] : S_NONE;
-#pragma unroll
-      for (int b = 0; b < S_B; b++) al[b] = (hh[b] != S_NONE) ? s.falive[hh[b] / 3] : (uint8_t)0;
-#pragma unroll
-      for (int b = 0; b < S_B; b++) {
-        const uint32_t* p = s.face + 3 * (uint64_t)((al[b] ? hh[b] : 0u) / 3);
-        fx[b][0] = p[0];
-        fx[b][1] = p[1];
-        fx[b][2] = p[2];
+      for (int c = 0; c < 3; c++) {
+        const uint32_t u = a[c], v = a[(c + 1) % 3];
+        if (!(u < v)) continue;  // one key per edge
+        // memo: 0 unknown, 1 parked (won a round, failed validation), 2 cost cached in
+        // ecost, 3 known to exceed max_error; dropped when an endpoint's ring changed
+        uint32_t es = (st >> (2 * c)) & 3u;
+        if (es != 0 && ((L.vflag[u] | L.vflag[v]) & VF_DIRTY)) es = 0;
+        if (es != 1 && es != 3) {
+          const uint64_t hg = 3 * (uint64_t)(L.tbase + f) + c;
+          float cf = 0.f;
+          if (es == 2) {
+            cf = A.ecost[hg];
+          } else {
+            SEval e;
+            sl_cost<SM>(A, L, u, v, &e);
+            if (!e.valid) {
+              es = 3;
+            } else {
+              cf = __double2float_rn(e.cost);
+              A.ecost[hg] = cf;
+              es = 2;
+            }
+          }
+          if (es == 2) {
+            const unsigned long long key =
+                ((unsigned long long)__float_as_uint(cf) << 32) | s_mix((3u * f + (uint32_t)c) ^ salt);
+            atomicMin(&L.key1[u], key);
+            atomicMin(&L.key1[v], key);
+          }
+        }
+        nst = (nst & ~(3u << (2 * c))) | (es << (2 * c));
       }
+      if (nst != st) L.fstate[f] = (uint8_t)nst;
+    }
+    __syncthreads();
+    // ---- P3: DIRTY consumed; LOSE = a face neighbour holds a smaller key
+    for (uint32_t v = tid; v < U; v += NT)
+      if (L.vflag[v] & VF_DIRTY) sl_vclear(L.vflag, v, VF_DIRTY);
+    for (uint32_t f = tid; f < T; f += NT) {
+      if (!(L.fstate[f] & 0x80u)) continue;
+      const uint32_t a0 = sl_fget<SM>(L, f, 0), a1 = sl_fget<SM>(L, f, 1), a2 = sl_fget<SM>(L, f, 2);
+      const unsigned long long k0 = L.key1[a0], k1 = L.key1[a1], k2 = L.key1[a2];
+      unsigned long long m = k0 < k1 ? k0 : k1;
+      m = k2 < m ? k2 : m;
+      if (k0 > m) sl_vor(L.vflag, a0, VF_LOSE);
+      if (k1 > m) sl_vor(L.vflag, a1, VF_LOSE);
+      if (k2 > m) sl_vor(L.vflag, a2, VF_LOSE);
+    }
+    __syncthreads();
+    // ---- P4: winners (marked on the start vertex of their half-edge)
+    for (uint32_t a = tid; a < U; a += NT) {
+      const uint32_t fl = L.vflag[a];
+      if (!(fl & VF_ALIVE) || (fl & VF_LOSE)) continue;
+      const unsigned long long key = L.key1[a];
+      if (key == S_KEYMAX) continue;
+      const uint32_t hl = s_unmix((uint32_t)(key & 0xFFFFFFFFu)) ^ salt;
+      const uint32_t f = hl / 3, c = hl - 3 * f;
+      if (sl_fget<SM>(L, f, (int)c) != a) continue;
+      const uint32_t v = sl_fget<SM>(L, f, (int)((c + 1) % 3));
+      if (L.key1[v] != key || (L.vflag[v] & VF_LOSE)) continue;
+      L.vflag[a] = (uint8_t)(fl | VF_WIN);
+    }
+    __syncthreads();
+    // ---- winners in batches of SL_WCAP (they are pairwise independent)
+    for (;;) {
+      if (tid == 0) sh.nslot = 0;
+      __syncthreads();
+      for (uint32_t a = tid; a < U; a += NT) {
+        if (!(L.vflag[a] & VF_WIN)) continue;
+        const uint32_t slot = atomicAdd(&sh.nslot, 1u);
+        if (slot >= (uint32_t)SL_WCAP) continue;  // next batch
+        const uint32_t hl = s_unmix((uint32_t)(L.key1[a] & 0xFFFFFFFFu)) ^ salt;
+        const uint32_t f = hl / 3, c = hl - 3 * f;
+        const uint32_t v = sl_fget<SM>(L, f, (int)((c + 1) % 3));
+        sh.win[slot].u = a;
+        sh.win[slot].v = v;
+        sh.win[slot].h = hl;
+        sh.win[slot].cnt[0] = 0;
+        sh.win[slot].cnt[1] = 0;
+        L.key1[a] = 2ull * slot;  // key1 is dead until P1: it now names the ring list
+        L.key1[v] = 2ull * slot + 1;
+        sl_vclear(L.vflag, a, VF_WIN);
+        sl_vor(L.vflag, a, VF_END);
+        sl_vor(L.vflag, v, VF_END);
+      }
+      __syncthreads();
+      const uint32_t total = sh.nslot;
+      const uint32_t nb = total < (uint32_t)SL_WCAP ? total : (uint32_t)SL_WCAP;
+      if (nb == 0) break;
+      // ---- E1: ring lists
+      for (uint32_t f = tid; f < T; f += NT) {
+        if (!(L.fstate[f] & 0x80u)) continue;
 #pragma unroll
-      for (int b = 0; b < S_B; b++) {
-        if (!al[b]) continue;
-        const uint32_t g = hh[b] / 3;
-        if (fx[b][0] == k || fx[b][1] == k || fx[b][2] == k) {
-          s.falive[g] = 0;
-          atomicSub(&s.alive_faces[s.flabel[g]], 1u);
-        } else {
-          s.face[3 * (uint64_t)g + hh[b] % 3] = k;
+        for (int c = 0; c < 3; c++) {
+          const uint32_t x = sl_fget<SM>(L, f, c);
+          if (!(L.vflag[x] & VF_END)) continue;
+          const uint32_t sl = (uint32_t)L.key1[x];
+          const uint32_t p = atomicAdd(&sh.win[sl >> 1].cnt[sl & 1u], 1u);
+          if (p < (uint32_t)S_MAXV) L.ring[sl * S_MAXV + p] = (typename SlLab<SM>::idx_t)f;
         }
       }
-    }
-    // k's new ring = alive entries of k's array (compacted in place) ++ alive entries of rm's
-    uint32_t nk = 0;
-    for (int pass = 0; pass < 2; pass++) {
-      const uint32_t* src = pass ? lr : lk;
-      const uint32_t cnt = pass ? cr : ck;
-      for (uint32_t j0 = 0; j0 < cnt; j0 += S_B) {
-        uint32_t hh[S_B], fx[S_B][3];
-        uint8_t al[S_B];
-#pragma unroll
-        for (int b = 0; b < S_B; b++) hh[b] = (j0 + b < cnt) ? src[j0 + b] : S_NONE;
-#pragma unroll
-        for (int b = 0; b < S_B; b++) al[b] = (hh[b] != S_NONE) ? s.falive[hh[b] / 3] : (uint8_t)0;
-#pragma unroll
-        for (int b = 0; b < S_B; b++) {
-          const uint32_t* p = s.face + 3 * (uint64_t)((al[b] ? hh[b] : 0u) / 3);
-          fx[b][0] = p[0];
-          fx[b][1] = p[1];
-          fx[b][2] = p[2];
+      __syncthreads();
+      // ---- E2: one warp validates and applies one winner
+      for (uint32_t slot = warp; slot < nb; slot += NW) {
+        const uint32_t u = sh.win[slot].u, v = sh.win[slot].v, hl = sh.win[slot].h;
+        const uint32_t nfu = sh.win[slot].cnt[0], nfv = sh.win[slot].cnt[1];
+        SEval e;
+        sl_cost<SM>(A, L, u, v, &e);
+        bool ok = e.valid && nfu <= (uint32_t)S_MAXV && nfv <= (uint32_t)S_MAXV;  // warp uniform
+        const bool hu = ok && lane < nfu, hv = ok && lane < nfv;
+        uint32_t au[3] = {0, 0, 0}, av[3] = {0, 0, 0}, fu = 0, fv = 0;
+        uint32_t x1 = 0xF0000000u + lane, x2 = 0xF1000000u + lane, y1 = 0xF2000000u + lane,
+                 y2 = 0xF3000000u + lane;
+        if (hu) {
+          fu = L.ring[(2 * slot) * S_MAXV + lane];
+          au[0] = sl_fget<SM>(L, fu, 0); au[1] = sl_fget<SM>(L, fu, 1); au[2] = sl_fget<SM>(L, fu, 2);
+          sl_others(au, u, &x1, &x2);
         }
-#pragma unroll
-        for (int b = 0; b < S_B; b++) {
-          if (!al[b]) continue;
-          lk[nk++] = hh[b];
-          s.vdirty[fx[b][0]] = 1;
-          s.vdirty[fx[b][1]] = 1;
-          s.vdirty[fx[b][2]] = 1;
+        if (hv) {
+          fv = L.ring[(2 * slot + 1) * S_MAXV + lane];
+          av[0] = sl_fget<SM>(L, fv, 0); av[1] = sl_fget<SM>(L, fv, 1); av[2] = sl_fget<SM>(L, fv, 2);
+          sl_others(av, v, &y1, &y2);
+        }
+        if (ok) {
+          bool f1, f2, g1, g2;
+          const uint32_t nnu = sl_distinct(x1, x2, nfu, lane, &f1, &f2);
+          const uint32_t nnv = sl_distinct(y1, y2, nfv, lane, &g1, &g2);
+          bool c1 = false, c2 = false;
+          for (uint32_t j = 0; j < nfv; j++) {
+            const uint32_t t1 = __shfl_sync(FULL, y1, j), t2 = __shfl_sync(FULL, y2, j);
+            c1 |= (x1 == t1) | (x1 == t2);
+            c2 |= (x2 == t1) | (x2 == t2);
+          }
+          const uint32_t common = __popc(__ballot_sync(FULL, f1 && c1)) + __popc(__ballot_sync(FULL, f2 && c2));
+          const uint32_t shared = __popc(__ballot_sync(FULL, hu && (x1 == v || x2 == v)));
+          bool bad = false;
+          if (hu && x1 != v && x2 != v) bad = sl_flips<SM>(A, L, au, u, e.p);
+          if (hv && y1 != u && y2 != u) bad = bad || sl_flips<SM>(A, L, av, v, e.p);
+          const bool anybad = __any_sync(FULL, bad);
+          ok = nnu <= (uint32_t)S_MAXV && nnv <= (uint32_t)S_MAXV && shared == 2 && common == 2 && !anybad;
+        }
+        if (!ok) {  // park the edge until one of its endpoints' rings changes
+          if (lane == 0) {
+            const uint32_t f = hl / 3, c = hl - 3 * f;
+            const uint32_t st = L.fstate[f];
+            L.fstate[f] = (uint8_t)((st & ~(3u << (2 * c))) | (1u << (2 * c)));
+            sl_vclear(L.vflag, u, VF_END);
+            sl_vclear(L.vflag, v, VF_END);
+            atomicOr(&sh.progress, 1u);
+          }
+          continue;
+        }
+        const uint32_t k = e.keep, rm = e.remove;
+        const bool rm_is_u = (rm == u);
+        const bool hr = rm_is_u ? hu : hv;
+        const uint32_t rf = rm_is_u ? fu : fv;
+        const uint32_t r0 = rm_is_u ? au[0] : av[0], r1 = rm_is_u ? au[1] : av[1], r2 = rm_is_u ? au[2] : av[2];
+        // faces of rm: those that also hold k die, the others get k in rm's corner
+        const bool dies = hr && (r0 == k || r1 == k || r2 == k);
+        if (hr) {
+          if (dies) L.fstate[rf] = (uint8_t)(L.fstate[rf] & 0x7Fu);
+          else sl_fset<SM>(L, rf, r0 == rm ? 0 : (r1 == rm ? 1 : 2), k);
+        }
+        const uint32_t dead = __popc(__ballot_sync(FULL, dies));
+        // the new ring of k: every vertex of it is DIRTY (memoised edge states are dropped)
+        if (hu && x1 != v && x2 != v) { sl_vor(L.vflag, x1, VF_DIRTY); sl_vor(L.vflag, x2, VF_DIRTY); }
+        if (hv && y1 != u && y2 != u) { sl_vor(L.vflag, y1, VF_DIRTY); sl_vor(L.vflag, y2, VF_DIRTY); }
+        double* Qk = A.Q + 10 * (uint64_t)(L.vbase + k);
+        const double* Qr = A.Q + 10 * (uint64_t)(L.vbase + rm);
+        if (lane < 10) Qk[lane] = Qk[lane] + Qr[lane];
+        if (lane == 0) {
+          double* pk = A.pos + 3 * (uint64_t)(L.vbase + k);
+          pk[0] = e.p[0]; pk[1] = e.p[1]; pk[2] = e.p[2];
+          sl_vor(L.vflag, k, VF_DIRTY);
+          sl_vclear(L.vflag, k, VF_END);
+          sl_vclear(L.vflag, rm, 0xFFu);
+          atomicSub(&sh.alive, dead);
+          atomicAdd(&sh.ncol, 1u);
+          atomicOr(&sh.progress, 1u);
         }
       }
+      __syncthreads();
+      if (total <= (uint32_t)SL_WCAP) break;
     }
-    s.vn[k] = nk;
-    s.vdirty[k] = 1;
-    s.valive[rm] = 0;
-    flags[1] = 1;
-    atomicAdd(&flags[2], 1u);
+    // ---- stop rules of the label
+    if (tid == 0) {
+      uint32_t stop = 0;
+      if (!sh.progress) {
+        stop = 1;  // nothing collapsed or parked: fixed point
+      } else {
+        // four consecutive rounds that each remove fewer than 0.2% of the remaining faces
+        if ((uint64_t)sh.ncol * 1000 < (uint64_t)sh.alive) sh.slow++;
+        else sh.slow = 0;
+        if (sh.slow >= 4) stop = 1;
+      }
+      sh.stop = stop;
+    }
+    __syncthreads();
+    if (sh.stop) {
+      r++;
+      break;
+    }
+  }
+  // ---- write the label back to the whole-task arrays
+  for (uint32_t f = tid; f < T; f += NT) {
+    const bool al = L.fstate[f] & 0x80u;
+    A.falive[L.tbase + f] = al ? 1 : 0;
+    if (SM && al) {
+      uint32_t* g = A.face + 3 * (uint64_t)(L.tbase + f);
+      g[0] = sl_fget<SM>(L, f, 0) + L.vbase;
+      g[1] = sl_fget<SM>(L, f, 1) + L.vbase;
+      g[2] = sl_fget<SM>(L, f, 2) + L.vbase;
+    }
+  }
+  for (uint32_t v = tid; v < U; v += NT) A.valive[L.vbase + v] = (L.vflag[v] & VF_ALIVE) ? 1 : 0;
+  if (tid == 0) {
+    atomicMax(&A.counters[1], (uint32_t)r);
+    atomicAdd(&A.counters[SM ? 2 : 3], 1u);
+  }
+}
+
+extern __shared__ __align__(16) unsigned char sl_smem[];
+
+__global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
+  __shared__ SlShared sh;
+  for (;;) {
+    __syncthreads();  // the previous label is completely written back; sh.work may be reused
+    if (threadIdx.x == 0) sh.work = atomicAdd(&A.counters[0], 1u);
+    __syncthreads();
+    const uint32_t wi = sh.work;
+    if (wi >= A.K) break;
+    const uint32_t l = A.order[wi];
+    const uint32_t tbase = A.tri_off[l], T = A.tri_off[l + 1] - tbase;
+    const uint32_t vbase = A.vert_off[l], U = A.vert_off[l + 1] - vbase;
+    const uint32_t target = A.target[l];
+    if (T == 0 || T <= target) continue;  // init left every face / vertex alive
+    // shared-memory layout: ring lists | key1 | faces SoA | face state | vertex flags
+    const size_t ring16 = (size_t)SL_WCAP * 2 * S_MAXV * 2;
+    const size_t o_key = ring16;
+    const size_t o_f0 = o_key + 8 * (size_t)U;
+    const size_t o_fs = o_f0 + 6 * (size_t)T;
+    const size_t o_vf = (o_fs + T + 3) & ~(size_t)3;
+    const size_t need = o_vf + U + 4;
+    if (need <= A.smem_bytes && T <= 65535u && U <= 65535u) {
+      SlLab<true> L;
+      L.T = T; L.U = U; L.tbase = tbase; L.vbase = vbase; L.target = target;
+      L.ring = (uint16_t*)sl_smem;
+      L.key1 = (unsigned long long*)(sl_smem + o_key);
+      L.fc0 = (uint16_t*)(sl_smem + o_f0);
+      L.fc1 = L.fc0 + T;
+      L.fc2 = L.fc1 + T;
+      L.gface = nullptr;
+      L.fstate = sl_smem + o_fs;
+      L.vflag = sl_smem + o_vf;
+      sl_run<true>(A, L, sh);
+    } else {
+      SlLab<false> L;
+      L.T = T; L.U = U; L.tbase = tbase; L.vbase = vbase; L.target = target;
+      L.ring = (uint32_t*)sl_smem;  // SL_WCAP * 2 * S_MAXV * 4 bytes, always available
+      L.key1 = A.key1 + vbase;
+      L.fc0 = L.fc1 = L.fc2 = nullptr;
+      L.gface = A.face + 3 * (uint64_t)tbase;
+      L.fstate = A.fstate + tbase;
+      L.vflag = A.vflag + vbase;
+      sl_run<false>(A, L, sh);
+    }
   }
 }
 
@@ -841,12 +797,11 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   cub::DeviceScan::ExclusiveSum(nullptr, scanb, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                 (int)(3 * T));
   const size_t tmpb = (sortb > scanb ? sortb : scanb) + 256;
-  const size_t need = align_up(U * 24, 256) + align_up(U * 80, 256) + 4 * align_up(3 * T * 4, 256) +
-                      align_up(U * S_VCAP * 4, 256) +
-                      3 * align_up(T * 4, 256) + 2 * align_up(T, 256) + 3 * align_up(U, 256) +
-                      4 * align_up(U * 4, 256) + 2 * align_up(U * 8, 256) + 6 * align_up((K + 2) * 4, 256) +
-                      2 * align_up(3 * T * 4, 256) + align_up(3 * T, 256) + align_up(3 * T * 4, 256) +
-                      align_up(U, 256) + align_up(3 * T * 4, 256) + 2 * align_up(U * 4, 256) + tmpb + (1 << 20);
+  const size_t need = align_up(U * 24, 256) + align_up(U * 80, 256) + 3 * align_up(3 * T * 4, 256) +
+                      align_up(U * S_VCAP * 4, 256) + align_up(T * 4, 256) + 2 * align_up(T, 256) +
+                      3 * align_up(U, 256) + 3 * align_up(U * 4, 256) + align_up(U * 8, 256) +
+                      6 * align_up((K + 2) * 4, 256) + align_up(3 * T * 4, 256) +
+                      2 * align_up(3 * T * 4, 256) + tmpb + (1 << 20);
   IGN_TRY(scratch_reserve(ctx, need));
   Simp s;
   s.U = U;
@@ -859,41 +814,33 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   uint32_t* node_h = (uint32_t*)scratch_take(ctx, 3 * T * 4);
   s.flabel = (uint32_t*)scratch_take(ctx, T * 4);
   s.falive = (uint8_t*)scratch_take(ctx, T);
+  uint8_t* fstate = (uint8_t*)scratch_take(ctx, T);
   s.valive = (uint8_t*)scratch_take(ctx, U);
   s.vbound = (uint8_t*)scratch_take(ctx, U);
+  uint8_t* vflag = (uint8_t*)scratch_take(ctx, U);
   s.vn = (uint32_t*)scratch_take(ctx, U * 4);
   uint32_t* vscan = (uint32_t*)scratch_take(ctx, U * 4);
-  uint32_t* vflag = (uint32_t*)scratch_take(ctx, U * 4);
-  s.key1 = (unsigned long long*)scratch_take(ctx, U * 8);
-  s.key2 = (unsigned long long*)scratch_take(ctx, U * 8);
-  s.alive_faces = (uint32_t*)scratch_take(ctx, (K + 2) * 4);
+  uint32_t* vflag32 = (uint32_t*)scratch_take(ctx, U * 4);
+  unsigned long long* key1 = (unsigned long long*)scratch_take(ctx, U * 8);
   uint32_t* d_target = (uint32_t*)scratch_take(ctx, (K + 2) * 4);
-  s.label_active = (uint8_t*)scratch_take(ctx, K + 2);
   uint32_t* d_tri_off = (uint32_t*)scratch_take(ctx, (K + 2) * 4);
   uint32_t* d_vert_off = (uint32_t*)scratch_take(ctx, (K + 2) * 4);
   uint32_t* d_new_tri_off = (uint32_t*)scratch_take(ctx, (K + 2) * 4);
   uint32_t* d_new_vert_off = (uint32_t*)scratch_take(ctx, (K + 2) * 4);
+  uint32_t* d_order = (uint32_t*)scratch_take(ctx, (K + 2) * 4);
   uint32_t* flags = (uint32_t*)scratch_take(ctx, 256);
-  s.estate = (uint8_t*)scratch_take(ctx, 3 * T);
-  s.ecost = (float*)scratch_take(ctx, 3 * T * 4);
-  s.vdirty = (uint8_t*)scratch_take(ctx, U);
-  s.elist = (uint32_t*)scratch_take(ctx, 3 * T * 4);
-  s.vlist = (uint32_t*)scratch_take(ctx, U * 4);
-  uint32_t* wlist = (uint32_t*)scratch_take(ctx, U * 4);
-  s.ne = s.nv = 0;
+  float* ecost = (float*)scratch_take(ctx, 3 * T * 4);
   void* tmp = scratch_take(ctx, tmpb);
   uint32_t* sorted_v = (uint32_t*)scratch_take(ctx, 3 * T * 4);
   uint32_t* sorted_h = (uint32_t*)scratch_take(ctx, 3 * T * 4);
-  if (!s.pos || !s.Q || !s.face || !s.vf || !node_v || !node_h || !s.flabel || !s.falive || !s.valive ||
-      !s.vbound || !s.vn || !vscan || !vflag || !s.key1 || !s.key2 || !s.alive_faces ||
-      !d_target || !s.label_active || !d_tri_off || !d_vert_off || !d_new_tri_off || !d_new_vert_off ||
-      !flags || !tmp || !sorted_v || !sorted_h || !s.estate || !s.ecost || !s.vdirty || !s.elist ||
-      !s.vlist || !wlist) {
+  if (!s.pos || !s.Q || !s.face || !s.vf || !node_v || !node_h || !s.flabel || !s.falive || !fstate ||
+      !s.valive || !s.vbound || !vflag || !s.vn || !vscan || !vflag32 || !key1 || !d_target || !d_tri_off ||
+      !d_vert_off || !d_new_tri_off || !d_new_vert_off || !d_order || !flags || !ecost || !tmp ||
+      !sorted_v || !sorted_h) {
     scratch_reset(ctx);
     set_error("scratch arena too small (simplify: %llu faces)", (unsigned long long)T);
     return IGN_ERR_NOMEM;
   }
-  s.target = d_target;
   s.tri_off = d_tri_off;
   auto done = [&](int code) {
     scratch_reset(ctx);
@@ -922,13 +869,17 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   std::vector<uint32_t> target(K + 2, 0);
   for (uint64_t l = 1; l <= K; l++)
     target[l] = (m->tri_off[l + 1] - m->tri_off[l]) / (uint32_t)reduction_factor;
+  // work order of the label kernel: largest labels first (the tail is made of small ones)
+  std::vector<uint32_t> order(K);
+  for (uint64_t l = 0; l < K; l++) order[l] = (uint32_t)(l + 1);
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    const uint32_t ta = m->tri_off[a + 1] - m->tri_off[a], tb = m->tri_off[b + 1] - m->tri_off[b];
+    return ta != tb ? ta > tb : a < b;
+  });
   S_TRY(small_h2d(ctx, d_target, target.data(), (K + 2) * 4));
   S_TRY(small_h2d(ctx, d_tri_off, m->tri_off.data(), (K + 2) * 4));
   S_TRY(small_h2d(ctx, d_vert_off, m->vert_off.data(), (K + 2) * 4));
-  S_CUDA(cudaMemsetAsync(s.alive_faces, 0, (K + 2) * 4, ctx->stream));
-  S_CUDA(cudaMemsetAsync(s.label_active, 0, K + 2, ctx->stream));
-  S_CUDA(cudaMemsetAsync(s.estate, 0, 3 * T, ctx->stream));
-  S_CUDA(cudaMemsetAsync(s.vdirty, 0, U, ctx->stream));
+  S_TRY(small_h2d(ctx, d_order, order.data(), K * 4));
   S_LAUNCH(k_simp_init_verts, blocks_for(U, 256), 256, m->d_uniq_vkeys, U, (double)resolution[0],
            (double)resolution[1], (double)resolution[2], s.pos, s.valive, s.vbound, s.vn);
   S_LAUNCH(k_simp_init_faces, blocks_for(T, 256), 256, m->d_faces, d_tri_off, d_vert_off, (uint32_t)K, T,
@@ -944,92 +895,64 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   S_CUDA(cudaMemsetAsync(flags, 0, 64, ctx->stream));
   S_LAUNCH(k_simp_link, blocks_for(3 * T, 256), 256, sorted_v, sorted_h, (uint64_t)(3 * T), s.vf, s.vn,
            flags + 12);
-  {
-    uint32_t* hf = (uint32_t*)ctx->pinned;
-    S_TRY(small_d2h(ctx, hf, flags + 12, 4));
-    S_TRY(small_sync(ctx));
-    if (hf[0] != 0) {
-      set_error("simplify: a vertex has more than %d incident faces", S_VCAP);
-      return done(IGN_ERR_UNSUPPORTED);
-    }
-  }
   S_LAUNCH(k_simp_quadrics, blocks_for(U, 128), 128, s);
   S_LAUNCH(k_simp_boundary, blocks_for(3 * T, 256), 256, s);
-  {
-    std::vector<uint32_t> af(K + 2, 0);
-    for (uint64_t l = 1; l <= K; l++) af[l] = m->tri_off[l + 1] - m->tri_off[l];
-    S_TRY(small_h2d(ctx, s.alive_faces, af.data(), (K + 2) * 4));
-    S_TRY(small_sync(ctx));
-  }
 
-  const double max_err2 = (double)max_error * (double)max_error;
-  const int max_rounds = 400;
-  const bool trace = getenv("IGN_SIMP_TRACE") != nullptr;  // per-round progress on stderr
-  // batched-gather ring walkers: same results, opt-in until validated on a GPU
-  const bool batch = getenv("IGN_SIMP_BATCH") != nullptr;
-  // work-list rebuild period and collapse grid cap: measured on B200 (tools/time_simplify.py),
-  // 4 / 8 / 16 rounds -> 187.7 / 177.4 / 175.3 ms per 257^3 task; the grid cap has no effect
-  const int rebuild_every = 16;
-  const unsigned collapse_cap = 1184u;
-  uint32_t* hflags = (uint32_t*)ctx->pinned;
-  int r = 0, slow = 0;
-  uint64_t cum_collapses = 0;
-  for (; r < max_rounds; r++) {
-    const uint32_t salt = (uint32_t)r * 0x9E3779B9u;
-    if (r % rebuild_every == 0) {  // rebuild the compact work lists
-      S_CUDA(cudaMemsetAsync(flags + 8, 0, 8, ctx->stream));
-      S_LAUNCH(k_simp_build_elist, blocks_for(3 * T, 256), 256, s, flags + 8);
-      S_LAUNCH(k_simp_build_vlist, blocks_for(U, 256), 256, s, flags + 8);
-      S_TRY(small_d2h(ctx, hflags + 8, flags + 8, 8));
-      S_TRY(small_sync(ctx));
-      s.ne = hflags[8];
-      s.nv = hflags[9];
+  // ---- all rounds of every label: one persistent CTA per SM pulls labels off the order list
+  static const size_t sl_dyn = 232448 - 1024 - ((sizeof(SlShared) + 255) / 256) * 256;
+  {
+    static int configured[64] = {0};  // per device
+    if (ctx->device < 64 && !configured[ctx->device]) {
+      S_CUDA(cudaFuncSetAttribute(k_simp_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl_dyn));
+      configured[ctx->device] = 1;
+    } else if (ctx->device >= 64) {
+      S_CUDA(cudaFuncSetAttribute(k_simp_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl_dyn));
     }
-    S_CUDA(cudaMemsetAsync(flags, 0, 16, ctx->stream));
-    const uint64_t nb = (s.nv > K + 1 ? s.nv : K + 1);
-    S_LAUNCH(k_simp_round_begin, blocks_for(nb, 256), 256, s, (uint32_t)K, flags);
-    if (s.ne) S_LAUNCH(k_simp_edge_keys, blocks_for(s.ne, 128), 128, s, max_err2, salt);
-    if (s.nv) {
-      if (batch) S_LAUNCH(k_simp_key2_b, blocks_for(s.nv, 256), 256, s);
-      else S_LAUNCH(k_simp_key2, blocks_for(s.nv, 256), 256, s);
-      S_LAUNCH(k_simp_select, blocks_for(s.nv, 256), 256, s, salt, wlist, flags);
-      // grid-stride over the device-side winner count: no host round trip in between
-      const unsigned cg = blocks_for(s.nv / 16 + 1, 128);
-      if (batch) S_LAUNCH(k_simp_collapse_b, cg < collapse_cap ? cg : collapse_cap, 128, s, max_err2, wlist, flags);
-      else S_LAUNCH(k_simp_collapse, cg < collapse_cap ? cg : collapse_cap, 128, s, max_err2, wlist, flags);
-    }
-    S_TRY(small_d2h(ctx, hflags, flags, 16));
-    S_TRY(small_sync(ctx));
-    if (hflags[0] == 0) break;           // every label reached its target before this round
-    if (hflags[1] == 0) { r++; break; }  // nothing collapsed or parked: fixed point
-    // early stop (mirrored by the oracle): four consecutive rounds that each remove
-    // fewer than 0.2% of the remaining faces
-    cum_collapses += hflags[2];
-    const uint64_t alive_total = T - 2 * cum_collapses;
-    if ((uint64_t)hflags[2] * 1000 < alive_total) slow++; else slow = 0;
-    if (trace)
-      fprintf(stderr, "round %d collapses %u alive %llu ne %u nv %u\n", r, hflags[2],
-              (unsigned long long)alive_total, s.ne, s.nv);
-    if (slow >= 4) { r++; break; }
   }
-  m->simp_rounds = r;
+  SlArgs A;
+  A.pos = s.pos; A.Q = s.Q; A.face = s.face; A.falive = s.falive; A.valive = s.valive; A.vbound = s.vbound;
+  A.ecost = ecost; A.key1 = key1; A.fstate = fstate; A.vflag = vflag;
+  A.tri_off = d_tri_off; A.vert_off = d_vert_off; A.target = d_target; A.order = d_order;
+  A.K = (uint32_t)K; A.counters = flags;
+  A.max_err2 = (double)max_error * (double)max_error;
+  A.max_rounds = 400;
+  // IGN_SIMP_GMEM=1 (test knob): run every label on the global-memory arrays, the path of
+  // labels that do not fit shared memory (only the winners' ring lists stay in smem)
+  const char* force_gmem = getenv("IGN_SIMP_GMEM");
+  A.smem_bytes = (force_gmem && force_gmem[0] == '1') ? (uint32_t)(SL_WCAP * 2 * S_MAXV * 4) : (uint32_t)sl_dyn;
+  {
+    const unsigned grid = (unsigned)(K < (uint64_t)ctx->sm_count ? K : (uint64_t)ctx->sm_count);
+    const int slot = prof_begin(ctx, IGN_PROF_SIMP);
+    k_simp_labels<<<grid, SL_THREADS, sl_dyn, ctx->stream>>>(A);
+    ctx->launches++;
+    prof_end(ctx, slot);
+    S_CUDA(cudaGetLastError());
+  }
 
   // ---- compaction
   uint32_t* fscan = node_v;   // 3T u32 >= T
   uint32_t* fflag = node_h;
   size_t tb = tmpb;
-  S_LAUNCH(k_simp_flags_u32, blocks_for(U, 256), 256, s.valive, U, vflag);
-  S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, vflag, vscan, (int)U, ctx->stream));
+  S_LAUNCH(k_simp_flags_u32, blocks_for(U, 256), 256, s.valive, U, vflag32);
+  S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, vflag32, vscan, (int)U, ctx->stream));
   S_LAUNCH(k_simp_flags_u32, blocks_for(T, 256), 256, s.falive, T, fflag);
   tb = tmpb;
   S_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, fflag, fscan, (int)T, ctx->stream));
   ctx->launches += 4;
-  uint32_t last[4];
+  uint32_t last[4], hflags[16];
   S_TRY(small_d2h(ctx, &last[0], vscan + (U - 1), 4));
-  S_TRY(small_d2h(ctx, &last[1], vflag + (U - 1), 4));
+  S_TRY(small_d2h(ctx, &last[1], vflag32 + (U - 1), 4));
   S_TRY(small_d2h(ctx, &last[2], fscan + (T - 1), 4));
   S_TRY(small_d2h(ctx, &last[3], fflag + (T - 1), 4));
+  S_TRY(small_d2h(ctx, hflags, flags, 64));
   S_TRY(small_sync(ctx));
+  if (hflags[12] != 0) {
+    set_error("simplify: a vertex has more than %d incident faces", S_VCAP);
+    return done(IGN_ERR_UNSUPPORTED);
+  }
+  m->simp_rounds = (int)hflags[1];
+  m->simp_labels_smem = hflags[2];
+  m->simp_labels_gmem = hflags[3];
   const uint32_t U2 = last[0] + last[1], T2 = last[2] + last[3];
   S_LAUNCH(k_simp_new_offsets, blocks_for(K + 2, 256), 256, d_vert_off, vscan, (uint32_t)(K + 2), U, U2,
            d_new_vert_off);

@@ -112,7 +112,7 @@ class Group:
     n_local = c.c_uint64(0)
     _shim.check(lib.ign_ccl6_volume_begin_dev(
       ctx.handle, _shim.ptr(pipe.d_in), c.c_int(pipe.code), c.c_uint64(sx), c.c_uint64(sy), c.c_uint64(sz),
-      c.c_uint64(0), c.c_void_p(p_first_v), c.c_void_p(p_first_l), c.c_void_p(p_last_v), c.c_void_p(p_last_l),
+      c.c_void_p(p_first_v), c.c_void_p(p_first_l), c.c_void_p(p_last_v), c.c_void_p(p_last_l),
       c.byref(h), c.byref(n_local)))
     try:
       head = np.zeros(32, dtype=np.uint64)

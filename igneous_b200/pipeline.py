@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _shim
 
-PROF_CLASSES = {"ccl_local": 0, "ccl_merge": 1, "ccl_label": 2, "pool": 3, "mc": 4}
+PROF_CLASSES = {"ccl_local": 0, "ccl_merge": 1, "ccl_label": 2, "pool": 3, "mc": 4, "simp_labels": 5}
 
 
 def _u64(v):
@@ -101,7 +101,7 @@ class VolumePipeline:
       return
     _shim.check(self.lib.ign_ccl6_volume_dev(
       self.ctx.handle, _shim.ptr(self.d_in), c.c_int(self.code), _u64(sx), _u64(sy), _u64(sz),
-      _shim.ptr(self.d_cc), c.c_int(_shim.dtype_code(self.ccl_out_dtype)), _u64(0), c.byref(n)))
+      _shim.ptr(self.d_cc), c.c_int(_shim.dtype_code(self.ccl_out_dtype)), c.byref(n)))
     self.n_components = int(n.value)
 
   def mesh_tasks(self):
@@ -260,14 +260,21 @@ class VolumePipeline:
 
   # --------------------------------------------------------------- profiling
   def prof_enable(self, on=True):
-    _shim.check(self.lib.ign_prof_enable(self.ctx.handle, c.c_int(int(on))))
+    for ctx in [self.ctx] + [w[0] for w in self._workers]:
+      _shim.check(self.lib.ign_prof_enable(ctx.handle, c.c_int(int(on))))
 
   def prof_read(self):
+    """(total ms, launches) per kernel class, summed over the main context and the mesh
+    streams (kernels of different mesh streams overlap: their sum can exceed the wall time)."""
     out = {}
     for name, cls in PROF_CLASSES.items():
-      ms, cnt = c.c_float(0), c.c_uint64(0)
-      _shim.check(self.lib.ign_prof_read(self.ctx.handle, c.c_int(cls), c.byref(ms), c.byref(cnt)))
-      out[name] = (float(ms.value), int(cnt.value))
+      tot, n = 0.0, 0
+      for ctx in [self.ctx] + [w[0] for w in self._workers]:
+        ms, cnt = c.c_float(0), c.c_uint64(0)
+        _shim.check(self.lib.ign_prof_read(ctx.handle, c.c_int(cls), c.byref(ms), c.byref(cnt)))
+        tot += float(ms.value)
+        n += int(cnt.value)
+      out[name] = (tot, n)
     return out
 
   # ------------------------------------------------------------- host results

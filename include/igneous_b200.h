@@ -150,40 +150,33 @@ IGN_API int ign_ccl6(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, ui
 IGN_API int ign_ccl6_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
                  uint64_t sz, void* out, int out_dtype, uint64_t* n_components);
 
-/* Multi-slab building blocks.  A volume too large for one call (or spread
- * over several GPUs) is cut into z-slabs; each slab's component structure is
- * built into a caller-owned `work` array (4 bytes per voxel), facing planes are
- * compared, the equivalences are solved on the host, and every slab is labelled
- * once through the composed lookup table.  This replaces the four file-based
- * passes of igneous/tasks/image/ccl.py (CCLFacesTask :126-194,
+/* Volumes that span several GPUs (one z-slab per rank).  This replaces the four
+ * file-based passes of igneous/tasks/image/ccl.py (CCLFacesTask :126-194,
  * CCLEquivalancesTask :196-294, create_relabeling :358-420, RelabelCCLTask
- * :296-356) for data that is resident in HBM.  The result is bit-identical to
- * one whole-volume ign_ccl6 call. */
-IGN_API int ign_ccl6_build_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
-                               uint64_t sz, uint32_t* work, uint64_t* n_local);
-IGN_API int ign_ccl6_plane_dev(ign_ctx* ctx, const void* in, int in_dtype, const uint32_t* work,
-                               uint64_t sx, uint64_t sy, uint64_t sz, uint64_t z, uint64_t* values,
-                               uint32_t* labels);
+ * :296-356) for data that is resident in HBM: every rank resolves its own volume
+ * (begin), the outer z-planes are exchanged and compared (ign_ccl6_link_dev),
+ * the equivalences are solved (ign_ccl6_solve, smaller id wins as ccl.py:70-73)
+ * and every rank expands its labels once through the composed table (finish).
+ * The result is bit-identical to one whole-volume ign_ccl6 call.
+ *
+ * ign_ccl6_volume_dev: one volume of up to 2^36 voxels in one call (no slabs: the
+ * union-find runs over x-runs, not voxels). */
 IGN_API int ign_ccl6_link_dev(ign_ctx* ctx, const uint64_t* values_a, const uint32_t* labels_a,
                               uint64_t offset_a, const uint64_t* values_b, const uint32_t* labels_b,
                               uint64_t offset_b, uint64_t n_plane, uint64_t* pairs_host,
                               uint64_t capacity, uint64_t* n_pairs);
 IGN_API int ign_ccl6_solve(const uint64_t* pairs, uint64_t n_pairs, uint64_t total, uint32_t* lut,
                            uint64_t* n_global);
-IGN_API int ign_ccl6_label_dev(ign_ctx* ctx, const uint32_t* work, uint64_t sx, uint64_t sy,
-                               uint64_t sz, const uint32_t* lut_dev, uint64_t offset, void* out,
-                               int out_dtype, uint64_t max_label);
 IGN_API int ign_ccl6_volume_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
-                                uint64_t sz, void* out, int out_dtype, uint64_t max_slab_voxels,
-                                uint64_t* n_components);
+                                uint64_t sz, void* out, int out_dtype, uint64_t* n_components);
 /* The same in two halves, so that several volumes (one per GPU) can be linked in
  * between: begin resolves the volume and fills its outer z-planes (voxel values
  * widened to u64 and volume-local ids 1..n_local; device buffers of sx*sy
- * entries, may be NULL); finish takes the caller's [n_local+1] table from
+ * entries, may be NULL); finish takes the caller's HOST table [n_local+1] from
  * volume-local to final ids (NULL = identity) and writes the labels. */
 typedef struct ign_ccl_volume ign_ccl_volume;
 IGN_API int ign_ccl6_volume_begin_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx,
-                                      uint64_t sy, uint64_t sz, uint64_t max_slab_voxels,
+                                      uint64_t sy, uint64_t sz,
                                       uint64_t* first_values, uint32_t* first_labels,
                                       uint64_t* last_values, uint32_t* last_labels,
                                       ign_ccl_volume** out, uint64_t* n_local);

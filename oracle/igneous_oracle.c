@@ -616,8 +616,7 @@ int orc_synth_seg_u64(uint64_t* out, uint64_t sx, uint64_t sy, uint64_t sz,
 /*     (float32 cost, half-edge id) key over its edges (key1), then    */
 /*     the minimum over its neighbours (key2); an edge collapses iff   */
 /*     its key equals key2 of both endpoints -> collapses of one round */
-/*     are independent.  A label stops when faces <= target at the     */
-/*     start of a round.                                               */
+/*     are independent.  Stop rules are per label (see orc_simplify).  */
 /* All arithmetic in double without FMA contraction.                   */
 /* ------------------------------------------------------------------ */
 #include <math.h>
@@ -852,11 +851,24 @@ int orc_simplify(uint64_t U, uint64_t T, double* pos, uint32_t* face, const uint
     uint32_t tw;
     if (simp_twins(&s, f, u, v, &tw) != 1) { s.vbound[u] = 1; s.vbound[v] = 1; }
   }
-  int r = 0, slow = 0;
-  uint64_t cum_collapses = 0;
+  /* stop rules are per label (labels are independent: the product runs each label to
+     completion inside one CTA): a label is finished when its faces <= target at the
+     start of a round, when a round produced no winner for it (nothing collapsed or
+     parked: fixed point), or after four consecutive rounds that each removed fewer than
+     0.2% of its remaining faces. */
+  uint8_t* stopped = (uint8_t*)calloc(K + 2, 1);
+  uint32_t* slow = (uint32_t*)calloc(K + 2, sizeof(uint32_t));
+  uint32_t* nsel = (uint32_t*)calloc(K + 2, sizeof(uint32_t));
+  uint32_t* ncol = (uint32_t*)calloc(K + 2, sizeof(uint32_t));
+  if (!stopped || !slow || !nsel || !ncol) return ORC_ENOMEM;
+  int r = 0;
   for (; r < max_rounds; r++) {
     int any_label = 0;
-    for (uint32_t l = 1; l <= K; l++) { label_active[l] = alive_faces[l] > target[l]; any_label |= label_active[l]; }
+    for (uint32_t l = 1; l <= K; l++) {
+      label_active[l] = !stopped[l] && alive_faces[l] > target[l];
+      any_label |= label_active[l];
+      nsel[l] = ncol[l] = 0;
+    }
     if (!any_label) break;
     const uint32_t salt = (uint32_t)r * 0x9E3779B9u;
     for (uint64_t v = 0; v < U; v++) s.key1[v] = SIMP_KEYMAX;
@@ -890,21 +902,24 @@ int orc_simplify(uint64_t U, uint64_t T, double* pos, uint32_t* face, const uint
       }
       s.key2[w] = m;
     }
+    /* dirty flags of inactive labels are irrelevant from now on (a label never becomes
+       active again), those of active labels were consumed by the edge pass */
     memset(vdirty, 0, U ? U : 1);
     /* select on the pre-round state, then apply (selected collapses are independent);
        winners that fail the full validation are parked until their neighbourhood changes */
-    uint64_t nsel = 0, ncol = 0;
     for (uint64_t a = 0; a < U; a++) {
       const uint64_t key = s.key1[a];
       if (!valive[a] || key == SIMP_KEYMAX) continue;
-      const uint32_t h = simp_key_edge(key, salt) + 3 * tri_off[flabel[s.head[a] / 3]];
+      const uint32_t lab = flabel[s.head[a] / 3];
+      const uint32_t h = simp_key_edge(key, salt) + 3 * tri_off[lab];
       const uint32_t f = h / 3, c = h % 3;
       const uint32_t u = face[3 * (uint64_t)f + c], v = face[3 * (uint64_t)f + (c + 1) % 3];
       if (a != u) continue;
       if (s.key2[u] != key || s.key2[v] != key) continue;
       simp_eval_t e;
       simp_evaluate(&s, u, v, max_err2, &e);
-      if (!e.valid) { estate[h] = 1; nsel++; continue; }
+      nsel[lab]++;
+      if (!e.valid) { estate[h] = 1; continue; }
       const uint32_t k = e.keep, rm = e.remove;
       pos[3 * (uint64_t)k + 0] = e.p[0]; pos[3 * (uint64_t)k + 1] = e.p[1]; pos[3 * (uint64_t)k + 2] = e.p[2];
       for (int i = 0; i < 10; i++) s.Q[10 * (uint64_t)k + i] = s.Q[10 * (uint64_t)k + i] + s.Q[10 * (uint64_t)rm + i];
@@ -918,8 +933,7 @@ int orc_simplify(uint64_t U, uint64_t T, double* pos, uint32_t* face, const uint
       s.next[s.tail[k]] = s.head[rm];
       s.tail[k] = s.tail[rm];
       valive[rm] = 0;
-      nsel++;
-      ncol++;
+      ncol[lab]++;
       vdirty[k] = 1;
       for (uint32_t hh = s.head[k]; hh != SIMP_NONE; hh = s.next[hh]) {
         const uint32_t g = hh / 3;
@@ -927,14 +941,15 @@ int orc_simplify(uint64_t U, uint64_t T, double* pos, uint32_t* face, const uint
         vdirty[face[3 * (uint64_t)g]] = 1; vdirty[face[3 * (uint64_t)g + 1]] = 1; vdirty[face[3 * (uint64_t)g + 2]] = 1;
       }
     }
-    if (getenv("ORC_SIMP_TRACE")) fprintf(stderr, "round %d winners %llu collapses %llu\n", r, (unsigned long long)nsel, (unsigned long long)ncol);
-    if (nsel == 0) { r++; break; }
-    /* early stop: four consecutive rounds that each remove < 0.2% of the remaining faces */
-    cum_collapses += ncol;
-    const uint64_t alive_total = T - 2 * cum_collapses;
-    if (ncol * 1000 < alive_total) slow++; else slow = 0;
-    if (slow >= 4) { r++; break; }
+    for (uint32_t l = 1; l <= K; l++) {
+      if (!label_active[l]) continue;
+      if (getenv("ORC_SIMP_TRACE")) fprintf(stderr, "round %d label %u winners %u collapses %u alive %u\n", r, l, nsel[l], ncol[l], alive_faces[l]);
+      if (nsel[l] == 0) { stopped[l] = 1; continue; }
+      if ((uint64_t)ncol[l] * 1000 < (uint64_t)alive_faces[l]) slow[l]++; else slow[l] = 0;
+      if (slow[l] >= 4) stopped[l] = 1;
+    }
   }
+  free(stopped); free(slow); free(nsel); free(ncol);
   *rounds = r;
   free(s.Q); free(s.vbound); free(s.next); free(s.head); free(s.tail); free(s.key1); free(s.key2);
   free(alive_faces); free(label_active); free(estate); free(vdirty);

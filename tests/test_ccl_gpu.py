@@ -116,12 +116,11 @@ def test_ccl_rejects_other_connectivity(ctx):
     cc3d.connected_components(np.zeros((4, 4, 4), np.uint8), connectivity=26)
 
 
-@pytest.mark.parametrize("shape,slab_vox", [((64, 48, 40), 64 * 48 * 7), ((33, 29, 17), 33 * 29 * 1),
-                                            ((70, 65, 9), 70 * 65 * 4), ((40, 40, 40), 40 * 40 * 40)])
+@pytest.mark.parametrize("shape", [(64, 48, 40), (33, 29, 17), (70, 65, 9), (40, 40, 40), (260, 20, 19)])
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint64])
-def test_multislab_volume_ccl_equals_whole_volume(ctx, oracle, shape, slab_vox, dtype):
-  """z-slabs + plane linkage + host union-find + one label pass must be
-  bit-identical to a single whole-volume CCL (and to the oracle)."""
+def test_volume_ccl_equals_whole_volume(ctx, oracle, shape, dtype):
+  """ign_ccl6_volume_dev (begin + finish, the halves a multi-GPU run links in between) must
+  be bit-identical to a single whole-volume CCL (and to the oracle)."""
   import ctypes as c
   from igneous_b200 import _shim
   rng = np.random.default_rng(21)
@@ -133,7 +132,7 @@ def test_multislab_volume_ccl_equals_whole_volume(ctx, oracle, shape, slab_vox, 
   _shim.check(ctx.lib.ign_ccl6_volume_dev(
     ctx.handle, _shim.ptr(d_in), c.c_int(_shim.dtype_code(dtype)), c.c_uint64(shape[0]),
     c.c_uint64(shape[1]), c.c_uint64(shape[2]), _shim.ptr(d_out), c.c_int(_shim.IGN_U32),
-    c.c_uint64(slab_vox), c.byref(n)))
+    c.byref(n)))
   got = ctx.to_host(d_out, shape, np.uint32)
   assert n.value == n_want
   assert np.array_equal(got, want.astype(np.uint32))
@@ -164,10 +163,9 @@ def test_ccl_device_resident_properties_1024(ctx):
     a = ctx.to_host(d_cc, (S, S, 64), np.uint32)   # first 64 z-planes
     b = ctx.to_host(d_cc2, (S, S, 64), np.uint32)
     assert np.array_equal(a, b)
-    # 4 z-slabs + plane linkage must give the same labelling as the single call
+    # the begin / finish halves must give the same labelling as the single call
     _shim.check(ctx.lib.ign_ccl6_volume_dev(ctx.handle, _shim.ptr(d_in), c.c_int(_shim.IGN_U64), *args,
-                                            _shim.ptr(d_cc2), c.c_int(_shim.IGN_U32), c.c_uint64(S * S * 256),
-                                            c.byref(n3)))
+                                            _shim.ptr(d_cc2), c.c_int(_shim.IGN_U32), c.byref(n3)))
     assert n3.value == n1.value
     assert np.array_equal(ctx.to_host(d_cc2, (S, S, 64), np.uint32), a)
     tail = np.empty((S, S, 8), dtype=np.uint32, order="F")
@@ -181,18 +179,26 @@ def test_ccl_device_resident_properties_1024(ctx):
 
 
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64])
-def test_ccl_v2_kernel_matches_oracle(ctx, oracle, monkeypatch, dtype):
-  """Opt-in 4-voxels-per-lane tile kernel (IGN_CCL_V2=1): same ids as the oracle on aligned
-  volumes with full and partial tiles, long runs and dense noise (task queue / start list
-  overflow paths)."""
+def test_ccl_tma_and_cooperative_fill_match_oracle(ctx, oracle, monkeypatch, dtype):
+  """The mask kernel stages tiles by TMA when the row pitch is 16-byte aligned and by
+  cooperative loads otherwise (IGN_CCL_NO_TMA=1 forces the latter): same ids as the oracle
+  from both, on aligned volumes with full and partial tiles, long runs and dense noise (the
+  tile-run overflow path of k_ccl_tiles), and on unaligned row pitches."""
   from igneous_b200 import cc3d
   rng = np.random.default_rng(0)
   vols = [oracle.synth_seg((512, 64, 40), pitch=16, num_ids=9).astype(dtype),
           rng.integers(0, 3, size=(256, 16, 24)).astype(dtype),
-          oracle.synth_seg((300, 40, 20), pitch=16, num_ids=5).astype(dtype)]
-  monkeypatch.setenv("IGN_CCL_V2", "1")
+          rng.integers(0, 3, size=(1024, 16, 16)).astype(dtype),
+          oracle.synth_seg((300, 40, 20), pitch=16, num_ids=5).astype(dtype),
+          oracle.synth_seg((129, 33, 17), pitch=8, num_ids=5).astype(dtype)]
   for v in vols:
     v = np.asfortranarray(v)
-    got, n = cc3d.connected_components(v, connectivity=6, out_dtype=np.uint64, return_N=True)
     want, wn = oracle.connected_components(v, return_N=True)
-    assert n == wn and np.array_equal(got, want)
+    for no_tma in (False, True):
+      if no_tma:
+        monkeypatch.setenv("IGN_CCL_NO_TMA", "1")
+      else:
+        monkeypatch.delenv("IGN_CCL_NO_TMA", raising=False)
+      got, n = cc3d.connected_components(v, connectivity=6, out_dtype=np.uint64, return_N=True)
+      assert n == wn and np.array_equal(got, want), (v.shape, no_tma)
+  monkeypatch.delenv("IGN_CCL_NO_TMA", raising=False)

@@ -164,9 +164,10 @@ def test_simplify_multilabel_matches_oracle(ctx, oracle, factor, max_error):
     m.get(m.ids()[0], reduction_factor=factor + 1, max_error=max_error)
 
 
-def test_simplify_batched_kernels_bit_exact(ctx, oracle, monkeypatch):
-  """IGN_SIMP_BATCH=1 (batched-gather ring walkers, what bench.py runs): identical meshes to the
-  serial kernels and to the oracle."""
+def test_simplify_shared_and_global_memory_classes_bit_exact(ctx, oracle, monkeypatch):
+  """k_simp_labels keeps a label's topology in shared memory when it fits and otherwise runs the
+  same code on the global-memory arrays (IGN_SIMP_GMEM=1 forces that class): identical meshes
+  from both, and both identical to the oracle."""
   from igneous_b200 import zmesh
 
   def meshes(seg, factor):
@@ -176,15 +177,15 @@ def test_simplify_batched_kernels_bit_exact(ctx, oracle, monkeypatch):
 
   for shape, pitch, factor in (((96, 80, 64), 24, 10), ((128, 128, 64), 32, 100)):
     seg = np.asfortranarray(oracle.synth_seg(shape, pitch=pitch, num_ids=9).astype(np.uint32))
-    monkeypatch.delenv("IGN_SIMP_BATCH", raising=False)
-    serial = meshes(seg, factor)
-    monkeypatch.setenv("IGN_SIMP_BATCH", "1")
-    batched = meshes(seg, factor)
-    monkeypatch.delenv("IGN_SIMP_BATCH", raising=False)
+    monkeypatch.delenv("IGN_SIMP_GMEM", raising=False)
+    smem = meshes(seg, factor)
+    monkeypatch.setenv("IGN_SIMP_GMEM", "1")
+    gmem = meshes(seg, factor)
+    monkeypatch.delenv("IGN_SIMP_GMEM", raising=False)
     tl, tv = oracle.marching_cubes(seg)
     want, _ = oracle.simplify_welded(oracle.WeldedMeshes(tl, tv), (16, 16, 40), factor, 40.0, True)
-    assert serial.keys() == batched.keys() == want.keys()
-    for k in serial:
-      assert np.array_equal(serial[k].vertices, batched[k].vertices)
-      assert np.array_equal(serial[k].faces, batched[k].faces)
-      assert np.array_equal(batched[k].vertices, want[k][0]) and np.array_equal(batched[k].faces, want[k][1])
+    assert smem.keys() == gmem.keys() == want.keys()
+    for k in smem:
+      assert np.array_equal(smem[k].vertices, gmem[k].vertices)
+      assert np.array_equal(smem[k].faces, gmem[k].faces)
+      assert np.array_equal(smem[k].vertices, want[k][0]) and np.array_equal(smem[k].faces, want[k][1])
