@@ -249,14 +249,226 @@ def cpu_baseline_sample(pipe, ctx, budget_s=20.0):
           "sample": "%dx%dx%d corner of the bench volume, %d repetitions, %.1f s" % (bx, by, bz, reps, dt)}
 
 
+# ------------------------------------------------------------ parity self-check
+def parity_check(ctx, pipe):
+  """Untimed check of the benchmark's own products against the CPU oracle (run once after the
+  timed loop, at the benchmark's full size): a 256x256x64 sub-box of the mips (bit-exact), the
+  CCL labels of the same sub-box (every oracle component carries exactly one label, two
+  components share a label only when they hold the same input id, 0 <-> 0) and every fragment
+  of one MeshTask body on a 129x129x65 cutout of the mesh mip (bit-exact vertices and faces)."""
+  from igneous_b200 import _shim, zmesh
+  from oracle import oracle as O
+  O.build()
+  sx, sy, sz = pipe.shape
+  bx, by, bz = min(sx, 256), min(sy, 256), min(sz, 64)
+
+  def box(dptr, shape, size, dtype):
+    d = ctx.alloc(int(np.prod(size)) * np.dtype(dtype).itemsize)
+    _shim.check(ctx.lib.ign_copy_box_dev(ctx.handle, _shim.ptr(dptr), c.c_int(_shim.dtype_code(dtype)),
+                                         c.c_uint64(shape[0]), c.c_uint64(shape[1]), c.c_uint64(shape[2]),
+                                         c.c_uint64(0), c.c_uint64(0), c.c_uint64(0), c.c_uint64(size[0]),
+                                         c.c_uint64(size[1]), c.c_uint64(size[2]), _shim.ptr(d)))
+    h = ctx.to_host(d, size, dtype)
+    d.free()
+    return h
+
+  out = {}
+  seg = box(pipe.d_in, pipe.shape, (bx, by, bz), np.uint32)
+  want = O.downsample_segmentation(seg, (2, 2, 1), num_mips=pipe.num_mips)
+  ok = True
+  for k, w in enumerate(want):
+    got = box(pipe.d_mips[k], pipe.mip_shapes[k], w.shape, np.uint32)
+    ok = ok and np.array_equal(got, w)
+  out["mips"] = "ok" if ok else "MISMATCH"
+  cc = box(pipe.d_cc, pipe.shape, (bx, by, bz), pipe.ccl_out_dtype).astype(np.uint64)
+  loc = O.connected_components(seg).astype(np.uint64)
+  ok = np.array_equal(cc == 0, seg == 0)
+  pairs = np.unique(np.stack([loc.ravel(), cc.ravel(), seg.ravel().astype(np.uint64)], axis=1), axis=0)
+  pairs = pairs[pairs[:, 0] != 0]
+  ok = ok and len(np.unique(pairs[:, 0])) == len(pairs)           # one label per oracle component
+  by_label = np.unique(pairs[:, 1:], axis=0)
+  ok = ok and len(np.unique(by_label[:, 0])) == len(by_label)     # one input id per label
+  out["ccl"] = "ok" if ok else "MISMATCH"
+  msrc = pipe.d_mips[-1] if pipe.num_mips else pipe.d_in
+  mshape = pipe.mip_shapes[-1] if pipe.num_mips else pipe.shape
+  cut = box(msrc, mshape, (min(mshape[0], 129), min(mshape[1], 129), min(mshape[2], 65)), np.uint32)
+  m = zmesh.Mesher(pipe.resolution)
+  m.mesh(cut)
+  tl, tv = O.marching_cubes(cut)
+  W = O.WeldedMeshes(tl, tv)
+  f = pipe.simplification_factor or 0
+  ok = sorted(m.ids()) == W.ids()
+  if f:
+    ref, _ = O.simplify_welded(W, pipe.resolution, f, float(pipe.max_simplification_error), True)
+  n_lab = 0
+  for lab in (W.ids() if ok else []):
+    g = m.get(lab, reduction_factor=f, max_error=pipe.max_simplification_error, voxel_centered=True)
+    wv, wf = ref[lab] if f else W.get(lab, pipe.resolution, True)
+    ok = ok and np.array_equal(g.vertices, wv) and np.array_equal(g.faces, wf)
+    n_lab += 1
+  out["mesh"] = ("ok (%d fragments bit-exact)" % n_lab) if ok else "MISMATCH"
+  out["status"] = "ok" if all(v.startswith("ok") for v in out.values()) else "FAILED"
+  return out
+
+
+def multigpu_check(ctx, group, rank, world, dist):
+  """N-rank parity of the sharded CCL (NCCL all-gather of the boundary planes) against a
+  whole-volume oracle CCL of the stacked dataset (tools/check_multigpu.py inside the bench)."""
+  import torch
+  from igneous_b200 import pipeline
+  from oracle import oracle as O
+  O.build()
+  shape = (96, 80, 40)
+  pipe = pipeline.VolumePipeline(ctx, shape, np.uint32, pitch=32, num_ids=6, offset=(0, 0, rank * shape[2]),
+                                 group=group, simplification_factor=0, mesh_shape=(32, 32, 32), mesh_streams=1)
+  pipe.synth()
+  pipe.ccl()
+  got = ctx.to_host(pipe.d_cc, shape, np.uint32)
+  whole = O.synth_seg((shape[0], shape[1], shape[2] * world), pitch=32, num_ids=6)
+  want, n_want = O.connected_components(whole, return_N=True)
+  ok = (pipe.n_components == n_want) and np.array_equal(
+    got, want[:, :, rank * shape[2]:(rank + 1) * shape[2]].astype(np.uint32))
+  pipe.free()
+  flag = torch.tensor([1 if ok else 0], device="cuda")
+  dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+  return "ok (%d ranks, %d components)" % (world, n_want) if int(flag.item()) == 1 else "MISMATCH"
+
+
+# ------------------------------------------------- per-config lines (BASELINE.json configs)
+def run_config(args, ctx, rank, world, dist):
+  """--config c1|c2|c3: one JSON line for a BASELINE.json config other than the headline."""
+  from igneous_b200 import _shim
+  peak, peak_src = measured_peaks()
+  lib = ctx.lib
+  line = {"metric": METRIC, "unit": "Mvoxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic"}
+  if args.config == "c2":
+    # DownsampleTask 5-level average pyramid on a 2048x2048x512 uint8 image, one 512^3 chunk per launch
+    S = 512
+    n = S ** 3
+    d_in = ctx.alloc(n)
+    _shim.check(lib.ign_synth_image_dev(ctx.handle, _shim.ptr(d_in), c.c_uint64(S), c.c_uint64(S), c.c_uint64(S),
+                                        c.c_int64(0), c.c_int64(0), c.c_int64(rank * S), c.c_uint64(0)))
+    shapes, x = [], S
+    for _ in range(5):
+      x = (x + 1) // 2
+      shapes.append((x, x, S))
+    outs = [ctx.alloc(int(np.prod(sh))) for sh in shapes]
+    call = lambda: _shim.check(lib.ign_pool_avg_2x2x1_dev(
+      ctx.handle, _shim.ptr(d_in), c.c_int(_shim.IGN_U8), c.c_uint64(S), c.c_uint64(S), c.c_uint64(S), c.c_int(5),
+      c.c_int(0), c.c_int(0), _shim.void_pp([o.ptr for o in outs])))
+    chunks = 16  # 2048x2048x512 = 4x4x1 chunks of 512^3: 16 launches per step
+    for _ in range(args.warmup):
+      for _ in range(chunks):
+        call()
+    ctx.sync()
+    ctx.timer_start(0)
+    for _ in range(args.steps * chunks):
+      call()
+    ctx.timer_stop(0)
+    ms = ctx.timer_ms(0) / args.steps
+    vox = n * chunks
+    bytes_alg = vox * (1 + sum(0.25 ** k for k in range(1, 6)))
+    line.update({"value": vox * world / (ms * 1e-3) / 1e6, "ms_per_step": ms, "dtype": "u8",
+                 "gpu_launches": 2 * chunks * args.steps,
+                 "config": {"workload": "C2: 5-level 2x2x1 average pyramid of a 2048x2048x512 uint8 image, one 512^3 chunk "
+                                        "per call (16 calls per step; the 128 MiB chunk is re-read from L2/HBM every call)",
+                            "l2": "one 512^3 u8 chunk (134 MB) + outputs exceed the 126 MB L2"},
+                 "roofline": {"bound": "hbm", "kernel": "k_avg_fused<u8>", "achieved": bytes_alg / 1e9 / (ms * 1e-3),
+                              "peak": peak, "unit": "GB/s", "frac": bytes_alg / 1e9 / (ms * 1e-3) / peak,
+                              "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_voxel": 1.333}})
+  elif args.config == "c3":
+    # CCLFacesTask family on 1024^3 uint64 (~4000 objects): one volume per GPU (z-slab of the dataset)
+    from igneous_b200 import pipeline, multigpu
+    S = args.size if args.size != 2048 else 1024
+    group = multigpu.Group(ctx, rank, world, dist) if world > 1 else None
+    pipe = pipeline.VolumePipeline(ctx, (S, S, S), np.uint64, num_mips=0, pitch=64, num_ids=4096, seed=0,
+                                   offset=(0, 0, rank * S), simplification_factor=0, group=group, mesh_streams=1,
+                                   ccl_out_dtype=np.uint64, id_base=1 << 32)
+    pipe.synth()
+    for _ in range(args.warmup):
+      pipe.ccl()
+    ctx.sync()
+    if dist is not None:
+      dist.barrier()
+    pipe.prof_enable(True)
+    ctx.timer_start(0)
+    for _ in range(args.steps):
+      pipe.ccl()
+    ctx.timer_stop(0)
+    ms = ctx.timer_ms(0) / args.steps
+    prof = pipe.prof_read()
+    pipe.prof_enable(False)
+    if dist is not None:
+      import torch
+      t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+    n = S ** 3
+    alg = n * 16
+    kern = {k: v[0] / args.steps for k, v in prof.items() if v[1]}
+    line.update({"value": n * world / (ms * 1e-3) / 1e6, "ms_per_step": ms, "dtype": "u64",
+                 "gpu_launches": int(sum(v[1] for v in prof.values())),
+                 "config": {"workload": "C3: 6-connected CCL of a %d^3 uint64 segmentation per GPU (ids >= 2^32, pitch 64), "
+                                        "uint64 labels out%s" % (S, ", one NCCL all-gather of the boundary planes" if world > 1 else ""),
+                            "components": pipe.n_components, "kernel_ms_per_step": kern},
+                 "roofline": {"bound": "hbm", "kernel": "CCL stage (k_ccl_masks + k_ccl_tiles/merge + k_ccl_expand)",
+                              "achieved": alg / 1e9 / (ms * 1e-3), "peak": peak, "unit": "GB/s",
+                              "frac": alg / 1e9 / (ms * 1e-3) / peak, "traffic": None, "peak_source": peak_src,
+                              "algorithmic_bytes_per_voxel": 16}})
+  elif args.config == "c1":
+    # DownsampleTask mip0 -> mip1 (2x2x1 mode) on 128x128x64 uint32 through LocalTaskQueue(parallel=1), file:// layer
+    import shutil, tempfile
+    from igneous_b200 import task_creation as tc
+    from igneous_b200._compat import CloudVolume, LocalTaskQueue
+    from oracle import oracle as O
+    O.build()
+    seg = O.synth_seg((128, 128, 64), pitch=16, num_ids=64)
+    root = tempfile.mkdtemp(prefix="ign_c1_")
+    times = []
+    try:
+      for it in range(args.warmup + args.steps):
+        path = "file://" + os.path.join(root, "layer%d" % it)
+        CloudVolume.from_numpy(seg[..., None], vol_path=path, resolution=(16, 16, 40), chunk_size=(64, 64, 64),
+                               layer_type="segmentation", max_mip=0)
+        t0 = time.perf_counter()
+        tq = LocalTaskQueue(parallel=1)
+        tq.insert_all(tc.create_downsampling_tasks(path, mip=0, num_mips=1, compress="gzip"))
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+          times.append(dt)
+      cv = CloudVolume(path)
+      cv.mip = 1
+      got = np.asarray(cv[cv.meta.bounds(1)])
+      want = O.downsample_segmentation(seg[..., None], (2, 2, 1, 1), num_mips=1)[0]
+      ok = np.array_equal(got, want)
+    finally:
+      shutil.rmtree(root, ignore_errors=True)
+    ms = 1e3 * float(np.median(times))
+    line.update({"value": seg.size / (ms * 1e-3) / 1e6, "ms_per_step": ms, "dtype": "u32", "gpu_launches": None,
+                 "config": {"workload": "C1: DownsampleTask mip0->mip1 (2x2x1 mode) on 128x128x64 uint32 through "
+                                        "create_downsampling_tasks + LocalTaskQueue(parallel=1) on a file:// layer "
+                                        "(task wall time: download, H2D, kernel, D2H, encode, upload)",
+                            "parity_vs_oracle": "ok" if ok else "MISMATCH"},
+                 "roofline": None})
+  if rank == 0:
+    print(json.dumps(line))
+
+
 # -------------------------------------------------------------------- main
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
   ap.add_argument("--steps", type=int, default=5)
   ap.add_argument("--warmup", type=int, default=3)
-  ap.add_argument("--size", type=int, default=2048, help="cube edge of the per-GPU volume")
+  ap.add_argument("--size", type=int, default=2048, help="cube edge of the per-GPU volume (weak scaling) / of the whole volume (strong)")
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--config", default="headline", choices=["headline", "c1", "c2", "c3"],
+                  help="BASELINE.json config: headline = the metric's 2048^3 pipeline; c1 / c2 / c3 print their own line")
+  ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                  help="weak: one size^3 volume per GPU; strong: ONE size^3 volume split into N z-slabs")
+  ap.add_argument("--check", action="store_true", help="N>1: also run the N-rank CCL parity check against the oracle")
+  ap.add_argument("--no-parity-check", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-cpu", action="store_true")
   ap.add_argument("--e2e-steps", type=int, default=2)
@@ -264,10 +476,6 @@ def main():
                   help="download the labels into the input host buffer (forced automatically when host RAM is tight)")
   ap.add_argument("--simplify", type=int, default=None, help="simplification factor (default 100)")
   ap.add_argument("--mesh-streams", type=int, default=8, help="concurrent MeshTask bodies per GPU")
-  ap.add_argument("--serial-simplify", action="store_true",
-                  help="use the serial ring walkers of the simplifier instead of the batched-gather kernels")
-  ap.add_argument("--ccl-v1", action="store_true",
-                  help="use k_ccl_local_fast instead of the 4-voxels-per-lane tile kernel k_ccl_local_v2")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == "b200":
     args.warmup = 3
@@ -278,6 +486,7 @@ def main():
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  bind_numa(local_rank)
   dist = None
   if world > 1:
     import torch
@@ -286,34 +495,26 @@ def main():
     dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dist = dist_mod
 
-  # The simplifier's batched-gather kernels (simplify.cu, IGN_SIMP_BATCH) give bit-identical
-  # meshes (tests/test_mesh_gpu.py::test_simplify_batched_kernels_bit_exact) and 28 % shorter
-  # MeshTask bodies; the library default is still the serial kernels until the whole GPU suite
-  # has run with them, so the bench opts in explicitly.
-  if args.serial_simplify:
-    os.environ.pop("IGN_SIMP_BATCH", None)
-  else:
-    os.environ.setdefault("IGN_SIMP_BATCH", "1")
-  # Same for the CCL tile kernel: k_ccl_local_v2 (ccl.cu, IGN_CCL_V2) is bit-exact
-  # (tests/test_ccl_gpu.py::test_ccl_v2_kernel_matches_oracle) and 11 % faster at 512^3.
-  if args.ccl_v1:
-    os.environ.pop("IGN_CCL_V2", None)
-  else:
-    os.environ.setdefault("IGN_CCL_V2", "1")
   from igneous_b200 import _shim, pipeline
   ctx = _shim.Context(local_rank)
+  if args.config != "headline":
+    run_config(args, ctx, rank, world, dist)
+    if dist is not None:
+      dist.barrier()
+      dist.destroy_process_group()
+    return
   S = args.size
-  shape = (S, S, S)
+  strong = args.scaling == "strong" and world > 1
+  sz_local = S // world if strong else S
+  shape = (S, S, sz_local)
   simplify = 100 if args.simplify is None else args.simplify
-  if not hasattr(ctx.lib, "ign_mesh_simplify"):
-    simplify = 0
   group = None
   if world > 1:
     from igneous_b200 import multigpu
     group = multigpu.Group(ctx, rank, world, dist)
   pipe = pipeline.VolumePipeline(ctx, shape, np.uint32, num_mips=2, mesh_shape=(256, 256, 256),
                                  resolution=RESOLUTION, pitch=PITCH, num_ids=NUM_IDS, seed=0,
-                                 offset=(0, 0, rank * S), simplification_factor=simplify, group=group,
+                                 offset=(0, 0, rank * sz_local), simplification_factor=simplify, group=group,
                                  mesh_streams=args.mesh_streams)
   pipe.synth()
   ctx.sync()
@@ -357,58 +558,77 @@ def main():
   voxels = pipe.n * world
   value = voxels / (ms_per_step * 1e-3) / 1e6
 
-  # ---- roofline of the dominant kernel group (CCL), SURVEY.md 8(d):
-  # algorithmic bytes = in_bytes + out_bytes per voxel of the CCL stage
+  # ---- roofline: the kernel class with the largest summed launch time per
+  # step, algorithmic bytes per launch / its average launch duration (CUDA events recorded by
+  # the library around those launches, on the stream they run on)
   peak, peak_src = measured_peaks()
   in_b, out_b = 4, pipe.ccl_out_dtype.itemsize
-  ccl_ms = sum(prof[k][0] for k in ("ccl_local", "ccl_merge", "ccl_label")) / args.steps
-  kern = {k: {"ms_per_step": prof[k][0] / args.steps, "launches_per_step": prof[k][1] / args.steps}
+  ms_in = pipe.mesh_stats
+  mip2_vox = int(np.prod(pipe.mip_shapes[-1]))
+  alg_step = {  # algorithmic bytes of one STEP per kernel class
+    "pool": pipe.n * 4 * (1 + 0.25 + 0.0625),
+    "ccl_local": pipe.n * in_b,          # k_ccl_masks: every voxel read once
+    "ccl_merge": pipe.n * 0.625,         # k_ccl_tiles / merge / roots: the masks (0.625 B/voxel)
+    "ccl_label": pipe.n * out_b,         # k_ccl_expand: every label written once
+    "mc": mip2_vox * 4,
+    "simp_labels": 12.0 * (ms_in.get("triangles_in", 0) + ms_in.get("vertices_in", 0) +
+                           ms_in.get("triangles", 0) + ms_in.get("vertices", 0)),
+  }
+  knames = {"pool": "k_mode_fused<u32,2>", "ccl_local": "k_ccl_masks<u32> (TMA)", "ccl_merge": "k_ccl_tiles + k_ccl_merge + run passes",
+            "ccl_label": "k_ccl_expand4<u32>", "mc": "k_mc", "simp_labels": "k_simp_labels"}
+  kern = {k: {"ms_per_step": prof[k][0] / args.steps, "launches_per_step": prof[k][1] / args.steps,
+              "algorithmic_GBps": (alg_step[k] / 1e9) / (prof[k][0] / args.steps * 1e-3) if prof[k][0] > 0 else None}
           for k in prof}
-  dominant = max(("ccl_local", "ccl_merge", "ccl_label", "pool"), key=lambda k: prof[k][0])
-  alg = {"ccl_local": in_b + 4, "ccl_merge": 0, "ccl_label": 4 + out_b, "pool": 4 * (1 + 0.25 + 0.0625)}
+  for k in kern:
+    if kern[k]["algorithmic_GBps"] is not None:
+      kern[k]["frac_of_hbm_peak"] = kern[k]["algorithmic_GBps"] / peak
+  dominant = max(prof, key=lambda k: prof[k][0])
   dom_ms = prof[dominant][0] / args.steps
   dom_launches = max(prof[dominant][1] / args.steps, 1)
-  dom_bytes_per_launch = pipe.n * alg[dominant] / dom_launches
-  achieved = (dom_bytes_per_launch / 1e9) / (dom_ms / dom_launches * 1e-3) if dom_ms > 0 else 0.0
+  achieved = (alg_step[dominant] / dom_launches / 1e9) / (dom_ms / dom_launches * 1e-3) if dom_ms > 0 else 0.0
+  ccl_ms = sum(prof[k][0] for k in ("ccl_local", "ccl_merge", "ccl_label")) / args.steps
   roofline = {
-    "bound": "hbm", "kernel": "k_" + dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-    "frac": achieved / peak,
-    # dram__bytes_read+write of this kernel from the ncu --set full capture in
-    # profiles/r01_ccl_local_fast_full_512_raw.csv: 7.657 B/voxel (537+491 MB at 512^3), scaled per launch
-    "traffic": (7.657 * pipe.n / dom_launches) if dominant == "ccl_local" else None,
-    "traffic_source": "ncu capture at 512^3 scaled by voxels per launch (profiles/%s; both tile kernels move 7.65 B/voxel)"
-                      % ("r01_ccl_local_v2_full_512_raw.csv" if os.environ.get("IGN_CCL_V2") else "r01_ccl_local_fast_full_512_raw.csv"),
-    "peak_source": peak_src,
-    "algorithmic_bytes_per_voxel": alg[dominant],
+    "bound": "hbm", "kernel": knames[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s",
+    "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(dominant, {}).get("bytes_per_launch"),
+    "traffic_source": NCU_TRAFFIC.get(dominant, {}).get("source"),
+    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_step[dominant] / dom_launches,
     "avg_launch_ms": dom_ms / dom_launches, "launches_per_step": dom_launches,
-    "stage_ccl": {"algorithmic_bytes_per_voxel": in_b + out_b, "ms_per_step": ccl_ms,
-                  "achieved": pipe.n * (in_b + out_b) / 1e9 / (ccl_ms * 1e-3) if ccl_ms > 0 else 0.0},
+    "share_of_step_kernel_time": prof[dominant][0] / max(sum(v[0] for v in prof.values()), 1e-9),
+    "stage_ccl": {"algorithmic_bytes_per_voxel": in_b + out_b, "kernel_ms_per_step": ccl_ms,
+                  "wall_ms_per_step": stage["ccl_ms"] / args.steps,
+                  "achieved": pipe.n * (in_b + out_b) / 1e9 / (stage["ccl_ms"] / args.steps * 1e-3) if stage["ccl_ms"] > 0 else 0.0},
+    "stage_pool": {"algorithmic_bytes_per_voxel": 5.3125, "wall_ms_per_step": stage["pool_ms"] / args.steps,
+                   "achieved": pipe.n * 5.3125 / 1e9 / (stage["pool_ms"] / args.steps * 1e-3) if stage["pool_ms"] > 0 else 0.0},
     "kernels": kern,
-    "note": "dominant own streaming kernel; the mesh stage (cub sorts + latency-bound simplification rounds on "
-            "%d concurrent streams) takes %.0f%% of the step and has no bandwidth roofline"
-            % (pipe.mesh_streams, 100.0 * stage["mesh_ms"] / max(sum(stage.values()), 1e-9)),
+    "note": "kernel = the class with the largest summed launch time per step (MeshTask bodies run on %d concurrent "
+            "streams, so class sums can exceed the stage wall time); stage_* use the stage wall time between CUDA "
+            "events on the main stream" % pipe.mesh_streams,
   }
   roofline["stage_ccl"]["frac"] = roofline["stage_ccl"]["achieved"] / peak
+  roofline["stage_pool"]["frac"] = roofline["stage_pool"]["achieved"] / peak
 
   line = {
     "metric": METRIC, "value": value, "unit": "Mvoxels/s", "n_gpus": world, "steps": args.steps,
-    "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+    "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+    "scaling": "strong" if strong else "weak",
     "vs_baseline": None, "dtype": "u32", "data": "synthetic", "gpu_launches": int(launches),
     "config": {
-      "workload": "%d^3 uint32 jittered-Voronoi segmentation per GPU (pitch %d): mode-pool 2 mips, "
+      "workload": "%dx%dx%d uint32 jittered-Voronoi segmentation per GPU (pitch %d)%s: mode-pool 2 mips, "
                   "6-connected CCL at mip 0 (u32 ids), marching cubes + weld%s at mip 2 in 256^3 tasks"
-                  % (S, PITCH, (" + quadric simplification x%d" % simplify) if simplify else
-                     " (simplification NOT in the timed region: kernel not landed yet)"),
+                  % (S, S, sz_local, PITCH, (" = one %d^3 volume split into %d z-slabs" % (S, world)) if strong else "",
+                     (" + quadric simplification x%d" % simplify) if simplify else ""),
       "volume_per_gpu": list(shape), "parallelism": "z-slab per GPU, %d rank(s)" % world,
       "l2": "inputs larger than L2 (%.1f GB volume vs 126 MB L2)" % (pipe.n * 4 / 1e9),
       "simplification_factor": simplify, "components": pipe.n_components, "mesh": pipe.mesh_stats, "mesh_streams": pipe.mesh_streams,
-      "simplify_kernels": "batched gathers (IGN_SIMP_BATCH=1)" if os.environ.get("IGN_SIMP_BATCH") else "serial ring walks",
-      "ccl_tile_kernel": "k_ccl_local_v2 (IGN_CCL_V2=1)" if os.environ.get("IGN_CCL_V2") else "k_ccl_local_fast",
       "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
     },
     "roofline": roofline, "clocks": clocks,
   }
 
+  if not args.no_parity_check:
+    line["parity_check"] = parity_check(ctx, pipe) if rank == 0 else None
+  if args.check and world > 1:
+    line["multi_gpu_parity"] = multigpu_check(ctx, group, rank, world, dist)
   if rank == 0 and not args.no_cpu:
     line["cpu_baseline"] = cpu_baseline_sample(pipe, ctx)
   if not args.no_e2e:
@@ -418,6 +638,30 @@ def main():
   if dist is not None:
     dist.barrier()
     dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {}
+
+
+def bind_numa(local_rank):
+  """Keep this rank's host threads (and therefore its first-touched pinned buffers) on the
+  NUMA node of its GPU: the e2e leg moves ~80 GB per step through host DRAM per rank."""
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+    n = (os.cpu_count() + 63) // 64
+    mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+    cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
+    allowed = set(os.sched_getaffinity(0))
+    cpus = [x for x in cpus if x in allowed]
+    if cpus:
+      os.sched_setaffinity(0, cpus)
+      return len(cpus)
+  except Exception:
+    pass
+  return None
 
 
 def _mem_available():

@@ -232,9 +232,12 @@ __global__ void __launch_bounds__(256) k_simp_boundary(Simp s) {
 //
 // Labels that do not fit (or have more than 65535 faces / vertices) run the same code
 // on the whole-task arrays in global memory (SM = false).
-constexpr uint32_t VF_ALIVE = 1, VF_BOUND = 2, VF_DIRTY = 4, VF_LOSE = 8, VF_WIN = 16, VF_END = 32;
+constexpr uint32_t VF_ALIVE = 1, VF_BOUND = 2, VF_CDIRTY = 4, VF_LOSE = 8, VF_DONE = 16, VF_END = 32, VF_RDIRTY = 64;
 constexpr int SL_THREADS = 1024;
-constexpr int SL_WCAP = 128;  // winners validated per batch (a round runs as many batches as it needs)
+constexpr int SL_WCAP = 128;   // winners validated per batch (a round runs as many batches as it needs)
+constexpr int SL_WQ = 1024;    // winners queued per selection pass
+constexpr int SL_EQ = 96;      // per-warp queue of half-edges whose cost must be (re)computed
+constexpr int SL_LIST_PER = 16;  // list entries per thread held in registers while a list is compacted in place
 
 struct SlArgs {
   double* pos;            // 3U
@@ -244,9 +247,12 @@ struct SlArgs {
   uint8_t* valive;        // U   (out)
   const uint8_t* vbound;  // U
   float* ecost;           // 3T  memoised float cost per half-edge
-  unsigned long long* key1;  // U   (global-memory class only)
-  uint8_t* fstate;        // T   (global-memory class only)
-  uint8_t* vflag;         // U   (global-memory class only)
+  // global-memory class only (labels that do not fit shared memory)
+  unsigned long long* key1;  // U
+  uint8_t* fstate;           // T
+  uint8_t* vflag;            // U
+  uint32_t *flist, *flist2;  // T  alive-face lists (ping-pong)
+  uint32_t *vlist, *vlist2;  // U
   const uint32_t* tri_off;   // [K+2]
   const uint32_t* vert_off;  // [K+2]
   const uint32_t* target;    // [K+2]
@@ -263,8 +269,9 @@ struct SlWin {
 };
 
 struct SlShared {
-  uint32_t work, alive, progress, ncol, nslot, stop, slow, pad;
+  uint32_t work, alive, progress, ncol, nwin, stop, slow, counter;
   SlWin win[SL_WCAP];
+  uint32_t winq[SL_WQ];
 };
 
 template <bool SM>
@@ -276,7 +283,8 @@ struct SlLab {
   uint8_t* fstate;         // bit 7 alive, bits 2c..2c+1 memo of half-edge c
   uint8_t* vflag;
   unsigned long long* key1;
-  idx_t* ring;  // [SL_WCAP][2][S_MAXV] face ids
+  idx_t* ring;  // [SL_WCAP][2][S_MAXV] face ids; doubles as the per-warp cost queues of the key pass
+  idx_t *flist, *flist2, *vlist, *vlist2;  // alive lists (flist2 / vlist2: global-memory class only)
 };
 
 template <bool SM>
@@ -305,10 +313,16 @@ __device__ __forceinline__ void sl_vclear(uint8_t* vflag, uint32_t v, uint32_t b
   const uintptr_t a = (uintptr_t)(vflag + v);
   atomicAnd((uint32_t*)(a & ~(uintptr_t)3), ~(bits << (8 * (a & 3))));
 }
+__device__ __forceinline__ void sl_post(unsigned long long* key1, uint32_t u, uint32_t v, unsigned long long key) {
+  if (key < *(volatile unsigned long long*)&key1[u]) atomicMin(&key1[u], key);
+  if (key < *(volatile unsigned long long*)&key1[v]) atomicMin(&key1[v], key);
+}
 
-// s_cost on label-local ids (same arithmetic, same order)
-template <bool SM>
-__device__ void sl_cost(const SlArgs& A, const SlLab<SM>& L, uint32_t u, uint32_t v, SEval* e) {
+// s_cost on label-local ids (same arithmetic, same order).  WARP = true: all 32 lanes call
+// with the same (u, v); the three candidate positions are evaluated by three different lanes
+// and shared by shuffles (bit-identical: each value is produced by the same operations).
+template <bool SM, bool WARP>
+__device__ __forceinline__ void sl_cost(const SlArgs& A, const SlLab<SM>& L, uint32_t u, uint32_t v, SEval* e) {
   e->valid = false;
   const bool bu = L.vflag[u] & VF_BOUND, bv = L.vflag[v] & VF_BOUND;
   if (bu && bv) return;
@@ -335,13 +349,25 @@ __device__ void sl_cost(const SlArgs& A, const SlLab<SM>& L, uint32_t u, uint32_
     e->remove = u < v ? v : u;
     const double* pk = u < v ? pu : pv;
     const double* pr = u < v ? pv : pu;
-    const double pk0 = pk[0], pk1 = pk[1], pk2 = pk[2], pr0 = pr[0], pr1 = pr[1], pr2 = pr[2];
-    double kk[3] = {pk0, pk1, pk2}, rr[3] = {pr0, pr1, pr2};
-    double mid[3] = {(pk0 + pr0) * 0.5, (pk1 + pr1) * 0.5, (pk2 + pr2) * 0.5};
-    const double ck = s_qeval(q, kk), cr = s_qeval(q, rr), cm = s_qeval(q, mid);
+    const double kk[3] = {pk[0], pk[1], pk[2]}, rr[3] = {pr[0], pr[1], pr[2]};
+    const double mid[3] = {(kk[0] + rr[0]) * 0.5, (kk[1] + rr[1]) * 0.5, (kk[2] + rr[2]) * 0.5};
+    double ck, cr, cm;
+    if (WARP) {
+      const uint32_t sel = (threadIdx.x & 31u) % 3u;
+      const double pt[3] = {sel == 0 ? kk[0] : (sel == 1 ? rr[0] : mid[0]), sel == 0 ? kk[1] : (sel == 1 ? rr[1] : mid[1]),
+                            sel == 0 ? kk[2] : (sel == 1 ? rr[2] : mid[2])};
+      const double c = s_qeval(q, pt);
+      ck = __shfl_sync(0xFFFFFFFFu, c, 0);
+      cr = __shfl_sync(0xFFFFFFFFu, c, 1);
+      cm = __shfl_sync(0xFFFFFFFFu, c, 2);
+    } else {
+      ck = s_qeval(q, kk);
+      cr = s_qeval(q, rr);
+      cm = s_qeval(q, mid);
+    }
     cost = ck;
-    best[0] = pk0; best[1] = pk1; best[2] = pk2;
-    if (cr < cost) { cost = cr; best[0] = pr0; best[1] = pr1; best[2] = pr2; }
+    best[0] = kk[0]; best[1] = kk[1]; best[2] = kk[2];
+    if (cr < cost) { cost = cr; best[0] = rr[0]; best[1] = rr[1]; best[2] = rr[2]; }
     if (cm < cost) { cost = cm; best[0] = mid[0]; best[1] = mid[1]; best[2] = mid[2]; }
   }
   if (cost < 0.0) cost = 0.0;
@@ -351,7 +377,7 @@ __device__ void sl_cost(const SlArgs& A, const SlLab<SM>& L, uint32_t u, uint32_
   e->p[0] = best[0]; e->p[1] = best[1]; e->p[2] = best[2];
 }
 
-// does face (a0,a1,a2) flip when vertex w moves to `best`?  (s_evaluate's test)
+// does face (a0,a1,a2) flip when vertex w moves to `best`?  (the validation's flip test)
 template <bool SM>
 __device__ __forceinline__ bool sl_flips(const SlArgs& A, const SlLab<SM>& L, const uint32_t* a, uint32_t w,
                                          const double* best) {
@@ -399,11 +425,73 @@ __device__ __forceinline__ uint32_t sl_distinct(uint32_t x1, uint32_t x2, uint32
   return __popc(__ballot_sync(FULL, *f1)) + __popc(__ballot_sync(FULL, *f2));
 }
 
+// drop the dead entries of an alive list (order is irrelevant).  SM: in place, the entries
+// pass through registers; global-memory class: into the second buffer, then swap.
+template <bool SM, typename IDX, typename PRED>
+__device__ __forceinline__ uint32_t sl_compact(IDX*& list, IDX*& list2, uint32_t n, uint32_t* counter, PRED alive) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  if (tid == 0) *counter = 0;
+  __syncthreads();
+  if (SM) {
+    IDX keep[SL_LIST_PER];
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < SL_LIST_PER; k++) {
+      const uint32_t i = tid + k * SL_THREADS;
+      keep[k] = 0;
+      if (i < n) {
+        const IDX e = list[i];
+        keep[k] = e;
+        if (alive((uint32_t)e)) m |= 1u << k;
+      }
+    }
+    __syncthreads();
+    const uint32_t cnt = __popc(m);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(FULL, inc, d);
+      if ((int)lane >= d) inc += o;
+    }
+    uint32_t base = 0;
+    if (lane == 31 && inc) base = atomicAdd(counter, inc);
+    base = __shfl_sync(FULL, base, 31) + inc - cnt;
+#pragma unroll
+    for (int k = 0; k < SL_LIST_PER; k++)
+      if ((m >> k) & 1u) list[base++] = keep[k];
+  } else {
+    for (uint32_t i0 = (tid & ~31u); i0 < n; i0 += SL_THREADS) {
+      const uint32_t i = i0 + lane;
+      IDX e = 0;
+      bool al = false;
+      if (i < n) {
+        e = list[i];
+        al = alive((uint32_t)e);
+      }
+      const uint32_t bal = __ballot_sync(FULL, al);
+      if (!bal) continue;
+      uint32_t base = 0;
+      const int leader = __ffs(bal) - 1;
+      if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(bal));
+      base = __shfl_sync(FULL, base, leader);
+      if (al) list2[base + __popc(bal & ((1u << lane) - 1u))] = e;
+    }
+    IDX* t = list;
+    list = list2;
+    list2 = t;
+  }
+  __syncthreads();
+  return *counter;
+}
+
 template <bool SM>
 __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
+  typedef typename SlLab<SM>::idx_t idx_t;
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t tid = threadIdx.x, NT = blockDim.x, lane = tid & 31u, warp = tid >> 5, NW = NT >> 5;
   const uint32_t T = L.T, U = L.U;
+  idx_t *flist = L.flist, *flist2 = L.flist2, *vlist = L.vlist, *vlist2 = L.vlist2;
   // ---- load the label
   for (uint32_t f = tid; f < T; f += NT) {
     if (SM) {
@@ -413,76 +501,125 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
       sl_fset<SM>(L, f, 2, g[2] - L.vbase);
     }
     L.fstate[f] = 0x80;
+    flist[f] = (idx_t)f;
   }
-  for (uint32_t v = tid; v < U; v += NT) L.vflag[v] = (uint8_t)(VF_ALIVE | (A.vbound[L.vbase + v] ? VF_BOUND : 0u));
+  for (uint32_t v = tid; v < U; v += NT) {
+    L.vflag[v] = (uint8_t)(VF_ALIVE | (A.vbound[L.vbase + v] ? VF_BOUND : 0u));
+    vlist[v] = (idx_t)v;
+  }
   if (tid == 0) {
     sh.alive = T;
     sh.slow = 0;
     sh.stop = 0;
   }
   __syncthreads();
+  uint32_t nF = T, nV = U;
 
   int r = 0;
   for (; r < A.max_rounds; r++) {
     if (sh.alive <= L.target) break;  // reached the target before this round
     const uint32_t salt = (uint32_t)r * 0x9E3779B9u;
     // ---- P1
-    for (uint32_t v = tid; v < U; v += NT) {
+    for (uint32_t i = tid; i < nV; i += NT) {
+      const uint32_t v = vlist[i];
       L.key1[v] = S_KEYMAX;
       const uint8_t b = L.vflag[v];
-      if (b & VF_LOSE) L.vflag[v] = (uint8_t)(b & ~VF_LOSE);
+      if (b & (VF_LOSE | VF_DONE)) L.vflag[v] = (uint8_t)(b & ~(VF_LOSE | VF_DONE));
     }
     if (tid == 0) {
       sh.progress = 0;
       sh.ncol = 0;
     }
     __syncthreads();
-    // ---- P2: keys of the canonical half-edges
-    for (uint32_t f = tid; f < T; f += NT) {
-      const uint32_t st = L.fstate[f];
-      if (!(st & 0x80u)) continue;
-      uint32_t a[3] = {sl_fget<SM>(L, f, 0), sl_fget<SM>(L, f, 1), sl_fget<SM>(L, f, 2)};
-      uint32_t nst = st;
+    // ---- P2: keys of the canonical half-edges.  A warp takes 32 alive faces; the half-edges
+    // whose memoised state was dropped go through a per-warp queue so that the double
+    // precision cost runs on dense lanes; the face's owner lane then posts the keys and
+    // writes the face's state byte (single writer).
+    {
+      uint32_t* wq = (uint32_t*)L.ring + warp * SL_EQ;
+      for (uint32_t base = warp * 32; base < nF; base += NT) {
+        const uint32_t i = base + lane;
+        uint32_t f = 0, st = 0, a[3] = {0, 0, 0};
+        if (i < nF) {
+          f = flist[i];
+          st = L.fstate[f];
+        }
+        const bool act = (st & 0x80u) != 0;
+        uint32_t pend = 0, nst = st;
+        if (act) {
+          a[0] = sl_fget<SM>(L, f, 0); a[1] = sl_fget<SM>(L, f, 1); a[2] = sl_fget<SM>(L, f, 2);
 #pragma unroll
-      for (int c = 0; c < 3; c++) {
-        const uint32_t u = a[c], v = a[(c + 1) % 3];
-        if (!(u < v)) continue;  // one key per edge
-        // memo: 0 unknown, 1 parked (won a round, failed validation), 2 cost cached in
-        // ecost, 3 known to exceed max_error; dropped when an endpoint's ring changed
-        uint32_t es = (st >> (2 * c)) & 3u;
-        if (es != 0 && ((L.vflag[u] | L.vflag[v]) & VF_DIRTY)) es = 0;
-        if (es != 1 && es != 3) {
-          const uint64_t hg = 3 * (uint64_t)(L.tbase + f) + c;
-          float cf = 0.f;
-          if (es == 2) {
-            cf = A.ecost[hg];
-          } else {
-            SEval e;
-            sl_cost<SM>(A, L, u, v, &e);
-            if (!e.valid) {
-              es = 3;
-            } else {
-              cf = __double2float_rn(e.cost);
-              A.ecost[hg] = cf;
-              es = 2;
+          for (int c = 0; c < 3; c++) {
+            const uint32_t u = a[c], v = a[(c + 1) % 3];
+            if (!(u < v)) continue;  // one key per edge
+            // memo: 0 unknown, 1 parked (won a round, failed validation), 2 cost cached in
+            // ecost, 3 known to exceed max_error.  2 / 3 are dropped when an endpoint moved
+            // (CDIRTY), 1 when an endpoint's ring changed (RDIRTY).
+            uint32_t es = (st >> (2 * c)) & 3u;
+            const uint32_t fl = (uint32_t)L.vflag[u] | (uint32_t)L.vflag[v];
+            if (es >= 2 && (fl & VF_CDIRTY)) es = 0;
+            else if (es == 1 && (fl & VF_RDIRTY)) es = 0;
+            if (es == 0) {
+              pend |= 1u << c;
+            } else if (es == 2) {
+              const float cf = A.ecost[3 * (uint64_t)(L.tbase + f) + c];
+              sl_post(L.key1, u, v, ((unsigned long long)__float_as_uint(cf) << 32) | s_mix((3u * f + (uint32_t)c) ^ salt));
             }
-          }
-          if (es == 2) {
-            const unsigned long long key =
-                ((unsigned long long)__float_as_uint(cf) << 32) | s_mix((3u * f + (uint32_t)c) ^ salt);
-            atomicMin(&L.key1[u], key);
-            atomicMin(&L.key1[v], key);
+            nst = (nst & ~(3u << (2 * c))) | (es << (2 * c));
           }
         }
-        nst = (nst & ~(3u << (2 * c))) | (es << (2 * c));
+        const uint32_t np = __popc(pend);
+        uint32_t inc = np;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(FULL, inc, d);
+          if ((int)lane >= d) inc += o;
+        }
+        const uint32_t nq = __shfl_sync(FULL, inc, 31);
+        if (nq) {
+          const uint32_t off = inc - np;
+          uint32_t w = off;
+          if (pend & 1u) wq[w++] = f * 4u;
+          if (pend & 2u) wq[w++] = f * 4u + 1u;
+          if (pend & 4u) wq[w++] = f * 4u + 2u;
+          __syncwarp();
+          for (uint32_t j = lane; j < nq; j += 32) {
+            const uint32_t e = wq[j], ef = e >> 2, ec = e & 3u;
+            const uint32_t u = sl_fget<SM>(L, ef, (int)ec), v = sl_fget<SM>(L, ef, (int)((ec + 1) % 3));
+            SEval ev;
+            sl_cost<SM, false>(A, L, u, v, &ev);
+            uint32_t res = 0xFFFFFFFFu;  // exceeds max_error
+            if (ev.valid) {
+              const float cf = __double2float_rn(ev.cost);
+              A.ecost[3 * (uint64_t)(L.tbase + ef) + ec] = cf;
+              res = __float_as_uint(cf);
+            }
+            wq[j] = res;
+          }
+          __syncwarp();
+          w = off;
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            if (!((pend >> c) & 1u)) continue;
+            const uint32_t res = wq[w++];
+            const uint32_t es = (res == 0xFFFFFFFFu) ? 3u : 2u;
+            if (es == 2) sl_post(L.key1, a[c], a[(c + 1) % 3],
+                                 ((unsigned long long)res << 32) | s_mix((3u * f + (uint32_t)c) ^ salt));
+            nst = (nst & ~(3u << (2 * c))) | (es << (2 * c));
+          }
+          __syncwarp();
+        }
+        if (act && nst != st) L.fstate[f] = (uint8_t)nst;
       }
-      if (nst != st) L.fstate[f] = (uint8_t)nst;
     }
     __syncthreads();
-    // ---- P3: DIRTY consumed; LOSE = a face neighbour holds a smaller key
-    for (uint32_t v = tid; v < U; v += NT)
-      if (L.vflag[v] & VF_DIRTY) sl_vclear(L.vflag, v, VF_DIRTY);
-    for (uint32_t f = tid; f < T; f += NT) {
+    // ---- P3: dirty flags consumed; LOSE = a face neighbour holds a smaller key
+    for (uint32_t i = tid; i < nV; i += NT) {
+      const uint32_t v = vlist[i];
+      if (L.vflag[v] & (VF_CDIRTY | VF_RDIRTY)) sl_vclear(L.vflag, v, VF_CDIRTY | VF_RDIRTY);
+    }
+    for (uint32_t i = tid; i < nF; i += NT) {
+      const uint32_t f = flist[i];
       if (!(L.fstate[f] & 0x80u)) continue;
       const uint32_t a0 = sl_fget<SM>(L, f, 0), a1 = sl_fget<SM>(L, f, 1), a2 = sl_fget<SM>(L, f, 2);
       const unsigned long long k0 = L.key1[a0], k1 = L.key1[a1], k2 = L.key1[a2];
@@ -493,140 +630,144 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
       if (k2 > m) sl_vor(L.vflag, a2, VF_LOSE);
     }
     __syncthreads();
-    // ---- P4: winners (marked on the start vertex of their half-edge)
-    for (uint32_t a = tid; a < U; a += NT) {
-      const uint32_t fl = L.vflag[a];
-      if (!(fl & VF_ALIVE) || (fl & VF_LOSE)) continue;
-      const unsigned long long key = L.key1[a];
-      if (key == S_KEYMAX) continue;
-      const uint32_t hl = s_unmix((uint32_t)(key & 0xFFFFFFFFu)) ^ salt;
-      const uint32_t f = hl / 3, c = hl - 3 * f;
-      if (sl_fget<SM>(L, f, (int)c) != a) continue;
-      const uint32_t v = sl_fget<SM>(L, f, (int)((c + 1) % 3));
-      if (L.key1[v] != key || (L.vflag[v] & VF_LOSE)) continue;
-      L.vflag[a] = (uint8_t)(fl | VF_WIN);
-    }
-    __syncthreads();
-    // ---- winners in batches of SL_WCAP (they are pairwise independent)
+    // ---- P4 + E: winners are queued (marked DONE on both endpoints) and processed in batches
     for (;;) {
-      if (tid == 0) sh.nslot = 0;
+      if (tid == 0) sh.nwin = 0;
       __syncthreads();
-      for (uint32_t a = tid; a < U; a += NT) {
-        if (!(L.vflag[a] & VF_WIN)) continue;
-        const uint32_t slot = atomicAdd(&sh.nslot, 1u);
-        if (slot >= (uint32_t)SL_WCAP) continue;  // next batch
-        const uint32_t hl = s_unmix((uint32_t)(L.key1[a] & 0xFFFFFFFFu)) ^ salt;
+      for (uint32_t i = tid; i < nV; i += NT) {
+        const uint32_t a = vlist[i];
+        const uint32_t fl = L.vflag[a];
+        if (!(fl & VF_ALIVE) || (fl & (VF_LOSE | VF_DONE))) continue;
+        const unsigned long long key = L.key1[a];
+        if (key == S_KEYMAX) continue;
+        const uint32_t hl = s_unmix((uint32_t)(key & 0xFFFFFFFFu)) ^ salt;
         const uint32_t f = hl / 3, c = hl - 3 * f;
+        if (sl_fget<SM>(L, f, (int)c) != a) continue;
         const uint32_t v = sl_fget<SM>(L, f, (int)((c + 1) % 3));
-        sh.win[slot].u = a;
-        sh.win[slot].v = v;
-        sh.win[slot].h = hl;
-        sh.win[slot].cnt[0] = 0;
-        sh.win[slot].cnt[1] = 0;
-        L.key1[a] = 2ull * slot;  // key1 is dead until P1: it now names the ring list
-        L.key1[v] = 2ull * slot + 1;
-        sl_vclear(L.vflag, a, VF_WIN);
-        sl_vor(L.vflag, a, VF_END);
-        sl_vor(L.vflag, v, VF_END);
+        if (L.key1[v] != key || (L.vflag[v] & (VF_LOSE | VF_DONE))) continue;
+        const uint32_t slot = atomicAdd(&sh.nwin, 1u);
+        if (slot < (uint32_t)SL_WQ) {
+          sh.winq[slot] = hl;
+          sl_vor(L.vflag, a, VF_DONE);
+          sl_vor(L.vflag, v, VF_DONE);
+        }
       }
       __syncthreads();
-      const uint32_t total = sh.nslot;
-      const uint32_t nb = total < (uint32_t)SL_WCAP ? total : (uint32_t)SL_WCAP;
-      if (nb == 0) break;
-      // ---- E1: ring lists
-      for (uint32_t f = tid; f < T; f += NT) {
-        if (!(L.fstate[f] & 0x80u)) continue;
+      const uint32_t total = sh.nwin;
+      const uint32_t nq = total < (uint32_t)SL_WQ ? total : (uint32_t)SL_WQ;
+      for (uint32_t b0 = 0; b0 < nq; b0 += SL_WCAP) {
+        const uint32_t nb = (nq - b0) < (uint32_t)SL_WCAP ? (nq - b0) : (uint32_t)SL_WCAP;
+        if (tid < nb) {
+          const uint32_t hl = sh.winq[b0 + tid];
+          const uint32_t f = hl / 3, c = hl - 3 * f;
+          const uint32_t u = sl_fget<SM>(L, f, (int)c), v = sl_fget<SM>(L, f, (int)((c + 1) % 3));
+          sh.win[tid].u = u;
+          sh.win[tid].v = v;
+          sh.win[tid].h = hl;
+          sh.win[tid].cnt[0] = 0;
+          sh.win[tid].cnt[1] = 0;
+          L.key1[u] = 2ull * tid;  // key1 is dead until P1: it now names the ring list
+          L.key1[v] = 2ull * tid + 1;
+          sl_vor(L.vflag, u, VF_END);
+          sl_vor(L.vflag, v, VF_END);
+        }
+        __syncthreads();
+        // ---- E1: ring lists
+        for (uint32_t i = tid; i < nF; i += NT) {
+          const uint32_t f = flist[i];
+          if (!(L.fstate[f] & 0x80u)) continue;
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const uint32_t x = sl_fget<SM>(L, f, c);
-          if (!(L.vflag[x] & VF_END)) continue;
-          const uint32_t sl = (uint32_t)L.key1[x];
-          const uint32_t p = atomicAdd(&sh.win[sl >> 1].cnt[sl & 1u], 1u);
-          if (p < (uint32_t)S_MAXV) L.ring[sl * S_MAXV + p] = (typename SlLab<SM>::idx_t)f;
-        }
-      }
-      __syncthreads();
-      // ---- E2: one warp validates and applies one winner
-      for (uint32_t slot = warp; slot < nb; slot += NW) {
-        const uint32_t u = sh.win[slot].u, v = sh.win[slot].v, hl = sh.win[slot].h;
-        const uint32_t nfu = sh.win[slot].cnt[0], nfv = sh.win[slot].cnt[1];
-        SEval e;
-        sl_cost<SM>(A, L, u, v, &e);
-        bool ok = e.valid && nfu <= (uint32_t)S_MAXV && nfv <= (uint32_t)S_MAXV;  // warp uniform
-        const bool hu = ok && lane < nfu, hv = ok && lane < nfv;
-        uint32_t au[3] = {0, 0, 0}, av[3] = {0, 0, 0}, fu = 0, fv = 0;
-        uint32_t x1 = 0xF0000000u + lane, x2 = 0xF1000000u + lane, y1 = 0xF2000000u + lane,
-                 y2 = 0xF3000000u + lane;
-        if (hu) {
-          fu = L.ring[(2 * slot) * S_MAXV + lane];
-          au[0] = sl_fget<SM>(L, fu, 0); au[1] = sl_fget<SM>(L, fu, 1); au[2] = sl_fget<SM>(L, fu, 2);
-          sl_others(au, u, &x1, &x2);
-        }
-        if (hv) {
-          fv = L.ring[(2 * slot + 1) * S_MAXV + lane];
-          av[0] = sl_fget<SM>(L, fv, 0); av[1] = sl_fget<SM>(L, fv, 1); av[2] = sl_fget<SM>(L, fv, 2);
-          sl_others(av, v, &y1, &y2);
-        }
-        if (ok) {
-          bool f1, f2, g1, g2;
-          const uint32_t nnu = sl_distinct(x1, x2, nfu, lane, &f1, &f2);
-          const uint32_t nnv = sl_distinct(y1, y2, nfv, lane, &g1, &g2);
-          bool c1 = false, c2 = false;
-          for (uint32_t j = 0; j < nfv; j++) {
-            const uint32_t t1 = __shfl_sync(FULL, y1, j), t2 = __shfl_sync(FULL, y2, j);
-            c1 |= (x1 == t1) | (x1 == t2);
-            c2 |= (x2 == t1) | (x2 == t2);
+          for (int c = 0; c < 3; c++) {
+            const uint32_t x = sl_fget<SM>(L, f, c);
+            if (!(L.vflag[x] & VF_END)) continue;
+            const uint32_t sl = (uint32_t)L.key1[x];
+            const uint32_t p = atomicAdd(&sh.win[sl >> 1].cnt[sl & 1u], 1u);
+            if (p < (uint32_t)S_MAXV) L.ring[sl * S_MAXV + p] = (idx_t)f;
           }
-          const uint32_t common = __popc(__ballot_sync(FULL, f1 && c1)) + __popc(__ballot_sync(FULL, f2 && c2));
-          const uint32_t shared = __popc(__ballot_sync(FULL, hu && (x1 == v || x2 == v)));
-          bool bad = false;
-          if (hu && x1 != v && x2 != v) bad = sl_flips<SM>(A, L, au, u, e.p);
-          if (hv && y1 != u && y2 != u) bad = bad || sl_flips<SM>(A, L, av, v, e.p);
-          const bool anybad = __any_sync(FULL, bad);
-          ok = nnu <= (uint32_t)S_MAXV && nnv <= (uint32_t)S_MAXV && shared == 2 && common == 2 && !anybad;
         }
-        if (!ok) {  // park the edge until one of its endpoints' rings changes
+        __syncthreads();
+        // ---- E2: one warp validates and applies one winner
+        for (uint32_t slot = warp; slot < nb; slot += NW) {
+          const uint32_t u = sh.win[slot].u, v = sh.win[slot].v, hl = sh.win[slot].h;
+          const uint32_t nfu = sh.win[slot].cnt[0], nfv = sh.win[slot].cnt[1];
+          SEval e;
+          sl_cost<SM, true>(A, L, u, v, &e);
+          bool ok = e.valid && nfu <= (uint32_t)S_MAXV && nfv <= (uint32_t)S_MAXV;  // warp uniform
+          const bool hu = ok && lane < nfu, hv = ok && lane < nfv;
+          uint32_t au[3] = {0, 0, 0}, av[3] = {0, 0, 0}, fu = 0, fv = 0;
+          uint32_t x1 = 0xF0000000u + lane, x2 = 0xF1000000u + lane, y1 = 0xF2000000u + lane,
+                   y2 = 0xF3000000u + lane;
+          if (hu) {
+            fu = L.ring[(2 * slot) * S_MAXV + lane];
+            au[0] = sl_fget<SM>(L, fu, 0); au[1] = sl_fget<SM>(L, fu, 1); au[2] = sl_fget<SM>(L, fu, 2);
+            sl_others(au, u, &x1, &x2);
+          }
+          if (hv) {
+            fv = L.ring[(2 * slot + 1) * S_MAXV + lane];
+            av[0] = sl_fget<SM>(L, fv, 0); av[1] = sl_fget<SM>(L, fv, 1); av[2] = sl_fget<SM>(L, fv, 2);
+            sl_others(av, v, &y1, &y2);
+          }
+          if (ok) {
+            bool f1, f2, g1, g2;
+            const uint32_t nnu = sl_distinct(x1, x2, nfu, lane, &f1, &f2);
+            const uint32_t nnv = sl_distinct(y1, y2, nfv, lane, &g1, &g2);
+            bool c1 = false, c2 = false;
+            for (uint32_t j = 0; j < nfv; j++) {
+              const uint32_t t1 = __shfl_sync(FULL, y1, j), t2 = __shfl_sync(FULL, y2, j);
+              c1 |= (x1 == t1) | (x1 == t2);
+              c2 |= (x2 == t1) | (x2 == t2);
+            }
+            const uint32_t common = __popc(__ballot_sync(FULL, f1 && c1)) + __popc(__ballot_sync(FULL, f2 && c2));
+            const uint32_t shared = __popc(__ballot_sync(FULL, hu && (x1 == v || x2 == v)));
+            bool bad = false;
+            if (hu && x1 != v && x2 != v) bad = sl_flips<SM>(A, L, au, u, e.p);
+            if (hv && y1 != u && y2 != u) bad = bad || sl_flips<SM>(A, L, av, v, e.p);
+            const bool anybad = __any_sync(FULL, bad);
+            ok = nnu <= (uint32_t)S_MAXV && nnv <= (uint32_t)S_MAXV && shared == 2 && common == 2 && !anybad;
+          }
+          if (!ok) {  // park the edge until one of its endpoints' rings changes
+            if (lane == 0) {
+              const uint32_t f = hl / 3, c = hl - 3 * f;
+              const uint32_t st = L.fstate[f];
+              L.fstate[f] = (uint8_t)((st & ~(3u << (2 * c))) | (1u << (2 * c)));
+              sl_vclear(L.vflag, u, VF_END);
+              sl_vclear(L.vflag, v, VF_END);
+              atomicOr(&sh.progress, 1u);
+            }
+            continue;
+          }
+          const uint32_t k = e.keep, rm = e.remove;
+          const bool rm_is_u = (rm == u);
+          const bool hr = rm_is_u ? hu : hv;
+          const uint32_t rf = rm_is_u ? fu : fv;
+          const uint32_t r0 = rm_is_u ? au[0] : av[0], r1 = rm_is_u ? au[1] : av[1], r2 = rm_is_u ? au[2] : av[2];
+          // faces of rm: those that also hold k die, the others get k in rm's corner
+          const bool dies = hr && (r0 == k || r1 == k || r2 == k);
+          if (hr) {
+            if (dies) L.fstate[rf] = (uint8_t)(L.fstate[rf] & 0x7Fu);
+            else sl_fset<SM>(L, rf, r0 == rm ? 0 : (r1 == rm ? 1 : 2), k);
+          }
+          const uint32_t dead = __popc(__ballot_sync(FULL, dies));
+          // the new ring of k: parked edges around it may be valid now
+          if (hu && x1 != v && x2 != v) { sl_vor(L.vflag, x1, VF_RDIRTY); sl_vor(L.vflag, x2, VF_RDIRTY); }
+          if (hv && y1 != u && y2 != u) { sl_vor(L.vflag, y1, VF_RDIRTY); sl_vor(L.vflag, y2, VF_RDIRTY); }
+          double* Qk = A.Q + 10 * (uint64_t)(L.vbase + k);
+          const double* Qr = A.Q + 10 * (uint64_t)(L.vbase + rm);
+          if (lane < 10) Qk[lane] = Qk[lane] + Qr[lane];
           if (lane == 0) {
-            const uint32_t f = hl / 3, c = hl - 3 * f;
-            const uint32_t st = L.fstate[f];
-            L.fstate[f] = (uint8_t)((st & ~(3u << (2 * c))) | (1u << (2 * c)));
-            sl_vclear(L.vflag, u, VF_END);
-            sl_vclear(L.vflag, v, VF_END);
+            double* pk = A.pos + 3 * (uint64_t)(L.vbase + k);
+            pk[0] = e.p[0]; pk[1] = e.p[1]; pk[2] = e.p[2];
+            sl_vor(L.vflag, k, VF_CDIRTY | VF_RDIRTY);  // k moved: cached costs of its edges are stale
+            sl_vclear(L.vflag, k, VF_END);
+            sl_vclear(L.vflag, rm, 0xFFu);
+            atomicSub(&sh.alive, dead);
+            atomicAdd(&sh.ncol, 1u);
             atomicOr(&sh.progress, 1u);
           }
-          continue;
         }
-        const uint32_t k = e.keep, rm = e.remove;
-        const bool rm_is_u = (rm == u);
-        const bool hr = rm_is_u ? hu : hv;
-        const uint32_t rf = rm_is_u ? fu : fv;
-        const uint32_t r0 = rm_is_u ? au[0] : av[0], r1 = rm_is_u ? au[1] : av[1], r2 = rm_is_u ? au[2] : av[2];
-        // faces of rm: those that also hold k die, the others get k in rm's corner
-        const bool dies = hr && (r0 == k || r1 == k || r2 == k);
-        if (hr) {
-          if (dies) L.fstate[rf] = (uint8_t)(L.fstate[rf] & 0x7Fu);
-          else sl_fset<SM>(L, rf, r0 == rm ? 0 : (r1 == rm ? 1 : 2), k);
-        }
-        const uint32_t dead = __popc(__ballot_sync(FULL, dies));
-        // the new ring of k: every vertex of it is DIRTY (memoised edge states are dropped)
-        if (hu && x1 != v && x2 != v) { sl_vor(L.vflag, x1, VF_DIRTY); sl_vor(L.vflag, x2, VF_DIRTY); }
-        if (hv && y1 != u && y2 != u) { sl_vor(L.vflag, y1, VF_DIRTY); sl_vor(L.vflag, y2, VF_DIRTY); }
-        double* Qk = A.Q + 10 * (uint64_t)(L.vbase + k);
-        const double* Qr = A.Q + 10 * (uint64_t)(L.vbase + rm);
-        if (lane < 10) Qk[lane] = Qk[lane] + Qr[lane];
-        if (lane == 0) {
-          double* pk = A.pos + 3 * (uint64_t)(L.vbase + k);
-          pk[0] = e.p[0]; pk[1] = e.p[1]; pk[2] = e.p[2];
-          sl_vor(L.vflag, k, VF_DIRTY);
-          sl_vclear(L.vflag, k, VF_END);
-          sl_vclear(L.vflag, rm, 0xFFu);
-          atomicSub(&sh.alive, dead);
-          atomicAdd(&sh.ncol, 1u);
-          atomicOr(&sh.progress, 1u);
-        }
+        __syncthreads();
       }
-      __syncthreads();
-      if (total <= (uint32_t)SL_WCAP) break;
+      if (total <= (uint32_t)SL_WQ) break;
     }
     // ---- stop rules of the label
     if (tid == 0) {
@@ -645,6 +786,11 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
     if (sh.stop) {
       r++;
       break;
+    }
+    // ---- dead entries leave the lists every second round
+    if (r & 1) {
+      nF = sl_compact<SM>(flist, flist2, nF, &sh.counter, [&](uint32_t f) { return (L.fstate[f] & 0x80u) != 0; });
+      nV = sl_compact<SM>(vlist, vlist2, nV, &sh.counter, [&](uint32_t v) { return (L.vflag[v] & VF_ALIVE) != 0; });
     }
   }
   // ---- write the label back to the whole-task arrays
@@ -680,14 +826,17 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
     const uint32_t vbase = A.vert_off[l], U = A.vert_off[l + 1] - vbase;
     const uint32_t target = A.target[l];
     if (T == 0 || T <= target) continue;  // init left every face / vertex alive
-    // shared-memory layout: ring lists | key1 | faces SoA | face state | vertex flags
+    // shared-memory layout: ring lists | key1 | faces SoA | face list | vertex list | face state | vertex flags
     const size_t ring16 = (size_t)SL_WCAP * 2 * S_MAXV * 2;
     const size_t o_key = ring16;
     const size_t o_f0 = o_key + 8 * (size_t)U;
-    const size_t o_fs = o_f0 + 6 * (size_t)T;
+    const size_t o_fl = o_f0 + 6 * (size_t)T;
+    const size_t o_vl = o_fl + 2 * (size_t)T;
+    const size_t o_fs = o_vl + 2 * (size_t)U;
     const size_t o_vf = (o_fs + T + 3) & ~(size_t)3;
     const size_t need = o_vf + U + 4;
-    if (need <= A.smem_bytes && T <= 65535u && U <= 65535u) {
+    const uint32_t cap = (uint32_t)SL_LIST_PER * SL_THREADS;
+    if (need <= A.smem_bytes && T <= cap && U <= cap) {
       SlLab<true> L;
       L.T = T; L.U = U; L.tbase = tbase; L.vbase = vbase; L.target = target;
       L.ring = (uint16_t*)sl_smem;
@@ -695,6 +844,9 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
       L.fc0 = (uint16_t*)(sl_smem + o_f0);
       L.fc1 = L.fc0 + T;
       L.fc2 = L.fc1 + T;
+      L.flist = (uint16_t*)(sl_smem + o_fl);
+      L.vlist = (uint16_t*)(sl_smem + o_vl);
+      L.flist2 = L.vlist2 = nullptr;
       L.gface = nullptr;
       L.fstate = sl_smem + o_fs;
       L.vflag = sl_smem + o_vf;
@@ -705,6 +857,8 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
       L.ring = (uint32_t*)sl_smem;  // SL_WCAP * 2 * S_MAXV * 4 bytes, always available
       L.key1 = A.key1 + vbase;
       L.fc0 = L.fc1 = L.fc2 = nullptr;
+      L.flist = A.flist + tbase; L.flist2 = A.flist2 + tbase;
+      L.vlist = A.vlist + vbase; L.vlist2 = A.vlist2 + vbase;
       L.gface = A.face + 3 * (uint64_t)tbase;
       L.fstate = A.fstate + tbase;
       L.vflag = A.vflag + vbase;
@@ -801,7 +955,8 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
                       align_up(U * S_VCAP * 4, 256) + align_up(T * 4, 256) + 2 * align_up(T, 256) +
                       3 * align_up(U, 256) + 3 * align_up(U * 4, 256) + align_up(U * 8, 256) +
                       6 * align_up((K + 2) * 4, 256) + align_up(3 * T * 4, 256) +
-                      2 * align_up(3 * T * 4, 256) + tmpb + (1 << 20);
+                      2 * align_up(3 * T * 4, 256) + 2 * align_up(T * 4, 256) + 2 * align_up(U * 4, 256) + tmpb +
+                      (1 << 20);
   IGN_TRY(scratch_reserve(ctx, need));
   Simp s;
   s.U = U;
@@ -830,12 +985,16 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   uint32_t* d_order = (uint32_t*)scratch_take(ctx, (K + 2) * 4);
   uint32_t* flags = (uint32_t*)scratch_take(ctx, 256);
   float* ecost = (float*)scratch_take(ctx, 3 * T * 4);
+  // alive lists of the global-memory class (ping-pong); the init scratch is free by then
+  uint32_t* gl_f[2] = {(uint32_t*)scratch_take(ctx, T * 4), (uint32_t*)scratch_take(ctx, T * 4)};
+  uint32_t* gl_v[2] = {(uint32_t*)scratch_take(ctx, U * 4), (uint32_t*)scratch_take(ctx, U * 4)};
   void* tmp = scratch_take(ctx, tmpb);
   uint32_t* sorted_v = (uint32_t*)scratch_take(ctx, 3 * T * 4);
   uint32_t* sorted_h = (uint32_t*)scratch_take(ctx, 3 * T * 4);
   if (!s.pos || !s.Q || !s.face || !s.vf || !node_v || !node_h || !s.flabel || !s.falive || !fstate ||
       !s.valive || !s.vbound || !vflag || !s.vn || !vscan || !vflag32 || !key1 || !d_target || !d_tri_off ||
-      !d_vert_off || !d_new_tri_off || !d_new_vert_off || !d_order || !flags || !ecost || !tmp ||
+      !d_vert_off || !d_new_tri_off || !d_new_vert_off || !d_order || !flags || !ecost || !tmp || !gl_f[0] ||
+      !gl_f[1] || !gl_v[0] || !gl_v[1] ||
       !sorted_v || !sorted_h) {
     scratch_reset(ctx);
     set_error("scratch arena too small (simplify: %llu faces)", (unsigned long long)T);
@@ -912,6 +1071,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   SlArgs A;
   A.pos = s.pos; A.Q = s.Q; A.face = s.face; A.falive = s.falive; A.valive = s.valive; A.vbound = s.vbound;
   A.ecost = ecost; A.key1 = key1; A.fstate = fstate; A.vflag = vflag;
+  A.flist = gl_f[0]; A.flist2 = gl_f[1]; A.vlist = gl_v[0]; A.vlist2 = gl_v[1];
   A.tri_off = d_tri_off; A.vert_off = d_vert_off; A.target = d_target; A.order = d_order;
   A.K = (uint32_t)K; A.counters = flags;
   A.max_err2 = (double)max_error * (double)max_error;

@@ -25,7 +25,7 @@ class VolumePipeline:
   def __init__(self, ctx, shape, dtype=np.uint32, num_mips=2, mesh_shape=(256, 256, 256),
                resolution=(16, 16, 40), pitch=64, num_ids=1 << 20, seed=0, offset=(0, 0, 0),
                ccl_out_dtype=np.uint32, simplification_factor=100, max_simplification_error=40,
-               group=None, mesh_streams=8):
+               group=None, mesh_streams=8, id_base=0):
     self.ctx = ctx
     self.lib = ctx.lib
     self.shape = tuple(int(s) for s in shape)
@@ -35,6 +35,7 @@ class VolumePipeline:
     self.mesh_shape = tuple(mesh_shape)
     self.resolution = tuple(resolution)
     self.pitch, self.num_ids, self.seed, self.offset = pitch, num_ids, seed, tuple(offset)
+    self.id_base = int(id_base)
     self.ccl_out_dtype = np.dtype(ccl_out_dtype)
     self.simplification_factor = simplification_factor
     self.max_simplification_error = max_simplification_error
@@ -79,7 +80,7 @@ class VolumePipeline:
     _shim.check(self.lib.ign_synth_seg_dev(
       self.ctx.handle, _shim.ptr(self.d_in), c.c_int(self.code), _u64(sx), _u64(sy), _u64(sz),
       c.c_int64(ox), c.c_int64(oy), c.c_int64(oz), c.c_uint32(self.pitch), _u64(self.num_ids),
-      _u64(self.seed), _u64(0)))
+      _u64(self.seed), _u64(self.id_base)))
 
   def load_host(self, arr):
     self.ctx.h2d(self.d_in, arr)
@@ -87,9 +88,10 @@ class VolumePipeline:
   # ------------------------------------------------------------------ stages
   def pool(self):
     sx, sy, sz = self.shape
-    _shim.check(self.lib.ign_pool_mode_2x2x1_dev(
-      self.ctx.handle, _shim.ptr(self.d_in), c.c_int(self.code), _u64(sx), _u64(sy), _u64(sz),
-      c.c_int(self.num_mips), c.c_int(0), _shim.void_pp([m.ptr for m in self.d_mips])))
+    if self.num_mips:
+      _shim.check(self.lib.ign_pool_mode_2x2x1_dev(
+        self.ctx.handle, _shim.ptr(self.d_in), c.c_int(self.code), _u64(sx), _u64(sy), _u64(sz),
+        c.c_int(self.num_mips), c.c_int(0), _shim.void_pp([m.ptr for m in self.d_mips])))
     self.ctx.timer_start(15)  # "mips ready" mark for the mesh streams
 
   def ccl(self):
@@ -126,6 +128,8 @@ class VolumePipeline:
     _shim.check(lib.ign_mesh_begin_dev(
       wctx.handle, _shim.ptr(d_task), c.c_int(self.code), _u64(bx), _u64(by), _u64(bz), c.byref(h)))
     try:
+      nv0, nf0 = c.c_uint64(0), c.c_uint64(0)
+      _shim.check(lib.ign_mesh_totals(h, c.byref(nv0), c.byref(nf0)))  # marching-cubes output (host counters)
       if self.simplification_factor and self.simplification_factor > 0:
         _shim.check(lib.ign_mesh_simplify(
           h, (c.c_float * 3)(*[float(r) for r in self.resolution]),
@@ -135,7 +139,7 @@ class VolumePipeline:
       _shim.check(lib.ign_mesh_num_ids(h, c.byref(nl)))
       if export is not None:
         export(task, h, int(nv.value), int(nf.value), int(nl.value), wctx)
-      return int(nf.value), int(nv.value), int(nl.value)
+      return int(nf.value), int(nv.value), int(nl.value), int(nf0.value), int(nv0.value)
     finally:
       lib.ign_mesh_free(h)
 
@@ -170,7 +174,9 @@ class VolumePipeline:
           results.extend(part)
     self.mesh_stats = {"tasks": len(tasks), "triangles": int(sum(r[0] for r in results)),
                        "vertices": int(sum(r[1] for r in results)),
-                       "label_fragments": int(sum(r[2] for r in results)), "streams": self.mesh_streams}
+                       "label_fragments": int(sum(r[2] for r in results)),
+                       "triangles_in": int(sum(r[3] for r in results)), "vertices_in": int(sum(r[4] for r in results)),
+                       "streams": self.mesh_streams}
 
   def launch_count(self):
     return self.ctx.launch_count() + sum(w[0].launch_count() for w in self._workers)

@@ -30,3 +30,13 @@ if __name__ == "__main__":
   run(ctx, np.uint32, (1024, 1024, 1024), 64, 1 << 20, out_dtype=np.uint32)
   run(ctx, np.uint32, (1024, 1024, 1024), 16, 1 << 20)
   run(ctx, np.uint8, (1024, 1024, 1024), 64, 200)
+  # per-kernel-class times of the last configuration (CUDA events recorded by the library)
+  from igneous_b200 import pipeline
+  c = ctypes
+  _shim.check(ctx.lib.ign_prof_enable(ctx.handle, c.c_int(1)))
+  run(ctx, np.uint32, (1024, 1024, 1024), 64, 1 << 20, out_dtype=np.uint32, reps=3)
+  for name, cls in pipeline.PROF_CLASSES.items():
+    ms, cnt = c.c_float(0), c.c_uint64(0)
+    _shim.check(ctx.lib.ign_prof_read(ctx.handle, c.c_int(cls), c.byref(ms), c.byref(cnt)))
+    if cnt.value:
+      print(name, "ms total", round(ms.value, 3), "launches", cnt.value, "ms/launch", round(ms.value / cnt.value, 4))
