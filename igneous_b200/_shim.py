@@ -49,6 +49,16 @@ def dtype_code(dtype):
     raise NotImplementedError("igneous_b200: unsupported dtype %s" % np.dtype(dtype))
 
 
+def require_unsigned(dtype, what):
+  """Signed integer arrays share the unsigned kernels, which is exact for equality-only work
+  (mode pooling, CCL on raw labels, remap) and WRONG for anything that orders or adds values:
+  negative voxels would count as large positives.  Those operations refuse signed input."""
+  dt = np.dtype(dtype)
+  if dt.kind == "i":
+    raise NotImplementedError("igneous_b200 %s: signed dtype %s is not supported (the kernels are unsigned; "
+                              "negative values would be treated as large positives)" % (what, dt))
+
+
 def code_dtype(code):
   return np.dtype(_CODE_DTYPE[code])
 

@@ -93,6 +93,8 @@ def ccl_task(image, shape, threshold_gte=None, threshold_lte=None, dust_threshol
   arr = _volume(image)
   if arr.dtype == np.bool_:
     arr = arr.view(np.uint8)
+  if threshold_gte is not None or threshold_lte is not None:
+    _shim.require_unsigned(arr.dtype, "thresholded CCL")
   ctx = ctx or _shim.default_context()
   sx, sy, sz = arr.shape
   out = np.zeros(arr.shape, dtype=np.uint64, order="F")

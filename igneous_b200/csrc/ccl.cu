@@ -147,7 +147,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // tile of the mask kernel: MT_BX x MT_BY x bz voxels (+1 halo row / plane on the low
 // side, +16 bytes of halo on the low x side: TMA boxes are multiples of 16 bytes)
 constexpr int MT_BX = 128, MT_BY = 8;
-constexpr int MT_THREADS = 256;
+constexpr int MT_THREADS = 512;
 template <typename T> struct MaskTile {
   static constexpr int BZ = sizeof(T) == 8 ? 4 : 8;
   static constexpr int HX = 16 / (int)sizeof(T);
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(MT_THREADS)
   }
   uint32_t it = 0;
   while (t < ntiles) {
-    const uint32_t cur = it & 1u;
+    const uint32_t cur = TMA ? (it & 1u) : 0u;  // the cooperative fill is synchronous: one buffer
     const uint32_t x0 = tx * MT_BX, y0 = ty * MT_BY, z0 = tz * MT::BZ;
     // next tile of this CTA (its coordinates replace tx/ty/tz from here on)
     const uint64_t tn = advance(t + gridDim.x);
@@ -256,29 +256,48 @@ __global__ void __launch_bounds__(MT_THREADS)
       const uint32_t ry0 = (warp / MT::BZ) * RPW;
       const uint32_t gz = z0 + iz - 1;
       if (gz < a.sz) {
+        constexpr int NXW = MT_BX / 32;
+        T upv[NXW];  // the previous row of this warp stays in registers
+        {
+          const T* rup = tile + ((size_t)iz * (MT_BY + 1) + ry0) * MT::PITCH + MT::HX;
+#pragma unroll
+          for (int xw = 0; xw < NXW; xw++) upv[xw] = rup[xw * 32 + lane];
+        }
+        const uint32_t w0 = x0 / 32;
+        const bool vec_ok = (a.wpr % NXW == 0);  // 16-byte aligned mask rows: one vector store per mask
 #pragma unroll 2
         for (uint32_t k = 0; k < (uint32_t)RPW; k++) {
           const uint32_t iy = ry0 + k + 1, gy = y0 + iy - 1;
           if (gy >= a.sy) break;
           const T* row = tile + ((size_t)iz * (MT_BY + 1) + iy) * MT::PITCH + MT::HX;
-          const T* rup = row - MT::PITCH;
           const T* rbk = row - (size_t)(MT_BY + 1) * MT::PITCH;
-          uint32_t mS = 0, mZ = 0, mY = 0, mB = 0;
+          uint32_t bS[NXW], bZ[NXW], bY[NXW], bB[NXW];
 #pragma unroll
-          for (uint32_t xw = 0; xw < MT_BX / 32; xw++) {
+          for (int xw = 0; xw < NXW; xw++) {
             const uint32_t ix = xw * 32 + lane;
-            const T v = row[ix], left = row[(int)ix - 1], up = rup[ix], back = rbk[ix];
+            const T v = row[ix], left = row[(int)ix - 1], back = rbk[ix];
             const bool nz = v != (T)0;
-            const uint32_t bS = __ballot_sync(FULL, nz && v != left);
-            const uint32_t bZ = __ballot_sync(FULL, nz);
-            const uint32_t bY = __ballot_sync(FULL, nz && v == up);
-            const uint32_t bB = __ballot_sync(FULL, nz && v == back);
-            if (lane == xw) { mS = bS; mZ = bZ; mY = bY; mB = bB; }
+            bS[xw] = __ballot_sync(FULL, nz && v != left);
+            bZ[xw] = __ballot_sync(FULL, nz);
+            bY[xw] = __ballot_sync(FULL, nz && v == upv[xw]);
+            bB[xw] = __ballot_sync(FULL, nz && v == back);
+            upv[xw] = v;
           }
-          const uint32_t w0 = x0 / 32;
-          if (lane < MT_BX / 32 && w0 + lane < a.wpr) {
-            const uint64_t wi = ((uint64_t)gz * a.sy + gy) * a.wpr + w0 + lane;
-            a.S[wi] = mS; a.Z[wi] = mZ; a.Ey[wi] = mY; a.Ez[wi] = mB;
+          if (lane == 0) {
+            const uint64_t wi = ((uint64_t)gz * a.sy + gy) * a.wpr + w0;
+            if (vec_ok) {
+              static_assert(NXW == 4, "vector stores cover 4 words");
+              *(uint4*)(a.S + wi) = make_uint4(bS[0], bS[1], bS[2], bS[3]);
+              *(uint4*)(a.Z + wi) = make_uint4(bZ[0], bZ[1], bZ[2], bZ[3]);
+              *(uint4*)(a.Ey + wi) = make_uint4(bY[0], bY[1], bY[2], bY[3]);
+              *(uint4*)(a.Ez + wi) = make_uint4(bB[0], bB[1], bB[2], bB[3]);
+            } else {
+#pragma unroll
+              for (int xw = 0; xw < NXW; xw++)
+                if (w0 + xw < a.wpr) {
+                  a.S[wi + xw] = bS[xw]; a.Z[wi + xw] = bZ[xw]; a.Ey[wi + xw] = bY[xw]; a.Ez[wi + xw] = bB[xw];
+                }
+            }
           }
         }
       }
@@ -290,25 +309,30 @@ __global__ void __launch_bounds__(MT_THREADS)
 }
 
 // ------------------------------------------------------------------ pass B
-constexpr int TB_WMAX = 4096;    // words of a tile (all words of TY x TZ rows)
-constexpr int TB_RCAP = 12288;   // runs of a tile resolved in shared memory
+constexpr int TB_WMAX = 4096;   // words of a tile (all words of TY x TZ rows)
+constexpr int TB_RCAP = 8192;   // runs of a tile resolved in shared memory
 constexpr int TB_THREADS = 256;
+constexpr int TB_QCAP = 128;    // per-warp queue of union tasks (4 per lane per round)
+constexpr uint32_t TB_GFLAG = 0x80000000u;
 
 struct TileArgs {
-  uint32_t sx, sy, sz, wpr, TY, TZ, nty, ntz;
+  uint32_t sx, sy, sz, wpr, TY, TZ, nty, ntz, wcap;  // wcap: words of a full tile (shared-memory layout)
   const uint32_t *S, *Ey, *Ez, *rbase;
   uint32_t* parent;
 };
 
 __device__ __forceinline__ uint32_t mask_le(uint32_t p) { return 0xFFFFFFFFu >> (31u - p); }
 
-// unions of one word against the same word of a neighbour row: one union per stretch of
-// E in which neither row starts a new run.  base / nbase: id of the first run that starts
-// in the word (own row / neighbour row).
+// positions of one word that need a union with the same word of a neighbour row: one per
+// stretch of E in which neither row starts a new run
+__device__ __forceinline__ uint32_t union_candidates(uint32_t E, uint32_t Eprev_bit31, uint32_t S, uint32_t Sn) {
+  return E & (S | Sn | ~((E << 1) | Eprev_bit31));
+}
+// base / nbase: id of the first run that starts in the word (own row / neighbour row)
 template <typename UNION>
 __device__ __forceinline__ void word_unions(uint32_t E, uint32_t Eprev_bit31, uint32_t S, uint32_t Sn, uint32_t base,
                                             uint32_t nbase, UNION&& unite) {
-  uint32_t cand = E & (S | Sn | ~((E << 1) | Eprev_bit31));
+  uint32_t cand = union_candidates(E, Eprev_bit31, S, Sn);
   while (cand) {
     const uint32_t p = __ffs(cand) - 1;
     cand &= cand - 1;
@@ -320,10 +344,11 @@ __device__ __forceinline__ void word_unions(uint32_t E, uint32_t Eprev_bit31, ui
 __global__ void __launch_bounds__(TB_THREADS) k_ccl_tiles(const TileArgs a) {
   extern __shared__ __align__(16) uint32_t tb_smem[];
   uint32_t* sS = tb_smem;
-  uint32_t* sEy = sS + TB_WMAX;
-  uint32_t* sEz = sEy + TB_WMAX;
-  uint32_t* par = sEz + TB_WMAX;                 // [TB_RCAP]
-  uint16_t* lbase = (uint16_t*)(par + TB_RCAP);  // [TB_WMAX]
+  uint32_t* sEy = sS + a.wcap;
+  uint32_t* sEz = sEy + a.wcap;
+  uint32_t* par = sEz + a.wcap;                                        // [TB_RCAP]
+  uint32_t* queue = par + TB_RCAP;                                     // [warps][TB_QCAP] packed (a << 16 | b)
+  uint16_t* lbase = (uint16_t*)(queue + (TB_THREADS / 32) * TB_QCAP);  // [wcap]
   __shared__ uint32_t warp_sums[TB_THREADS / 32];
   __shared__ uint32_t total_runs;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -366,64 +391,120 @@ __global__ void __launch_bounds__(TB_THREADS) k_ccl_tiles(const TileArgs a) {
   __syncthreads();
   const uint32_t RL = total_runs;
   const bool fits = RL <= (uint32_t)TB_RCAP;
-  if (fits) {
-#pragma unroll
-    for (int k = 0; k < WPT; k++) {
-      const uint32_t lw = tid * WPT + k;
-      if (lw < W) {
-        lbase[lw] = (uint16_t)run;
-        run += __popc(sS[lw]);
-      }
-    }
-    for (uint32_t i = tid; i < RL; i += TB_THREADS) par[i] = i;
-  } else {
-    // too many runs for shared memory (noise-like data): unions go to the global array
+  if (!fits) {
+    // too many runs for shared memory (noise-like data): every union goes to the global array
     for (uint32_t lw = tid; lw < W; lw += TB_THREADS) {
       const uint32_t b = a.rbase[gword(lw)], c = __popc(sS[lw]);
       for (uint32_t k = 0; k < c; k++) a.parent[b + k] = b + k;
     }
-  }
-  __syncthreads();
-  // ---- unions along y and z inside the tile
-  for (uint32_t lw = tid; lw < W; lw += TB_THREADS) {
-    const uint32_t lz = lw / rowsw, r = lw - lz * rowsw, ly = r / wpr, xw = r - ly * wpr;
-    const uint32_t S = sS[lw];
-    const uint32_t ey = ly > 0 ? sEy[lw] : 0u, ez = lz > 0 ? sEz[lw] : 0u;
-    if (!(ey | ez)) continue;
-    if (fits) {
-      const uint32_t base = lbase[lw];
-      auto un = [&](uint32_t x, uint32_t y) { uf_union(par, x, y); };
-      if (ey) word_unions(ey, xw > 0 ? sEy[lw - 1] >> 31 : 0u, S, sS[lw - wpr], base, (uint32_t)lbase[lw - wpr], un);
-      if (ez) word_unions(ez, xw > 0 ? sEz[lw - 1] >> 31 : 0u, S, sS[lw - rowsw], base, (uint32_t)lbase[lw - rowsw], un);
-    } else {
-      const uint32_t base = a.rbase[gword(lw)];
+    __syncthreads();
+    for (uint32_t lw = tid; lw < W; lw += TB_THREADS) {
+      const uint32_t lz = lw / rowsw, r = lw - lz * rowsw, ly = r / wpr, xw = r - ly * wpr;
+      const uint32_t ey = ly > 0 ? sEy[lw] : 0u, ez = lz > 0 ? sEz[lw] : 0u;
+      if (!(ey | ez)) continue;
+      const uint32_t S = sS[lw], base = a.rbase[gword(lw)];
       auto un = [&](uint32_t x, uint32_t y) { uf_union(a.parent, x, y); };
       if (ey) word_unions(ey, xw > 0 ? sEy[lw - 1] >> 31 : 0u, S, sS[lw - wpr], base, a.rbase[gword(lw - wpr)], un);
       if (ez) word_unions(ez, xw > 0 ? sEz[lw - 1] >> 31 : 0u, S, sS[lw - rowsw], base, a.rbase[gword(lw - rowsw)], un);
     }
+    return;
   }
-  if (!fits) return;
+#pragma unroll
+  for (int k = 0; k < WPT; k++) {
+    const uint32_t lw = tid * WPT + k;
+    if (lw < W) {
+      lbase[lw] = (uint16_t)run;
+      run += __popc(sS[lw]);
+    }
+  }
+  for (uint32_t i = tid; i < RL; i += TB_THREADS) par[i] = i;
   __syncthreads();
-  // ---- every run's parent = global id of its tile root
+  // ---- unions along y and z inside the tile.  A warp takes 32 words; the lanes queue their
+  // union tasks (4 per lane per round) and the warp then runs the queue on dense lanes.
+  {
+    uint32_t* q = queue + warp * TB_QCAP;
+    for (uint32_t base0 = warp * 32; base0 < W; base0 += TB_THREADS) {
+      const uint32_t lw = base0 + lane;
+      uint32_t cy = 0, cz = 0, S = 0, Sy = 0, Sz = 0, lb = 0, lby = 0, lbz = 0;
+      if (lw < W) {
+        const uint32_t lz = lw / rowsw, r = lw - lz * rowsw, ly = r / wpr, xw = r - ly * wpr;
+        S = sS[lw];
+        lb = lbase[lw];
+        if (ly > 0) {
+          const uint32_t E = sEy[lw];
+          if (E) {
+            Sy = sS[lw - wpr];
+            lby = lbase[lw - wpr];
+            cy = union_candidates(E, xw > 0 ? sEy[lw - 1] >> 31 : 0u, S, Sy);
+          }
+        }
+        if (lz > 0) {
+          const uint32_t E = sEz[lw];
+          if (E) {
+            Sz = sS[lw - rowsw];
+            lbz = lbase[lw - rowsw];
+            cz = union_candidates(E, xw > 0 ? sEz[lw - 1] >> 31 : 0u, S, Sz);
+          }
+        }
+      }
+      while (__any_sync(FULL, (cy | cz) != 0)) {
+        uint32_t t[4], nt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (cy) {
+            const uint32_t p = __ffs(cy) - 1, le = mask_le(p);
+            cy &= cy - 1;
+            t[nt++] = ((lb + __popc(S & le) - 1) << 16) | (lby + __popc(Sy & le) - 1);
+          } else if (cz) {
+            const uint32_t p = __ffs(cz) - 1, le = mask_le(p);
+            cz &= cz - 1;
+            t[nt++] = ((lb + __popc(S & le) - 1) << 16) | (lbz + __popc(Sz & le) - 1);
+          }
+        }
+        uint32_t off = nt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(FULL, off, d);
+          if ((int)lane >= d) off += o;
+        }
+        const uint32_t total = __shfl_sync(FULL, off, 31);
+        off -= nt;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (k < (int)nt) q[off + k] = t[k];
+        __syncwarp();
+        for (uint32_t j = lane; j < total; j += 32) {
+          const uint32_t e = q[j];
+          uf_union(par, e >> 16, e & 0xFFFFu);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+  // ---- flatten; roots take their global id (flagged); every run then stores the global id of its root
+  for (uint32_t i = tid; i < RL; i += TB_THREADS) {
+    const uint32_t r = uf_find(par, i);
+    if (r != i) par[i] = r;
+  }
+  __syncthreads();
   for (uint32_t lw = tid; lw < W; lw += TB_THREADS) {
     const uint32_t c = __popc(sS[lw]);
     if (c == 0) continue;
     const uint32_t lb = lbase[lw], gb = a.rbase[gword(lw)];
+    sEy[lw] = gb;  // the E masks are dead: keep the word's global run base
+    for (uint32_t k = 0; k < c; k++)
+      if (par[lb + k] == lb + k) par[lb + k] = TB_GFLAG | (gb + k);
+  }
+  __syncthreads();
+  for (uint32_t lw = tid; lw < W; lw += TB_THREADS) {
+    const uint32_t c = __popc(sS[lw]);
+    if (c == 0) continue;
+    const uint32_t lb = lbase[lw], gb = sEy[lw];
     for (uint32_t k = 0; k < c; k++) {
-      const uint32_t root = uf_find(par, lb + k);
-      uint32_t groot = gb + k;
-      if (root != lb + k) {
-        // word of the root: the last word whose lbase <= root (words without starts share
-        // the lbase of the next word with starts and come before it)
-        uint32_t lo = 0, hi = lw;  // the root is never after lw (it is the minimum)
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi + 1) >> 1;
-          if (lbase[mid] <= root) lo = mid;
-          else hi = mid - 1;
-        }
-        groot = a.rbase[gword(lo)] + (root - lbase[lo]);
-      }
-      a.parent[gb + k] = groot;
+      uint32_t v = par[lb + k];
+      if (!(v & TB_GFLAG)) v = par[v];  // flattened: v is a root, its entry is flagged
+      a.parent[gb + k] = v & ~TB_GFLAG;
     }
   }
 }
@@ -512,38 +593,13 @@ struct ExpandArgs {
   const uint32_t *S, *Z, *rbase, *label;
 };
 
-// a lane owns 4 consecutive voxels (one vector store); a warp covers 4 words
+// The expansion is two dependent loads (masks -> run label) followed by a store, so a warp
+// keeps EX_G independent 128-voxel groups in flight (a single group per warp is latency bound:
+// 2.2 TB/s measured).  A lane owns 4 consecutive voxels of each group (one vector store).
+constexpr int EX_G = 4;
+
 template <typename OUT>
-__global__ void __launch_bounds__(256) k_ccl_expand4(const ExpandArgs a, OUT* __restrict__ out) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t groups = (a.wpr + 3) / 4;  // 128-voxel groups per row
-  const uint64_t gi = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-  if (gi >= a.rows * groups) return;
-  const uint64_t row = gi / groups;
-  const uint32_t g = (uint32_t)(gi - row * groups);
-  const uint32_t xw = g * 4 + (lane >> 3);
-  const uint32_t x = xw * 32 + (lane & 7u) * 4;
-  if (xw >= a.wpr || x >= a.sx) return;  // sx % 4 == 0: a quad is all in or all out
-  const uint64_t wi = row * a.wpr + xw;
-  const uint32_t S = a.S[wi], Z = a.Z[wi], rb = a.rbase[wi];
-  const uint32_t b0 = (lane & 7u) * 4;
-  OUT v[4];
-  uint32_t last_idx = 0xFFFFFFFFu, last_lab = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const uint32_t b = b0 + j;
-    OUT o = 0;
-    if ((Z >> b) & 1u) {
-      const uint32_t idx = rb + __popc(S & mask_le(b)) - 1;
-      if (idx != last_idx) {
-        last_idx = idx;
-        last_lab = a.label[idx];
-      }
-      o = last_lab ? (OUT)(last_lab + a.offset) : (OUT)0;
-    }
-    v[j] = o;
-  }
-  OUT* dst = out + row * a.sx + x;
+__device__ __forceinline__ void ex_store4(OUT* dst, const OUT* v) {
   if constexpr (sizeof(OUT) == 2) {
     *(uint2*)dst = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
   } else if constexpr (sizeof(OUT) == 4) {
@@ -554,23 +610,94 @@ __global__ void __launch_bounds__(256) k_ccl_expand4(const ExpandArgs a, OUT* __
   }
 }
 
-// any row pitch: a lane owns one voxel
+template <typename OUT>
+__global__ void __launch_bounds__(256) k_ccl_expand4(const ExpandArgs a, OUT* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t groups = (a.wpr + 3) / 4;  // 128-voxel groups per row
+  const uint64_t total = a.rows * groups;
+  const uint64_t g0 = ((blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5) * EX_G;
+  if (g0 >= total) return;
+  const uint32_t b0 = (lane & 7u) * 4;
+  uint32_t S[EX_G], Z[EX_G], rb[EX_G], lab[EX_G], idx0[EX_G];
+  uint64_t at[EX_G];
+  bool ok[EX_G];
+#pragma unroll
+  for (int g = 0; g < EX_G; g++) {
+    const uint64_t gi = g0 + g;
+    const uint64_t row = gi / groups;
+    const uint32_t xw = (uint32_t)(gi - row * groups) * 4 + (lane >> 3);
+    const uint32_t x = xw * 32 + b0;
+    ok[g] = gi < total && xw < a.wpr && x < a.sx;  // sx % 4 == 0: a quad is all in or all out
+    const uint64_t wi = row * a.wpr + xw;
+    at[g] = row * a.sx + x;
+    S[g] = ok[g] ? a.S[wi] : 0u;
+    Z[g] = ok[g] ? a.Z[wi] : 0u;
+    rb[g] = ok[g] ? a.rbase[wi] : 0u;
+  }
+#pragma unroll
+  for (int g = 0; g < EX_G; g++) {  // the label of the first non-zero voxel of the quad (usually of all four)
+    const uint32_t zq = (Z[g] >> b0) & 15u;
+    const uint32_t first = zq ? b0 + (uint32_t)__ffs(zq) - 1 : b0;
+    idx0[g] = rb[g] + __popc(S[g] & mask_le(first)) - 1;
+    lab[g] = zq ? a.label[idx0[g]] : 0u;
+  }
+#pragma unroll
+  for (int g = 0; g < EX_G; g++) {
+    if (!ok[g]) continue;
+    OUT v[4];
+    const uint32_t zq = (Z[g] >> b0) & 15u, sq = (S[g] >> b0) & 15u;
+    const OUT l0 = lab[g] ? (OUT)(lab[g] + a.offset) : (OUT)0;
+    // no run starts after the quad's first non-zero voxel: its non-zero voxels are one run
+    if (zq == 0 || (sq >> __ffs(zq)) == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = ((zq >> j) & 1u) ? l0 : (OUT)0;
+    } else {
+      uint32_t cur_idx = idx0[g], cur_lab = lab[g];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t b = b0 + j;
+        OUT o = 0;
+        if ((Z[g] >> b) & 1u) {
+          const uint32_t idx = rb[g] + __popc(S[g] & mask_le(b)) - 1;
+          if (idx != cur_idx) {  // another run inside the quad
+            cur_idx = idx;
+            cur_lab = a.label[idx];
+          }
+          o = cur_lab ? (OUT)(cur_lab + a.offset) : (OUT)0;
+        }
+        v[j] = o;
+      }
+    }
+    ex_store4(out + at[g], v);
+  }
+}
+
+// any row pitch: a lane owns one voxel of each of EX_G consecutive words
 template <typename OUT>
 __global__ void __launch_bounds__(256) k_ccl_expand1(const ExpandArgs a, OUT* __restrict__ out) {
   const uint32_t lane = threadIdx.x & 31u;
-  const uint64_t wi = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-  if (wi >= a.rows * a.wpr) return;
-  const uint64_t row = wi / a.wpr;
-  const uint32_t xw = (uint32_t)(wi - row * a.wpr);
-  const uint32_t x = xw * 32 + lane;
-  if (x >= a.sx) return;
-  const uint32_t S = a.S[wi], Z = a.Z[wi];
-  OUT o = 0;
-  if ((Z >> lane) & 1u) {
-    const uint32_t l = a.label[a.rbase[wi] + __popc(S & mask_le(lane)) - 1];
-    o = l ? (OUT)(l + a.offset) : (OUT)0;
+  const uint64_t total = a.rows * a.wpr;
+  const uint64_t w0 = ((blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5) * EX_G;
+  if (w0 >= total) return;
+  uint32_t lab[EX_G];
+  uint64_t at[EX_G];
+  bool ok[EX_G], nz[EX_G];
+#pragma unroll
+  for (int g = 0; g < EX_G; g++) {
+    const uint64_t wi = w0 + g;
+    const uint64_t row = wi / a.wpr;
+    const uint32_t x = (uint32_t)(wi - row * a.wpr) * 32 + lane;
+    ok[g] = wi < total && x < a.sx;
+    at[g] = row * a.sx + x;
+    const uint32_t S = ok[g] ? a.S[wi] : 0u, Z = ok[g] ? a.Z[wi] : 0u;
+    nz[g] = (Z >> lane) & 1u;
+    lab[g] = nz[g] ? a.rbase[wi] + __popc(S & mask_le(lane)) - 1 : 0u;  // run id for now
   }
-  out[row * a.sx + x] = o;
+#pragma unroll
+  for (int g = 0; g < EX_G; g++) lab[g] = nz[g] ? a.label[lab[g]] : 0u;
+#pragma unroll
+  for (int g = 0; g < EX_G; g++)
+    if (ok[g]) out[at[g]] = lab[g] ? (OUT)(lab[g] + a.offset) : (OUT)0;
 }
 
 // one z-plane: voxel values widened to u64 and run labels (multi-GPU face exchange)
@@ -805,8 +932,8 @@ static int ccl_structure(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, ui
     IGN_REQUIRE(r == CUDA_SUCCESS, IGN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %ux%ux%u", (int)r, sx, sy, sz);
   }
   {
-    const size_t smem = 2 * MT::BYTES;
-    const unsigned per_sm = (unsigned)(200 * 1024 / (smem + 1024));
+    const size_t smem = (use_tma ? 2 : 1) * MT::BYTES;
+    const unsigned per_sm = (unsigned)(200 * 1024 / (smem + 1024)) < 8u ? (unsigned)(200 * 1024 / (smem + 1024)) : 8u;
     const uint64_t cap = (uint64_t)ctx->sm_count * (per_sm ? per_sm : 1);
     const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
     IGN_CUDA(cudaMemsetAsync(p.S + W, 0, 8, ctx->stream));  // sentinel words S[W], S[W+1]
@@ -834,6 +961,7 @@ static int ccl_structure(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, ui
     return IGN_OK;
   }
   if (hR == 0) return IGN_OK;
+  IGN_REQUIRE(hR < 0x7FFFFFF0u, IGN_ERR_OVERFLOW, "CCL: %u runs exceed the 2^31 limit; split the volume into tasks", hR);
   const uint32_t Rn = hR;
   // ---- pass B: tiles, then the rows on tile faces
   uint32_t TY = 8;
@@ -844,7 +972,9 @@ static int ccl_structure(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, ui
   ta.ntz = (sz + TY - 1) / TY;
   ta.S = p.S; ta.Ey = p.Ey; ta.Ez = p.Ez; ta.rbase = p.rbase; ta.parent = p.label;
   {
-    const size_t smem = (size_t)3 * TB_WMAX * 4 + (size_t)TB_RCAP * 4 + (size_t)(TB_WMAX + 2) * 2;
+    ta.wcap = (p.wpr * TY * TY + 3u) & ~3u;
+    const size_t smem = (size_t)3 * ta.wcap * 4 + (size_t)TB_RCAP * 4 + (size_t)(TB_THREADS / 32) * TB_QCAP * 4 +
+                        (size_t)(ta.wcap + 2) * 2;
     IGN_CUDA(cudaFuncSetAttribute(k_ccl_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     IGN_REQUIRE((uint64_t)ta.nty * ta.ntz < 0x7FFFFFFFull, IGN_ERR_OVERFLOW, "too many CCL tiles");
     IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, k_ccl_tiles, ta.nty * ta.ntz, TB_THREADS, smem, ta);
@@ -892,7 +1022,8 @@ static int launch_expand(ign_ctx* ctx, const CclPlan& p, uint64_t offset, void* 
                          uint64_t max_label) {
   const ExpandArgs e = p.expand_args(offset);
   const bool vec = (p.sx % 4 == 0) && ((uintptr_t)out % 16 == 0);
-  const uint64_t warps = vec ? e.rows * ((p.wpr + 3) / 4) : e.rows * p.wpr;
+  const uint64_t items = vec ? e.rows * ((p.wpr + 3) / 4) : e.rows * p.wpr;  // 128-voxel groups / words
+  const uint64_t warps = (items + EX_G - 1) / EX_G;
   IGN_REQUIRE(warps * 32 / 256 < 0x7FFFFFFFull, IGN_ERR_OVERFLOW, "CCL expand grid too large");
   const unsigned grid = blocks_for(warps * 32, 256);
   switch (out_dtype) {

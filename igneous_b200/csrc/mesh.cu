@@ -481,7 +481,7 @@ int ign_mesh_begin_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx,
       ctx->mesh_pool_busy = 1;
     } else {
       MESH_CUDA(cudaMalloc((void**)&m->d_faces, 3 * T * 4));
-      MESH_CUDA(cudaMalloc((void**)&m->d_uniq_vkeys, U * 8));
+      MESH_CUDA(cudaMalloc((void**)&m->d_uniq_vkeys, U * 12));  // 12: float3 positions after simplification
     }
   }
   MESH_LAUNCH(k_vertex_assign, blocks_for(3 * T, 256), 256, vkeys_s, corner_s, heads, rank,

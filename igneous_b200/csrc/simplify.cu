@@ -482,7 +482,9 @@ __device__ __forceinline__ uint32_t sl_compact(IDX*& list, IDX*& list2, uint32_t
     list2 = t;
   }
   __syncthreads();
-  return *counter;
+  const uint32_t kept = *counter;
+  __syncthreads();  // everyone has read the count: the counter may be reused by the next call
+  return kept;
 }
 
 template <bool SM>
@@ -942,7 +944,6 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
     m->d_pos_f = nullptr;
     return IGN_OK;
   }
-  IGN_REQUIRE(m->pooled, IGN_ERR_UNSUPPORTED, "simplification needs the pooled mesher buffers");
   IGN_REQUIRE(ctx->scratch_used == 0, IGN_ERR_INVALID, "ign_mesh_simplify must own the scratch arena");
 
   size_t sortb = 0, scanb = 0;
@@ -1118,7 +1119,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
            d_new_vert_off);
   S_LAUNCH(k_simp_new_offsets, blocks_for(K + 2, 256), 256, d_tri_off, fscan, (uint32_t)(K + 2), T, T2,
            d_new_tri_off);
-  // results overwrite the pooled mesher buffers (inputs were copied into the arena)
+  // results overwrite the mesher's buffers (inputs were copied into the arena; the vertex buffer holds 12 B / vertex)
   float* pos_f = (float*)m->d_uniq_vkeys;
   S_LAUNCH(k_simp_compact_verts, blocks_for(U, 256), 256, s, vscan, pos_f);
   S_LAUNCH(k_simp_compact_faces, blocks_for(T, 256), 256, s, vscan, fscan, d_new_vert_off, m->d_faces);

@@ -8,8 +8,11 @@ under {key}/ccl/{faces,equivalences,relabel}, union rule and label offsets):
   (4) RelabelCCLTask      :296-356   apply and write without the overlap
 Each task's threshold -> rails blackout -> dust -> CCL -> offset chain is ONE
 fused GPU call (cc3d.ccl_task); face linkage and the final remap use the GPU
-fastremap kernels.  Face files keep the reference names (`*.ckl`) but hold a
-self-describing raw array, not the crackle codec (a next row in DESIGN.md).
+fastremap kernels.  The reference writes its face files as crackle streams
+(`*.ckl`, ccl.py:183); no crackle codec exists here, so the faces are written as
+`.npy` files next to where the reference puts its `.ckl` files -- never under the
+reference's names -- and pass 2 refuses to mix the two formats: a job must run all
+four passes with one implementation.
 """
 import io
 from collections import defaultdict
@@ -86,7 +89,20 @@ def _encode_face(face):
   return buf.getvalue()
 
 
-def _decode_face(data):
+FACE_SUFFIX = ".npy"  # the reference's `.ckl` names are reserved for real crackle streams
+
+
+class ForeignFaceFormat(ValueError):
+  """A CCL face file that was not written by this implementation."""
+
+
+def _decode_face(data, name=""):
+  if data[:4] == b"crkl":
+    raise ForeignFaceFormat(
+      "CCL face %s is a crackle stream written by a stock igneous worker; igneous_b200 has no crackle "
+      "codec: run all four CCL passes of a job with one implementation" % name)
+  if data[:6] != b"\x93NUMPY":
+    raise ForeignFaceFormat("CCL face %s is not an igneous_b200 face file (unknown magic %r)" % (name, data[:6]))
   return np.load(io.BytesIO(data), allow_pickle=False)
 
 
@@ -119,7 +135,7 @@ def CCLFacesTask(cloudpath, mip, shape, offset, threshold_gte=None, threshold_lt
   cc_labels, _ = _task_ccl(cv, bounds, shape, threshold_gte, threshold_lte, dust_threshold, label_offset)
   faces = {"xy": cc_labels[:, :, -1], "xz": cc_labels[:, -1, :], "yz": cc_labels[-1, :, :]}
   cf = CloudFiles(cloudpath)
-  cf.puts(((cf.join(cv.key, "ccl", "faces", "%d-%d-%d-%s.ckl" % (gp[0], gp[1], gp[2], k)), _encode_face(v))
+  cf.puts(((cf.join(cv.key, "ccl", "faces", "%d-%d-%d-%s%s" % (gp[0], gp[1], gp[2], k, FACE_SUFFIX)), _encode_face(v))
            for k, v in faces.items()), compress="br")
 
 
@@ -137,15 +153,20 @@ def CCLEquivalancesTask(cloudpath, mip, shape, offset, threshold_gte=None, thres
   cf = CloudFiles(cloudpath)
   sx, sy, sz = (int(v) for v in shape)
   neighbours = [  # (file of the neighbouring task's back face, my front plane over the same voxels)
-    ("%d-%d-%d-xy.ckl" % (gp[0], gp[1], gp[2] - 1), lambda f: f[:sx, :sy], cc_labels[:sx, :sy, 0]),
-    ("%d-%d-%d-xz.ckl" % (gp[0], gp[1] - 1, gp[2]), lambda f: f[:sx, :sz], cc_labels[:sx, 0, :sz]),
-    ("%d-%d-%d-yz.ckl" % (gp[0] - 1, gp[1], gp[2]), lambda f: f[:sy, :sz], cc_labels[0, :sy, :sz]),
+    ("%d-%d-%d-xy" % (gp[0], gp[1], gp[2] - 1), lambda f: f[:sx, :sy], cc_labels[:sx, :sy, 0]),
+    ("%d-%d-%d-xz" % (gp[0], gp[1] - 1, gp[2]), lambda f: f[:sx, :sz], cc_labels[:sx, 0, :sz]),
+    ("%d-%d-%d-yz" % (gp[0] - 1, gp[1], gp[2]), lambda f: f[:sy, :sz], cc_labels[0, :sy, :sz]),
   ]
-  for fname, crop, cur in neighbours:
+  for stem, crop, cur in neighbours:
+    fname = stem + FACE_SUFFIX
     data = cf.get(cf.join(cv.key, "ccl", "faces", fname))
     if data is None:
+      if cf.exists(cf.join(cv.key, "ccl", "faces", stem + ".ckl")):  # pass 1 ran on a stock igneous worker
+        raise ForeignFaceFormat(
+          "face %s.ckl was written by a stock igneous worker (crackle); igneous_b200 cannot read it: run all "
+          "four CCL passes of a job with one implementation" % stem)
       continue
-    prev = crop(_decode_face(data))
+    prev = crop(_decode_face(data, fname))
     cur = cur[:prev.shape[0], :prev.shape[1]]
     prev = prev[:cur.shape[0], :cur.shape[1]]
     for task_label, adj_labels in fastremap.inverse_component_map(cur, prev).items():

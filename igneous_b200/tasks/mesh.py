@@ -92,8 +92,7 @@ class MeshTask(RegisteredTask):
                    dtype=self._volume.dtype, order="F")
     if not inner.subvoxel():
       sl = tuple(slice(int(a - o), int(b - o)) for a, b, o in zip(inner.minpt, inner.maxpt, bounds.minpt))
-      out[sl] = self._volume.download(inner, mip=self.options["mip"]) \
-          if "mip" in self._volume.download.__code__.co_varnames else self._volume.download(inner)
+      out[sl] = self._volume.download(inner, mip=self.options["mip"])  # mesh.py:177-182
     return out
 
   def _handle_dataset_boundary(self, data, bbox):
@@ -152,15 +151,20 @@ class MeshTask(RegisteredTask):
   def _upload_individuals(self, binaries, generate_manifests):
     cf = CloudFiles(self.layer_path)
     lod, name = self.options["lod"], self._bounds.to_filename()
+    # mesh.py:399-430: fragments carry the mesh content type and the task's cache_control,
+    # manifests are stored uncompressed
     cf.puts((("%s/%s:%s:%s" % (self._mesh_dir, segid, lod, name), b) for segid, b in binaries.items()),
-            compress=self.options["compress"])
+            compress=self.options["compress"], cache_control=self.options["cache_control"],
+            content_type="model/mesh")
     if generate_manifests:
       cf.put_jsons((("%s/%s:%s" % (self._mesh_dir, segid, lod),
-                     {"fragments": ["%s:%s:%s" % (segid, lod, name)]}) for segid in binaries))
+                     {"fragments": ["%s:%s:%s" % (segid, lod, name)]}) for segid in binaries),
+                   compress=None, cache_control=self.options["cache_control"])
 
   def _upload_spatial_index(self, bbox, mesh_bboxes):
     cf = CloudFiles(self.layer_path)
     res = self._volume.meta.resolution(self.options["mip"])
     phys = bbox.astype(np.asarray(res).dtype) * res
     cf.put_json("%s/%s.spatial" % (self._mesh_dir, phys.to_filename(self._volume.mesh.spatial_index.precision)),
-                {str(k): v for k, v in mesh_bboxes.items()}, compress=self.options["compress"])
+                {str(k): v for k, v in mesh_bboxes.items()}, compress=self.options["compress"],
+                cache_control=False)  # mesh.py:452-464

@@ -45,6 +45,8 @@ def _pool(img, factor, num_mips, mode, flag, ctx):
   ndim = img.ndim
   arr, sx, sy, nz = _shim.as_fortran_volume(img)
   code = _shim.dtype_code(arr.dtype)
+  if not mode:
+    _shim.require_unsigned(arr.dtype, "averaging")
   if not mode and code == _shim.IGN_U64:
     raise NotImplementedError("igneous_b200 averaging: uint64 images are not supported")
   ctx = ctx or _shim.default_context()
@@ -91,6 +93,8 @@ def _select(img, factor, num_mips, op, ctx):
     raise NotImplementedError("igneous_b200 pooling: factors must be 1 or 2 per axis, got %r" % (factor,))
   num_mips = int(num_mips)
   img = np.asarray(img)
+  if op not in (_OP_STRIDE, _OP_MODE):  # min / max / averages / sparse modes order or add values
+    _shim.require_unsigned(img.dtype, "min / max / average / sparse pooling")
   if num_mips < 1:
     return []
   arr = np.asfortranarray(img)

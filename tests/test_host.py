@@ -2,6 +2,7 @@
 import ctypes as c
 
 import numpy as np
+import pytest
 
 from igneous_b200 import _shim
 
@@ -96,3 +97,29 @@ def test_storage_standin_roundtrip(tmp_path):
     with pytest.raises(EmptyVolumeException):
       cv2[cv2.meta.bounds(0)]
     assert CloudVolume(path, fill_missing=True)[cv2.meta.bounds(0)].shape == data.shape
+
+
+def test_ccl_face_files_refuse_foreign_formats():
+  """faces are never written under the reference's crackle names, and a crackle
+  stream (or anything else foreign) is refused with a clear error instead of being mis-decoded."""
+  from igneous_b200.tasks import ccl as C
+  face = np.arange(12, dtype=np.uint64).reshape(3, 4)
+  assert np.array_equal(C._decode_face(C._encode_face(face)), face)
+  assert C.FACE_SUFFIX != ".ckl"
+  with pytest.raises(C.ForeignFaceFormat, match="crackle"):
+    C._decode_face(b"crkl\x00\x8a\x00" + b"\x00" * 32, "0-0-0-xy.ckl")
+  with pytest.raises(C.ForeignFaceFormat):
+    C._decode_face(b"\x1f\x8b garbage")
+
+
+def test_signed_dtypes_refused_where_order_matters():
+  """int8..int64 alias the unsigned kernels, which is exact only for equality-only
+  operations; averaging, min / max pooling and thresholded CCL must refuse them loudly."""
+  from igneous_b200 import tinybrain, cc3d
+  img = np.full((4, 4, 2), -3, dtype=np.int16)
+  for fn in (tinybrain.downsample_with_averaging, tinybrain.downsample_with_min_pooling,
+             tinybrain.downsample_with_max_pooling):
+    with pytest.raises(NotImplementedError, match="signed"):
+      fn(img, (2, 2, 1), num_mips=1)
+  with pytest.raises(NotImplementedError, match="signed"):
+    cc3d.ccl_task(img, (3, 3, 1), threshold_gte=0)

@@ -119,7 +119,7 @@ def test_ccl_tasks_checker(ctx, tmp_path, upper, dust_threshold):
   _run_ccl(path, dest, (128, 128, 128), threshold_lte=upper, dust_threshold=dust_threshold)
   cf = CloudFiles(path)
   faces = cf.list("1_1_1/ccl/faces")
-  want_faces = sorted("1_1_1/ccl/faces/%d-%d-0-%s.ckl" % (x, y, k) for x in range(4) for y in range(4)
+  want_faces = sorted("1_1_1/ccl/faces/%d-%d-0-%s.npy" % (x, y, k) for x in range(4) for y in range(4)
                       for k in ("xy", "xz", "yz"))
   assert sorted(faces) == want_faces
   assert sorted(cf.list("1_1_1/ccl/equivalences")) == sorted(
