@@ -7,3 +7,26 @@ first use (`igneous_b200._shim.load()`), and compute calls raise if it or a
 CUDA device is missing -- there is no CPU fallback.
 """
 __version__ = "0.1.0"
+
+
+# The import surface of igneous/__init__.py:1-4 (`from igneous import DownsampleTask, MeshTask,
+# Mesher, LocalTaskQueue, CloudVolume ...`, used by test/test_tasks.py:18-23), resolved lazily so
+# that importing the package stays free of side effects (no native library, no storage layer).
+_TASK_NAMES = ("DownsampleTask", "TransferTask", "CCLFacesTask", "CCLEquivalancesTask", "RelabelCCLTask",
+               "create_relabeling", "clean_intermediate_files", "MeshTask", "downsample_and_upload",
+               "downsample_method_to_fn", "threshold_image", "blackout_non_face_rails", "DisjointSet")
+_COMPAT_NAMES = ("CloudVolume", "EmptyVolumeException", "LocalTaskQueue", "RegisteredTask", "queueable")
+__all__ = ["Mesher", "__version__"] + list(_TASK_NAMES) + list(_COMPAT_NAMES)
+
+
+def __getattr__(name):
+  if name == "Mesher":
+    from .zmesh import Mesher
+    return Mesher
+  if name in _TASK_NAMES:
+    from . import tasks
+    return getattr(tasks, name)
+  if name in _COMPAT_NAMES:
+    from . import _compat
+    return getattr(_compat, name)
+  raise AttributeError("module 'igneous_b200' has no attribute %r" % name)

@@ -49,7 +49,7 @@
 #include <type_traits>
 #include <vector>
 
-#include "common.cuh"
+#include "group.h"
 
 namespace ign {
 
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(MT_THREADS)
     const uint32_t x0 = tx * MT_BX, y0 = ty * MT_BY, z0 = tz * MT::BZ;
     // next tile of this CTA (its coordinates replace tx/ty/tz from here on)
     const uint64_t tn = advance(t + gridDim.x);
-    T* tile = buf[cur];
+    T* tile = (T*)(mt_smem + (size_t)cur * MT::BYTES);
     if constexpr (TMA) {
       if (tid == 0 && tn < ntiles) {  // the other buffer was released by the barrier that ended the previous iteration
         mbar_expect_tx(&bars[cur ^ 1u], (uint32_t)(MT::ELEMS * sizeof(T)));
@@ -248,56 +248,53 @@ __global__ void __launch_bounds__(MT_THREADS)
       if constexpr (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
     }
-    // ---- masks: warp w owns plane w % BZ; with BZ = 4 the two warps of a plane split its rows
+    // ---- masks: warp w owns plane w % BZ and RPW of its rows.  Straight-line code: rows /
+    // planes outside the volume are zero in the tile, so only the STORES are predicated and
+    // every ballot runs in converged code.
     {
       constexpr int WPP = (MT_THREADS / 32) / MT::BZ;  // warps per plane
       constexpr int RPW = MT_BY / WPP;                 // rows per warp
+      constexpr int NXW = MT_BX / 32;
+      constexpr uint32_t PLANE = (MT_BY + 1) * MT::PITCH;
+      const T* ts = (const T*)(mt_smem + (size_t)cur * MT::BYTES);  // shared-space addressing
       const uint32_t iz = warp % MT::BZ + 1;
       const uint32_t ry0 = (warp / MT::BZ) * RPW;
       const uint32_t gz = z0 + iz - 1;
-      if (gz < a.sz) {
-        constexpr int NXW = MT_BX / 32;
-        T upv[NXW];  // the previous row of this warp stays in registers
-        {
-          const T* rup = tile + ((size_t)iz * (MT_BY + 1) + ry0) * MT::PITCH + MT::HX;
+      const uint32_t e0 = (iz * (MT_BY + 1) + ry0) * MT::PITCH + MT::HX + lane;  // row above the warp's first row
+      T upv[NXW];  // the previous row stays in registers
 #pragma unroll
-          for (int xw = 0; xw < NXW; xw++) upv[xw] = rup[xw * 32 + lane];
+      for (int xw = 0; xw < NXW; xw++) upv[xw] = ts[e0 + xw * 32];
+      const uint32_t w0 = x0 / 32;
+      const bool vec_ok = (a.wpr % NXW == 0);  // 16-byte aligned mask rows: one vector store per mask
+#pragma unroll
+      for (int k = 0; k < RPW; k++) {
+        const uint32_t e = e0 + (k + 1) * MT::PITCH;
+        uint32_t bS[NXW], bZ[NXW], bY[NXW], bB[NXW];
+#pragma unroll
+        for (int xw = 0; xw < NXW; xw++) {
+          const T v = ts[e + xw * 32], left = ts[e + xw * 32 - 1], back = ts[e + xw * 32 - PLANE];
+          const bool nz = v != (T)0;
+          bS[xw] = __ballot_sync(FULL, nz && v != left);
+          bZ[xw] = __ballot_sync(FULL, nz);
+          bY[xw] = __ballot_sync(FULL, nz && v == upv[xw]);
+          bB[xw] = __ballot_sync(FULL, nz && v == back);
+          upv[xw] = v;
         }
-        const uint32_t w0 = x0 / 32;
-        const bool vec_ok = (a.wpr % NXW == 0);  // 16-byte aligned mask rows: one vector store per mask
-#pragma unroll 2
-        for (uint32_t k = 0; k < (uint32_t)RPW; k++) {
-          const uint32_t iy = ry0 + k + 1, gy = y0 + iy - 1;
-          if (gy >= a.sy) break;
-          const T* row = tile + ((size_t)iz * (MT_BY + 1) + iy) * MT::PITCH + MT::HX;
-          const T* rbk = row - (size_t)(MT_BY + 1) * MT::PITCH;
-          uint32_t bS[NXW], bZ[NXW], bY[NXW], bB[NXW];
+        const uint32_t gy = y0 + ry0 + k;
+        if (lane == 0 && gz < a.sz && gy < a.sy) {
+          const uint64_t wi = ((uint64_t)gz * a.sy + gy) * a.wpr + w0;
+          if (vec_ok) {
+            static_assert(NXW == 4, "vector stores cover 4 words");
+            *(uint4*)(a.S + wi) = make_uint4(bS[0], bS[1], bS[2], bS[3]);
+            *(uint4*)(a.Z + wi) = make_uint4(bZ[0], bZ[1], bZ[2], bZ[3]);
+            *(uint4*)(a.Ey + wi) = make_uint4(bY[0], bY[1], bY[2], bY[3]);
+            *(uint4*)(a.Ez + wi) = make_uint4(bB[0], bB[1], bB[2], bB[3]);
+          } else {
 #pragma unroll
-          for (int xw = 0; xw < NXW; xw++) {
-            const uint32_t ix = xw * 32 + lane;
-            const T v = row[ix], left = row[(int)ix - 1], back = rbk[ix];
-            const bool nz = v != (T)0;
-            bS[xw] = __ballot_sync(FULL, nz && v != left);
-            bZ[xw] = __ballot_sync(FULL, nz);
-            bY[xw] = __ballot_sync(FULL, nz && v == upv[xw]);
-            bB[xw] = __ballot_sync(FULL, nz && v == back);
-            upv[xw] = v;
-          }
-          if (lane == 0) {
-            const uint64_t wi = ((uint64_t)gz * a.sy + gy) * a.wpr + w0;
-            if (vec_ok) {
-              static_assert(NXW == 4, "vector stores cover 4 words");
-              *(uint4*)(a.S + wi) = make_uint4(bS[0], bS[1], bS[2], bS[3]);
-              *(uint4*)(a.Z + wi) = make_uint4(bZ[0], bZ[1], bZ[2], bZ[3]);
-              *(uint4*)(a.Ey + wi) = make_uint4(bY[0], bY[1], bY[2], bY[3]);
-              *(uint4*)(a.Ez + wi) = make_uint4(bB[0], bB[1], bB[2], bB[3]);
-            } else {
-#pragma unroll
-              for (int xw = 0; xw < NXW; xw++)
-                if (w0 + xw < a.wpr) {
-                  a.S[wi + xw] = bS[xw]; a.Z[wi + xw] = bZ[xw]; a.Ey[wi + xw] = bY[xw]; a.Ez[wi + xw] = bB[xw];
-                }
-            }
+            for (int xw = 0; xw < NXW; xw++)
+              if (w0 + xw < a.wpr) {
+                a.S[wi + xw] = bS[xw]; a.Z[wi + xw] = bZ[xw]; a.Ey[wi + xw] = bY[xw]; a.Ez[wi + xw] = bB[xw];
+              }
           }
         }
       }
@@ -483,9 +480,16 @@ __global__ void __launch_bounds__(TB_THREADS) k_ccl_tiles(const TileArgs a) {
   }
   __syncthreads();
   // ---- flatten; roots take their global id (flagged); every run then stores the global id of its root
+  // (read-only walks: a path-halving write of another thread could otherwise replace an entry
+  // that already holds its root by a mere ancestor)
   for (uint32_t i = tid; i < RL; i += TB_THREADS) {
-    const uint32_t r = uf_find(par, i);
-    if (r != i) par[i] = r;
+    volatile uint32_t* P = par;
+    uint32_t cur = i, p = P[cur];
+    while (p != cur) {
+      cur = p;
+      p = P[cur];
+    }
+    if (cur != i) P[i] = cur;
   }
   __syncthreads();
   for (uint32_t lw = tid; lw < W; lw += TB_THREADS) {
@@ -613,26 +617,28 @@ __device__ __forceinline__ void ex_store4(OUT* dst, const OUT* v) {
 template <typename OUT>
 __global__ void __launch_bounds__(256) k_ccl_expand4(const ExpandArgs a, OUT* __restrict__ out) {
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t groups = (a.wpr + 3) / 4;  // 128-voxel groups per row
-  const uint64_t total = a.rows * groups;
-  const uint64_t g0 = ((blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5) * EX_G;
-  if (g0 >= total) return;
+  // a warp owns EX_G consecutive 128-voxel groups of ONE row (chunk c of the row)
+  const uint32_t gpr = (a.wpr + 3) / 4;               // groups per row
+  const uint32_t cpr = (gpr + EX_G - 1) / EX_G;       // warp chunks per row
+  const uint64_t wid = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t row = wid / cpr;
+  if (row >= a.rows) return;
+  const uint32_t chunk = (uint32_t)(wid - row * cpr);
   const uint32_t b0 = (lane & 7u) * 4;
+  const uint32_t xw0 = chunk * (EX_G * 4) + (lane >> 3);
+  const uint32_t* Sr = a.S + row * a.wpr;
+  const uint32_t* Zr = a.Z + row * a.wpr;
+  const uint32_t* Rr = a.rbase + row * a.wpr;
+  OUT* orow = out + row * a.sx;
   uint32_t S[EX_G], Z[EX_G], rb[EX_G], lab[EX_G], idx0[EX_G];
-  uint64_t at[EX_G];
   bool ok[EX_G];
 #pragma unroll
   for (int g = 0; g < EX_G; g++) {
-    const uint64_t gi = g0 + g;
-    const uint64_t row = gi / groups;
-    const uint32_t xw = (uint32_t)(gi - row * groups) * 4 + (lane >> 3);
-    const uint32_t x = xw * 32 + b0;
-    ok[g] = gi < total && xw < a.wpr && x < a.sx;  // sx % 4 == 0: a quad is all in or all out
-    const uint64_t wi = row * a.wpr + xw;
-    at[g] = row * a.sx + x;
-    S[g] = ok[g] ? a.S[wi] : 0u;
-    Z[g] = ok[g] ? a.Z[wi] : 0u;
-    rb[g] = ok[g] ? a.rbase[wi] : 0u;
+    const uint32_t xw = xw0 + g * 4;
+    ok[g] = xw < a.wpr && xw * 32 + b0 < a.sx;  // sx % 4 == 0: a quad is all in or all out
+    S[g] = ok[g] ? Sr[xw] : 0u;
+    Z[g] = ok[g] ? Zr[xw] : 0u;
+    rb[g] = ok[g] ? Rr[xw] : 0u;
   }
 #pragma unroll
   for (int g = 0; g < EX_G; g++) {  // the label of the first non-zero voxel of the quad (usually of all four)
@@ -668,7 +674,7 @@ __global__ void __launch_bounds__(256) k_ccl_expand4(const ExpandArgs a, OUT* __
         v[j] = o;
       }
     }
-    ex_store4(out + at[g], v);
+    ex_store4(orow + (xw0 + g * 4) * 32 + b0, v);
   }
 }
 
@@ -800,6 +806,31 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
+}
+
+// multi-GPU merge on the device: the equivalences between two facing planes go straight into
+// a union-find over the dataset-wide provisional ids (offset + volume-local id)
+__global__ void __launch_bounds__(256)
+    k_ccl_link_union(const uint64_t* __restrict__ va, const uint32_t* __restrict__ la, uint32_t offa,
+                     const uint64_t* __restrict__ vb, const uint32_t* __restrict__ lb, uint32_t offb,
+                     uint64_t nplane, uint32_t* parent) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= nplane) return;
+  const uint64_t v = va[i];
+  if (v == 0 || v != vb[i]) return;
+  // runs of the same pair along x unite once
+  if (i > 0 && la[i - 1] == la[i] && lb[i - 1] == lb[i] && va[i - 1] == v && vb[i - 1] == v) return;
+  uf_union(parent, offa + la[i], offb + lb[i]);
+}
+__global__ void __launch_bounds__(256) k_iota_u32(uint32_t* p, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+// parent[i] (flattened) -> rank of its root; id 0 is a root of its own and ranks 0
+__global__ void __launch_bounds__(256)
+    k_ccl_rank_of_root(uint32_t* parent, const uint32_t* __restrict__ rank, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) parent[i] = rank[parent[i]];
 }
 
 // ------------------------------------------------------------- host driver
@@ -1022,8 +1053,8 @@ static int launch_expand(ign_ctx* ctx, const CclPlan& p, uint64_t offset, void* 
                          uint64_t max_label) {
   const ExpandArgs e = p.expand_args(offset);
   const bool vec = (p.sx % 4 == 0) && ((uintptr_t)out % 16 == 0);
-  const uint64_t items = vec ? e.rows * ((p.wpr + 3) / 4) : e.rows * p.wpr;  // 128-voxel groups / words
-  const uint64_t warps = (items + EX_G - 1) / EX_G;
+  // vector path: a warp owns EX_G 128-voxel groups of one row; scalar path: EX_G consecutive words
+  const uint64_t warps = vec ? e.rows * (((p.wpr + 3) / 4 + EX_G - 1) / EX_G) : (e.rows * p.wpr + EX_G - 1) / EX_G;
   IGN_REQUIRE(warps * 32 / 256 < 0x7FFFFFFFull, IGN_ERR_OVERFLOW, "CCL expand grid too large");
   const unsigned grid = blocks_for(warps * 32, 256);
   switch (out_dtype) {
@@ -1213,6 +1244,94 @@ static int volume_begin_typed(ign_ctx* ctx, ign_ccl_volume* v, uint64_t sx, uint
     }
     IGN_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  return IGN_OK;
+}
+
+static int grow(char** buf, size_t* have, size_t need) {
+  if (*have >= need) return IGN_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *have = 0;
+  const size_t want = need + need / 4;
+  cudaError_t e = cudaMalloc((void**)buf, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("multi-GPU CCL: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    return IGN_ERR_NOMEM;
+  }
+  *have = want;
+  return IGN_OK;
+}
+
+// One rank's share of a CCL over a dataset that is split into z-slabs (rank r above rank r-1).
+// Exactly ONE collective: an all-gather of [n_local | first plane | last plane]; linking the
+// N-1 boundaries, the replicated union-find and the relabelling all run on the device.
+template <typename T>
+static int ccl_sharded_typed(ign_group* g, ign_ccl_volume* v, uint64_t sx, uint64_t sy, uint64_t sz, void* out,
+                             int out_dtype, uint64_t* n_global) {
+  ign_ctx* ctx = g->ctx;
+  const int N = g->nranks, me = g->rank;
+  const uint64_t np = sx * sy;
+  const size_t rec = 256 + 2 * np * 8 + 2 * np * 4;
+  IGN_TRY(grow(&g->d_send, &g->send_bytes, rec));
+  IGN_TRY(grow(&g->d_recv, &g->recv_bytes, rec * (size_t)N));
+  uint64_t* first_v = (uint64_t*)(g->d_send + 256);
+  uint64_t* last_v = first_v + np;
+  uint32_t* first_l = (uint32_t*)(last_v + np);
+  uint32_t* last_l = first_l + np;
+  IGN_TRY(volume_begin_typed<T>(ctx, v, sx, sy, sz, first_v, first_l, last_v, last_l));
+  CclPlan& p = v->plan;
+  uint64_t head[32] = {0};
+  head[0] = v->n_local;
+  IGN_TRY(small_h2d(ctx, g->d_send, head, 256));
+  IGN_TRY(ign_group_allgather(g, g->d_send, rec, g->d_recv));
+  std::vector<uint64_t> nloc(N, 0);
+  for (int r = 0; r < N; r++) IGN_TRY(small_d2h(ctx, &nloc[r], g->d_recv + (size_t)r * rec, 8));
+  IGN_TRY(small_sync(ctx));
+  std::vector<uint64_t> off(N + 1, 0);
+  for (int r = 0; r < N; r++) off[r + 1] = off[r] + nloc[r];
+  const uint64_t total = off[N];
+  IGN_REQUIRE(total < 0x7FFFFFF0ull, IGN_ERR_OVERFLOW, "multi-GPU CCL: too many provisional components");
+  const uint32_t items = (uint32_t)total + 2;  // ids 0..total and one sentinel
+  const size_t cubb = ccl_cub_bytes(items);
+  IGN_TRY(grow(&g->d_solve, &g->solve_bytes, 2 * align_up((size_t)items * 4, 256) + align_up(cubb, 256)));
+  uint32_t* parent = (uint32_t*)g->d_solve;
+  uint32_t* rank = (uint32_t*)(g->d_solve + align_up((size_t)items * 4, 256));
+  void* tmp = g->d_solve + 2 * align_up((size_t)items * 4, 256);
+  IGN_LAUNCH(ctx, k_iota_u32, blocks_for(items, 256), 256, 0, parent, items);
+  for (int b = 0; b + 1 < N; b++) {
+    const char* ra = g->d_recv + (size_t)b * rec;
+    const char* rb = g->d_recv + (size_t)(b + 1) * rec;
+    const uint64_t* va = (const uint64_t*)(ra + 256) + np;                     // last plane of rank b
+    const uint32_t* la = (const uint32_t*)(ra + 256 + 2 * np * 8) + np;
+    const uint64_t* vb = (const uint64_t*)(rb + 256);                          // first plane of rank b+1
+    const uint32_t* lb = (const uint32_t*)(rb + 256 + 2 * np * 8);
+    IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, k_ccl_link_union, blocks_for(np, 256), 256, 0, va, la, (uint32_t)off[b], vb, lb,
+                    (uint32_t)off[b + 1], np, parent);
+  }
+  // roots in ascending id order: the exclusive scan is the dataset-wide cc3d numbering
+  IGN_LAUNCH(ctx, k_ccl_flatten, blocks_for(items - 1, 256), 256, 0, parent, items - 1);
+  IGN_CUDA(cudaMemsetAsync(parent + (items - 1), 0xFF, 4, ctx->stream));  // sentinel: not a root
+  {
+    IsRootOp op;
+    op.parent = parent;
+    auto it = thrust::make_transform_iterator(thrust::counting_iterator<uint32_t>(0), op);
+    size_t tb = cubb;
+    IGN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, it, rank, (int)items, ctx->stream));
+    ctx->launches += 2;
+  }
+  uint32_t hN = 0;
+  IGN_TRY(small_d2h(ctx, &hN, rank + (items - 1), 4));  // roots incl. id 0
+  IGN_LAUNCH(ctx, k_ccl_rank_of_root, blocks_for(items - 1, 256), 256, 0, parent, rank, items - 1);
+  const uint64_t nglob_max = total;
+  if (p.R > 0) {
+    IGN_LAUNCH(ctx, k_ccl_relabel_runs, blocks_for(p.R, 256), 256, 0, p.label, p.R, (const uint32_t*)parent + off[me]);
+    IGN_TRY(launch_expand(ctx, p, 0, out, out_dtype, nglob_max));
+  } else {
+    IGN_CUDA(cudaMemsetAsync(out, 0, sx * sy * sz * dtype_size(out_dtype), ctx->stream));
+  }
+  IGN_TRY(small_sync(ctx));
+  if (n_global) *n_global = hN ? hN - 1 : 0;
   return IGN_OK;
 }
 
@@ -1490,6 +1609,31 @@ int ign_ccl6_volume_dev(ign_ctx* ctx, const void* in, int in_dtype, uint64_t sx,
   IGN_TRY(ign_ccl6_volume_finish_dev(v, nullptr, n, out, out_dtype));
   if (n_components) *n_components = n;
   return IGN_OK;
+}
+
+
+int ign_ccl6_sharded_dev(ign_group* g, const void* in, int in_dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+                         void* out, int out_dtype, uint64_t* n_global) {
+  IGN_REQUIRE(g && in && out, IGN_ERR_INVALID, "null argument");
+  ign_ctx* ctx = g->ctx;
+  IGN_TRY(activate(ctx));
+  IGN_TRY(check_ccl_dims(sx, sy, sz));
+  IGN_REQUIRE(dtype_size(out_dtype) > 0, IGN_ERR_UNSUPPORTED, "unsupported out dtype");
+  IGN_REQUIRE(ctx->scratch_used == 0, IGN_ERR_INVALID, "sharded CCL must own the scratch arena");
+  ign_ccl_volume v;
+  v.ctx = ctx;
+  v.in = in;
+  v.in_dtype = in_dtype;
+  int rc;
+  switch (in_dtype) {
+    case IGN_U8: rc = ccl_sharded_typed<uint8_t>(g, &v, sx, sy, sz, out, out_dtype, n_global); break;
+    case IGN_U16: rc = ccl_sharded_typed<uint16_t>(g, &v, sx, sy, sz, out, out_dtype, n_global); break;
+    case IGN_U32: rc = ccl_sharded_typed<uint32_t>(g, &v, sx, sy, sz, out, out_dtype, n_global); break;
+    case IGN_U64: rc = ccl_sharded_typed<uint64_t>(g, &v, sx, sy, sz, out, out_dtype, n_global); break;
+    default: set_error("sharded CCL: unsupported input dtype %d", in_dtype); rc = IGN_ERR_UNSUPPORTED;
+  }
+  scratch_reset(ctx);
+  return rc;
 }
 
 }  // extern "C"

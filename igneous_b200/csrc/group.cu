@@ -4,7 +4,7 @@
 // NCCL is resolved with dlopen at first use; nothing links against it.
 #include <dlfcn.h>
 
-#include "common.cuh"
+#include "group.h"
 
 namespace {
 
@@ -59,12 +59,6 @@ int nccl_fail(const char* what, int rc) {
 
 }  // namespace
 
-struct ign_group {
-  ign_ctx* ctx;
-  nccl_comm_t comm;
-  int rank, nranks;
-};
-
 using namespace ign;
 
 extern "C" {
@@ -89,7 +83,9 @@ int ign_group_init(ign_ctx* ctx, int rank, int nranks, const void* id128, ign_gr
   g->ctx = ctx;
   g->rank = rank;
   g->nranks = nranks;
-  const int rc = g_nccl.init_rank(&g->comm, nranks, uid, rank);
+  g->d_send = g->d_recv = g->d_solve = nullptr;
+  g->send_bytes = g->recv_bytes = g->solve_bytes = 0;
+  const int rc = g_nccl.init_rank((nccl_comm_t*)&g->comm, nranks, uid, rank);
   if (rc != 0) {
     delete g;
     return nccl_fail("ncclCommInitRank", rc);
@@ -100,7 +96,11 @@ int ign_group_init(ign_ctx* ctx, int rank, int nranks, const void* id128, ign_gr
 
 int ign_group_destroy(ign_group* g) {
   if (!g) return IGN_OK;
-  if (g_nccl.destroy) g_nccl.destroy(g->comm);
+  if (g_nccl.destroy) g_nccl.destroy((nccl_comm_t)g->comm);
+  cudaSetDevice(g->ctx->device);
+  if (g->d_send) cudaFree(g->d_send);
+  if (g->d_recv) cudaFree(g->d_recv);
+  if (g->d_solve) cudaFree(g->d_solve);
   delete g;
   return IGN_OK;
 }
@@ -108,7 +108,7 @@ int ign_group_destroy(ign_group* g) {
 int ign_group_allgather(ign_group* g, const void* send_dev, uint64_t bytes, void* recv_dev) {
   IGN_REQUIRE(g && send_dev && recv_dev, IGN_ERR_INVALID, "null argument");
   IGN_TRY(activate(g->ctx));
-  const int rc = g_nccl.allgather(send_dev, recv_dev, (size_t)bytes, /*ncclUint8*/ 1, g->comm, g->ctx->stream);
+  const int rc = g_nccl.allgather(send_dev, recv_dev, (size_t)bytes, /*ncclUint8*/ 1, (nccl_comm_t)g->comm, g->ctx->stream);
   if (rc != 0) return nccl_fail("ncclAllGather", rc);
   g->ctx->launches++;  // NCCL's kernel
   return IGN_OK;

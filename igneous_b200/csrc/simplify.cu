@@ -232,10 +232,12 @@ __global__ void __launch_bounds__(256) k_simp_boundary(Simp s) {
 //
 // Labels that do not fit (or have more than 65535 faces / vertices) run the same code
 // on the whole-task arrays in global memory (SM = false).
+// vertex flags: CDIRTY the vertex moved (cached costs of its edges are stale), RDIRTY its ring
+// changed (parked edges around it may be valid now)
 constexpr uint32_t VF_ALIVE = 1, VF_BOUND = 2, VF_CDIRTY = 4, VF_LOSE = 8, VF_DONE = 16, VF_END = 32, VF_RDIRTY = 64;
 constexpr int SL_THREADS = 1024;
-constexpr int SL_WCAP = 128;   // winners validated per batch (a round runs as many batches as it needs)
-constexpr int SL_WQ = 1024;    // winners queued per selection pass
+constexpr int SL_WCAP = 512;  // winners validated per selection pass (a round runs as many passes as it needs)
+constexpr uint32_t WF_BAD = 1, WF_OK = 2;  // winner flags: failed validation / validated
 constexpr int SL_EQ = 96;      // per-warp queue of half-edges whose cost must be (re)computed
 constexpr int SL_LIST_PER = 16;  // list entries per thread held in registers while a list is compacted in place
 
@@ -262,16 +264,18 @@ struct SlArgs {
   double max_err2;
   int max_rounds;
   uint32_t smem_bytes;  // dynamic shared memory of the launch
+  uint32_t* ring;       // [gridDim.x][SL_WCAP * 2 * S_MAXV] ring lists of the round's winners
+  double* wbest;        // [gridDim.x][SL_WCAP][3] placement of the round's winners
+  uint32_t* trace;      // IGN_SIMP_TRACE=1: [round][4] = winners, collapses, alive faces, list length of the largest label
 };
 
 struct SlWin {
-  uint32_t u, v, h, cnt[2];
+  uint32_t u, v, h, cnt[2], keep, flags, pad;
 };
 
 struct SlShared {
   uint32_t work, alive, progress, ncol, nwin, stop, slow, counter;
   SlWin win[SL_WCAP];
-  uint32_t winq[SL_WQ];
 };
 
 template <bool SM>
@@ -283,7 +287,9 @@ struct SlLab {
   uint8_t* fstate;         // bit 7 alive, bits 2c..2c+1 memo of half-edge c
   uint8_t* vflag;
   unsigned long long* key1;
-  idx_t* ring;  // [SL_WCAP][2][S_MAXV] face ids; doubles as the per-warp cost queues of the key pass
+  uint32_t* wq;    // [warps][SL_EQ] per-warp cost queues of the key pass (shared memory)
+  uint32_t* ring;  // [SL_WCAP][2][S_MAXV] face ids of the winners' rings (global memory, per CTA)
+  double* wbest;   // [SL_WCAP][3]
   idx_t *flist, *flist2, *vlist, *vlist2;  // alive lists (flist2 / vlist2: global-memory class only)
 };
 
@@ -318,10 +324,8 @@ __device__ __forceinline__ void sl_post(unsigned long long* key1, uint32_t u, ui
   if (key < *(volatile unsigned long long*)&key1[v]) atomicMin(&key1[v], key);
 }
 
-// s_cost on label-local ids (same arithmetic, same order).  WARP = true: all 32 lanes call
-// with the same (u, v); the three candidate positions are evaluated by three different lanes
-// and shared by shuffles (bit-identical: each value is produced by the same operations).
-template <bool SM, bool WARP>
+// s_cost on label-local ids (same arithmetic, same order)
+template <bool SM>
 __device__ __forceinline__ void sl_cost(const SlArgs& A, const SlLab<SM>& L, uint32_t u, uint32_t v, SEval* e) {
   e->valid = false;
   const bool bu = L.vflag[u] & VF_BOUND, bv = L.vflag[v] & VF_BOUND;
@@ -351,20 +355,7 @@ __device__ __forceinline__ void sl_cost(const SlArgs& A, const SlLab<SM>& L, uin
     const double* pr = u < v ? pv : pu;
     const double kk[3] = {pk[0], pk[1], pk[2]}, rr[3] = {pr[0], pr[1], pr[2]};
     const double mid[3] = {(kk[0] + rr[0]) * 0.5, (kk[1] + rr[1]) * 0.5, (kk[2] + rr[2]) * 0.5};
-    double ck, cr, cm;
-    if (WARP) {
-      const uint32_t sel = (threadIdx.x & 31u) % 3u;
-      const double pt[3] = {sel == 0 ? kk[0] : (sel == 1 ? rr[0] : mid[0]), sel == 0 ? kk[1] : (sel == 1 ? rr[1] : mid[1]),
-                            sel == 0 ? kk[2] : (sel == 1 ? rr[2] : mid[2])};
-      const double c = s_qeval(q, pt);
-      ck = __shfl_sync(0xFFFFFFFFu, c, 0);
-      cr = __shfl_sync(0xFFFFFFFFu, c, 1);
-      cm = __shfl_sync(0xFFFFFFFFu, c, 2);
-    } else {
-      ck = s_qeval(q, kk);
-      cr = s_qeval(q, rr);
-      cm = s_qeval(q, mid);
-    }
+    const double ck = s_qeval(q, kk), cr = s_qeval(q, rr), cm = s_qeval(q, mid);
     cost = ck;
     best[0] = kk[0]; best[1] = kk[1]; best[2] = kk[2];
     if (cr < cost) { cost = cr; best[0] = rr[0]; best[1] = rr[1]; best[2] = rr[2]; }
@@ -409,20 +400,6 @@ __device__ __forceinline__ void sl_others(const uint32_t* a, uint32_t w, uint32_
   if (a[0] == w) { *o1 = a[1]; *o2 = a[2]; }
   else if (a[1] == w) { *o1 = a[2]; *o2 = a[0]; }
   else { *o1 = a[0]; *o2 = a[1]; }
-}
-
-// distinct values among the (x1, x2) of the first n lanes; f1 / f2 flag the first occurrences
-__device__ __forceinline__ uint32_t sl_distinct(uint32_t x1, uint32_t x2, uint32_t n, uint32_t lane, bool* f1,
-                                                bool* f2) {
-  const uint32_t FULL = 0xFFFFFFFFu;
-  const bool have = lane < n;
-  const uint32_t m1 = __match_any_sync(FULL, x1);
-  const uint32_t m2 = __match_any_sync(FULL, x2);
-  *f1 = have && ((int)lane == __ffs(m1) - 1);
-  bool in1 = false;
-  for (uint32_t j = 0; j < n; j++) in1 |= (__shfl_sync(FULL, x1, j) == x2);
-  *f2 = have && ((int)lane == __ffs(m2) - 1) && !in1;
-  return __popc(__ballot_sync(FULL, *f1)) + __popc(__ballot_sync(FULL, *f2));
 }
 
 // drop the dead entries of an alive list (order is irrelevant).  SM: in place, the entries
@@ -520,6 +497,9 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
   int r = 0;
   for (; r < A.max_rounds; r++) {
     if (sh.alive <= L.target) break;  // reached the target before this round
+    // per-round salt: equal-cost edges get a fresh pseudo-random priority every round (a fixed
+    // one lets the same validation failures win again and again: 8738 instead of 454 faces on the
+    // reference's box volume)
     const uint32_t salt = (uint32_t)r * 0x9E3779B9u;
     // ---- P1
     for (uint32_t i = tid; i < nV; i += NT) {
@@ -533,34 +513,36 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
       sh.ncol = 0;
     }
     __syncthreads();
-    // ---- P2: keys of the canonical half-edges.  A warp takes 32 alive faces; the half-edges
-    // whose memoised state was dropped go through a per-warp queue so that the double
-    // precision cost runs on dense lanes; the face's owner lane then posts the keys and
-    // writes the face's state byte (single writer).
+    // ---- P2: keys of the canonical half-edges.  A warp takes 32 alive faces; the half-edges whose memoised state was dropped go through a per-warp queue
+    // so that the double precision cost runs on dense lanes; the face's owner lane then posts
+    // the keys and writes the face's state byte (single writer).
     {
-      uint32_t* wq = (uint32_t*)L.ring + warp * SL_EQ;
+      uint32_t* wq = L.wq + warp * SL_EQ;
       for (uint32_t base = warp * 32; base < nF; base += NT) {
         const uint32_t i = base + lane;
-        uint32_t f = 0, st = 0, a[3] = {0, 0, 0};
+        uint32_t f = 0, st = 0, a[3] = {0, 0, 0}, fl[3] = {0, 0, 0};
         if (i < nF) {
           f = flist[i];
           st = L.fstate[f];
         }
-        const bool act = (st & 0x80u) != 0;
-        uint32_t pend = 0, nst = st;
+        bool act = (st & 0x80u) != 0;
         if (act) {
           a[0] = sl_fget<SM>(L, f, 0); a[1] = sl_fget<SM>(L, f, 1); a[2] = sl_fget<SM>(L, f, 2);
+          fl[0] = L.vflag[a[0]]; fl[1] = L.vflag[a[1]]; fl[2] = L.vflag[a[2]];
+        }
+        uint32_t pend = 0, nst = st;
+        if (act) {
 #pragma unroll
           for (int c = 0; c < 3; c++) {
             const uint32_t u = a[c], v = a[(c + 1) % 3];
+            const uint32_t fe = fl[c] | fl[(c + 1) % 3];
             if (!(u < v)) continue;  // one key per edge
             // memo: 0 unknown, 1 parked (won a round, failed validation), 2 cost cached in
             // ecost, 3 known to exceed max_error.  2 / 3 are dropped when an endpoint moved
             // (CDIRTY), 1 when an endpoint's ring changed (RDIRTY).
             uint32_t es = (st >> (2 * c)) & 3u;
-            const uint32_t fl = (uint32_t)L.vflag[u] | (uint32_t)L.vflag[v];
-            if (es >= 2 && (fl & VF_CDIRTY)) es = 0;
-            else if (es == 1 && (fl & VF_RDIRTY)) es = 0;
+            if (es >= 2 && (fe & VF_CDIRTY)) es = 0;
+            else if (es == 1 && (fe & VF_RDIRTY)) es = 0;
             if (es == 0) {
               pend |= 1u << c;
             } else if (es == 2) {
@@ -589,7 +571,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
             const uint32_t e = wq[j], ef = e >> 2, ec = e & 3u;
             const uint32_t u = sl_fget<SM>(L, ef, (int)ec), v = sl_fget<SM>(L, ef, (int)((ec + 1) % 3));
             SEval ev;
-            sl_cost<SM, false>(A, L, u, v, &ev);
+            sl_cost<SM>(A, L, u, v, &ev);
             uint32_t res = 0xFFFFFFFFu;  // exceeds max_error
             if (ev.valid) {
               const float cf = __double2float_rn(ev.cost);
@@ -632,7 +614,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
       if (k2 > m) sl_vor(L.vflag, a2, VF_LOSE);
     }
     __syncthreads();
-    // ---- P4 + E: winners are queued (marked DONE on both endpoints) and processed in batches
+    // ---- P4 + E: the round's winners (marked DONE on both endpoints), SL_WCAP per pass
     for (;;) {
       if (tid == 0) sh.nwin = 0;
       __syncthreads();
@@ -648,130 +630,168 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
         const uint32_t v = sl_fget<SM>(L, f, (int)((c + 1) % 3));
         if (L.key1[v] != key || (L.vflag[v] & (VF_LOSE | VF_DONE))) continue;
         const uint32_t slot = atomicAdd(&sh.nwin, 1u);
-        if (slot < (uint32_t)SL_WQ) {
-          sh.winq[slot] = hl;
-          sl_vor(L.vflag, a, VF_DONE);
-          sl_vor(L.vflag, v, VF_DONE);
+        if (slot < (uint32_t)SL_WCAP) {
+          sh.win[slot].u = a;
+          sh.win[slot].v = v;
+          sh.win[slot].h = hl;
+          sh.win[slot].cnt[0] = 0;
+          sh.win[slot].cnt[1] = 0;
+          sh.win[slot].flags = 0;
+          sl_vor(L.vflag, a, VF_DONE | VF_END);
+          sl_vor(L.vflag, v, VF_DONE | VF_END);
         }
       }
       __syncthreads();
       const uint32_t total = sh.nwin;
-      const uint32_t nq = total < (uint32_t)SL_WQ ? total : (uint32_t)SL_WQ;
-      for (uint32_t b0 = 0; b0 < nq; b0 += SL_WCAP) {
-        const uint32_t nb = (nq - b0) < (uint32_t)SL_WCAP ? (nq - b0) : (uint32_t)SL_WCAP;
-        if (tid < nb) {
-          const uint32_t hl = sh.winq[b0 + tid];
-          const uint32_t f = hl / 3, c = hl - 3 * f;
-          const uint32_t u = sl_fget<SM>(L, f, (int)c), v = sl_fget<SM>(L, f, (int)((c + 1) % 3));
-          sh.win[tid].u = u;
-          sh.win[tid].v = v;
-          sh.win[tid].h = hl;
-          sh.win[tid].cnt[0] = 0;
-          sh.win[tid].cnt[1] = 0;
-          L.key1[u] = 2ull * tid;  // key1 is dead until P1: it now names the ring list
-          L.key1[v] = 2ull * tid + 1;
-          sl_vor(L.vflag, u, VF_END);
-          sl_vor(L.vflag, v, VF_END);
-        }
-        __syncthreads();
-        // ---- E1: ring lists
-        for (uint32_t i = tid; i < nF; i += NT) {
-          const uint32_t f = flist[i];
-          if (!(L.fstate[f] & 0x80u)) continue;
+      const uint32_t nb = total < (uint32_t)SL_WCAP ? total : (uint32_t)SL_WCAP;
+      if (nb == 0) break;
+      // key1 is dead until the next P1: the winners' entries now name their ring lists
+      for (uint32_t i = tid; i < nb; i += NT) {
+        L.key1[sh.win[i].u] = 2ull * i;
+        L.key1[sh.win[i].v] = 2ull * i + 1;
+      }
+      __syncthreads();
+      // ---- E1: ring lists (global memory, one pass over the alive faces for all winners)
+      for (uint32_t i = tid; i < nF; i += NT) {
+        const uint32_t f = flist[i];
+        if (!(L.fstate[f] & 0x80u)) continue;
 #pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const uint32_t x = sl_fget<SM>(L, f, c);
+          if (!(L.vflag[x] & VF_END)) continue;
+          const uint32_t sl = (uint32_t)L.key1[x];
+          const uint32_t p = atomicAdd(&sh.win[sl >> 1].cnt[sl & 1u], 1u);
+          if (p < (uint32_t)S_MAXV) L.ring[sl * S_MAXV + p] = f;
+        }
+      }
+      __syncthreads();
+      // ---- E2: validation and collapse as dense passes over (winner) and (winner, ring face)
+      // work items -- no warp walks a winner's ring serially.
+      // E2a: placement and cost of every winner (one thread each)
+      for (uint32_t i = tid; i < nb; i += NT) {
+        SEval e;
+        sl_cost<SM>(A, L, sh.win[i].u, sh.win[i].v, &e);
+        uint32_t fl = 0;
+        if (!e.valid || sh.win[i].cnt[0] > (uint32_t)S_MAXV || sh.win[i].cnt[1] > (uint32_t)S_MAXV) fl = WF_BAD;
+        sh.win[i].keep = e.valid ? e.keep : sh.win[i].u;
+        sh.win[i].flags = fl;
+        if (e.valid) {
+          L.wbest[3 * i + 0] = e.p[0]; L.wbest[3 * i + 1] = e.p[1]; L.wbest[3 * i + 2] = e.p[2];
+        }
+      }
+      __syncthreads();
+      // E2b: one flip test per (winner, side, ring entry)
+      for (uint32_t item = tid; item < nb * 64; item += NT) {
+        const uint32_t i = item >> 6, side = (item >> 5) & 1u, j = item & 31u;
+        if (sh.win[i].flags & WF_BAD) continue;
+        if (j >= sh.win[i].cnt[side]) continue;
+        const uint32_t w = side ? sh.win[i].v : sh.win[i].u, other = side ? sh.win[i].u : sh.win[i].v;
+        const uint32_t f = L.ring[(2 * i + side) * S_MAXV + j];
+        const uint32_t a[3] = {sl_fget<SM>(L, f, 0), sl_fget<SM>(L, f, 1), sl_fget<SM>(L, f, 2)};
+        if (a[0] == other || a[1] == other || a[2] == other) continue;  // dies with the edge
+        const double best[3] = {L.wbest[3 * i], L.wbest[3 * i + 1], L.wbest[3 * i + 2]};
+        if (sl_flips<SM>(A, L, a, w, best)) atomicOr(&sh.win[i].flags, WF_BAD);
+      }
+      __syncthreads();
+      // E2c: link condition (one thread per winner: distinct neighbours of both rings, the
+      // common ones, the shared faces)
+      for (uint32_t i = tid; i < nb; i += NT) {
+        if (sh.win[i].flags & WF_BAD) continue;
+        const uint32_t u = sh.win[i].u, v = sh.win[i].v;
+        const uint32_t nfu = sh.win[i].cnt[0], nfv = sh.win[i].cnt[1];
+        uint32_t nu[S_MAXV], nnu = 0, nnv = 0, shared = 0, common = 0;
+        bool ok = true;
+        for (uint32_t j = 0; j < nfu && ok; j++) {
+          const uint32_t f = L.ring[(2 * i) * S_MAXV + j];
+          const uint32_t a[3] = {sl_fget<SM>(L, f, 0), sl_fget<SM>(L, f, 1), sl_fget<SM>(L, f, 2)};
+          if (a[0] == v || a[1] == v || a[2] == v) shared++;
           for (int c = 0; c < 3; c++) {
-            const uint32_t x = sl_fget<SM>(L, f, c);
-            if (!(L.vflag[x] & VF_END)) continue;
-            const uint32_t sl = (uint32_t)L.key1[x];
-            const uint32_t p = atomicAdd(&sh.win[sl >> 1].cnt[sl & 1u], 1u);
-            if (p < (uint32_t)S_MAXV) L.ring[sl * S_MAXV + p] = (idx_t)f;
+            const uint32_t x = a[c];
+            if (x == u) continue;
+            bool seen = false;
+            for (uint32_t t = 0; t < nnu; t++) seen |= (nu[t] == x);
+            if (!seen) {
+              if (nnu >= (uint32_t)S_MAXV) { ok = false; break; }
+              nu[nnu++] = x;
+            }
           }
         }
-        __syncthreads();
-        // ---- E2: one warp validates and applies one winner
-        for (uint32_t slot = warp; slot < nb; slot += NW) {
-          const uint32_t u = sh.win[slot].u, v = sh.win[slot].v, hl = sh.win[slot].h;
-          const uint32_t nfu = sh.win[slot].cnt[0], nfv = sh.win[slot].cnt[1];
-          SEval e;
-          sl_cost<SM, true>(A, L, u, v, &e);
-          bool ok = e.valid && nfu <= (uint32_t)S_MAXV && nfv <= (uint32_t)S_MAXV;  // warp uniform
-          const bool hu = ok && lane < nfu, hv = ok && lane < nfv;
-          uint32_t au[3] = {0, 0, 0}, av[3] = {0, 0, 0}, fu = 0, fv = 0;
-          uint32_t x1 = 0xF0000000u + lane, x2 = 0xF1000000u + lane, y1 = 0xF2000000u + lane,
-                   y2 = 0xF3000000u + lane;
-          if (hu) {
-            fu = L.ring[(2 * slot) * S_MAXV + lane];
-            au[0] = sl_fget<SM>(L, fu, 0); au[1] = sl_fget<SM>(L, fu, 1); au[2] = sl_fget<SM>(L, fu, 2);
-            sl_others(au, u, &x1, &x2);
-          }
-          if (hv) {
-            fv = L.ring[(2 * slot + 1) * S_MAXV + lane];
-            av[0] = sl_fget<SM>(L, fv, 0); av[1] = sl_fget<SM>(L, fv, 1); av[2] = sl_fget<SM>(L, fv, 2);
-            sl_others(av, v, &y1, &y2);
-          }
-          if (ok) {
-            bool f1, f2, g1, g2;
-            const uint32_t nnu = sl_distinct(x1, x2, nfu, lane, &f1, &f2);
-            const uint32_t nnv = sl_distinct(y1, y2, nfv, lane, &g1, &g2);
-            bool c1 = false, c2 = false;
-            for (uint32_t j = 0; j < nfv; j++) {
-              const uint32_t t1 = __shfl_sync(FULL, y1, j), t2 = __shfl_sync(FULL, y2, j);
-              c1 |= (x1 == t1) | (x1 == t2);
-              c2 |= (x2 == t1) | (x2 == t2);
+        uint32_t nv[S_MAXV];
+        for (uint32_t j = 0; j < nfv && ok; j++) {
+          const uint32_t f = L.ring[(2 * i + 1) * S_MAXV + j];
+          const uint32_t a[3] = {sl_fget<SM>(L, f, 0), sl_fget<SM>(L, f, 1), sl_fget<SM>(L, f, 2)};
+          for (int c = 0; c < 3; c++) {
+            const uint32_t x = a[c];
+            if (x == v) continue;
+            bool seen = false;
+            for (uint32_t t = 0; t < nnv; t++) seen |= (nv[t] == x);
+            if (!seen) {
+              if (nnv >= (uint32_t)S_MAXV) { ok = false; break; }
+              nv[nnv++] = x;
+              for (uint32_t t = 0; t < nnu; t++) common += (nu[t] == x);
             }
-            const uint32_t common = __popc(__ballot_sync(FULL, f1 && c1)) + __popc(__ballot_sync(FULL, f2 && c2));
-            const uint32_t shared = __popc(__ballot_sync(FULL, hu && (x1 == v || x2 == v)));
-            bool bad = false;
-            if (hu && x1 != v && x2 != v) bad = sl_flips<SM>(A, L, au, u, e.p);
-            if (hv && y1 != u && y2 != u) bad = bad || sl_flips<SM>(A, L, av, v, e.p);
-            const bool anybad = __any_sync(FULL, bad);
-            ok = nnu <= (uint32_t)S_MAXV && nnv <= (uint32_t)S_MAXV && shared == 2 && common == 2 && !anybad;
           }
-          if (!ok) {  // park the edge until one of its endpoints' rings changes
-            if (lane == 0) {
-              const uint32_t f = hl / 3, c = hl - 3 * f;
-              const uint32_t st = L.fstate[f];
-              L.fstate[f] = (uint8_t)((st & ~(3u << (2 * c))) | (1u << (2 * c)));
-              sl_vclear(L.vflag, u, VF_END);
-              sl_vclear(L.vflag, v, VF_END);
-              atomicOr(&sh.progress, 1u);
-            }
-            continue;
+        }
+        sh.win[i].flags = (ok && shared == 2 && common == 2) ? WF_OK : WF_BAD;
+      }
+      __syncthreads();
+      // E2d: apply.  Ring entries: faces of the removed vertex die (they also hold the kept one)
+      // or get the kept vertex in its corner; every vertex of the new ring is RDIRTY.
+      for (uint32_t item = tid; item < nb * 64; item += NT) {
+        const uint32_t i = item >> 6, side = (item >> 5) & 1u, j = item & 31u;
+        if (!(sh.win[i].flags & WF_OK)) continue;
+        if (j >= sh.win[i].cnt[side]) continue;
+        const uint32_t u = sh.win[i].u, v = sh.win[i].v, k = sh.win[i].keep, rm = (k == u) ? v : u;
+        const uint32_t w = side ? v : u, other = side ? u : v;
+        const uint32_t f = L.ring[(2 * i + side) * S_MAXV + j];
+        const uint32_t a[3] = {sl_fget<SM>(L, f, 0), sl_fget<SM>(L, f, 1), sl_fget<SM>(L, f, 2)};
+        const bool both = (a[0] == other || a[1] == other || a[2] == other);
+        if (both) {
+          if (w == rm) {  // seen once from the removed vertex's side
+            L.fstate[f] = (uint8_t)(L.fstate[f] & 0x7Fu);
+            atomicSub(&sh.alive, 1u);
           }
-          const uint32_t k = e.keep, rm = e.remove;
-          const bool rm_is_u = (rm == u);
-          const bool hr = rm_is_u ? hu : hv;
-          const uint32_t rf = rm_is_u ? fu : fv;
-          const uint32_t r0 = rm_is_u ? au[0] : av[0], r1 = rm_is_u ? au[1] : av[1], r2 = rm_is_u ? au[2] : av[2];
-          // faces of rm: those that also hold k die, the others get k in rm's corner
-          const bool dies = hr && (r0 == k || r1 == k || r2 == k);
-          if (hr) {
-            if (dies) L.fstate[rf] = (uint8_t)(L.fstate[rf] & 0x7Fu);
-            else sl_fset<SM>(L, rf, r0 == rm ? 0 : (r1 == rm ? 1 : 2), k);
-          }
-          const uint32_t dead = __popc(__ballot_sync(FULL, dies));
-          // the new ring of k: parked edges around it may be valid now
-          if (hu && x1 != v && x2 != v) { sl_vor(L.vflag, x1, VF_RDIRTY); sl_vor(L.vflag, x2, VF_RDIRTY); }
-          if (hv && y1 != u && y2 != u) { sl_vor(L.vflag, y1, VF_RDIRTY); sl_vor(L.vflag, y2, VF_RDIRTY); }
+          continue;
+        }
+        if (w == rm) sl_fset<SM>(L, f, a[0] == rm ? 0 : (a[1] == rm ? 1 : 2), k);
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          if (a[c] != w) sl_vor(L.vflag, a[c], VF_RDIRTY);
+      }
+      // winners: the kept vertex moves and absorbs the quadric; failures park their edge
+      for (uint32_t i = tid; i < nb; i += NT) {
+        const uint32_t u = sh.win[i].u, v = sh.win[i].v;
+        if (sh.win[i].flags & WF_OK) {
+          const uint32_t k = sh.win[i].keep, rm = (k == u) ? v : u;
+          double* pk = A.pos + 3 * (uint64_t)(L.vbase + k);
+          pk[0] = L.wbest[3 * i]; pk[1] = L.wbest[3 * i + 1]; pk[2] = L.wbest[3 * i + 2];
           double* Qk = A.Q + 10 * (uint64_t)(L.vbase + k);
           const double* Qr = A.Q + 10 * (uint64_t)(L.vbase + rm);
-          if (lane < 10) Qk[lane] = Qk[lane] + Qr[lane];
-          if (lane == 0) {
-            double* pk = A.pos + 3 * (uint64_t)(L.vbase + k);
-            pk[0] = e.p[0]; pk[1] = e.p[1]; pk[2] = e.p[2];
-            sl_vor(L.vflag, k, VF_CDIRTY | VF_RDIRTY);  // k moved: cached costs of its edges are stale
-            sl_vclear(L.vflag, k, VF_END);
-            sl_vclear(L.vflag, rm, 0xFFu);
-            atomicSub(&sh.alive, dead);
-            atomicAdd(&sh.ncol, 1u);
-            atomicOr(&sh.progress, 1u);
-          }
+#pragma unroll
+          for (int q = 0; q < 10; q++) Qk[q] = Qk[q] + Qr[q];
+          sl_vor(L.vflag, k, VF_CDIRTY | VF_RDIRTY);  // k moved: cached costs of its edges are stale
+          sl_vclear(L.vflag, k, VF_END);
+          sl_vclear(L.vflag, rm, 0xFFu);
+          atomicAdd(&sh.ncol, 1u);
+        } else {  // park the edge until one of its endpoints' rings changes
+          const uint32_t hl = sh.win[i].h, f = hl / 3, c = hl - 3 * f;
+          const uint32_t st = L.fstate[f];
+          L.fstate[f] = (uint8_t)((st & ~(3u << (2 * c))) | (1u << (2 * c)));
+          sl_vclear(L.vflag, u, VF_END);
+          sl_vclear(L.vflag, v, VF_END);
         }
-        __syncthreads();
+        atomicOr(&sh.progress, 1u);
       }
-      if (total <= (uint32_t)SL_WQ) break;
+      __syncthreads();
+      if (total <= (uint32_t)SL_WCAP) break;
     }
     // ---- stop rules of the label
+    if (tid == 0 && A.trace != nullptr && sh.work == 0 && r < 400) {
+      A.trace[4 * r + 0] = sh.progress;
+      A.trace[4 * r + 1] = sh.ncol;
+      A.trace[4 * r + 2] = sh.alive;
+      A.trace[4 * r + 3] = nF;
+    }
     if (tid == 0) {
       uint32_t stop = 0;
       if (!sh.progress) {
@@ -828,20 +848,24 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
     const uint32_t vbase = A.vert_off[l], U = A.vert_off[l + 1] - vbase;
     const uint32_t target = A.target[l];
     if (T == 0 || T <= target) continue;  // init left every face / vertex alive
-    // shared-memory layout: ring lists | key1 | faces SoA | face list | vertex list | face state | vertex flags
-    const size_t ring16 = (size_t)SL_WCAP * 2 * S_MAXV * 2;
-    const size_t o_key = ring16;
+    // shared-memory layout: cost queues | key1 | faces SoA | face list | vertex list | face state | vertex flags
+    const size_t wq_bytes = (size_t)(SL_THREADS / 32) * SL_EQ * 4;
+    const size_t o_key = wq_bytes;
     const size_t o_f0 = o_key + 8 * (size_t)U;
     const size_t o_fl = o_f0 + 6 * (size_t)T;
     const size_t o_vl = o_fl + 2 * (size_t)T;
     const size_t o_fs = o_vl + 2 * (size_t)U;
     const size_t o_vf = (o_fs + T + 3) & ~(size_t)3;
     const size_t need = o_vf + U + 4;
+    uint32_t* ring = A.ring + (size_t)blockIdx.x * ((size_t)SL_WCAP * 2 * S_MAXV);
+    double* wbest = A.wbest + (size_t)blockIdx.x * ((size_t)SL_WCAP * 3);
     const uint32_t cap = (uint32_t)SL_LIST_PER * SL_THREADS;
     if (need <= A.smem_bytes && T <= cap && U <= cap) {
       SlLab<true> L;
       L.T = T; L.U = U; L.tbase = tbase; L.vbase = vbase; L.target = target;
-      L.ring = (uint16_t*)sl_smem;
+      L.wq = (uint32_t*)sl_smem;
+      L.ring = ring;
+      L.wbest = wbest;
       L.key1 = (unsigned long long*)(sl_smem + o_key);
       L.fc0 = (uint16_t*)(sl_smem + o_f0);
       L.fc1 = L.fc0 + T;
@@ -856,7 +880,9 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
     } else {
       SlLab<false> L;
       L.T = T; L.U = U; L.tbase = tbase; L.vbase = vbase; L.target = target;
-      L.ring = (uint32_t*)sl_smem;  // SL_WCAP * 2 * S_MAXV * 4 bytes, always available
+      L.wq = (uint32_t*)sl_smem;  // the cost queues always fit
+      L.ring = ring;
+      L.wbest = wbest;
       L.key1 = A.key1 + vbase;
       L.fc0 = L.fc1 = L.fc2 = nullptr;
       L.flist = A.flist + tbase; L.flist2 = A.flist2 + tbase;
@@ -957,7 +983,8 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
                       3 * align_up(U, 256) + 3 * align_up(U * 4, 256) + align_up(U * 8, 256) +
                       6 * align_up((K + 2) * 4, 256) + align_up(3 * T * 4, 256) +
                       2 * align_up(3 * T * 4, 256) + 2 * align_up(T * 4, 256) + 2 * align_up(U * 4, 256) + tmpb +
-                      (1 << 20);
+                      align_up((size_t)ctx->sm_count * SL_WCAP * 2 * S_MAXV * 4, 256) +
+                      align_up((size_t)ctx->sm_count * SL_WCAP * 3 * 8, 256) + (1 << 20);
   IGN_TRY(scratch_reserve(ctx, need));
   Simp s;
   s.U = U;
@@ -1079,10 +1106,21 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   A.max_rounds = 400;
   // IGN_SIMP_GMEM=1 (test knob): run every label on the global-memory arrays, the path of
   // labels that do not fit shared memory (only the winners' ring lists stay in smem)
+  A.trace = nullptr;
+  if (getenv("IGN_SIMP_TRACE") != nullptr) {
+    A.trace = (uint32_t*)scratch_take(ctx, 400 * 16);
+    if (A.trace) S_CUDA(cudaMemsetAsync(A.trace, 0, 400 * 16, ctx->stream));
+  }
   const char* force_gmem = getenv("IGN_SIMP_GMEM");
-  A.smem_bytes = (force_gmem && force_gmem[0] == '1') ? (uint32_t)(SL_WCAP * 2 * S_MAXV * 4) : (uint32_t)sl_dyn;
+  A.smem_bytes = (force_gmem && force_gmem[0] == '1') ? (uint32_t)((SL_THREADS / 32) * SL_EQ * 4) : (uint32_t)sl_dyn;
   {
     const unsigned grid = (unsigned)(K < (uint64_t)ctx->sm_count ? K : (uint64_t)ctx->sm_count);
+    A.ring = (uint32_t*)scratch_take(ctx, (size_t)grid * SL_WCAP * 2 * S_MAXV * 4);
+    A.wbest = (double*)scratch_take(ctx, (size_t)grid * SL_WCAP * 3 * 8);
+    if (!A.ring || !A.wbest) {
+      set_error("scratch arena too small (simplify: winner ring lists)");
+      return done(IGN_ERR_NOMEM);
+    }
     const int slot = prof_begin(ctx, IGN_PROF_SIMP);
     k_simp_labels<<<grid, SL_THREADS, sl_dyn, ctx->stream>>>(A);
     ctx->launches++;
@@ -1110,6 +1148,12 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   if (hflags[12] != 0) {
     set_error("simplify: a vertex has more than %d incident faces", S_VCAP);
     return done(IGN_ERR_UNSUPPORTED);
+  }
+  if (A.trace) {
+    std::vector<uint32_t> tr(1600);
+    S_CUDA(cudaMemcpy(tr.data(), A.trace, 1600 * 4, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < 400 && (tr[4 * r + 2] || tr[4 * r + 3]); r++)
+      fprintf(stderr, "gpu round %d progress %u collapses %u alive %u list %u\n", r, tr[4 * r], tr[4 * r + 1], tr[4 * r + 2], tr[4 * r + 3]);
   }
   m->simp_rounds = (int)hflags[1];
   m->simp_labels_smem = hflags[2];

@@ -3,14 +3,15 @@ dataset (rank r above rank r-1), and ONE all-gather of the ranks' outer planes
 replaces the face / equivalence / relabel files of
 igneous/tasks/image/ccl.py:177-194, :245-294 and :358-420.
 
-  1. each rank resolves its own volume (ign_ccl6_volume_begin_dev) and exposes
-     its first and last z-plane as (voxel value, volume-local id);
+  1. each rank resolves its own volume and exposes its first and last z-plane
+     as (voxel value, volume-local id);
   2. all ranks all-gather [n_local | first plane | last plane]  (NCCL over
      NVLink / NVSwitch; ~48 MB per rank for 2048^2 planes);
-  3. every rank links the N-1 rank boundaries (device kernel on the gathered
-     planes), solves the identical small union-find on the host
-     (ign_ccl6_solve: smaller id wins) and labels its slab once with the composed
-     table (ign_ccl6_volume_finish_dev).
+  3. every rank links the N-1 rank boundaries straight into a union-find over the
+     dataset-wide provisional ids (k_ccl_link_union), solves it (smaller id wins,
+     final ids by ascending minimum) and expands its slab once -- all on the device,
+     inside ign_ccl6_sharded_dev.  solve_global / solve_pairs / link_planes_numpy
+     below are the host statement of the same steps (CPU tests, world_size-2 gloo).
 The result is bit-identical to one whole-volume cc3d call on the stacked
 dataset.  Downsampling and meshing need no communication (replicas).
 """
@@ -99,51 +100,13 @@ class Group:
     return self._bufs
 
   def ccl_sharded(self, pipe, _unused=None):
-    """CCL of pipe.d_in (this rank's slab) -> pipe.d_cc with dataset-wide ids;
-    returns the global number of components."""
-    ctx, lib = self.ctx, self.lib
+    """CCL of pipe.d_in (this rank's slab) -> pipe.d_cc with dataset-wide ids; returns the
+    global number of components.  One C call (ign_ccl6_sharded_dev): local CCL, ONE NCCL
+    all-gather of the boundary planes, then linking, the replicated union-find and the
+    relabelling on the device of every rank."""
     sx, sy, sz = pipe.shape
-    npl = sx * sy
-    rec, send, recv = self._buffers(npl)
-    base = send.ptr
-    p_first_v, p_last_v = base + 256, base + 256 + npl * 8
-    p_first_l, p_last_l = base + 256 + 2 * npl * 8, base + 256 + 2 * npl * 8 + npl * 4
-    h = c.c_void_p()
-    n_local = c.c_uint64(0)
-    _shim.check(lib.ign_ccl6_volume_begin_dev(
-      ctx.handle, _shim.ptr(pipe.d_in), c.c_int(pipe.code), c.c_uint64(sx), c.c_uint64(sy), c.c_uint64(sz),
-      c.c_void_p(p_first_v), c.c_void_p(p_first_l), c.c_void_p(p_last_v), c.c_void_p(p_last_l),
-      c.byref(h), c.byref(n_local)))
-    try:
-      head = np.zeros(32, dtype=np.uint64)
-      head[0] = n_local.value
-      ctx.h2d(send, head)
-      _shim.check(lib.ign_group_allgather(self.handle, _shim.ptr(send), c.c_uint64(rec), _shim.ptr(recv)))
-      heads = np.zeros((self.world, 32), dtype=np.uint64)
-      for r in range(self.world):
-        ctx.d2h(heads[r], recv.ptr + r * rec, 256)
-      ctx.sync()
-      n_locals = [int(heads[r, 0]) for r in range(self.world)]
-
-      def link(r, off_lo, off_hi):
-        a, b = recv.ptr + r * rec, recv.ptr + (r + 1) * rec
-        args = (ctx.handle, c.c_void_p(a + 256 + npl * 8), c.c_void_p(a + 256 + 2 * npl * 8 + npl * 4),
-                c.c_uint64(off_lo), c.c_void_p(b + 256), c.c_void_p(b + 256 + 2 * npl * 8), c.c_uint64(off_hi),
-                c.c_uint64(npl))
-        cnt = c.c_uint64(0)
-        _shim.check(lib.ign_ccl6_link_dev(*args, None, c.c_uint64(0), c.byref(cnt)))  # count
-        out = np.zeros((int(cnt.value), 2), dtype=np.uint64)
-        if cnt.value:
-          _shim.check(lib.ign_ccl6_link_dev(*args, _shim.ptr(out), c.c_uint64(cnt.value), c.byref(cnt)))
-        return out
-
-      offs, lut, n_global = solve_global(n_locals, link, solve_pairs)
-      lo = int(offs[self.rank])
-      mine = np.zeros(n_locals[self.rank] + 1, dtype=np.uint32)  # volume-local id -> dataset id
-      mine[1:] = lut[lo + 1:lo + n_locals[self.rank] + 1]
-    except Exception:
-      lib.ign_ccl6_volume_abort(h)
-      raise
-    _shim.check(lib.ign_ccl6_volume_finish_dev(h, _shim.ptr(mine), c.c_uint64(n_global), _shim.ptr(pipe.d_cc),
-                                               c.c_int(_shim.dtype_code(pipe.ccl_out_dtype))))
-    return n_global
+    n = c.c_uint64(0)
+    _shim.check(self.lib.ign_ccl6_sharded_dev(
+      self.handle, _shim.ptr(pipe.d_in), c.c_int(pipe.code), c.c_uint64(sx), c.c_uint64(sy), c.c_uint64(sz),
+      _shim.ptr(pipe.d_cc), c.c_int(_shim.dtype_code(pipe.ccl_out_dtype)), c.byref(n)))
+    return int(n.value)

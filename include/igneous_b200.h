@@ -265,6 +265,27 @@ IGN_API int ign_mesh_export(ign_mesher* m, const float resolution[3], int voxel_
                             uint64_t* face_offsets);
 IGN_API int ign_mesh_free(ign_mesher* m);
 
+/* ------------------------------------------------- compressed_segmentation codec
+ * The Precomputed `compressed_segmentation` chunk encoding that CloudVolume applies on the host
+ * before uploading / after downloading a segmentation chunk around the hot path
+ * (igneous/tasks/image/image.py:95-100 `vol[new_bounds] = mipped`, ccl.py:346-356 RelabelCCLTask's
+ * output, igneous/task_creation/common.py:215-236 set_encoding).  labels: Fortran order [x,y,z,c],
+ * uint32 / uint64; block (bx,by,bz) is (8,8,8) in every Precomputed layer.  The stream is the
+ * uint32 word sequence of the file.  encode: *n_words = words needed; nothing is written when
+ * out is NULL or cap_words is too small.  One call = one chunk (24-bit table offsets). */
+IGN_API int ign_cseg_encode(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx, uint64_t sy, uint64_t sz,
+                            uint64_t sc, uint32_t bx, uint32_t by, uint32_t bz, uint32_t* out,
+                            uint64_t cap_words, uint64_t* n_words);
+IGN_API int ign_cseg_encode_dev(ign_ctx* ctx, const void* labels, int dtype, uint64_t sx, uint64_t sy,
+                                uint64_t sz, uint64_t sc, uint32_t bx, uint32_t by, uint32_t bz,
+                                uint32_t* out, uint64_t cap_words, uint64_t* n_words);
+IGN_API int ign_cseg_decode(ign_ctx* ctx, const uint32_t* in, uint64_t n_words, int dtype, uint64_t sx,
+                            uint64_t sy, uint64_t sz, uint64_t sc, uint32_t bx, uint32_t by, uint32_t bz,
+                            void* out);
+IGN_API int ign_cseg_decode_dev(ign_ctx* ctx, const uint32_t* in, uint64_t n_words, int dtype, uint64_t sx,
+                                uint64_t sy, uint64_t sz, uint64_t sc, uint32_t bx, uint32_t by,
+                                uint32_t bz, void* out);
+
 /* --------------------------------------------------- synthetic volumes (bench)
  * jittered-grid Voronoi segmentation / hash-byte image,
  * bit-identical to oracle.synth_seg / oracle.synth_image. */
@@ -288,6 +309,14 @@ IGN_API int ign_group_destroy(ign_group* g);
 /* the single collective of the path: every rank contributes `bytes` bytes (its
  * component count + outer planes), everyone receives nranks*bytes */
 IGN_API int ign_group_allgather(ign_group* g, const void* send_dev, uint64_t bytes, void* recv_dev);
+/* SURVEY.md 8(b) `ign_ccl6_sharded`: this rank's z-slab of a dataset split over the group's ranks
+ * (rank r above rank r-1).  Local CCL, ONE all-gather of [n_local | first plane | last plane],
+ * then -- on the device, identically on every rank -- the N-1 boundaries are linked, the small
+ * dataset-wide union-find is solved (smaller id wins, ccl.py:70-73) and the slab's labels are
+ * expanded once with dataset-wide ids.  Bit-identical to one whole-volume ign_ccl6 call on the
+ * stacked dataset.  Replaces ccl.py:177-194, :245-294, :358-420, :296-356. */
+IGN_API int ign_ccl6_sharded_dev(ign_group* g, const void* in, int in_dtype, uint64_t sx, uint64_t sy,
+                                 uint64_t sz, void* out, int out_dtype, uint64_t* n_global);
 
 #ifdef __cplusplus
 }

