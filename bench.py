@@ -356,7 +356,7 @@ def run_config(args, ctx, rank, world, dist):
     outs = [ctx.alloc(int(np.prod(sh))) for sh in shapes]
     call = lambda: _shim.check(lib.ign_pool_avg_2x2x1_dev(
       ctx.handle, _shim.ptr(d_in), c.c_int(_shim.IGN_U8), c.c_uint64(S), c.c_uint64(S), c.c_uint64(S), c.c_int(5),
-      c.c_int(0), c.c_int(0), _shim.void_pp([o.ptr for o in outs])))
+      c.c_int(_shim.ROUND_FLOOR), _shim.void_pp([o.ptr for o in outs])))
     chunks = 16  # 2048x2048x512 = 4x4x1 chunks of 512^3: 16 launches per step
     for _ in range(args.warmup):
       for _ in range(chunks):

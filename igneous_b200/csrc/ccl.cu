@@ -521,32 +521,49 @@ struct MergeArgs {
   uint32_t* parent;
 };
 
+// Latency bound (dependent loads, a handful of unions): a thread owns MG_W consecutive words of a
+// face row and issues all their loads before the first union.
+constexpr int MG_W = 4;
+
 __global__ void __launch_bounds__(256) k_ccl_merge(const MergeArgs a) {
+  const uint32_t gpr = (a.wpr + MG_W - 1) / MG_W;  // word groups per row
+  const uint64_t rows_y = (uint64_t)(a.nty - 1) * a.sz, rows_z = (uint64_t)(a.ntz - 1) * a.sy;
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= a.words_y + a.words_z) return;
-  uint32_t y, z, xw;
+  if (i >= (rows_y + rows_z) * gpr) return;
+  const uint64_t r = i / gpr;
+  const uint32_t xw0 = (uint32_t)(i - r * gpr) * MG_W;
+  uint32_t y, z;
   bool ydir;
-  if (i < a.words_y) {  // rows y = k*TY (k >= 1), every z
+  if (r < rows_y) {  // rows y = k*TY (k >= 1), every z
     ydir = true;
-    xw = (uint32_t)(i % a.wpr);
-    const uint64_t r = i / a.wpr;
     y = ((uint32_t)(r % (a.nty - 1)) + 1) * a.TY;
     z = (uint32_t)(r / (a.nty - 1));
   } else {  // rows of planes z = k*TZ (k >= 1), every y
     ydir = false;
-    const uint64_t j = i - a.words_y;
-    xw = (uint32_t)(j % a.wpr);
-    const uint64_t r = j / a.wpr;
-    y = (uint32_t)(r % a.sy);
-    z = ((uint32_t)(r / a.sy) + 1) * a.TZ;
+    const uint64_t j = r - rows_y;
+    y = (uint32_t)(j % a.sy);
+    z = ((uint32_t)(j / a.sy) + 1) * a.TZ;
   }
-  const uint64_t g = ((uint64_t)z * a.sy + y) * a.wpr + xw;
-  const uint32_t E = ydir ? a.Ey[g] : a.Ez[g];
-  if (!E) return;
-  const uint64_t gn = ydir ? g - a.wpr : g - (uint64_t)a.sy * a.wpr;
-  const uint32_t prev = xw > 0 ? ((ydir ? a.Ey[g - 1] : a.Ez[g - 1]) >> 31) : 0u;
+  const uint64_t g0 = ((uint64_t)z * a.sy + y) * a.wpr + xw0;
+  const uint64_t n0 = ydir ? g0 - a.wpr : g0 - (uint64_t)a.sy * a.wpr;
+  const uint32_t* Em = ydir ? a.Ey : a.Ez;
+  uint32_t E[MG_W], S[MG_W], Sn[MG_W], rb[MG_W], rn[MG_W];
+  uint32_t prev = xw0 > 0 ? Em[g0 - 1] >> 31 : 0u;
+#pragma unroll
+  for (int k = 0; k < MG_W; k++) {
+    const bool in = xw0 + k < a.wpr;
+    E[k] = in ? Em[g0 + k] : 0u;
+    S[k] = in ? a.S[g0 + k] : 0u;
+    Sn[k] = in ? a.S[n0 + k] : 0u;
+    rb[k] = in ? a.rbase[g0 + k] : 0u;
+    rn[k] = in ? a.rbase[n0 + k] : 0u;
+  }
   auto un = [&](uint32_t x, uint32_t yv) { uf_union(a.parent, x, yv); };
-  word_unions(E, prev, a.S[g], a.S[gn], a.rbase[g], a.rbase[gn], un);
+#pragma unroll
+  for (int k = 0; k < MG_W; k++) {
+    if (E[k]) word_unions(E[k], prev, S[k], Sn[k], rb[k], rn[k], un);
+    prev = E[k] >> 31;
+  }
 }
 
 // ------------------------------------------------------------------ runs
@@ -1016,7 +1033,7 @@ static int ccl_structure(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, ui
     me.words_y = (uint64_t)(ta.nty - 1) * sz * p.wpr;
     me.words_z = (uint64_t)(ta.ntz - 1) * sy * p.wpr;
     me.S = p.S; me.Ey = p.Ey; me.Ez = p.Ez; me.rbase = p.rbase; me.parent = p.label;
-    const uint64_t mitems = me.words_y + me.words_z;
+    const uint64_t mitems = ((uint64_t)(ta.nty - 1) * sz + (uint64_t)(ta.ntz - 1) * sy) * ((p.wpr + MG_W - 1) / MG_W);
     IGN_REQUIRE(mitems / 256 < 0x7FFFFFFFull, IGN_ERR_OVERFLOW, "too many CCL face words");
     IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_MERGE, k_ccl_merge, blocks_for(mitems, 256), 256, 0, me);
   }

@@ -402,6 +402,20 @@ __device__ __forceinline__ void sl_others(const uint32_t* a, uint32_t w, uint32_
   else { *o1 = a[0]; *o2 = a[1]; }
 }
 
+// distinct values among the (x1, x2) of the first n lanes; f1 / f2 flag the first occurrences
+__device__ __forceinline__ uint32_t sl_distinct(uint32_t x1, uint32_t x2, uint32_t n, uint32_t lane, bool* f1,
+                                                bool* f2) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const bool have = lane < n;
+  const uint32_t m1 = __match_any_sync(FULL, x1);
+  const uint32_t m2 = __match_any_sync(FULL, x2);
+  *f1 = have && ((int)lane == __ffs(m1) - 1);
+  bool in1 = false;
+  for (uint32_t j = 0; j < n; j++) in1 |= (__shfl_sync(FULL, x1, j) == x2);
+  *f2 = have && ((int)lane == __ffs(m2) - 1) && !in1;
+  return __popc(__ballot_sync(FULL, *f1)) + __popc(__ballot_sync(FULL, *f2));
+}
+
 // drop the dead entries of an alive list (order is irrelevant).  SM: in place, the entries
 // pass through registers; global-memory class: into the second buffer, then swap.
 template <bool SM, typename IDX, typename PRED>
@@ -415,7 +429,7 @@ __device__ __forceinline__ uint32_t sl_compact(IDX*& list, IDX*& list2, uint32_t
     uint32_t m = 0;
 #pragma unroll
     for (int k = 0; k < SL_LIST_PER; k++) {
-      const uint32_t i = tid + k * SL_THREADS;
+      const uint32_t i = tid + k * blockDim.x;
       keep[k] = 0;
       if (i < n) {
         const IDX e = list[i];
@@ -438,7 +452,7 @@ __device__ __forceinline__ uint32_t sl_compact(IDX*& list, IDX*& list2, uint32_t
     for (int k = 0; k < SL_LIST_PER; k++)
       if ((m >> k) & 1u) list[base++] = keep[k];
   } else {
-    for (uint32_t i0 = (tid & ~31u); i0 < n; i0 += SL_THREADS) {
+    for (uint32_t i0 = (tid & ~31u); i0 < n; i0 += blockDim.x) {
       const uint32_t i = i0 + lane;
       IDX e = 0;
       bool al = false;
@@ -665,8 +679,9 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
         }
       }
       __syncthreads();
-      // ---- E2: validation and collapse as dense passes over (winner) and (winner, ring face)
-      // work items -- no warp walks a winner's ring serially.
+      // ---- E2: the double precision parts (placement / cost, flip tests) as dense passes over
+      // (winner) and (winner, ring face) work items; the link condition and the collapse by one
+      // warp per winner on shared-memory data only.
       // E2a: placement and cost of every winner (one thread each)
       for (uint32_t i = tid; i < nb; i += NT) {
         SEval e;
@@ -693,94 +708,92 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
         if (sl_flips<SM>(A, L, a, w, best)) atomicOr(&sh.win[i].flags, WF_BAD);
       }
       __syncthreads();
-      // E2c: link condition (one thread per winner: distinct neighbours of both rings, the
-      // common ones, the shared faces)
-      for (uint32_t i = tid; i < nb; i += NT) {
-        if (sh.win[i].flags & WF_BAD) continue;
-        const uint32_t u = sh.win[i].u, v = sh.win[i].v;
-        const uint32_t nfu = sh.win[i].cnt[0], nfv = sh.win[i].cnt[1];
-        uint32_t nu[S_MAXV], nnu = 0, nnv = 0, shared = 0, common = 0;
-        bool ok = true;
-        for (uint32_t j = 0; j < nfu && ok; j++) {
-          const uint32_t f = L.ring[(2 * i) * S_MAXV + j];
-          const uint32_t a[3] = {sl_fget<SM>(L, f, 0), sl_fget<SM>(L, f, 1), sl_fget<SM>(L, f, 2)};
-          if (a[0] == v || a[1] == v || a[2] == v) shared++;
-          for (int c = 0; c < 3; c++) {
-            const uint32_t x = a[c];
-            if (x == u) continue;
-            bool seen = false;
-            for (uint32_t t = 0; t < nnu; t++) seen |= (nu[t] == x);
-            if (!seen) {
-              if (nnu >= (uint32_t)S_MAXV) { ok = false; break; }
-              nu[nnu++] = x;
+      // E2c: one WARP per winner: link condition by ballots / shuffles over the ring lists (a
+      // lane holds one ring face of each endpoint), then the collapse itself.  The ring
+      // entries of the warp's next winner are fetched before the current one is processed.
+      {
+        uint32_t nfu_n = 0, nfv_n = 0, fu_n = 0, fv_n = 0;
+        uint32_t slot = warp;
+        if (slot < nb) {
+          nfu_n = sh.win[slot].cnt[0]; nfv_n = sh.win[slot].cnt[1];
+          if (lane < nfu_n && lane < (uint32_t)S_MAXV) fu_n = L.ring[(2 * slot) * S_MAXV + lane];
+          if (lane < nfv_n && lane < (uint32_t)S_MAXV) fv_n = L.ring[(2 * slot + 1) * S_MAXV + lane];
+        }
+        for (; slot < nb; slot += NW) {
+          const uint32_t nfu = nfu_n, nfv = nfv_n, fu = fu_n, fv = fv_n;
+          const uint32_t nxt = slot + NW;
+          if (nxt < nb) {
+            nfu_n = sh.win[nxt].cnt[0]; nfv_n = sh.win[nxt].cnt[1];
+            if (lane < nfu_n && lane < (uint32_t)S_MAXV) fu_n = L.ring[(2 * nxt) * S_MAXV + lane];
+            if (lane < nfv_n && lane < (uint32_t)S_MAXV) fv_n = L.ring[(2 * nxt + 1) * S_MAXV + lane];
+          }
+          const uint32_t u = sh.win[slot].u, v = sh.win[slot].v, hl = sh.win[slot].h;
+          bool ok = !(sh.win[slot].flags & WF_BAD);  // warp uniform
+          const bool hu = ok && lane < nfu, hv = ok && lane < nfv;
+          uint32_t au[3] = {0, 0, 0}, av[3] = {0, 0, 0};
+          uint32_t x1 = 0xF0000000u + lane, x2 = 0xF1000000u + lane, y1 = 0xF2000000u + lane,
+                   y2 = 0xF3000000u + lane;
+          if (hu) {
+            au[0] = sl_fget<SM>(L, fu, 0); au[1] = sl_fget<SM>(L, fu, 1); au[2] = sl_fget<SM>(L, fu, 2);
+            sl_others(au, u, &x1, &x2);
+          }
+          if (hv) {
+            av[0] = sl_fget<SM>(L, fv, 0); av[1] = sl_fget<SM>(L, fv, 1); av[2] = sl_fget<SM>(L, fv, 2);
+            sl_others(av, v, &y1, &y2);
+          }
+          if (ok) {
+            bool f1, f2, g1, g2;
+            const uint32_t nnu = sl_distinct(x1, x2, nfu, lane, &f1, &f2);
+            const uint32_t nnv = sl_distinct(y1, y2, nfv, lane, &g1, &g2);
+            bool c1 = false, c2 = false;
+            for (uint32_t j = 0; j < nfv; j++) {
+              const uint32_t t1 = __shfl_sync(FULL, y1, j), t2 = __shfl_sync(FULL, y2, j);
+              c1 |= (x1 == t1) | (x1 == t2);
+              c2 |= (x2 == t1) | (x2 == t2);
             }
+            const uint32_t common = __popc(__ballot_sync(FULL, f1 && c1)) + __popc(__ballot_sync(FULL, f2 && c2));
+            const uint32_t shared = __popc(__ballot_sync(FULL, hu && (x1 == v || x2 == v)));
+            ok = nnu <= (uint32_t)S_MAXV && nnv <= (uint32_t)S_MAXV && shared == 2 && common == 2;
           }
-        }
-        uint32_t nv[S_MAXV];
-        for (uint32_t j = 0; j < nfv && ok; j++) {
-          const uint32_t f = L.ring[(2 * i + 1) * S_MAXV + j];
-          const uint32_t a[3] = {sl_fget<SM>(L, f, 0), sl_fget<SM>(L, f, 1), sl_fget<SM>(L, f, 2)};
-          for (int c = 0; c < 3; c++) {
-            const uint32_t x = a[c];
-            if (x == v) continue;
-            bool seen = false;
-            for (uint32_t t = 0; t < nnv; t++) seen |= (nv[t] == x);
-            if (!seen) {
-              if (nnv >= (uint32_t)S_MAXV) { ok = false; break; }
-              nv[nnv++] = x;
-              for (uint32_t t = 0; t < nnu; t++) common += (nu[t] == x);
+          if (!ok) {  // park the edge until one of its endpoints' rings changes
+            if (lane == 0) {
+              const uint32_t f = hl / 3, c = hl - 3 * f;
+              const uint32_t st = L.fstate[f];
+              L.fstate[f] = (uint8_t)((st & ~(3u << (2 * c))) | (1u << (2 * c)));
+              sl_vclear(L.vflag, u, VF_END);
+              sl_vclear(L.vflag, v, VF_END);
+              atomicOr(&sh.progress, 1u);
             }
+            continue;
           }
-        }
-        sh.win[i].flags = (ok && shared == 2 && common == 2) ? WF_OK : WF_BAD;
-      }
-      __syncthreads();
-      // E2d: apply.  Ring entries: faces of the removed vertex die (they also hold the kept one)
-      // or get the kept vertex in its corner; every vertex of the new ring is RDIRTY.
-      for (uint32_t item = tid; item < nb * 64; item += NT) {
-        const uint32_t i = item >> 6, side = (item >> 5) & 1u, j = item & 31u;
-        if (!(sh.win[i].flags & WF_OK)) continue;
-        if (j >= sh.win[i].cnt[side]) continue;
-        const uint32_t u = sh.win[i].u, v = sh.win[i].v, k = sh.win[i].keep, rm = (k == u) ? v : u;
-        const uint32_t w = side ? v : u, other = side ? u : v;
-        const uint32_t f = L.ring[(2 * i + side) * S_MAXV + j];
-        const uint32_t a[3] = {sl_fget<SM>(L, f, 0), sl_fget<SM>(L, f, 1), sl_fget<SM>(L, f, 2)};
-        const bool both = (a[0] == other || a[1] == other || a[2] == other);
-        if (both) {
-          if (w == rm) {  // seen once from the removed vertex's side
-            L.fstate[f] = (uint8_t)(L.fstate[f] & 0x7Fu);
-            atomicSub(&sh.alive, 1u);
+          const uint32_t k = sh.win[slot].keep, rm = (k == u) ? v : u;
+          const bool rm_is_u = (rm == u);
+          const bool hr = rm_is_u ? hu : hv;
+          const uint32_t rf = rm_is_u ? fu : fv;
+          const uint32_t r0 = rm_is_u ? au[0] : av[0], r1 = rm_is_u ? au[1] : av[1], r2 = rm_is_u ? au[2] : av[2];
+          // faces of rm: those that also hold k die, the others get k in rm's corner
+          const bool dies = hr && (r0 == k || r1 == k || r2 == k);
+          if (hr) {
+            if (dies) L.fstate[rf] = (uint8_t)(L.fstate[rf] & 0x7Fu);
+            else sl_fset<SM>(L, rf, r0 == rm ? 0 : (r1 == rm ? 1 : 2), k);
           }
-          continue;
-        }
-        if (w == rm) sl_fset<SM>(L, f, a[0] == rm ? 0 : (a[1] == rm ? 1 : 2), k);
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-          if (a[c] != w) sl_vor(L.vflag, a[c], VF_RDIRTY);
-      }
-      // winners: the kept vertex moves and absorbs the quadric; failures park their edge
-      for (uint32_t i = tid; i < nb; i += NT) {
-        const uint32_t u = sh.win[i].u, v = sh.win[i].v;
-        if (sh.win[i].flags & WF_OK) {
-          const uint32_t k = sh.win[i].keep, rm = (k == u) ? v : u;
-          double* pk = A.pos + 3 * (uint64_t)(L.vbase + k);
-          pk[0] = L.wbest[3 * i]; pk[1] = L.wbest[3 * i + 1]; pk[2] = L.wbest[3 * i + 2];
+          const uint32_t dead = __popc(__ballot_sync(FULL, dies));
+          // the new ring of k: parked edges around it may be valid now
+          if (hu && x1 != v && x2 != v) { sl_vor(L.vflag, x1, VF_RDIRTY); sl_vor(L.vflag, x2, VF_RDIRTY); }
+          if (hv && y1 != u && y2 != u) { sl_vor(L.vflag, y1, VF_RDIRTY); sl_vor(L.vflag, y2, VF_RDIRTY); }
           double* Qk = A.Q + 10 * (uint64_t)(L.vbase + k);
           const double* Qr = A.Q + 10 * (uint64_t)(L.vbase + rm);
-#pragma unroll
-          for (int q = 0; q < 10; q++) Qk[q] = Qk[q] + Qr[q];
-          sl_vor(L.vflag, k, VF_CDIRTY | VF_RDIRTY);  // k moved: cached costs of its edges are stale
-          sl_vclear(L.vflag, k, VF_END);
-          sl_vclear(L.vflag, rm, 0xFFu);
-          atomicAdd(&sh.ncol, 1u);
-        } else {  // park the edge until one of its endpoints' rings changes
-          const uint32_t hl = sh.win[i].h, f = hl / 3, c = hl - 3 * f;
-          const uint32_t st = L.fstate[f];
-          L.fstate[f] = (uint8_t)((st & ~(3u << (2 * c))) | (1u << (2 * c)));
-          sl_vclear(L.vflag, u, VF_END);
-          sl_vclear(L.vflag, v, VF_END);
+          if (lane < 10) Qk[lane] = Qk[lane] + Qr[lane];
+          if (lane >= 16 && lane < 19) A.pos[3 * (uint64_t)(L.vbase + k) + (lane - 16)] = L.wbest[3 * slot + (lane - 16)];
+          if (lane == 0) {
+            sl_vor(L.vflag, k, VF_CDIRTY | VF_RDIRTY);  // k moved: cached costs of its edges are stale
+            sl_vclear(L.vflag, k, VF_END);
+            sl_vclear(L.vflag, rm, 0xFFu);
+            atomicSub(&sh.alive, dead);
+            atomicAdd(&sh.ncol, 1u);
+            atomicOr(&sh.progress, 1u);
+          }
         }
-        atomicOr(&sh.progress, 1u);
       }
       __syncthreads();
       if (total <= (uint32_t)SL_WCAP) break;
@@ -859,7 +872,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
     const size_t need = o_vf + U + 4;
     uint32_t* ring = A.ring + (size_t)blockIdx.x * ((size_t)SL_WCAP * 2 * S_MAXV);
     double* wbest = A.wbest + (size_t)blockIdx.x * ((size_t)SL_WCAP * 3);
-    const uint32_t cap = (uint32_t)SL_LIST_PER * SL_THREADS;
+    const uint32_t cap = (uint32_t)SL_LIST_PER * blockDim.x;
     if (need <= A.smem_bytes && T <= cap && U <= cap) {
       SlLab<true> L;
       L.T = T; L.U = U; L.tbase = tbase; L.vbase = vbase; L.target = target;
@@ -983,8 +996,8 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
                       3 * align_up(U, 256) + 3 * align_up(U * 4, 256) + align_up(U * 8, 256) +
                       6 * align_up((K + 2) * 4, 256) + align_up(3 * T * 4, 256) +
                       2 * align_up(3 * T * 4, 256) + 2 * align_up(T * 4, 256) + 2 * align_up(U * 4, 256) + tmpb +
-                      align_up((size_t)ctx->sm_count * SL_WCAP * 2 * S_MAXV * 4, 256) +
-                      align_up((size_t)ctx->sm_count * SL_WCAP * 3 * 8, 256) + (1 << 20);
+                      align_up((size_t)ctx->sm_count * 4 * SL_WCAP * 2 * S_MAXV * 4, 256) +
+                      align_up((size_t)ctx->sm_count * 4 * SL_WCAP * 3 * 8, 256) + (1 << 20);
   IGN_TRY(scratch_reserve(ctx, need));
   Simp s;
   s.U = U;
@@ -1085,17 +1098,18 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   S_LAUNCH(k_simp_quadrics, blocks_for(U, 128), 128, s);
   S_LAUNCH(k_simp_boundary, blocks_for(3 * T, 256), 256, s);
 
-  // ---- all rounds of every label: one persistent CTA per SM pulls labels off the order list
-  static const size_t sl_dyn = 232448 - 1024 - ((sizeof(SlShared) + 255) / 256) * 256;
-  {
-    static int configured[64] = {0};  // per device
-    if (ctx->device < 64 && !configured[ctx->device]) {
-      S_CUDA(cudaFuncSetAttribute(k_simp_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl_dyn));
-      configured[ctx->device] = 1;
-    } else if (ctx->device >= 64) {
-      S_CUDA(cudaFuncSetAttribute(k_simp_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl_dyn));
-    }
-  }
+  // ---- all rounds of every label: persistent CTAs pull labels off the order list.  The kernel is
+  // latency bound (barriers, dependent loads), so several CTAs per SM overlap each other's
+  // stalls; the shared-memory budget of a label is the SM's divided by the CTAs per SM
+  // (IGN_SIMP_THREADS / IGN_SIMP_CTAS override the default for experiments).
+  int sl_threads = 1024, sl_ctas = 1;  // measured on B200: 1024x1 76 ms, 512x2 94 ms, 256x4 91 ms per 257^3 task
+  if (const char* e = getenv("IGN_SIMP_THREADS")) sl_threads = atoi(e);
+  if (const char* e = getenv("IGN_SIMP_CTAS")) sl_ctas = atoi(e);
+  if (sl_threads != 256 && sl_threads != 512 && sl_threads != 1024) sl_threads = 1024;
+  if (sl_ctas < 1 || sl_ctas * sl_threads > 1024) sl_ctas = 1024 / sl_threads;
+  const size_t sl_static = ((sizeof(SlShared) + 255) / 256) * 256 + 1024;
+  const size_t sl_dyn = ((232448 / (size_t)sl_ctas) > sl_static + 16384 ? (232448 / (size_t)sl_ctas) - sl_static : 16384) & ~(size_t)255;
+  S_CUDA(cudaFuncSetAttribute(k_simp_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl_dyn));
   SlArgs A;
   A.pos = s.pos; A.Q = s.Q; A.face = s.face; A.falive = s.falive; A.valive = s.valive; A.vbound = s.vbound;
   A.ecost = ecost; A.key1 = key1; A.fstate = fstate; A.vflag = vflag;
@@ -1114,7 +1128,8 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   const char* force_gmem = getenv("IGN_SIMP_GMEM");
   A.smem_bytes = (force_gmem && force_gmem[0] == '1') ? (uint32_t)((SL_THREADS / 32) * SL_EQ * 4) : (uint32_t)sl_dyn;
   {
-    const unsigned grid = (unsigned)(K < (uint64_t)ctx->sm_count ? K : (uint64_t)ctx->sm_count);
+    const uint64_t slots = (uint64_t)ctx->sm_count * sl_ctas;
+    const unsigned grid = (unsigned)(K < slots ? K : slots);
     A.ring = (uint32_t*)scratch_take(ctx, (size_t)grid * SL_WCAP * 2 * S_MAXV * 4);
     A.wbest = (double*)scratch_take(ctx, (size_t)grid * SL_WCAP * 3 * 8);
     if (!A.ring || !A.wbest) {
@@ -1122,7 +1137,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
       return done(IGN_ERR_NOMEM);
     }
     const int slot = prof_begin(ctx, IGN_PROF_SIMP);
-    k_simp_labels<<<grid, SL_THREADS, sl_dyn, ctx->stream>>>(A);
+    k_simp_labels<<<grid, sl_threads, sl_dyn, ctx->stream>>>(A);
     ctx->launches++;
     prof_end(ctx, slot);
     S_CUDA(cudaGetLastError());

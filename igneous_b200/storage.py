@@ -508,6 +508,33 @@ class CloudVolume:
           if not c.subvoxel():
             yield c
 
+  # chunk codecs: `raw` is the bytes of the Fortran-order array; `compressed_segmentation` goes
+  # through the device codec (igneous_b200.codecs); anything else the Precomputed format knows
+  # (jpeg, compresso, crackle, ...) is outside this stand-in
+  def _encoding(self, mip):
+    return self.info["scales"][mip].get("encoding", "raw")
+
+  def _cseg_block(self, mip):
+    return tuple(int(v) for v in self.info["scales"][mip].get("compressed_segmentation_block_size", (8, 8, 8)))
+
+  def _encode_chunk(self, block, mip):
+    enc = self._encoding(mip)
+    if enc == "raw":
+      return block.tobytes(order="F")
+    if enc == "compressed_segmentation":
+      from . import codecs
+      return codecs.cseg_encode(block, self._cseg_block(mip))
+    raise NotImplementedError("storage stand-in: chunk encoding %r is not supported" % enc)
+
+  def _decode_chunk(self, data, mip, shape):
+    enc = self._encoding(mip)
+    if enc == "raw":
+      return np.frombuffer(data, dtype=self.dtype).reshape(shape, order="F")
+    if enc == "compressed_segmentation":
+      from . import codecs
+      return codecs.cseg_decode(data, shape, self.dtype, self._cseg_block(mip))
+    raise NotImplementedError("storage stand-in: chunk encoding %r is not supported" % enc)
+
   def _to_bbox(self, key):
     if isinstance(key, Bbox):
       return key.clone()
@@ -536,7 +563,7 @@ class CloudVolume:
         if not self.fill_missing:
           raise EmptyVolumeException(self._chunk_name(mip, c))
         continue
-      chunk = np.frombuffer(data, dtype=self.dtype).reshape(tuple(int(v) for v in c.size3()) + (self.num_channels,), order="F")
+      chunk = self._decode_chunk(data, mip, tuple(int(v) for v in c.size3()) + (self.num_channels,))
       src = tuple(slice(int(a - o), int(b - o)) for a, b, o in zip(inter.minpt, inter.maxpt, c.minpt))
       dst = tuple(slice(int(a - o), int(b - o)) for a, b, o in zip(inter.minpt, inter.maxpt, bbox.minpt))
       out[dst] = chunk[src]
@@ -566,7 +593,7 @@ class CloudVolume:
       if self.delete_black_uploads and not np.any(block != self.background_color):
         self.cf.delete(name)
         continue
-      self.cf.put(name, block.tobytes(order="F"), compress=self.compress)
+      self.cf.put(name, self._encode_chunk(block, mip), compress=self.compress)
 
 
 # --------------------------------------------------------------------- queue

@@ -202,3 +202,30 @@ def test_mesh_task_object_ids_and_creator(ctx, oracle, tmp_path):
   names = cf.list("m2/")
   assert "m2/1:0:0-32_0-64_0-64" in names and "m2/2:0:32-64_0-64_0-64" in names
   assert any(n.endswith(".spatial") for n in names)
+
+
+def test_downsample_task_compressed_segmentation_encoding(ctx, oracle, tmp_path):
+  """a DownsampleTask whose new mips are `compressed_segmentation` layers
+  (create_downsampling_tasks(encoding=...), igneous/task_creation/image.py:284-286): the chunks
+  are written by the device codec, byte-identical to the oracle encoder, and read back through
+  the device decoder."""
+  import gzip
+  import igneous_b200.task_creation as tc
+  from igneous_b200._compat import CloudVolume, CloudFiles, LocalTaskQueue
+  seg = oracle.synth_seg((256, 256, 64), pitch=16, num_ids=64)[..., np.newaxis]
+  path = _layer(tmp_path, seg, "segmentation")
+  LocalTaskQueue(parallel=1).insert_all(tc.create_downsampling_tasks(
+    path, mip=0, num_mips=2, encoding="compressed_segmentation", compress="gzip"))
+  cv = CloudVolume(path)
+  assert [s["encoding"] for s in cv.info["scales"]] == ["raw", "compressed_segmentation", "compressed_segmentation"]
+  want = oracle.downsample_segmentation(seg, (2, 2, 1, 1), num_mips=2)
+  for m in (1, 2):
+    cv.mip = m
+    assert np.array_equal(cv[cv.meta.bounds(m)], want[m - 1])
+  # the stored chunk IS the oracle's stream
+  cf = CloudFiles(path)
+  name = [n for n in cf.list(cv.info["scales"][1]["key"])][0]
+  raw = cf.get(name)
+  box = [tuple(int(v) for v in part.split("-")) for part in name.split("/")[-1].split("_")]
+  chunk = want[0][box[0][0]:box[0][1], box[1][0]:box[1][1], box[2][0]:box[2][1]]
+  assert raw == oracle.cseg_encode(np.asfortranarray(chunk)).tobytes()
