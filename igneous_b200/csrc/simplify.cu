@@ -236,9 +236,9 @@ __global__ void __launch_bounds__(256) k_simp_boundary(Simp s) {
 // changed (parked edges around it may be valid now)
 constexpr uint32_t VF_ALIVE = 1, VF_BOUND = 2, VF_CDIRTY = 4, VF_LOSE = 8, VF_DONE = 16, VF_END = 32, VF_RDIRTY = 64;
 constexpr int SL_THREADS = 1024;
-constexpr int SL_WCAP = 512;  // winners validated per selection pass (a round runs as many passes as it needs)
+constexpr int SL_WCAP = 256;  // winners validated per selection pass (a round runs as many passes as it needs)
 constexpr uint32_t WF_BAD = 1, WF_OK = 2;  // winner flags: failed validation / validated
-constexpr int SL_EQ = 96;      // per-warp queue of half-edges whose cost must be (re)computed
+constexpr int SL_EQ = 96;      // per-warp queue of faces with half-edges whose cost must be (re)computed
 constexpr int SL_LIST_PER = 16;  // list entries per thread held in registers while a list is compacted in place
 
 struct SlArgs {
@@ -275,6 +275,8 @@ struct SlWin {
 
 struct SlShared {
   uint32_t work, alive, progress, ncol, nwin, stop, slow, counter;
+  unsigned long long ph[10];  // phase timers (IGN_SIMP_TRACE)
+  long long t_prev;
   SlWin win[SL_WCAP];
 };
 
@@ -478,8 +480,22 @@ __device__ __forceinline__ uint32_t sl_compact(IDX*& list, IDX*& list2, uint32_t
   return kept;
 }
 
+// phase timers (IGN_SIMP_TRACE=1): thread 0 attributes the cycles since the previous mark to a phase
+#define SL_MARK(id)                                   \
+  do {                                                \
+    if (A.trace != nullptr && tid == 0) {             \
+      const long long _t = clock64();                 \
+      sh.ph[id] += (unsigned long long)(_t - sh.t_prev); \
+      sh.t_prev = _t;                                 \
+    }                                                 \
+  } while (0)
+
 template <bool SM>
 __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
+  if (A.trace != nullptr && threadIdx.x == 0) {
+    for (int q = 0; q < 10; q++) sh.ph[q] = 0;
+    sh.t_prev = clock64();
+  }
   typedef typename SlLab<SM>::idx_t idx_t;
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t tid = threadIdx.x, NT = blockDim.x, lane = tid & 31u, warp = tid >> 5, NW = NT >> 5;
@@ -498,7 +514,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
   }
   for (uint32_t v = tid; v < U; v += NT) {
     L.vflag[v] = (uint8_t)(VF_ALIVE | (A.vbound[L.vbase + v] ? VF_BOUND : 0u));
-    vlist[v] = (idx_t)v;
+    if (!SM) vlist[v] = (idx_t)v;  // the shared-memory class scans its vertices directly (no list: 2 B / vertex saved)
   }
   if (tid == 0) {
     sh.alive = T;
@@ -517,7 +533,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
     const uint32_t salt = (uint32_t)r * 0x9E3779B9u;
     // ---- P1
     for (uint32_t i = tid; i < nV; i += NT) {
-      const uint32_t v = vlist[i];
+      const uint32_t v = SM ? i : (uint32_t)vlist[i];
       L.key1[v] = S_KEYMAX;
       const uint8_t b = L.vflag[v];
       if (b & (VF_LOSE | VF_DONE)) L.vflag[v] = (uint8_t)(b & ~(VF_LOSE | VF_DONE));
@@ -527,18 +543,32 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
       sh.ncol = 0;
     }
     __syncthreads();
-    // ---- P2: keys of the canonical half-edges.  A warp takes 32 alive faces; the half-edges whose memoised state was dropped go through a per-warp queue
-    // so that the double precision cost runs on dense lanes; the face's owner lane then posts
-    // the keys and writes the face's state byte (single writer).
+    SL_MARK(0);
+    // ---- P2: keys of the canonical half-edges.  A warp takes 32 alive faces per iteration and
+    // posts the cached keys; faces with half-edges whose memoised state was dropped collect in
+    // a per-warp queue that is evaluated (double precision cost) on dense lanes.
     {
       uint32_t* wq = L.wq + warp * SL_EQ;
+      uint32_t qn = 0;  // faces in the warp's queue (warp uniform)
+      // software pipeline: the face id and the three cached costs of the NEXT iteration are
+      // requested (global loads, L2 latency) before the current face is processed
+      const float* ecb = A.ecost + 3 * (uint64_t)L.tbase;
+      uint32_t f_n = 0;
+      float ec_n[3] = {0.f, 0.f, 0.f};
+      if (warp * 32 + lane < nF) {
+        f_n = flist[warp * 32 + lane];
+        ec_n[0] = ecb[3 * (uint64_t)f_n]; ec_n[1] = ecb[3 * (uint64_t)f_n + 1]; ec_n[2] = ecb[3 * (uint64_t)f_n + 2];
+      }
       for (uint32_t base = warp * 32; base < nF; base += NT) {
         const uint32_t i = base + lane;
-        uint32_t f = 0, st = 0, a[3] = {0, 0, 0}, fl[3] = {0, 0, 0};
-        if (i < nF) {
-          f = flist[i];
-          st = L.fstate[f];
+        const uint32_t f = f_n;
+        const float ec[3] = {ec_n[0], ec_n[1], ec_n[2]};
+        if (i + NT < nF) {
+          f_n = flist[i + NT];
+          ec_n[0] = ecb[3 * (uint64_t)f_n]; ec_n[1] = ecb[3 * (uint64_t)f_n + 1]; ec_n[2] = ecb[3 * (uint64_t)f_n + 2];
         }
+        uint32_t st = 0, a[3] = {0, 0, 0}, fl[3] = {0, 0, 0};
+        if (i < nF) st = L.fstate[f];
         bool act = (st & 0x80u) != 0;
         if (act) {
           a[0] = sl_fget<SM>(L, f, 0); a[1] = sl_fget<SM>(L, f, 1); a[2] = sl_fget<SM>(L, f, 2);
@@ -560,60 +590,51 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
             if (es == 0) {
               pend |= 1u << c;
             } else if (es == 2) {
-              const float cf = A.ecost[3 * (uint64_t)(L.tbase + f) + c];
-              sl_post(L.key1, u, v, ((unsigned long long)__float_as_uint(cf) << 32) | s_mix((3u * f + (uint32_t)c) ^ salt));
+              sl_post(L.key1, u, v, ((unsigned long long)__float_as_uint(ec[c]) << 32) | s_mix((3u * f + (uint32_t)c) ^ salt));
             }
             nst = (nst & ~(3u << (2 * c))) | (es << (2 * c));
           }
         }
-        const uint32_t np = __popc(pend);
-        uint32_t inc = np;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t o = __shfl_up_sync(FULL, inc, d);
-          if ((int)lane >= d) inc += o;
-        }
-        const uint32_t nq = __shfl_sync(FULL, inc, 31);
-        if (nq) {
-          const uint32_t off = inc - np;
-          uint32_t w = off;
-          if (pend & 1u) wq[w++] = f * 4u;
-          if (pend & 2u) wq[w++] = f * 4u + 1u;
-          if (pend & 4u) wq[w++] = f * 4u + 2u;
+        if (act && nst != st) L.fstate[f] = (uint8_t)nst;  // pending corners hold memo 0 until they are evaluated
+        // faces with pending corners accumulate in the warp's queue over the iterations; the
+        // queue is evaluated when the next iteration might not fit (>= 3 dense passes) and at the end
+        const uint32_t has = pend ? 1u : 0u;
+        const uint32_t bal = __ballot_sync(FULL, has);
+        if (has) wq[qn + __popc(bal & ((1u << lane) - 1u))] = (f << 3) | pend;
+        qn += __popc(bal);
+        const bool last = base + NT >= nF;
+        if (qn > (uint32_t)SL_EQ - 32 || (last && qn)) {
           __syncwarp();
-          for (uint32_t j = lane; j < nq; j += 32) {
-            const uint32_t e = wq[j], ef = e >> 2, ec = e & 3u;
-            const uint32_t u = sl_fget<SM>(L, ef, (int)ec), v = sl_fget<SM>(L, ef, (int)((ec + 1) % 3));
-            SEval ev;
-            sl_cost<SM>(A, L, u, v, &ev);
-            uint32_t res = 0xFFFFFFFFu;  // exceeds max_error
-            if (ev.valid) {
-              const float cf = __double2float_rn(ev.cost);
-              A.ecost[3 * (uint64_t)(L.tbase + ef) + ec] = cf;
-              res = __float_as_uint(cf);
+          for (uint32_t j = lane; j < qn; j += 32) {
+            const uint32_t e = wq[j], ef = e >> 3, ep = e & 7u;
+            uint32_t est = L.fstate[ef];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              if (!((ep >> c) & 1u)) continue;
+              const uint32_t u = sl_fget<SM>(L, ef, c), v = sl_fget<SM>(L, ef, (c + 1) % 3);
+              SEval ev;
+              sl_cost<SM>(A, L, u, v, &ev);
+              uint32_t es = 3;  // exceeds max_error
+              if (ev.valid) {
+                const float cf = __double2float_rn(ev.cost);
+                A.ecost[3 * (uint64_t)(L.tbase + ef) + c] = cf;
+                es = 2;
+                sl_post(L.key1, u, v, ((unsigned long long)__float_as_uint(cf) << 32) | s_mix((3u * ef + (uint32_t)c) ^ salt));
+              }
+              est = (est & ~(3u << (2 * c))) | (es << (2 * c));
             }
-            wq[j] = res;
+            L.fstate[ef] = (uint8_t)est;  // the queue holds a face once: single writer
           }
           __syncwarp();
-          w = off;
-#pragma unroll
-          for (int c = 0; c < 3; c++) {
-            if (!((pend >> c) & 1u)) continue;
-            const uint32_t res = wq[w++];
-            const uint32_t es = (res == 0xFFFFFFFFu) ? 3u : 2u;
-            if (es == 2) sl_post(L.key1, a[c], a[(c + 1) % 3],
-                                 ((unsigned long long)res << 32) | s_mix((3u * f + (uint32_t)c) ^ salt));
-            nst = (nst & ~(3u << (2 * c))) | (es << (2 * c));
-          }
-          __syncwarp();
+          qn = 0;
         }
-        if (act && nst != st) L.fstate[f] = (uint8_t)nst;
       }
     }
     __syncthreads();
+    SL_MARK(1);
     // ---- P3: dirty flags consumed; LOSE = a face neighbour holds a smaller key
     for (uint32_t i = tid; i < nV; i += NT) {
-      const uint32_t v = vlist[i];
+      const uint32_t v = SM ? i : (uint32_t)vlist[i];
       if (L.vflag[v] & (VF_CDIRTY | VF_RDIRTY)) sl_vclear(L.vflag, v, VF_CDIRTY | VF_RDIRTY);
     }
     for (uint32_t i = tid; i < nF; i += NT) {
@@ -628,12 +649,13 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
       if (k2 > m) sl_vor(L.vflag, a2, VF_LOSE);
     }
     __syncthreads();
+    SL_MARK(2);
     // ---- P4 + E: the round's winners (marked DONE on both endpoints), SL_WCAP per pass
     for (;;) {
       if (tid == 0) sh.nwin = 0;
       __syncthreads();
       for (uint32_t i = tid; i < nV; i += NT) {
-        const uint32_t a = vlist[i];
+        const uint32_t a = SM ? i : (uint32_t)vlist[i];
         const uint32_t fl = L.vflag[a];
         if (!(fl & VF_ALIVE) || (fl & (VF_LOSE | VF_DONE))) continue;
         const unsigned long long key = L.key1[a];
@@ -656,6 +678,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
         }
       }
       __syncthreads();
+      SL_MARK(3);
       const uint32_t total = sh.nwin;
       const uint32_t nb = total < (uint32_t)SL_WCAP ? total : (uint32_t)SL_WCAP;
       if (nb == 0) break;
@@ -665,6 +688,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
         L.key1[sh.win[i].v] = 2ull * i + 1;
       }
       __syncthreads();
+      SL_MARK(4);
       // ---- E1: ring lists (global memory, one pass over the alive faces for all winners)
       for (uint32_t i = tid; i < nF; i += NT) {
         const uint32_t f = flist[i];
@@ -679,6 +703,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
         }
       }
       __syncthreads();
+      SL_MARK(5);
       // ---- E2: the double precision parts (placement / cost, flip tests) as dense passes over
       // (winner) and (winner, ring face) work items; the link condition and the collapse by one
       // warp per winner on shared-memory data only.
@@ -695,6 +720,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
         }
       }
       __syncthreads();
+      SL_MARK(6);
       // E2b: one flip test per (winner, side, ring entry)
       for (uint32_t item = tid; item < nb * 64; item += NT) {
         const uint32_t i = item >> 6, side = (item >> 5) & 1u, j = item & 31u;
@@ -708,6 +734,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
         if (sl_flips<SM>(A, L, a, w, best)) atomicOr(&sh.win[i].flags, WF_BAD);
       }
       __syncthreads();
+      SL_MARK(7);
       // E2c: one WARP per winner: link condition by ballots / shuffles over the ring lists (a
       // lane holds one ring face of each endpoint), then the collapse itself.  The ring
       // entries of the warp's next winner are fetched before the current one is processed.
@@ -796,6 +823,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
         }
       }
       __syncthreads();
+      SL_MARK(8);
       if (total <= (uint32_t)SL_WCAP) break;
     }
     // ---- stop rules of the label
@@ -818,6 +846,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
       sh.stop = stop;
     }
     __syncthreads();
+    SL_MARK(9);
     if (sh.stop) {
       r++;
       break;
@@ -825,7 +854,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
     // ---- dead entries leave the lists every second round
     if (r & 1) {
       nF = sl_compact<SM>(flist, flist2, nF, &sh.counter, [&](uint32_t f) { return (L.fstate[f] & 0x80u) != 0; });
-      nV = sl_compact<SM>(vlist, vlist2, nV, &sh.counter, [&](uint32_t v) { return (L.vflag[v] & VF_ALIVE) != 0; });
+      if (!SM) nV = sl_compact<SM>(vlist, vlist2, nV, &sh.counter, [&](uint32_t v) { return (L.vflag[v] & VF_ALIVE) != 0; });
     }
   }
   // ---- write the label back to the whole-task arrays
@@ -840,6 +869,8 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
     }
   }
   for (uint32_t v = tid; v < U; v += NT) A.valive[L.vbase + v] = (L.vflag[v] & VF_ALIVE) ? 1 : 0;
+  if (tid == 0 && A.trace != nullptr)
+    for (int q = 0; q < 10; q++) atomicAdd((unsigned long long*)(A.trace + 1600) + q, sh.ph[q]);
   if (tid == 0) {
     atomicMax(&A.counters[1], (uint32_t)r);
     atomicAdd(&A.counters[SM ? 2 : 3], 1u);
@@ -861,13 +892,12 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
     const uint32_t vbase = A.vert_off[l], U = A.vert_off[l + 1] - vbase;
     const uint32_t target = A.target[l];
     if (T == 0 || T <= target) continue;  // init left every face / vertex alive
-    // shared-memory layout: cost queues | key1 | faces SoA | face list | vertex list | face state | vertex flags
+    // shared-memory layout: cost queues | key1 | faces SoA | face list | face state | vertex flags
     const size_t wq_bytes = (size_t)(SL_THREADS / 32) * SL_EQ * 4;
     const size_t o_key = wq_bytes;
     const size_t o_f0 = o_key + 8 * (size_t)U;
     const size_t o_fl = o_f0 + 6 * (size_t)T;
-    const size_t o_vl = o_fl + 2 * (size_t)T;
-    const size_t o_fs = o_vl + 2 * (size_t)U;
+    const size_t o_fs = o_fl + 2 * (size_t)T;
     const size_t o_vf = (o_fs + T + 3) & ~(size_t)3;
     const size_t need = o_vf + U + 4;
     uint32_t* ring = A.ring + (size_t)blockIdx.x * ((size_t)SL_WCAP * 2 * S_MAXV);
@@ -884,7 +914,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
       L.fc1 = L.fc0 + T;
       L.fc2 = L.fc1 + T;
       L.flist = (uint16_t*)(sl_smem + o_fl);
-      L.vlist = (uint16_t*)(sl_smem + o_vl);
+      L.vlist = nullptr;
       L.flist2 = L.vlist2 = nullptr;
       L.gface = nullptr;
       L.fstate = sl_smem + o_fs;
@@ -896,13 +926,23 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
       L.wq = (uint32_t*)sl_smem;  // the cost queues always fit
       L.ring = ring;
       L.wbest = wbest;
-      L.key1 = A.key1 + vbase;
       L.fc0 = L.fc1 = L.fc2 = nullptr;
       L.flist = A.flist + tbase; L.flist2 = A.flist2 + tbase;
       L.vlist = A.vlist + vbase; L.vlist2 = A.vlist2 + vbase;
       L.gface = A.face + 3 * (uint64_t)tbase;
-      L.fstate = A.fstate + tbase;
-      L.vflag = A.vflag + vbase;
+      // the arrays that take the atomics (keys, vertex flags) and the face states stay in shared
+      // memory whenever they fit; only the faces and the alive lists are read from global memory
+      const size_t h_fs = o_key + 8 * (size_t)U;
+      const size_t h_vf = (h_fs + T + 3) & ~(size_t)3;
+      if (h_vf + U + 4 <= A.smem_bytes) {
+        L.key1 = (unsigned long long*)(sl_smem + o_key);
+        L.fstate = sl_smem + h_fs;
+        L.vflag = sl_smem + h_vf;
+      } else {
+        L.key1 = A.key1 + vbase;
+        L.fstate = A.fstate + tbase;
+        L.vflag = A.vflag + vbase;
+      }
       sl_run<false>(A, L, sh);
     }
   }
@@ -1122,8 +1162,8 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   // labels that do not fit shared memory (only the winners' ring lists stay in smem)
   A.trace = nullptr;
   if (getenv("IGN_SIMP_TRACE") != nullptr) {
-    A.trace = (uint32_t*)scratch_take(ctx, 400 * 16);
-    if (A.trace) S_CUDA(cudaMemsetAsync(A.trace, 0, 400 * 16, ctx->stream));
+    A.trace = (uint32_t*)scratch_take(ctx, 400 * 16 + 256);
+    if (A.trace) S_CUDA(cudaMemsetAsync(A.trace, 0, 400 * 16 + 256, ctx->stream));
   }
   const char* force_gmem = getenv("IGN_SIMP_GMEM");
   A.smem_bytes = (force_gmem && force_gmem[0] == '1') ? (uint32_t)((SL_THREADS / 32) * SL_EQ * 4) : (uint32_t)sl_dyn;
@@ -1167,7 +1207,14 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   if (A.trace) {
     std::vector<uint32_t> tr(1600);
     S_CUDA(cudaMemcpy(tr.data(), A.trace, 1600 * 4, cudaMemcpyDeviceToHost));
-    for (int r = 0; r < 400 && (tr[4 * r + 2] || tr[4 * r + 3]); r++)
+    unsigned long long phs[10];
+    S_CUDA(cudaMemcpy(phs, A.trace + 1600, 80, cudaMemcpyDeviceToHost));
+    static const char* names[10] = {"P1", "P2 keys", "P3 lose", "P4 select", "setup", "E1 rings", "E2a cost", "E2b flips", "E2c link+collapse", "stop+compact"};
+    unsigned long long tot = 0;
+    for (int q = 0; q < 10; q++) tot += phs[q];
+    for (int q = 0; q < 10; q++)
+      fprintf(stderr, "phase %-18s %6.2f %%  %10.3f Mcycles\n", names[q], 100.0 * phs[q] / (tot ? tot : 1), phs[q] / 1e6);
+    for (int r = 0; r < 400 && getenv("IGN_SIMP_TRACE_ROUNDS") && (tr[4 * r + 2] || tr[4 * r + 3]); r++)
       fprintf(stderr, "gpu round %d progress %u collapses %u alive %u list %u\n", r, tr[4 * r], tr[4 * r + 1], tr[4 * r + 2], tr[4 * r + 3]);
   }
   m->simp_rounds = (int)hflags[1];
