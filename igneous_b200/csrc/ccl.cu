@@ -148,8 +148,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // side, +16 bytes of halo on the low x side: TMA boxes are multiples of 16 bytes)
 constexpr int MT_BX = 128, MT_BY = 8;
 constexpr int MT_THREADS = 512;
+#ifndef MT_BZ_OVERRIDE
+#define MT_BZ_OVERRIDE 0
+#endif
 template <typename T> struct MaskTile {
-  static constexpr int BZ = sizeof(T) == 8 ? 4 : 8;
+  static constexpr int BZ = MT_BZ_OVERRIDE ? MT_BZ_OVERRIDE : (sizeof(T) == 8 ? 4 : 8);
   static constexpr int HX = 16 / (int)sizeof(T);
   static constexpr int PITCH = MT_BX + HX;             // elements per tile row
   static constexpr int ROWS = (MT_BY + 1) * (BZ + 1);  // rows incl. halo

@@ -23,6 +23,17 @@ def run(ctx, dtype, shape, pitch, num_ids, out_dtype=np.uint64, reps=5):
 
 if __name__ == "__main__":
   ctx = _shim.default_context()
+  if len(sys.argv) > 1 and sys.argv[1] == "2048":
+    from igneous_b200 import pipeline
+    c = ctypes
+    _shim.check(ctx.lib.ign_prof_enable(ctx.handle, c.c_int(1)))
+    run(ctx, np.uint32, (2048, 2048, 2048), 64, 1 << 20, out_dtype=np.uint32, reps=3)
+    for name, cls in pipeline.PROF_CLASSES.items():
+      ms, cnt = c.c_float(0), c.c_uint64(0)
+      _shim.check(ctx.lib.ign_prof_read(ctx.handle, c.c_int(cls), c.byref(ms), c.byref(cnt)))
+      if cnt.value:
+        print(name, "ms total", round(ms.value, 3), "launches", cnt.value, "ms/launch", round(ms.value / cnt.value, 4))
+    sys.exit(0)
   run(ctx, np.uint32, (512, 512, 512), 64, 1 << 20)
   run(ctx, np.uint32, (513, 513, 513), 64, 1 << 20)
   run(ctx, np.uint64, (1024, 1024, 1024), 64, 4096)
