@@ -6,6 +6,7 @@ Mirrors the functions of igneous/downsample_scales.py that sit on the hot path:
   compute_scales         :184-212
   create_downsample_scales :214-244 adds the new scales to the info file
 """
+import copy
 import math
 
 import numpy as np
@@ -83,4 +84,25 @@ def create_downsample_scales(layer_path, mip, ds_shape, axis="z", preserve_chunk
   for i in range(mip + 1, mip + len(resolutions) + 1):
     vol.scales[i]["chunk_sizes"] = new_cs
   vol.commit_info()
+  return vol
+
+
+def add_scales(layer_path, mip, num_mips, preserve_chunk_size=True, chunk_size=None, encoding=None, factor=None):
+  """igneous/downsample_scales.py:246-278: append exactly `num_mips` scales above `mip`
+  (no memory-driven truncation; used by the sharded downsample creator)."""
+  vol = CloudVolume(layer_path, mip=mip)
+  if factor is None:
+    factor = (2, 2, 1)
+  for _ in range(num_mips):
+    res = [r * f for r, f in zip(vol.meta.resolution(mip), factor)]
+    vol.meta.add_resolution(res, encoding=encoding, chunk_size=chunk_size)
+    if chunk_size is None:
+      new_cs = vol.scales[mip if preserve_chunk_size else mip + 1]["chunk_sizes"]
+    else:
+      new_cs = [list(chunk_size)]
+    if encoding is None:
+      encoding = vol.scales[mip]["encoding"]
+    vol.scales[mip + 1]["chunk_sizes"] = copy.deepcopy(new_cs)
+    mip += 1
+    vol.mip = mip
   return vol

@@ -12,6 +12,7 @@ This is not a storage engine and it is never on the compute path: when the
 real packages import, `igneous_b200._compat` uses them instead.
 """
 import copy
+import math
 import gzip
 import json
 import os
@@ -322,9 +323,56 @@ class _Meta:
   def join(self, *parts):
     return self._cv.join(*parts)
 
+  def key(self, mip):
+    return self._cv.key_at(mip)
+
+  @property
+  def cloudpath(self):
+    return self._cv.cloudpath
+
   @property
   def info(self):
     return self._cv.info
+
+
+class _ImageSource:
+  """cv.image: the two shard builders ImageShardDownsampleTask calls
+  (igneous/tasks/image/image.py:664-669,818,833)."""
+
+  def __init__(self, cv):
+    self._cv = cv
+
+  def make_shard_chunks(self, img, bbox, mip):
+    """Cut `img` (occupying `bbox` at `mip`) into the scale's chunks -> {chunk id: encoded bytes}."""
+    cv = self._cv
+    img = np.asarray(img)
+    if img.ndim == 3:
+      img = img[..., np.newaxis]
+    bbox = Bbox.create(bbox) if not isinstance(bbox, Bbox) else bbox
+    spec = cv._sharding(mip)
+    if spec is None:
+      raise ValueError("mip %d of %s is not sharded" % (mip, cv.cloudpath))
+    cs, off = cv.chunk_size_at(mip), cv.voxel_offset_at(mip)
+    if np.any((np.asarray(bbox.minpt) - np.asarray(off)) % np.asarray(cs)):
+      raise ValueError("shard cutout %r is not chunk aligned" % (bbox,))
+    out = {}
+    for c in cv._chunks(mip, Bbox.clamp(bbox, cv.bounds_at(mip))):
+      src = tuple(slice(int(a - o), int(b - o)) for a, b, o in zip(c.minpt, c.maxpt, bbox.minpt))
+      block = np.asfortranarray(img[src].astype(cv.dtype, copy=False))
+      if tuple(block.shape[:3]) != tuple(int(v) for v in c.size3()):
+        raise ValueError("image %r does not cover chunk %r of %r" % (img.shape, c, bbox))
+      out[cv._chunk_id(mip, c)] = cv._encode_chunk(block, mip)
+    return out
+
+  def make_shard(self, img, bbox, mip, progress=False):
+    """-> (file name, shard bytes).  `img` is an array or a {chunk id: bytes} dict."""
+    cv = self._cv
+    spec = cv._sharding(mip)
+    chunks = img if isinstance(img, dict) else self.make_shard_chunks(img, bbox, mip)
+    if not chunks:
+      raise ValueError("no chunks inside %r" % (bbox,))
+    shard_no = spec.locate(next(iter(chunks)))[0]
+    return spec.shard_filename(shard_no), spec.synthesize_shard(chunks)
 
 
 class CloudVolume:
@@ -356,6 +404,10 @@ class CloudVolume:
   @property
   def meta(self):
     return _Meta(self)
+
+  @property
+  def image(self):
+    return _ImageSource(self)
 
   @classmethod
   def create_new_info(cls, num_channels, layer_type, data_type, encoding, resolution, voxel_offset,
@@ -508,6 +560,32 @@ class CloudVolume:
           if not c.subvoxel():
             yield c
 
+  # sharded scales (neuroglancer_uint64_sharded_v1, igneous_b200.sharding)
+  def _sharding(self, mip):
+    spec = self.info["scales"][mip].get("sharding")
+    if not spec:
+      return None
+    from . import sharding
+    return sharding.ShardingSpecification(spec)
+
+  def _chunk_id(self, mip, chunk_box):
+    from . import sharding
+    cs, off = self.chunk_size_at(mip), self.voxel_offset_at(mip)
+    grid = [int(math.ceil(int(v) / int(c))) for v, c in zip(self.volume_size_at(mip), cs)]
+    pt = [int((int(a) - int(o)) // int(c)) for a, o, c in zip(chunk_box.minpt, off, cs)]
+    return int(sharding.compressed_morton_code(pt, grid))
+
+  def _read_chunk(self, mip, chunk_box, shard_cache):
+    spec = self._sharding(mip)
+    if spec is None:
+      return self.cf.get(self._chunk_name(mip, chunk_box))
+    cid = self._chunk_id(mip, chunk_box)
+    name = self.key_at(mip) + "/" + spec.shard_filename(spec.locate(cid)[0])
+    if name not in shard_cache:
+      shard_cache[name] = self.cf.get(name)
+    blob = shard_cache[name]
+    return None if blob is None else spec.read_chunk(blob, cid)
+
   # chunk codecs: `raw` is the bytes of the Fortran-order array; `compressed_segmentation` goes
   # through the device codec (igneous_b200.codecs); anything else the Precomputed format knows
   # (jpeg, compresso, crackle, ...) is outside this stand-in
@@ -548,14 +626,23 @@ class CloudVolume:
       return Bbox(lo, hi)
     raise TypeError(key)
 
-  def download(self, bbox, mip=None, **kwargs):
+  def download(self, bbox, mip=None, renumber=False, **kwargs):
+    """Cutout as an F-order [x, y, z, c] array.  renumber=True -> (array of the smallest
+    dtype holding 1..N, {old: new}) with the relabelling done on the GPU
+    (cloudvolume's download(renumber=True), image.py:745-752)."""
+    if renumber:
+      from . import fastremap
+      img = self.download(bbox, mip=mip, **kwargs)
+      small, mapping = fastremap.renumber(img, preserve_zero=True, in_place=False)
+      return small, mapping
     mip = self._mip if mip is None else mip
     bbox = self._to_bbox(bbox)
     if self.bounded and not (np.all(bbox.minpt >= self.bounds_at(mip).minpt) and np.all(bbox.maxpt <= self.bounds_at(mip).maxpt)):
       raise OutOfBoundsError("%r is outside %r" % (bbox, self.bounds_at(mip)))
     out = np.zeros(tuple(int(v) for v in bbox.size3()) + (self.num_channels,), dtype=self.dtype, order="F")
+    shard_cache = {}
     for c in self._chunks(mip, bbox):
-      data = self.cf.get(self._chunk_name(mip, c))
+      data = self._read_chunk(mip, c, shard_cache)
       inter = Bbox.intersection(c, bbox)
       if inter.subvoxel():
         continue
@@ -581,6 +668,8 @@ class CloudVolume:
     if tuple(img.shape[:3]) != tuple(int(v) for v in bbox.size3()):
       raise ValueError("image %r does not fit %r" % (img.shape, bbox))
     img = img.astype(self.dtype, copy=False)
+    if self._sharding(mip) is not None:
+      raise NotImplementedError("writes to a sharded scale go through image.make_shard (whole shards only)")
     for c in self._chunks(mip, bbox):
       inter = Bbox.intersection(c, bbox)
       if inter.subvoxel():

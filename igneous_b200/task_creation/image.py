@@ -1,6 +1,6 @@
-"""create_downsampling_tasks and the three CCL task creators
-(igneous/task_creation/image.py:170-345, 1726-1889): same signatures, same
-info / provenance side effects, tasks from igneous_b200.tasks."""
+"""create_downsampling_tasks, create_image_shard_downsample_tasks and the three CCL
+task creators (igneous/task_creation/image.py:170-345, 639-770, 1726-1889): same
+signatures, same info / provenance side effects, tasks from igneous_b200.tasks."""
 import copy
 import math
 from functools import partial, reduce
@@ -8,9 +8,9 @@ from time import strftime
 
 import numpy as np
 
-from .. import downsample_scales, fastremap
+from .. import downsample_scales, fastremap, sharding, shards
 from .._compat import CloudVolume, CloudFiles, InfoUnavailableError, Vec
-from ..tasks import DownsampleTask, CCLFacesTask, CCLEquivalancesTask, RelabelCCLTask
+from ..tasks import DownsampleTask, ImageShardDownsampleTask, CCLFacesTask, CCLEquivalancesTask, RelabelCCLTask
 from ..types import DownsampleMethods
 from .common import FinelyDividedTaskIterator, get_bounds, operator_contact
 
@@ -86,6 +86,76 @@ def create_downsampling_tasks(layer_path, mip=0, fill_missing=False, axis="z", n
            downsample_method=int(method))
 
   return DownsampleTaskIterator(roi, shape)
+
+
+def set_encoding(cv, mip, encoding, encoding_level, encoding_effort):
+  """task_creation/common.py:215-236 (the lossy-codec quality keys are recorded but those
+  codecs are outside this implementation)."""
+  scale = cv.scales[mip]
+  if encoding is not None:
+    scale["encoding"] = encoding
+    if encoding == "compressed_segmentation" and "compressed_segmentation_block_size" not in scale:
+      scale["compressed_segmentation_block_size"] = (8, 8, 8)
+  if encoding_level is None:
+    return
+  key = {"jpeg": "jpeg_quality", "jxl": "jxl_quality", "png": "png_level", "fpzip": "fpzip_precision"}.get(encoding)
+  if key:
+    scale[key] = int(encoding_level)
+  if encoding == "jxl" and encoding_effort is not None:
+    scale["jxl_effort"] = int(encoding_effort)
+
+
+def create_image_shard_downsample_tasks(cloudpath, mip=0, fill_missing=False, sparse=False, chunk_size=None,
+                                        encoding=None, memory_target=MEMORY_TARGET, agglomerate=False,
+                                        timestamp=None, factor=(2, 2, 1), bounds=None, bounds_mip=0,
+                                        encoding_level=None, encoding_effort=None,
+                                        method=DownsampleMethods.AUTO, num_mips=None, truncate_scales=True):
+  """Downsample an (un)sharded layer into SHARDED scales mip+1 .. mip+num_mips
+  (task_creation/image.py:639-770).  One task covers the footprint of one shard of
+  mip+1 scaled up by factor^num_mips."""
+  if num_mips is None:
+    num_mips = 3
+  cv = CloudVolume(cloudpath)
+  if truncate_scales:
+    cv.info["scales"] = cv.info["scales"][:mip + 1]
+    cv.commit_info()
+  cv = downsample_scales.add_scales(cloudpath, mip, num_mips, preserve_chunk_size=True, chunk_size=chunk_size,
+                                    encoding=encoding, factor=factor)
+  for i in range(1, num_mips + 1):
+    scale = cv.scales[mip + i]
+    scale["sharding"] = sharding.create_sharded_image_info(
+      dataset_size=scale["size"], chunk_size=scale["chunk_sizes"][0], encoding=scale["encoding"],
+      dtype=cv.dtype, uncompressed_shard_bytesize=int(memory_target))
+  cv.mip = mip
+  for i in range(num_mips):
+    set_encoding(cv, mip + i + 1, encoding, encoding_level, encoding_effort)
+  if num_mips > 1:  # keep the top level lossless so that further levels can be built on it
+    if encoding == "jxl":
+      set_encoding(cv, mip + num_mips, encoding, 100, encoding_effort)
+    elif encoding == "jpeg":
+      set_encoding(cv, mip + num_mips, "png", 9, encoding_effort)
+  cv.commit_info()
+  base_shape = shards.image_shard_shape_from_spec(cv.info["scales"][mip + 1]["sharding"],
+                                                  cv.meta.volume_size(mip + 1), cv.meta.chunk_size(mip + 1))
+  shape = Vec(*[int(b) * int(f) ** num_mips for b, f in zip(base_shape, factor)])
+  cv.mip = mip
+  roi = get_bounds(cv, bounds, mip, bounds_mip=bounds_mip, chunk_size=cv.meta.chunk_size(mip + 1))
+
+  class ImageShardDownsampleTaskIterator(FinelyDividedTaskIterator):
+    def task(self, shape, offset):
+      return partial(ImageShardDownsampleTask, cloudpath, shape=tuple(int(v) for v in shape),
+                     offset=tuple(int(v) for v in offset), mip=int(mip), fill_missing=bool(fill_missing),
+                     sparse=bool(sparse), agglomerate=bool(agglomerate), timestamp=timestamp,
+                     factor=tuple(factor), method=method, num_mips=int(num_mips))
+
+    def on_finish(self):
+      cv.provenance.sources = [cloudpath]
+      _log(cv, "ImageShardDownsampleTask", cloudpath=cloudpath, shape=[int(v) for v in shape],
+           fill_missing=fill_missing, sparse=bool(sparse), bounds=[roi.minpt.tolist(), roi.maxpt.tolist()],
+           mip=mip, agglomerate=agglomerate, timestamp=timestamp, method=int(method),
+           encoding_level=encoding_level, encoding_effort=encoding_effort, num_mips=int(num_mips))
+
+  return ImageShardDownsampleTaskIterator(roi, shape)
 
 
 def _ccl_creator(task_fn, task_name, cloudpath, mip, shape, **opts):

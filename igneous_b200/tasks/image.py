@@ -3,15 +3,18 @@
 Same names, arguments and side effects as igneous/tasks/image/image.py:
   downsample_method_to_fn :37-55, downsample_and_upload :57-100,
   TransferTask :434-516, DownsampleTask :518-549.
+  ImageShardDownsampleTask :672-843.
 Only the library behind `fn(image, factors[0], num_mips=...)` (:91) changes:
 igneous_b200.tinybrain instead of the CPU tinybrain wheel.
 """
+import math
+from collections import defaultdict
 from functools import partial
 
 import numpy as np
 
-from .. import downsample_scales, tinybrain
-from .._compat import CloudVolume, Bbox, Vec, min2, queueable
+from .. import downsample_scales, fastremap, sharding, shards, tinybrain
+from .._compat import CloudVolume, CloudFiles, Bbox, Vec, min2, queueable
 from ..types import DownsampleMethods
 
 
@@ -87,3 +90,115 @@ def DownsampleTask(layer_path, mip, shape, offset, fill_missing=False, axis="z",
                       delete_black_uploads=delete_black_uploads, background_color=background_color,
                       sparse=sparse, axis=axis, compress=compress, factor=factor, max_mips=max_mips,
                       downsample_method=DownsampleMethods.AUTO)
+
+
+@queueable
+def ImageShardDownsampleTask(src_path, shape, offset, mip=0, fill_missing=False, sparse=False,
+                             agglomerate=False, timestamp=None, factor=(2, 2, 1),
+                             method=DownsampleMethods.AUTO, num_mips=1, progress=False):
+  """Downsample the region under one (stack of) output shard(s) and write whole shard files
+  for mips mip+1 .. mip+num_mips (image.py:672-843).
+
+  As in the reference the region is walked in z-layers one chunk thick at the coarsest
+  mip; segmentation layers are renumbered to a small dtype before pooling and mapped back
+  afterwards (renumber / pooling / remap run on the GPU).  Chunks are collected per output
+  shard -- keyed by the shard number their chunk id hashes to, which for the identity hash
+  is the reference's (shard_x, shard_y, shard_z) box -- and every shard is written once."""
+  shape, offset = Vec(*shape), Vec(*offset)
+  mip, num_mips = int(mip), int(num_mips)
+  factor = tuple(int(f) for f in factor)
+  src = CloudVolume(src_path, fill_missing=bool(fill_missing), mip=mip, bounded=False)
+  chunk_size = src.meta.chunk_size(mip)
+  bbox = Bbox.clamp(Bbox(offset, offset + shape), src.meta.bounds(mip))
+  bbox = bbox.expand_to_chunk_size(chunk_size, offset=src.meta.voxel_offset(mip))
+
+  def shard_shape_at(m):
+    return shards.image_shard_shape_from_spec(src.scales[m]["sharding"], src.meta.volume_size(m),
+                                              src.meta.chunk_size(m))
+
+  first = shard_shape_at(mip + 1)
+  upper = offset // Vec(*factor)
+  upper_box = Bbox.clamp(Bbox(upper, upper + Vec(*[int(v) for v in first])), src.meta.bounds(mip + 1))
+  if upper_box.subvoxel():
+    return
+  fn = downsample_method_to_fn(method, sparse, src)
+  renumber = src.layer_type == "segmentation"
+  cz = int(chunk_size[2]) * factor[2] ** num_mips
+  nz = int(math.ceil(int(bbox.size3()[2]) / cz))
+  f3 = np.asarray(factor, dtype=int)
+  pending = [defaultdict(dict) for _ in range(num_mips)]  # per mip: shard grid position -> {chunk id: bytes}
+  zbox = bbox.clone()
+  zbox.maxpt[2] = zbox.minpt[2] + cz
+  for _ in range(nz):
+    if renumber:
+      img, mapping = src.download(zbox, agglomerate=agglomerate, timestamp=timestamp, renumber=True)
+      back = {int(new): int(old) for old, new in mapping.items()}
+      back[src.background_color] = src.background_color
+    else:
+      img = src.download(zbox, agglomerate=agglomerate, timestamp=timestamp)
+    mips = fn(img, factor, num_mips=num_mips)  # <- the kernel call (image.py:764)
+    del img
+    for i in range(num_mips):
+      m = mip + i + 1
+      cutout = mips[i]
+      if renumber:
+        cutout = fastremap.remap(cutout.astype(src.dtype), back, preserve_missing_labels=False)
+      lo = np.asarray(zbox.minpt, dtype=int) // (f3 ** (i + 1))
+      box = Bbox(lo, lo + np.asarray(cutout.shape[:3], dtype=int))
+      bounds_m = src.meta.bounds(m)
+      if box.minpt[2] >= bounds_m.maxpt[2]:
+        continue
+      sshape = np.asarray(shard_shape_at(m), dtype=int)
+      origin = np.asarray(src.meta.voxel_offset(m), dtype=int)
+      g0 = (np.asarray(box.minpt) - origin) // sshape
+      g1 = -((-(np.asarray(box.maxpt) - origin)) // sshape)
+      for gz in range(int(g0[2]), int(g1[2])):
+        for gy in range(int(g0[1]), int(g1[1])):
+          for gx in range(int(g0[0]), int(g1[0])):
+            smin = origin + np.asarray([gx, gy, gz]) * sshape
+            part = Bbox.intersection(Bbox(smin, smin + sshape), box)
+            if part.subvoxel():
+              continue
+            sl = tuple(slice(int(a - o), int(b - o)) for a, b, o in zip(part.minpt, part.maxpt, box.minpt))
+            pending[i][(gx, gy, gz)].update(_shard_chunks(src, cutout[sl], part, m))
+    del mips
+    zbox.minpt[2] += cz
+    zbox.maxpt[2] += cz
+  for i in range(num_mips):
+    m = mip + i + 1
+    sshape = np.asarray(shard_shape_at(m), dtype=int)
+    origin = np.asarray(src.meta.voxel_offset(m), dtype=int)
+    base = src.meta.join(src.cloudpath, src.meta.key(m))
+    done = Bbox(np.asarray(bbox.minpt, dtype=int) // (f3 ** (i + 1)), -((-np.asarray(bbox.maxpt, dtype=int)) // (f3 ** (i + 1))))
+    for grid_pos, chunk_dict in pending[i].items():
+      smin = origin + np.asarray(grid_pos) * sshape
+      shard_box = Bbox(smin, smin + sshape)
+      inside = Bbox.clamp(shard_box, src.meta.bounds(m))
+      if not (np.all(inside.minpt >= done.minpt) and np.all(inside.maxpt <= done.maxpt)):
+        # a coarser shard that is taller than this task (the reference would let the last task win):
+        # keep the chunks other tasks already stored in it
+        spec = sharding.ShardingSpecification(src.scales[m]["sharding"])
+        name = spec.shard_filename(spec.locate(next(iter(chunk_dict)))[0])
+        old = CloudFiles(base).get(name)
+        if old is not None:
+          merged = {cid: spec.read_chunk(old, cid) for cid in spec.chunk_ids(old)}
+          merged.update(chunk_dict)
+          chunk_dict = merged
+      filename, blob = src.image.make_shard(chunk_dict, shard_box, m, progress=False)
+      CloudFiles(base).put(filename, blob, compress=None)
+    pending[i] = None
+
+
+def _shard_chunks(vol, cutout, box, mip):
+  """make_shard_chunks on a cutout whose far edges may be short of a chunk boundary: pad with the
+  background colour (image.py:797-799) and let the chunker clamp to the dataset bounds."""
+  cs = np.asarray(vol.meta.chunk_size(mip), dtype=int)
+  off = np.asarray(vol.meta.voxel_offset(mip), dtype=int)
+  want = np.ceil((np.asarray(box.maxpt) - off) / cs).astype(int) * cs + off
+  pad = [(0, int(max(w - h, 0))) for w, h in zip(want, box.maxpt)]
+  if any(p[1] for p in pad):
+    if cutout.ndim == 4:
+      pad = pad + [(0, 0)]
+    cutout = np.pad(cutout, pad, mode="constant", constant_values=vol.background_color)
+    box = Bbox(box.minpt, np.asarray(box.minpt) + np.asarray(cutout.shape[:3]))
+  return vol.image.make_shard_chunks(cutout, box, mip)

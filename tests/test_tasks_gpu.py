@@ -229,3 +229,32 @@ def test_downsample_task_compressed_segmentation_encoding(ctx, oracle, tmp_path)
   box = [tuple(int(v) for v in part.split("-")) for part in name.split("/")[-1].split("_")]
   chunk = want[0][box[0][0]:box[0][1], box[1][0]:box[1][1], box[2][0]:box[2][1]]
   assert raw == oracle.cseg_encode(np.asfortranarray(chunk)).tobytes()
+
+
+@pytest.mark.parametrize("factor,shape,offset,encoding", [
+  ((2, 2, 1), (256, 192, 96), (0, 0, 0), "raw"),
+  ((2, 2, 2), (128, 128, 128), (3, 5, 7), "raw"),                       # test_downsample_with_offset_sharded_2x2x2
+  ((2, 2, 1), (128, 128, 160), (0, 0, 0), "compressed_segmentation"),   # coarse shards taller than a task
+])
+def test_image_shard_downsample_task(ctx, oracle, tmp_path, factor, shape, offset, encoding):
+  """create_image_shard_downsample_tasks + ImageShardDownsampleTask
+  (test/test_tasks.py:73-124,154-245): sharded mips equal the pooling of the whole volume;
+  renumber -> pooling -> remap and the chunk codec run on the GPU, the shard container on the host."""
+  import igneous_b200.task_creation as tc
+  from igneous_b200._compat import CloudVolume, LocalTaskQueue
+  seg = oracle.synth_seg(shape, pitch=24, num_ids=1 << 20).astype(np.uint32)[..., np.newaxis]
+  seg[seg != 0] += np.uint32(1 << 24)            # ids that do not fit the renumbered dtype
+  path = "file://" + str(tmp_path / "seg")
+  CloudVolume.from_numpy(seg, vol_path=path, resolution=(16, 16, 40), voxel_offset=offset, chunk_size=(32, 32, 32),
+                         layer_type="segmentation")
+  tasks = tc.create_image_shard_downsample_tasks(path, mip=0, num_mips=2, factor=factor, encoding=encoding,
+                                                 memory_target=32 ** 3 * 4 * (4 if shape[2] == 160 else 8))
+  LocalTaskQueue(parallel=1).insert_all(tasks)
+  cv = CloudVolume(path)
+  assert cv.available_mips == [0, 1, 2]
+  assert all(cv.scales[m]["sharding"]["@type"] == "neuroglancer_uint64_sharded_v1" for m in (1, 2))
+  assert all(cv.scales[m]["encoding"] == encoding for m in (1, 2))
+  want = oracle.downsample_segmentation(seg, tuple(factor) + (1,), num_mips=2)
+  for m in (1, 2):
+    cv.mip = m
+    assert np.array_equal(cv[cv.meta.bounds(m)], want[m - 1]), m
