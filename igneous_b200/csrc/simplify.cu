@@ -70,6 +70,21 @@ __device__ __forceinline__ uint32_t s_unmix(uint32_t x) {
   x ^= x >> 16; x *= 0x43021123U; x ^= x >> 15 ^ x >> 30; x *= 0x1d69e2a5U; x ^= x >> 16;
   return x;
 }
+// 16-bit variant for labels whose half-edge ids fit 16 bits (oracle: simp_mix16 / simp_unmix16)
+__device__ __forceinline__ uint32_t s_mix16(uint32_t x) {
+  x &= 0xFFFFu;
+  x = (x * 0x2F35u) & 0xFFFFu; x ^= x >> 7;
+  x = (x * 0x4A6Bu) & 0xFFFFu; x ^= x >> 9;
+  x = (x * 0x9E37u) & 0xFFFFu; x ^= x >> 8;
+  return x;
+}
+__device__ __forceinline__ uint32_t s_unmix16(uint32_t x) {
+  x &= 0xFFFFu;
+  x ^= x >> 8; x = (x * 0x7787u) & 0xFFFFu;
+  x ^= x >> 9; x = (x * 0x1243u) & 0xFFFFu;
+  x ^= x >> 7; x ^= x >> 14; x = (x * 0xEB1Du) & 0xFFFFu;
+  return x;
+}
 __device__ __forceinline__ unsigned long long s_key(double cost, uint32_t h, uint32_t salt) {
   const float c = __double2float_rn(cost);
   return ((unsigned long long)__float_as_uint(c) << 32) | s_mix(h ^ salt);
@@ -234,7 +249,7 @@ __global__ void __launch_bounds__(256) k_simp_boundary(Simp s) {
 // on the whole-task arrays in global memory (SM = false).
 // vertex flags: CDIRTY the vertex moved (cached costs of its edges are stale), RDIRTY its ring
 // changed (parked edges around it may be valid now)
-constexpr uint32_t VF_ALIVE = 1, VF_BOUND = 2, VF_CDIRTY = 4, VF_LOSE = 8, VF_DONE = 16, VF_END = 32, VF_RDIRTY = 64;
+constexpr uint32_t VF_ALIVE = 1, VF_BOUND = 2, VF_CDIRTY = 4, VF_DONE = 16, VF_END = 32, VF_RDIRTY = 64;
 constexpr int SL_THREADS = 1024;
 constexpr int SL_WCAP = 256;  // winners validated per selection pass (a round runs as many passes as it needs)
 constexpr uint32_t WF_BAD = 1, WF_OK = 2;  // winner flags: failed validation / validated
@@ -253,6 +268,7 @@ struct SlArgs {
   unsigned long long* key1;  // U
   uint8_t* fstate;           // T
   uint8_t* vflag;            // U
+  uint8_t* vlose;            // U  LOSE marks of the round (plain byte stores)
   uint32_t *flist, *flist2;  // T  alive-face lists (ping-pong)
   uint32_t *vlist, *vlist2;  // U
   const uint32_t* tri_off;   // [K+2]
@@ -265,7 +281,7 @@ struct SlArgs {
   int max_rounds;
   uint32_t smem_bytes;  // dynamic shared memory of the launch
   uint32_t* ring;       // [gridDim.x][SL_WCAP * 2 * S_MAXV] ring lists of the round's winners
-  double* wbest;        // [gridDim.x][SL_WCAP][3] placement of the round's winners
+  uint32_t* lrec;       // IGN_SIMP_TRACE=1: [work item][4] = faces, rounds, kilocycles, face visits (sum of list lengths)
   uint32_t* trace;      // IGN_SIMP_TRACE=1: [round][4] = winners, collapses, alive faces, list length of the largest label
 };
 
@@ -275,9 +291,12 @@ struct SlWin {
 
 struct SlShared {
   uint32_t work, alive, progress, ncol, nwin, stop, slow, counter;
+  unsigned long long visits, wins;  // IGN_SIMP_TRACE
+  long long t_label;
   unsigned long long ph[10];  // phase timers (IGN_SIMP_TRACE)
   long long t_prev;
   SlWin win[SL_WCAP];
+  double wbest[SL_WCAP * 3];  // placement of the round's winners
 };
 
 template <bool SM>
@@ -288,10 +307,15 @@ struct SlLab {
   uint32_t* gface;         // !SM: AoS global ids in place
   uint8_t* fstate;         // bit 7 alive, bits 2c..2c+1 memo of half-edge c
   uint8_t* vflag;
-  unsigned long long* key1;
+  uint8_t* vlose;  // a face neighbour holds a smaller key this round (written with plain byte stores: every writer stores 1)
+  // key format (oracle: simp_key): labels with 3T <= 65536 use 32-bit keys (bf16-like cost | 16-bit id
+  // permutation).  The shared-memory class only takes such labels and stores them in 32 bits (native
+  // shared-memory min); the other classes keep 64-bit slots for both formats.
+  typedef typename std::conditional<SM, uint32_t, unsigned long long>::type key_t;
+  key_t* key1;
+  bool fmt16;
   uint32_t* wq;    // [warps][SL_EQ] per-warp cost queues of the key pass (shared memory)
   uint32_t* ring;  // [SL_WCAP][2][S_MAXV] face ids of the winners' rings (global memory, per CTA)
-  double* wbest;   // [SL_WCAP][3]
   idx_t *flist, *flist2, *vlist, *vlist2;  // alive lists (flist2 / vlist2: global-memory class only)
 };
 
@@ -312,18 +336,49 @@ __device__ __forceinline__ void sl_fset(const SlLab<SM>& L, uint32_t f, int c, u
   }
 }
 // flag bytes are modified with word atomics whenever two threads may touch the same word
+// (SM: the flags are in shared memory for sure -> shared-space reductions instead of generic atomics)
+template <bool SM>
 __device__ __forceinline__ void sl_vor(uint8_t* vflag, uint32_t v, uint32_t bits) {
   const uintptr_t a = (uintptr_t)(vflag + v);
   if ((*(volatile uint8_t*)a & bits) == bits) return;
-  atomicOr((uint32_t*)(a & ~(uintptr_t)3), bits << (8 * (a & 3)));
+  const uint32_t word = bits << (8 * (a & 3));
+  if (SM) {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared((void*)(a & ~(uintptr_t)3))), "r"(word) : "memory");
+  } else {
+    atomicOr((uint32_t*)(a & ~(uintptr_t)3), word);
+  }
 }
+template <bool SM>
 __device__ __forceinline__ void sl_vclear(uint8_t* vflag, uint32_t v, uint32_t bits) {
   const uintptr_t a = (uintptr_t)(vflag + v);
-  atomicAnd((uint32_t*)(a & ~(uintptr_t)3), ~(bits << (8 * (a & 3))));
+  const uint32_t word = ~(bits << (8 * (a & 3)));
+  if (SM) {
+    asm volatile("red.shared.and.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared((void*)(a & ~(uintptr_t)3))), "r"(word) : "memory");
+  } else {
+    atomicAnd((uint32_t*)(a & ~(uintptr_t)3), word);
+  }
 }
 __device__ __forceinline__ void sl_post(unsigned long long* key1, uint32_t u, uint32_t v, unsigned long long key) {
   if (key < *(volatile unsigned long long*)&key1[u]) atomicMin(&key1[u], key);
   if (key < *(volatile unsigned long long*)&key1[v]) atomicMin(&key1[v], key);
+}
+__device__ __forceinline__ void sl_post(uint32_t* key1, uint32_t u, uint32_t v, uint32_t key) {  // shared memory only
+  if (key < *(volatile uint32_t*)&key1[u])
+    asm volatile("red.shared.min.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(key1 + u)), "r"(key) : "memory");
+  if (key < *(volatile uint32_t*)&key1[v])
+    asm volatile("red.shared.min.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(key1 + v)), "r"(key) : "memory");
+}
+template <bool SM>
+__device__ __forceinline__ typename SlLab<SM>::key_t sl_key(const SlLab<SM>& L, float cost, uint32_t hl, uint32_t salt) {
+  typedef typename SlLab<SM>::key_t key_t;
+  const uint32_t bits = __float_as_uint(cost);
+  if (SM || L.fmt16) return (key_t)((((bits >> 15) & 0xFFFFu) << 16) | s_mix16((hl ^ salt) & 0xFFFFu));
+  return (key_t)(((unsigned long long)bits << 32) | s_mix(hl ^ salt));
+}
+template <bool SM>
+__device__ __forceinline__ uint32_t sl_key_edge(const SlLab<SM>& L, typename SlLab<SM>::key_t key, uint32_t salt) {
+  if (SM || L.fmt16) return s_unmix16((uint32_t)key & 0xFFFFu) ^ (salt & 0xFFFFu);
+  return s_unmix((uint32_t)((unsigned long long)key & 0xFFFFFFFFull)) ^ salt;
 }
 
 // s_cost on label-local ids (same arithmetic, same order)
@@ -495,8 +550,12 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
   if (A.trace != nullptr && threadIdx.x == 0) {
     for (int q = 0; q < 10; q++) sh.ph[q] = 0;
     sh.t_prev = clock64();
+    sh.t_label = sh.t_prev;
+    sh.visits = 0;
+    sh.wins = 0;
   }
   typedef typename SlLab<SM>::idx_t idx_t;
+  typedef typename SlLab<SM>::key_t key_t;
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t tid = threadIdx.x, NT = blockDim.x, lane = tid & 31u, warp = tid >> 5, NW = NT >> 5;
   const uint32_t T = L.T, U = L.U;
@@ -534,9 +593,10 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
     // ---- P1
     for (uint32_t i = tid; i < nV; i += NT) {
       const uint32_t v = SM ? i : (uint32_t)vlist[i];
-      L.key1[v] = S_KEYMAX;
+      L.key1[v] = (key_t)S_KEYMAX;
+      L.vlose[v] = 0;
       const uint8_t b = L.vflag[v];
-      if (b & (VF_LOSE | VF_DONE)) L.vflag[v] = (uint8_t)(b & ~(VF_LOSE | VF_DONE));
+      if (b & VF_DONE) L.vflag[v] = (uint8_t)(b & ~VF_DONE);
     }
     if (tid == 0) {
       sh.progress = 0;
@@ -590,7 +650,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
             if (es == 0) {
               pend |= 1u << c;
             } else if (es == 2) {
-              sl_post(L.key1, u, v, ((unsigned long long)__float_as_uint(ec[c]) << 32) | s_mix((3u * f + (uint32_t)c) ^ salt));
+              sl_post(L.key1, u, v, sl_key<SM>(L, ec[c], 3u * f + (uint32_t)c, salt));
             }
             nst = (nst & ~(3u << (2 * c))) | (es << (2 * c));
           }
@@ -619,7 +679,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
                 const float cf = __double2float_rn(ev.cost);
                 A.ecost[3 * (uint64_t)(L.tbase + ef) + c] = cf;
                 es = 2;
-                sl_post(L.key1, u, v, ((unsigned long long)__float_as_uint(cf) << 32) | s_mix((3u * ef + (uint32_t)c) ^ salt));
+                sl_post(L.key1, u, v, sl_key<SM>(L, cf, 3u * ef + (uint32_t)c, salt));
               }
               est = (est & ~(3u << (2 * c))) | (es << (2 * c));
             }
@@ -635,18 +695,34 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
     // ---- P3: dirty flags consumed; LOSE = a face neighbour holds a smaller key
     for (uint32_t i = tid; i < nV; i += NT) {
       const uint32_t v = SM ? i : (uint32_t)vlist[i];
-      if (L.vflag[v] & (VF_CDIRTY | VF_RDIRTY)) sl_vclear(L.vflag, v, VF_CDIRTY | VF_RDIRTY);
+      if (L.vflag[v] & (VF_CDIRTY | VF_RDIRTY)) sl_vclear<SM>(L.vflag, v, VF_CDIRTY | VF_RDIRTY);
     }
-    for (uint32_t i = tid; i < nF; i += NT) {
-      const uint32_t f = flist[i];
-      if (!(L.fstate[f] & 0x80u)) continue;
-      const uint32_t a0 = sl_fget<SM>(L, f, 0), a1 = sl_fget<SM>(L, f, 1), a2 = sl_fget<SM>(L, f, 2);
-      const unsigned long long k0 = L.key1[a0], k1 = L.key1[a1], k2 = L.key1[a2];
-      unsigned long long m = k0 < k1 ? k0 : k1;
-      m = k2 < m ? k2 : m;
-      if (k0 > m) sl_vor(L.vflag, a0, VF_LOSE);
-      if (k1 > m) sl_vor(L.vflag, a1, VF_LOSE);
-      if (k2 > m) sl_vor(L.vflag, a2, VF_LOSE);
+    // two faces per thread and iteration, the loads of both issued before anything depends on them
+    for (uint32_t i = tid; i < nF; i += 2 * NT) {
+      const uint32_t i2 = i + NT;
+      const bool two = i2 < nF;
+      const uint32_t fa = flist[i], fb = two ? (uint32_t)flist[i2] : fa;
+      const bool la = (L.fstate[fa] & 0x80u) != 0, lb = two && (L.fstate[fb] & 0x80u) != 0;
+      uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+      if (la) { a0 = sl_fget<SM>(L, fa, 0); a1 = sl_fget<SM>(L, fa, 1); a2 = sl_fget<SM>(L, fa, 2); }
+      if (lb) { b0 = sl_fget<SM>(L, fb, 0); b1 = sl_fget<SM>(L, fb, 1); b2 = sl_fget<SM>(L, fb, 2); }
+      key_t ka0 = 0, ka1 = 0, ka2 = 0, kb0 = 0, kb1 = 0, kb2 = 0;
+      if (la) { ka0 = L.key1[a0]; ka1 = L.key1[a1]; ka2 = L.key1[a2]; }
+      if (lb) { kb0 = L.key1[b0]; kb1 = L.key1[b1]; kb2 = L.key1[b2]; }
+      if (la) {
+        key_t m = ka0 < ka1 ? ka0 : ka1;
+        m = ka2 < m ? ka2 : m;
+        if (ka0 > m) L.vlose[a0] = 1;
+        if (ka1 > m) L.vlose[a1] = 1;
+        if (ka2 > m) L.vlose[a2] = 1;
+      }
+      if (lb) {
+        key_t m = kb0 < kb1 ? kb0 : kb1;
+        m = kb2 < m ? kb2 : m;
+        if (kb0 > m) L.vlose[b0] = 1;
+        if (kb1 > m) L.vlose[b1] = 1;
+        if (kb2 > m) L.vlose[b2] = 1;
+      }
     }
     __syncthreads();
     SL_MARK(2);
@@ -657,14 +733,14 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
       for (uint32_t i = tid; i < nV; i += NT) {
         const uint32_t a = SM ? i : (uint32_t)vlist[i];
         const uint32_t fl = L.vflag[a];
-        if (!(fl & VF_ALIVE) || (fl & (VF_LOSE | VF_DONE))) continue;
-        const unsigned long long key = L.key1[a];
-        if (key == S_KEYMAX) continue;
-        const uint32_t hl = s_unmix((uint32_t)(key & 0xFFFFFFFFu)) ^ salt;
+        if (!(fl & VF_ALIVE) || (fl & VF_DONE) || L.vlose[a]) continue;
+        const key_t key = L.key1[a];
+        if (key == (key_t)S_KEYMAX) continue;
+        const uint32_t hl = sl_key_edge<SM>(L, key, salt);
         const uint32_t f = hl / 3, c = hl - 3 * f;
         if (sl_fget<SM>(L, f, (int)c) != a) continue;
         const uint32_t v = sl_fget<SM>(L, f, (int)((c + 1) % 3));
-        if (L.key1[v] != key || (L.vflag[v] & (VF_LOSE | VF_DONE))) continue;
+        if (L.key1[v] != key || (L.vflag[v] & VF_DONE) || L.vlose[v]) continue;
         const uint32_t slot = atomicAdd(&sh.nwin, 1u);
         if (slot < (uint32_t)SL_WCAP) {
           sh.win[slot].u = a;
@@ -673,8 +749,8 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
           sh.win[slot].cnt[0] = 0;
           sh.win[slot].cnt[1] = 0;
           sh.win[slot].flags = 0;
-          sl_vor(L.vflag, a, VF_DONE | VF_END);
-          sl_vor(L.vflag, v, VF_DONE | VF_END);
+          sl_vor<SM>(L.vflag, a, VF_DONE | VF_END);
+          sl_vor<SM>(L.vflag, v, VF_DONE | VF_END);
         }
       }
       __syncthreads();
@@ -682,55 +758,66 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
       const uint32_t total = sh.nwin;
       const uint32_t nb = total < (uint32_t)SL_WCAP ? total : (uint32_t)SL_WCAP;
       if (nb == 0) break;
+      if (A.trace != nullptr && tid == 0) sh.wins += nb;
       // key1 is dead until the next P1: the winners' entries now name their ring lists
       for (uint32_t i = tid; i < nb; i += NT) {
-        L.key1[sh.win[i].u] = 2ull * i;
-        L.key1[sh.win[i].v] = 2ull * i + 1;
+        L.key1[sh.win[i].u] = (key_t)(2u * i);
+        L.key1[sh.win[i].v] = (key_t)(2u * i + 1u);
       }
       __syncthreads();
       SL_MARK(4);
-      // ---- E1: ring lists (global memory, one pass over the alive faces for all winners)
-      for (uint32_t i = tid; i < nF; i += NT) {
-        const uint32_t f = flist[i];
-        if (!(L.fstate[f] & 0x80u)) continue;
+      // ---- E1 + E2a in one barrier interval (they do not depend on each other): the first warps
+      // compute placement and cost of the winners (one thread each, double precision, L2 latency)
+      // while the others build the ring lists with one pass over the alive faces.
+      {
+        const uint32_t nbt = (nb + 31u) & ~31u;
+        const bool split = NT - nbt >= NT / 2;
+        if (tid < nb) {
+          const uint32_t i = tid;
+          SEval e;
+          sl_cost<SM>(A, L, sh.win[i].u, sh.win[i].v, &e);
+          sh.win[i].keep = e.valid ? e.keep : sh.win[i].u;
+          sh.win[i].flags = e.valid ? 0u : WF_BAD;
+          if (e.valid) {
+            sh.wbest[3 * i + 0] = e.p[0]; sh.wbest[3 * i + 1] = e.p[1]; sh.wbest[3 * i + 2] = e.p[2];
+          }
+        }
+        if (!split || tid >= nbt) {
+          const uint32_t first = split ? tid - nbt : tid, step = split ? NT - nbt : NT;
+          for (uint32_t i = first; i < nF; i += 2 * step) {
+            const uint32_t i2 = i + step;
+            const bool two = i2 < nF;
+            const uint32_t fa = flist[i], fb = two ? (uint32_t)flist[i2] : fa;
+            const bool la = (L.fstate[fa] & 0x80u) != 0, lb = two && (L.fstate[fb] & 0x80u) != 0;
+            uint32_t x[6] = {0, 0, 0, 0, 0, 0}, fl[6] = {0, 0, 0, 0, 0, 0};
+            if (la) { x[0] = sl_fget<SM>(L, fa, 0); x[1] = sl_fget<SM>(L, fa, 1); x[2] = sl_fget<SM>(L, fa, 2); }
+            if (lb) { x[3] = sl_fget<SM>(L, fb, 0); x[4] = sl_fget<SM>(L, fb, 1); x[5] = sl_fget<SM>(L, fb, 2); }
+            if (la) { fl[0] = L.vflag[x[0]]; fl[1] = L.vflag[x[1]]; fl[2] = L.vflag[x[2]]; }
+            if (lb) { fl[3] = L.vflag[x[3]]; fl[4] = L.vflag[x[4]]; fl[5] = L.vflag[x[5]]; }
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const uint32_t x = sl_fget<SM>(L, f, c);
-          if (!(L.vflag[x] & VF_END)) continue;
-          const uint32_t sl = (uint32_t)L.key1[x];
-          const uint32_t p = atomicAdd(&sh.win[sl >> 1].cnt[sl & 1u], 1u);
-          if (p < (uint32_t)S_MAXV) L.ring[sl * S_MAXV + p] = f;
+            for (int c = 0; c < 6; c++) {
+              if (!(fl[c] & VF_END)) continue;
+              const uint32_t sl = (uint32_t)L.key1[x[c]];
+              const uint32_t p = atomicAdd(&sh.win[sl >> 1].cnt[sl & 1u], 1u);
+              if (p < (uint32_t)S_MAXV) L.ring[sl * S_MAXV + p] = c < 3 ? fa : fb;
+            }
+          }
         }
       }
       __syncthreads();
       SL_MARK(5);
-      // ---- E2: the double precision parts (placement / cost, flip tests) as dense passes over
-      // (winner) and (winner, ring face) work items; the link condition and the collapse by one
-      // warp per winner on shared-memory data only.
-      // E2a: placement and cost of every winner (one thread each)
-      for (uint32_t i = tid; i < nb; i += NT) {
-        SEval e;
-        sl_cost<SM>(A, L, sh.win[i].u, sh.win[i].v, &e);
-        uint32_t fl = 0;
-        if (!e.valid || sh.win[i].cnt[0] > (uint32_t)S_MAXV || sh.win[i].cnt[1] > (uint32_t)S_MAXV) fl = WF_BAD;
-        sh.win[i].keep = e.valid ? e.keep : sh.win[i].u;
-        sh.win[i].flags = fl;
-        if (e.valid) {
-          L.wbest[3 * i + 0] = e.p[0]; L.wbest[3 * i + 1] = e.p[1]; L.wbest[3 * i + 2] = e.p[2];
-        }
-      }
-      __syncthreads();
       SL_MARK(6);
       // E2b: one flip test per (winner, side, ring entry)
       for (uint32_t item = tid; item < nb * 64; item += NT) {
         const uint32_t i = item >> 6, side = (item >> 5) & 1u, j = item & 31u;
         if (sh.win[i].flags & WF_BAD) continue;
+        if (sh.win[i].cnt[0] > (uint32_t)S_MAXV || sh.win[i].cnt[1] > (uint32_t)S_MAXV) continue;  // fails in E2c
         if (j >= sh.win[i].cnt[side]) continue;
         const uint32_t w = side ? sh.win[i].v : sh.win[i].u, other = side ? sh.win[i].u : sh.win[i].v;
         const uint32_t f = L.ring[(2 * i + side) * S_MAXV + j];
         const uint32_t a[3] = {sl_fget<SM>(L, f, 0), sl_fget<SM>(L, f, 1), sl_fget<SM>(L, f, 2)};
         if (a[0] == other || a[1] == other || a[2] == other) continue;  // dies with the edge
-        const double best[3] = {L.wbest[3 * i], L.wbest[3 * i + 1], L.wbest[3 * i + 2]};
+        const double best[3] = {sh.wbest[3 * i], sh.wbest[3 * i + 1], sh.wbest[3 * i + 2]};
         if (sl_flips<SM>(A, L, a, w, best)) atomicOr(&sh.win[i].flags, WF_BAD);
       }
       __syncthreads();
@@ -755,7 +842,14 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
             if (lane < nfv_n && lane < (uint32_t)S_MAXV) fv_n = L.ring[(2 * nxt + 1) * S_MAXV + lane];
           }
           const uint32_t u = sh.win[slot].u, v = sh.win[slot].v, hl = sh.win[slot].h;
-          bool ok = !(sh.win[slot].flags & WF_BAD);  // warp uniform
+          bool ok = !(sh.win[slot].flags & WF_BAD) && nfu <= (uint32_t)S_MAXV && nfv <= (uint32_t)S_MAXV;  // warp uniform
+          // the quadrics of the two endpoints are needed only if the collapse happens, but the L2 round
+          // trip is as long as the whole link test: request them now
+          const uint32_t k = sh.win[slot].keep, rm = (k == u) ? v : u;
+          double* Qk = A.Q + 10 * (uint64_t)(L.vbase + k);
+          const double* Qr = A.Q + 10 * (uint64_t)(L.vbase + rm);
+          double qk = 0.0, qr = 0.0;
+          if (ok && lane < 10) { qk = Qk[lane]; qr = Qr[lane]; }
           const bool hu = ok && lane < nfu, hv = ok && lane < nfv;
           uint32_t au[3] = {0, 0, 0}, av[3] = {0, 0, 0};
           uint32_t x1 = 0xF0000000u + lane, x2 = 0xF1000000u + lane, y1 = 0xF2000000u + lane,
@@ -787,13 +881,12 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
               const uint32_t f = hl / 3, c = hl - 3 * f;
               const uint32_t st = L.fstate[f];
               L.fstate[f] = (uint8_t)((st & ~(3u << (2 * c))) | (1u << (2 * c)));
-              sl_vclear(L.vflag, u, VF_END);
-              sl_vclear(L.vflag, v, VF_END);
+              sl_vclear<SM>(L.vflag, u, VF_END);
+              sl_vclear<SM>(L.vflag, v, VF_END);
               atomicOr(&sh.progress, 1u);
             }
             continue;
           }
-          const uint32_t k = sh.win[slot].keep, rm = (k == u) ? v : u;
           const bool rm_is_u = (rm == u);
           const bool hr = rm_is_u ? hu : hv;
           const uint32_t rf = rm_is_u ? fu : fv;
@@ -806,16 +899,14 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
           }
           const uint32_t dead = __popc(__ballot_sync(FULL, dies));
           // the new ring of k: parked edges around it may be valid now
-          if (hu && x1 != v && x2 != v) { sl_vor(L.vflag, x1, VF_RDIRTY); sl_vor(L.vflag, x2, VF_RDIRTY); }
-          if (hv && y1 != u && y2 != u) { sl_vor(L.vflag, y1, VF_RDIRTY); sl_vor(L.vflag, y2, VF_RDIRTY); }
-          double* Qk = A.Q + 10 * (uint64_t)(L.vbase + k);
-          const double* Qr = A.Q + 10 * (uint64_t)(L.vbase + rm);
-          if (lane < 10) Qk[lane] = Qk[lane] + Qr[lane];
-          if (lane >= 16 && lane < 19) A.pos[3 * (uint64_t)(L.vbase + k) + (lane - 16)] = L.wbest[3 * slot + (lane - 16)];
+          if (hu && x1 != v && x2 != v) { sl_vor<SM>(L.vflag, x1, VF_RDIRTY); sl_vor<SM>(L.vflag, x2, VF_RDIRTY); }
+          if (hv && y1 != u && y2 != u) { sl_vor<SM>(L.vflag, y1, VF_RDIRTY); sl_vor<SM>(L.vflag, y2, VF_RDIRTY); }
+          if (lane < 10) Qk[lane] = qk + qr;
+          if (lane >= 16 && lane < 19) A.pos[3 * (uint64_t)(L.vbase + k) + (lane - 16)] = sh.wbest[3 * slot + (lane - 16)];
           if (lane == 0) {
-            sl_vor(L.vflag, k, VF_CDIRTY | VF_RDIRTY);  // k moved: cached costs of its edges are stale
-            sl_vclear(L.vflag, k, VF_END);
-            sl_vclear(L.vflag, rm, 0xFFu);
+            sl_vor<SM>(L.vflag, k, VF_CDIRTY | VF_RDIRTY);  // k moved: cached costs of its edges are stale
+            sl_vclear<SM>(L.vflag, k, VF_END);
+            sl_vclear<SM>(L.vflag, rm, 0xFFu);
             atomicSub(&sh.alive, dead);
             atomicAdd(&sh.ncol, 1u);
             atomicOr(&sh.progress, 1u);
@@ -833,6 +924,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
       A.trace[4 * r + 2] = sh.alive;
       A.trace[4 * r + 3] = nF;
     }
+    if (A.trace != nullptr && tid == 0) sh.visits += nF;
     if (tid == 0) {
       uint32_t stop = 0;
       if (!sh.progress) {
@@ -869,8 +961,16 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
     }
   }
   for (uint32_t v = tid; v < U; v += NT) A.valive[L.vbase + v] = (L.vflag[v] & VF_ALIVE) ? 1 : 0;
-  if (tid == 0 && A.trace != nullptr)
+  if (tid == 0 && A.trace != nullptr) {
     for (int q = 0; q < 10; q++) atomicAdd((unsigned long long*)(A.trace + 1600) + q, sh.ph[q]);
+    uint32_t* rec = A.lrec + 6 * (size_t)sh.work;
+    rec[0] = T;
+    rec[1] = (uint32_t)r;
+    rec[2] = (uint32_t)((clock64() - sh.t_label) >> 10);
+    rec[3] = (uint32_t)(sh.visits > 0xFFFFFFFFull ? 0xFFFFFFFFull : sh.visits);
+    rec[4] = (uint32_t)sh.wins;
+    rec[5] = SM ? 1u : ((const void*)L.key1 == (const void*)(A.key1 + L.vbase) ? 3u : 2u);
+  }
   if (tid == 0) {
     atomicMax(&A.counters[1], (uint32_t)r);
     atomicAdd(&A.counters[SM ? 2 : 3], 1u);
@@ -895,21 +995,22 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
     // shared-memory layout: cost queues | key1 | faces SoA | face list | face state | vertex flags
     const size_t wq_bytes = (size_t)(SL_THREADS / 32) * SL_EQ * 4;
     const size_t o_key = wq_bytes;
-    const size_t o_f0 = o_key + 8 * (size_t)U;
+    const size_t o_f0 = o_key + 4 * (size_t)U;  // 32-bit keys
     const size_t o_fl = o_f0 + 6 * (size_t)T;
     const size_t o_fs = o_fl + 2 * (size_t)T;
     const size_t o_vf = (o_fs + T + 3) & ~(size_t)3;
-    const size_t need = o_vf + U + 4;
+    const size_t o_vl = (o_vf + U + 3) & ~(size_t)3;
+    const size_t need = o_vl + U + 4;
     uint32_t* ring = A.ring + (size_t)blockIdx.x * ((size_t)SL_WCAP * 2 * S_MAXV);
-    double* wbest = A.wbest + (size_t)blockIdx.x * ((size_t)SL_WCAP * 3);
     const uint32_t cap = (uint32_t)SL_LIST_PER * blockDim.x;
-    if (need <= A.smem_bytes && T <= cap && U <= cap) {
+    const bool fmt16 = 3ull * T <= 65536ull;
+    if (need <= A.smem_bytes && T <= cap && U <= cap && fmt16) {
       SlLab<true> L;
       L.T = T; L.U = U; L.tbase = tbase; L.vbase = vbase; L.target = target;
       L.wq = (uint32_t*)sl_smem;
       L.ring = ring;
-      L.wbest = wbest;
-      L.key1 = (unsigned long long*)(sl_smem + o_key);
+      L.key1 = (uint32_t*)(sl_smem + o_key);
+      L.fmt16 = true;
       L.fc0 = (uint16_t*)(sl_smem + o_f0);
       L.fc1 = L.fc0 + T;
       L.fc2 = L.fc1 + T;
@@ -919,29 +1020,33 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
       L.gface = nullptr;
       L.fstate = sl_smem + o_fs;
       L.vflag = sl_smem + o_vf;
+      L.vlose = sl_smem + o_vl;
       sl_run<true>(A, L, sh);
     } else {
       SlLab<false> L;
       L.T = T; L.U = U; L.tbase = tbase; L.vbase = vbase; L.target = target;
       L.wq = (uint32_t*)sl_smem;  // the cost queues always fit
       L.ring = ring;
-      L.wbest = wbest;
       L.fc0 = L.fc1 = L.fc2 = nullptr;
       L.flist = A.flist + tbase; L.flist2 = A.flist2 + tbase;
       L.vlist = A.vlist + vbase; L.vlist2 = A.vlist2 + vbase;
       L.gface = A.face + 3 * (uint64_t)tbase;
+      L.fmt16 = fmt16;
       // the arrays that take the atomics (keys, vertex flags) and the face states stay in shared
       // memory whenever they fit; only the faces and the alive lists are read from global memory
       const size_t h_fs = o_key + 8 * (size_t)U;
       const size_t h_vf = (h_fs + T + 3) & ~(size_t)3;
-      if (h_vf + U + 4 <= A.smem_bytes) {
+      const size_t h_vl = (h_vf + U + 3) & ~(size_t)3;
+      if (h_vl + U + 4 <= A.smem_bytes) {
         L.key1 = (unsigned long long*)(sl_smem + o_key);
         L.fstate = sl_smem + h_fs;
         L.vflag = sl_smem + h_vf;
+        L.vlose = sl_smem + h_vl;
       } else {
         L.key1 = A.key1 + vbase;
         L.fstate = A.fstate + tbase;
         L.vflag = A.vflag + vbase;
+        L.vlose = A.vlose + vbase;
       }
       sl_run<false>(A, L, sh);
     }
@@ -1033,7 +1138,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   const size_t tmpb = (sortb > scanb ? sortb : scanb) + 256;
   const size_t need = align_up(U * 24, 256) + align_up(U * 80, 256) + 3 * align_up(3 * T * 4, 256) +
                       align_up(U * S_VCAP * 4, 256) + align_up(T * 4, 256) + 2 * align_up(T, 256) +
-                      3 * align_up(U, 256) + 3 * align_up(U * 4, 256) + align_up(U * 8, 256) +
+                      4 * align_up(U, 256) + 3 * align_up(U * 4, 256) + align_up(U * 8, 256) +
                       6 * align_up((K + 2) * 4, 256) + align_up(3 * T * 4, 256) +
                       2 * align_up(3 * T * 4, 256) + 2 * align_up(T * 4, 256) + 2 * align_up(U * 4, 256) + tmpb +
                       align_up((size_t)ctx->sm_count * 4 * SL_WCAP * 2 * S_MAXV * 4, 256) +
@@ -1054,6 +1159,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   s.valive = (uint8_t*)scratch_take(ctx, U);
   s.vbound = (uint8_t*)scratch_take(ctx, U);
   uint8_t* vflag = (uint8_t*)scratch_take(ctx, U);
+  uint8_t* vlose = (uint8_t*)scratch_take(ctx, U);
   s.vn = (uint32_t*)scratch_take(ctx, U * 4);
   uint32_t* vscan = (uint32_t*)scratch_take(ctx, U * 4);
   uint32_t* vflag32 = (uint32_t*)scratch_take(ctx, U * 4);
@@ -1073,7 +1179,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   uint32_t* sorted_v = (uint32_t*)scratch_take(ctx, 3 * T * 4);
   uint32_t* sorted_h = (uint32_t*)scratch_take(ctx, 3 * T * 4);
   if (!s.pos || !s.Q || !s.face || !s.vf || !node_v || !node_h || !s.flabel || !s.falive || !fstate ||
-      !s.valive || !s.vbound || !vflag || !s.vn || !vscan || !vflag32 || !key1 || !d_target || !d_tri_off ||
+      !s.valive || !s.vbound || !vflag || !vlose || !s.vn || !vscan || !vflag32 || !key1 || !d_target || !d_tri_off ||
       !d_vert_off || !d_new_tri_off || !d_new_vert_off || !d_order || !flags || !ecost || !tmp || !gl_f[0] ||
       !gl_f[1] || !gl_v[0] || !gl_v[1] ||
       !sorted_v || !sorted_h) {
@@ -1152,7 +1258,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   S_CUDA(cudaFuncSetAttribute(k_simp_labels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl_dyn));
   SlArgs A;
   A.pos = s.pos; A.Q = s.Q; A.face = s.face; A.falive = s.falive; A.valive = s.valive; A.vbound = s.vbound;
-  A.ecost = ecost; A.key1 = key1; A.fstate = fstate; A.vflag = vflag;
+  A.ecost = ecost; A.key1 = key1; A.fstate = fstate; A.vflag = vflag; A.vlose = vlose;
   A.flist = gl_f[0]; A.flist2 = gl_f[1]; A.vlist = gl_v[0]; A.vlist2 = gl_v[1];
   A.tri_off = d_tri_off; A.vert_off = d_vert_off; A.target = d_target; A.order = d_order;
   A.K = (uint32_t)K; A.counters = flags;
@@ -1161,9 +1267,13 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   // IGN_SIMP_GMEM=1 (test knob): run every label on the global-memory arrays, the path of
   // labels that do not fit shared memory (only the winners' ring lists stay in smem)
   A.trace = nullptr;
+  A.lrec = nullptr;
   if (getenv("IGN_SIMP_TRACE") != nullptr) {
     A.trace = (uint32_t*)scratch_take(ctx, 400 * 16 + 256);
+    A.lrec = (uint32_t*)scratch_take(ctx, (size_t)K * 24 + 64);
+    if (!A.lrec) A.trace = nullptr;
     if (A.trace) S_CUDA(cudaMemsetAsync(A.trace, 0, 400 * 16 + 256, ctx->stream));
+    if (A.trace) S_CUDA(cudaMemsetAsync(A.lrec, 0, (size_t)K * 24 + 64, ctx->stream));
   }
   const char* force_gmem = getenv("IGN_SIMP_GMEM");
   A.smem_bytes = (force_gmem && force_gmem[0] == '1') ? (uint32_t)((SL_THREADS / 32) * SL_EQ * 4) : (uint32_t)sl_dyn;
@@ -1171,8 +1281,7 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
     const uint64_t slots = (uint64_t)ctx->sm_count * sl_ctas;
     const unsigned grid = (unsigned)(K < slots ? K : slots);
     A.ring = (uint32_t*)scratch_take(ctx, (size_t)grid * SL_WCAP * 2 * S_MAXV * 4);
-    A.wbest = (double*)scratch_take(ctx, (size_t)grid * SL_WCAP * 3 * 8);
-    if (!A.ring || !A.wbest) {
+    if (!A.ring) {
       set_error("scratch arena too small (simplify: winner ring lists)");
       return done(IGN_ERR_NOMEM);
     }
@@ -1214,6 +1323,31 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
     for (int q = 0; q < 10; q++) tot += phs[q];
     for (int q = 0; q < 10; q++)
       fprintf(stderr, "phase %-18s %6.2f %%  %10.3f Mcycles\n", names[q], 100.0 * phs[q] / (tot ? tot : 1), phs[q] / 1e6);
+    {
+      // per-label records: where do the cycles go -- per round (fixed latency) or per face visit?
+      std::vector<uint32_t> rec(6 * (size_t)K);
+      S_CUDA(cudaMemcpy(rec.data(), A.lrec, rec.size() * 4, cudaMemcpyDeviceToHost));
+      static const uint32_t edges[] = {0, 500, 1000, 2000, 4000, 8000, 16000, 32000, 64000, 0xFFFFFFFFu};
+      fprintf(stderr, "%12s %7s %8s %10s %10s %9s %9s  class(sm/hy/gl)\n", "faces<", "labels", "rounds", "Mcycles", "Mvisits", "kwins", "cyc/round");
+      double sr = 0, sv = 0, sc = 0, srr = 0, svv = 0, srv = 0, src = 0, svc = 0;
+      for (int b = 0; b + 1 < 10; b++) {
+        uint64_t n = 0, rounds = 0, kc = 0, vis = 0, wins = 0, cls[4] = {0, 0, 0, 0};
+        for (uint64_t i = 0; i < K; i++) {
+          const uint32_t* q = &rec[6 * i];
+          if (q[1] == 0 || q[0] < edges[b] || q[0] >= edges[b + 1]) continue;
+          n++; rounds += q[1]; kc += q[2]; vis += q[3]; wins += q[4]; cls[q[5] & 3]++;
+          const double R = q[1], V = q[3], C = q[2] * 1024.0;
+          sr += R; sv += V; sc += C; srr += R * R; svv += V * V; srv += R * V; src += R * C; svc += V * C;
+        }
+        if (n) fprintf(stderr, "%12u %7llu %8.1f %10.2f %10.3f %9.1f %9.0f  %llu/%llu/%llu\n", edges[b + 1], (unsigned long long)n, (double)rounds / n,
+                       kc * 1024.0 / 1e6, vis / 1e6, wins / 1e3, rounds ? kc * 1024.0 / rounds : 0.0,
+                       (unsigned long long)cls[1], (unsigned long long)cls[2], (unsigned long long)cls[3]);
+      }
+      // least squares cycles = a * rounds + b * visits (no intercept)
+      const double det = srr * svv - srv * srv;
+      if (det != 0) fprintf(stderr, "fit: cycles ~= %.0f * rounds + %.2f * face visits   (totals: %.0f rounds, %.3g visits, %.3g cycles)\n",
+                            (src * svv - svc * srv) / det, (svc * srr - src * srv) / det, sr, sv, sc);
+    }
     for (int r = 0; r < 400 && getenv("IGN_SIMP_TRACE_ROUNDS") && (tr[4 * r + 2] || tr[4 * r + 3]); r++)
       fprintf(stderr, "gpu round %d progress %u collapses %u alive %u list %u\n", r, tr[4 * r], tr[4 * r + 1], tr[4 * r + 2], tr[4 * r + 3]);
   }

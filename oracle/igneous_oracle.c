@@ -787,17 +787,42 @@ static uint32_t simp_unmix(uint32_t x) {
   x ^= x >> 16; x *= 0x43021123U; x ^= x >> 15 ^ x >> 30; x *= 0x1d69e2a5U; x ^= x >> 16;
   return x;
 }
-static uint64_t simp_key(double cost, uint32_t h, uint32_t salt) {
+/* 16-bit variant (odd multipliers and xor-shifts are bijections of [0, 65536)) */
+static uint32_t simp_mix16(uint32_t x) {
+  x &= 0xFFFFu;
+  x = (x * 0x2F35u) & 0xFFFFu; x ^= x >> 7;
+  x = (x * 0x4A6Bu) & 0xFFFFu; x ^= x >> 9;
+  x = (x * 0x9E37u) & 0xFFFFu; x ^= x >> 8;
+  return x;
+}
+static uint32_t simp_unmix16(uint32_t x) {
+  x &= 0xFFFFu;
+  x ^= x >> 8; x = (x * 0x7787u) & 0xFFFFu;
+  x ^= x >> 9; x = (x * 0x1243u) & 0xFFFFu;
+  x ^= x >> 7; x ^= x >> 14; x = (x * 0xEB1Du) & 0xFFFFu;
+  return x;
+}
+/* Priority key of an edge: (cost, per-round pseudo-random tie-break that also names the
+   half-edge).  Labels whose half-edge ids fit 16 bits (3 * faces <= 65536: every label the
+   product keeps in shared memory) use a 32-bit key -- the float cost truncated to its upper
+   16 magnitude bits (8 exponent + 8 mantissa bits), then a 16-bit permutation of the id --
+   so that the product can post keys with native 32-bit shared-memory atomics; larger labels
+   keep the full float cost and a 32-bit permutation in a 64-bit key. */
+static uint64_t simp_key(double cost, uint32_t h, uint32_t salt, int fmt16) {
   const float c = (float)cost;
   uint32_t bits;
   memcpy(&bits, &c, 4);
+  if (fmt16) return (uint64_t)((((bits >> 15) & 0xFFFFu) << 16) | simp_mix16((h ^ salt) & 0xFFFFu));
   return ((uint64_t)bits << 32) | simp_mix(h ^ salt);
 }
-static uint32_t simp_key_edge(uint64_t key, uint32_t salt) {
+static uint32_t simp_key_edge(uint64_t key, uint32_t salt, int fmt16) {
+  if (fmt16) return simp_unmix16((uint32_t)(key & 0xFFFFu)) ^ (salt & 0xFFFFu);
   return simp_unmix((uint32_t)(key & 0xFFFFFFFFu)) ^ salt;
 }
 uint32_t orc_simp_mix(uint32_t x) { return simp_mix(x); }
 uint32_t orc_simp_unmix(uint32_t x) { return simp_unmix(x); }
+uint32_t orc_simp_mix16(uint32_t x) { return simp_mix16(x); }
+uint32_t orc_simp_unmix16(uint32_t x) { return simp_unmix16(x); }
 
 /*
  * pos: 3U doubles (in/out), face: 3T global vertex ids (in/out), flabel: T dense labels 1..K,
@@ -835,6 +860,9 @@ int orc_simplify(uint64_t U, uint64_t T, double* pos, uint32_t* face, const uint
     s.tail[v] = (uint32_t)h;
   }
   for (uint64_t f = 0; f < T; f++) { falive[f] = 1; alive_faces[flabel[f]]++; }
+  uint8_t* fmt16 = (uint8_t*)calloc(K + 2, 1); /* key format of each label (see simp_key) */
+  if (!fmt16) return ORC_ENOMEM;
+  for (uint32_t l = 1; l <= K; l++) fmt16[l] = 3ull * alive_faces[l] <= 65536ull;
   /* quadrics: per vertex, faces in list order */
   for (uint64_t v = 0; v < U; v++)
     for (uint32_t h = s.head[v]; h != SIMP_NONE; h = s.next[h]) {
@@ -885,7 +913,7 @@ int orc_simplify(uint64_t U, uint64_t T, double* pos, uint32_t* face, const uint
       simp_eval_t e;
       simp_cost(&s, u, v, max_err2, &e);
       if (!e.valid) continue;
-      const uint64_t key = simp_key(e.cost, (uint32_t)h - 3 * tri_off[flabel[f]], salt); /* label-local id */
+      const uint64_t key = simp_key(e.cost, (uint32_t)h - 3 * tri_off[flabel[f]], salt, fmt16[flabel[f]]); /* label-local id */
       if (key < s.key1[u]) s.key1[u] = key;
       if (key < s.key1[v]) s.key1[v] = key;
     }
@@ -911,7 +939,7 @@ int orc_simplify(uint64_t U, uint64_t T, double* pos, uint32_t* face, const uint
       const uint64_t key = s.key1[a];
       if (!valive[a] || key == SIMP_KEYMAX) continue;
       const uint32_t lab = flabel[s.head[a] / 3];
-      const uint32_t h = simp_key_edge(key, salt) + 3 * tri_off[lab];
+      const uint32_t h = simp_key_edge(key, salt, fmt16[lab]) + 3 * tri_off[lab];
       const uint32_t f = h / 3, c = h % 3;
       const uint32_t u = face[3 * (uint64_t)f + c], v = face[3 * (uint64_t)f + (c + 1) % 3];
       if (a != u) continue;
@@ -952,7 +980,7 @@ int orc_simplify(uint64_t U, uint64_t T, double* pos, uint32_t* face, const uint
   free(stopped); free(slow); free(nsel); free(ncol);
   *rounds = r;
   free(s.Q); free(s.vbound); free(s.next); free(s.head); free(s.tail); free(s.key1); free(s.key2);
-  free(alive_faces); free(label_active); free(estate); free(vdirty);
+  free(alive_faces); free(label_active); free(estate); free(vdirty); free(fmt16);
   return ORC_OK;
 }
 
