@@ -185,6 +185,10 @@ class Context:
   def sync(self):
     check(self.lib.ign_sync(self.handle))
 
+  def set_priority(self, high=True):
+    """Re-create the context's stream with the device's greatest / least stream priority."""
+    check(self.lib.ign_stream_priority(self.handle, ctypes.c_int(int(bool(high)))))
+
   def to_device(self, arr):
     arr = np.asarray(arr)
     if not (arr.flags.f_contiguous or arr.flags.c_contiguous):

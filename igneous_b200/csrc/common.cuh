@@ -53,6 +53,8 @@ static inline int dtype_size(int dt) {
 }  // namespace ign
 
 // grow-only device scratch arena, bump allocated per API call
+constexpr int IGN_TIMER_SLOTS = 64;  // CUDA event pairs per context: timers and cross-stream marks
+
 struct ign_ctx {
   int device;
   int sm_count;
@@ -63,7 +65,7 @@ struct ign_ctx {
   size_t scratch_used;
   char* pinned;  // staging for scalars / small results
   size_t pinned_bytes;
-  cudaEvent_t timers[16][2];
+  cudaEvent_t timers[IGN_TIMER_SLOTS][2];
   uint64_t launches;
   // optional per-kernel-class profiling (ign_prof_enable): CUDA events recorded
   // on the ctx stream around selected launches
@@ -112,6 +114,8 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 //   small_h2d: host_src is consumed before the call returns.
 //   small_sync: cudaStreamSynchronize(ctx->stream) + delivery of pending small_d2h results.
 int small_d2h(ign_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
+// bulk device -> pinned host copy issued as a kernel on the ctx stream (falls back to the copy engine for pageable memory)
+int d2h_by_kernel(ign_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
 int small_h2d(ign_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
 int small_sync(ign_ctx* ctx);
 

@@ -624,8 +624,8 @@ int ign_mesh_export(ign_mesher* m, const float resolution[3], int voxel_centered
   IGN_TRY(scratch_reserve(ctx, m->U * 12 + 4096));
   float* d_pos = (float*)scratch_take(ctx, m->U * 12);
   IGN_TRY(mesher_positions(m, 0, m->U, resolution, voxel_centered, d_pos));
-  IGN_CUDA(cudaMemcpyAsync(vertices, d_pos, m->U * 12, cudaMemcpyDeviceToHost, ctx->stream));
-  IGN_CUDA(cudaMemcpyAsync(faces, m->d_faces, m->T * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  IGN_TRY(d2h_by_kernel(ctx, vertices, d_pos, m->U * 12));
+  IGN_TRY(d2h_by_kernel(ctx, faces, m->d_faces, m->T * 12));
   IGN_CUDA(cudaStreamSynchronize(ctx->stream));
   scratch_reset(ctx);
   return IGN_OK;

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) k_simp_boundary(Simp s) {
 // changed (parked edges around it may be valid now)
 constexpr uint32_t VF_ALIVE = 1, VF_BOUND = 2, VF_CDIRTY = 4, VF_DONE = 16, VF_END = 32, VF_RDIRTY = 64;
 constexpr int SL_THREADS = 1024;
-constexpr int SL_WCAP = 256;  // winners validated per selection pass (a round runs as many passes as it needs)
+constexpr int SL_WCAP = 128;  // winners validated per selection pass (a round runs as many passes as it needs)
 constexpr uint32_t WF_BAD = 1, WF_OK = 2;  // winner flags: failed validation / validated
 constexpr int SL_EQ = 96;      // per-warp queue of faces with half-edges whose cost must be (re)computed
 constexpr int SL_LIST_PER = 16;  // list entries per thread held in registers while a list is compacted in place
@@ -280,7 +280,6 @@ struct SlArgs {
   double max_err2;
   int max_rounds;
   uint32_t smem_bytes;  // dynamic shared memory of the launch
-  uint32_t* ring;       // [gridDim.x][SL_WCAP * 2 * S_MAXV] ring lists of the round's winners
   uint32_t* lrec;       // IGN_SIMP_TRACE=1: [work item][4] = faces, rounds, kilocycles, face visits (sum of list lengths)
   uint32_t* trace;      // IGN_SIMP_TRACE=1: [round][4] = winners, collapses, alive faces, list length of the largest label
 };
@@ -315,7 +314,7 @@ struct SlLab {
   key_t* key1;
   bool fmt16;
   uint32_t* wq;    // [warps][SL_EQ] per-warp cost queues of the key pass (shared memory)
-  uint32_t* ring;  // [SL_WCAP][2][S_MAXV] face ids of the winners' rings (global memory, per CTA)
+  idx_t* ring;     // [SL_WCAP][2][S_MAXV] face ids of the winners' rings (shared memory)
   idx_t *flist, *flist2, *vlist, *vlist2;  // alive lists (flist2 / vlist2: global-memory class only)
 };
 
@@ -799,7 +798,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
               if (!(fl[c] & VF_END)) continue;
               const uint32_t sl = (uint32_t)L.key1[x[c]];
               const uint32_t p = atomicAdd(&sh.win[sl >> 1].cnt[sl & 1u], 1u);
-              if (p < (uint32_t)S_MAXV) L.ring[sl * S_MAXV + p] = c < 3 ? fa : fb;
+              if (p < (uint32_t)S_MAXV) L.ring[sl * S_MAXV + p] = (idx_t)(c < 3 ? fa : fb);
             }
           }
         }
@@ -979,10 +978,14 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
 
 extern __shared__ __align__(16) unsigned char sl_smem[];
 
+// One label per CTA (the launch has one CTA per label; a CTA takes the next label of the size-sorted
+// order from a counter, so big labels start first whatever order the hardware dispatches CTAs in).
+// CTAs that end after one label keep returning their SM to the block scheduler: kernels of
+// other streams -- the CCL passes of the volume pipeline run on a higher-priority stream while
+// MeshTasks are in flight -- get SMs within a label's run time instead of a whole task's.
 __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
   __shared__ SlShared sh;
-  for (;;) {
-    __syncthreads();  // the previous label is completely written back; sh.work may be reused
+  do {
     if (threadIdx.x == 0) sh.work = atomicAdd(&A.counters[0], 1u);
     __syncthreads();
     const uint32_t wi = sh.work;
@@ -991,24 +994,25 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
     const uint32_t tbase = A.tri_off[l], T = A.tri_off[l + 1] - tbase;
     const uint32_t vbase = A.vert_off[l], U = A.vert_off[l + 1] - vbase;
     const uint32_t target = A.target[l];
-    if (T == 0 || T <= target) continue;  // init left every face / vertex alive
-    // shared-memory layout: cost queues | key1 | faces SoA | face list | face state | vertex flags
+    if (T == 0 || T <= target) break;  // init left every face / vertex alive
+    // shared-memory layout: cost queues | ring lists | key1 | faces SoA | face list | face state | vertex flags
     const size_t wq_bytes = (size_t)(SL_THREADS / 32) * SL_EQ * 4;
-    const size_t o_key = wq_bytes;
+    const size_t ring_sm = (size_t)SL_WCAP * 2 * S_MAXV * 2, ring_gl = (size_t)SL_WCAP * 2 * S_MAXV * 4;
+    const size_t o_key = wq_bytes + ring_sm;   // shared-memory class: 16-bit face ids
+    const size_t o_keyg = wq_bytes + ring_gl;  // other classes: 32-bit
     const size_t o_f0 = o_key + 4 * (size_t)U;  // 32-bit keys
     const size_t o_fl = o_f0 + 6 * (size_t)T;
     const size_t o_fs = o_fl + 2 * (size_t)T;
     const size_t o_vf = (o_fs + T + 3) & ~(size_t)3;
     const size_t o_vl = (o_vf + U + 3) & ~(size_t)3;
     const size_t need = o_vl + U + 4;
-    uint32_t* ring = A.ring + (size_t)blockIdx.x * ((size_t)SL_WCAP * 2 * S_MAXV);
     const uint32_t cap = (uint32_t)SL_LIST_PER * blockDim.x;
     const bool fmt16 = 3ull * T <= 65536ull;
     if (need <= A.smem_bytes && T <= cap && U <= cap && fmt16) {
       SlLab<true> L;
       L.T = T; L.U = U; L.tbase = tbase; L.vbase = vbase; L.target = target;
       L.wq = (uint32_t*)sl_smem;
-      L.ring = ring;
+      L.ring = (uint16_t*)(sl_smem + wq_bytes);
       L.key1 = (uint32_t*)(sl_smem + o_key);
       L.fmt16 = true;
       L.fc0 = (uint16_t*)(sl_smem + o_f0);
@@ -1025,8 +1029,8 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
     } else {
       SlLab<false> L;
       L.T = T; L.U = U; L.tbase = tbase; L.vbase = vbase; L.target = target;
-      L.wq = (uint32_t*)sl_smem;  // the cost queues always fit
-      L.ring = ring;
+      L.wq = (uint32_t*)sl_smem;  // the cost queues and the ring lists always fit
+      L.ring = (uint32_t*)(sl_smem + wq_bytes);
       L.fc0 = L.fc1 = L.fc2 = nullptr;
       L.flist = A.flist + tbase; L.flist2 = A.flist2 + tbase;
       L.vlist = A.vlist + vbase; L.vlist2 = A.vlist2 + vbase;
@@ -1034,11 +1038,11 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
       L.fmt16 = fmt16;
       // the arrays that take the atomics (keys, vertex flags) and the face states stay in shared
       // memory whenever they fit; only the faces and the alive lists are read from global memory
-      const size_t h_fs = o_key + 8 * (size_t)U;
+      const size_t h_fs = o_keyg + 8 * (size_t)U;
       const size_t h_vf = (h_fs + T + 3) & ~(size_t)3;
       const size_t h_vl = (h_vf + U + 3) & ~(size_t)3;
       if (h_vl + U + 4 <= A.smem_bytes) {
-        L.key1 = (unsigned long long*)(sl_smem + o_key);
+        L.key1 = (unsigned long long*)(sl_smem + o_keyg);
         L.fstate = sl_smem + h_fs;
         L.vflag = sl_smem + h_vf;
         L.vlose = sl_smem + h_vl;
@@ -1050,7 +1054,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
       }
       sl_run<false>(A, L, sh);
     }
-  }
+  } while (false);
 }
 
 __global__ void __launch_bounds__(256)
@@ -1276,17 +1280,11 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
     if (A.trace) S_CUDA(cudaMemsetAsync(A.lrec, 0, (size_t)K * 24 + 64, ctx->stream));
   }
   const char* force_gmem = getenv("IGN_SIMP_GMEM");
-  A.smem_bytes = (force_gmem && force_gmem[0] == '1') ? (uint32_t)((SL_THREADS / 32) * SL_EQ * 4) : (uint32_t)sl_dyn;
+  const uint32_t sl_fixed = (uint32_t)((SL_THREADS / 32) * SL_EQ * 4 + SL_WCAP * 2 * S_MAXV * 4);  // queues + ring lists
+  A.smem_bytes = (force_gmem && force_gmem[0] == '1') ? sl_fixed : (uint32_t)sl_dyn;
   {
-    const uint64_t slots = (uint64_t)ctx->sm_count * sl_ctas;
-    const unsigned grid = (unsigned)(K < slots ? K : slots);
-    A.ring = (uint32_t*)scratch_take(ctx, (size_t)grid * SL_WCAP * 2 * S_MAXV * 4);
-    if (!A.ring) {
-      set_error("scratch arena too small (simplify: winner ring lists)");
-      return done(IGN_ERR_NOMEM);
-    }
     const int slot = prof_begin(ctx, IGN_PROF_SIMP);
-    k_simp_labels<<<grid, sl_threads, sl_dyn, ctx->stream>>>(A);
+    k_simp_labels<<<(unsigned)K, sl_threads, sl_dyn, ctx->stream>>>(A);
     ctx->launches++;
     prof_end(ctx, slot);
     S_CUDA(cudaGetLastError());

@@ -59,6 +59,12 @@ class VolumePipeline:
     # The main context's stream is left free during the mesh stage so that the D2H
     # of the CCL labels / mips (e2e) overlaps with meshing.
     self.mesh_streams = max(1, int(mesh_streams))
+    # Whole-volume passes (pooling, CCL) run on a high-priority stream: their thread blocks are
+    # dispatched first whenever a MeshTask CTA retires (k_simp_labels runs one label per CTA), so a
+    # 46 ms CCL is not stretched over the mesh stage it shares the SMs with.  A second context
+    # drains finished products to the host while the main stream keeps uploading / computing.
+    ctx.set_priority(True)
+    self._dl = _shim.Context(ctx.device)
     self._workers = []
     for _ in range(self.mesh_streams):
       wctx = _shim.Context(ctx.device)
@@ -72,6 +78,7 @@ class VolumePipeline:
     for wctx, buf in self._workers:
       buf.free()
       wctx.close()
+    self._dl.close()
 
   # ------------------------------------------------------------------ inputs
   def synth(self):
@@ -147,8 +154,9 @@ class VolumePipeline:
     """MeshTask bodies over the mesh mip.  `export(task, mesher, nv, nf, nl, ctx)` may
     pull results to the host (e2e); without it only the totals are read back.
     `wait_for(task)` (streamed step) blocks the calling mesh thread until the host
-    has enqueued the mip planes the task reads; the mesh stream then waits on the
-    device for mark 15, which by then covers those planes."""
+    has enqueued the mip planes the task reads and returns the event slot recorded after
+    them; the mesh stream then waits on the device for exactly that event (not for whatever
+    the main stream has enqueued since)."""
     tasks = list(self.mesh_tasks())
     if wait_for is None:
       for wctx, _ in self._workers:  # mesh streams start when the mip pyramid is complete
@@ -161,8 +169,8 @@ class VolumePipeline:
       out = []
       for t in tasks[widx::self.mesh_streams]:
         if wait_for is not None:
-          wait_for(t)
-          _shim.check(self.lib.ign_stream_wait_mark(wctx.handle, self.ctx.handle, c.c_int(15)))
+          mark = wait_for(t)  # the mark the main stream recorded after the last layer this task reads
+          _shim.check(self.lib.ign_stream_wait_mark(wctx.handle, self.ctx.handle, c.c_int(mark)))
         out.append(self._mesh_one(wctx, buf, t, export))
       wctx.sync()
       return out
@@ -213,12 +221,16 @@ class VolumePipeline:
     cond = threading.Condition()
     state = {"ready": 0, "error": None}
 
+    def layer_mark(k):  # one event per layer (slots 16..63; a reused slot only makes a late waiter wait longer)
+      return 16 + k % 48
+
     def wait_for(task):
       need = min(n_layers, task[2] // mz + 2)
       with cond:
         cond.wait_for(lambda: state["ready"] >= need or state["error"] is not None)
         if state["error"] is not None:
           raise RuntimeError("upload failed") from state["error"]
+      return layer_mark(need - 1)
 
     mesh_err = []
 
@@ -228,10 +240,21 @@ class VolumePipeline:
       except BaseException as e:  # re-raised on the caller's thread
         mesh_err.append(e)
 
+    import os, time
+    trace = os.environ.get("IGN_PIPE_TRACE") is not None
+    # finished products are downloaded on a second context's stream while the main stream keeps
+    # uploading / computing (ign_d2h only enqueues)
+    def download(mark, dst, srcp, nbytes):
+      _shim.check(self.lib.ign_stream_wait_mark(self._dl.handle, self.ctx.handle, c.c_int(mark)))
+      _shim.check(self.lib.ign_d2h(self._dl.handle, c.c_void_p(dst), c.c_void_p(srcp), _u64(nbytes)))
+
+    t_host0 = time.perf_counter()
     th = threading.Thread(target=mesh_thread)
     th.start()
     try:
       src = host_in.ctypes.data
+      if trace:
+        self.ctx.timer_start(10)
       for k in range(n_layers):
         z0, z1 = k * mz, min(sz, (k + 1) * mz)
         off = z0 * sx * sy * es
@@ -242,13 +265,28 @@ class VolumePipeline:
           _shim.check(self.lib.ign_pool_mode_2x2x1_dev(
             self.ctx.handle, c.c_void_p(self.d_in.ptr + off), c.c_int(self.code), _u64(sx), _u64(sy),
             _u64(z1 - z0), c.c_int(self.num_mips), c.c_int(0), _shim.void_pp(outs)))
-        self.ctx.timer_start(15)
+        self.ctx.timer_start(layer_mark(k))
+        if host_out is not None and self.num_mips:
+          # the mip planes of this layer are final: download them now (the D2H engine is idle
+          # while the volume is still being uploaded), on the second context's stream
+          for dst, m, s3 in zip(host_out["mips"], self.d_mips, self.mip_shapes):
+            o = z0 * s3[0] * s3[1] * es
+            download(layer_mark(k), dst.ctypes.data + o, m.ptr + o, (z1 - z0) * s3[0] * s3[1] * es)
         with cond:
           state["ready"] = k + 1
           cond.notify_all()
+      if trace:
+        self.ctx.timer_stop(10)
+        self.ctx.timer_start(11)
       self.ccl()
+      if trace:
+        self.ctx.timer_stop(11)
+        self.ctx.timer_start(12)
       if host_out is not None:
-        self.results_to_host(host_out)
+        self.ctx.timer_start(14)
+        download(14, host_out["cc"].ctypes.data, self.d_cc.ptr, host_out["cc"].nbytes)
+      if trace:
+        self.ctx.timer_stop(12)
     except BaseException as e:
       with cond:
         state["error"] = e
@@ -256,9 +294,16 @@ class VolumePipeline:
       th.join()
       raise
     th.join()
+    t_mesh = time.perf_counter()
     if mesh_err:
       raise mesh_err[0]
+    self._dl.sync()
     self.ctx.sync()
+    if trace:
+      import sys
+      print("step_streamed: upload+pool %.0f ms, ccl %.0f ms, (label d2h queued %.0f ms) (stream time); mesh threads done at %.0f ms, "
+            "all done at %.0f ms (host clock)" % (self.ctx.timer_ms(10), self.ctx.timer_ms(11), self.ctx.timer_ms(12),
+                                                  1e3 * (t_mesh - t_host0), 1e3 * (time.perf_counter() - t_host0)), file=sys.stderr)
 
   def stage_ms(self):
     return {"pool_ms": self.ctx.timer_ms(1), "ccl_ms": self.ctx.timer_ms(2),

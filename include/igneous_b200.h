@@ -81,13 +81,18 @@ IGN_API int ign_d2h(ign_ctx* ctx, void* dst, const void* src, uint64_t bytes);  
 IGN_API int ign_d2d(ign_ctx* ctx, void* dst, const void* src, uint64_t bytes);
 IGN_API int ign_memset(ign_ctx* ctx, void* dst, int byte, uint64_t bytes);
 
-/* CUDA-event timers on the ctx stream: slot in [0,16) */
+/* CUDA-event timers on the ctx stream: slot in [0,64) */
 IGN_API int ign_timer_start(ign_ctx* ctx, int slot);
 IGN_API int ign_timer_stop(ign_ctx* ctx, int slot);
 IGN_API int ign_timer_ms(ign_ctx* ctx, int slot, float* ms); /* synchronises on the stop event */
 /* cross-context ordering on one device: waiter's stream waits for the point where
  * producer last called ign_timer_start(producer, slot); no host synchronisation */
 IGN_API int ign_stream_wait_mark(ign_ctx* waiter, ign_ctx* producer, int slot);
+/* Re-creates the ctx stream (after synchronising it) with the device's greatest (high != 0) or least
+ * stream priority.  Thread blocks of a higher-priority stream are dispatched first whenever an SM
+ * frees up: a worker that runs short whole-volume passes (CCL: igneous/tasks/image/ccl.py:173) next to
+ * long MeshTask streams (tasks/mesh/mesh.py:371-383) asks for high priority on the former. */
+IGN_API int ign_stream_priority(ign_ctx* ctx, int high);
 
 /* per-kernel-class CUDA-event profiling on the ctx stream (bench.py roofline):
  * classes 0 ccl_local, 1 ccl_merge, 2 ccl_label, 3 pool, 4 marching cubes */
