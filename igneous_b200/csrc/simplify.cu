@@ -280,6 +280,7 @@ struct SlArgs {
   double max_err2;
   int max_rounds;
   uint32_t smem_bytes;  // dynamic shared memory of the launch
+  int persist;          // 1: a CTA keeps taking labels until the list is empty (IGN_SIMP_PERSIST=1)
   uint32_t* lrec;       // IGN_SIMP_TRACE=1: [work item][4] = faces, rounds, kilocycles, face visits (sum of list lengths)
   uint32_t* trace;      // IGN_SIMP_TRACE=1: [round][4] = winners, collapses, alive faces, list length of the largest label
 };
@@ -289,7 +290,7 @@ struct SlWin {
 };
 
 struct SlShared {
-  uint32_t work, alive, progress, ncol, nwin, stop, slow, counter;
+  uint32_t work, alive, progress, ncol, nwin, stop, slow, counter, nbig;
   unsigned long long visits, wins;  // IGN_SIMP_TRACE
   long long t_label;
   unsigned long long ph[10];  // phase timers (IGN_SIMP_TRACE)
@@ -544,6 +545,124 @@ __device__ __forceinline__ uint32_t sl_compact(IDX*& list, IDX*& list2, uint32_t
     }                                                 \
   } while (0)
 
+// One pass of E2c with groups of W lanes (16: two winners per warp side by side, only winners whose
+// rings fit 16 lanes; 32: the winners left over).  Both halves of a warp run the same instructions;
+// everything that differs between them is predicated and loop counts are made warp uniform.
+template <bool SM, int W>
+__device__ __forceinline__ void sl_collapse_pass(const SlArgs& A, const SlLab<SM>& L, SlShared& sh, uint32_t nb) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, NW = blockDim.x >> 5;
+  constexpr uint32_t G = 32 / W;                       // groups per warp
+  const uint32_t gl = lane & (W - 1), goff = lane & ~(uint32_t)(W - 1);
+  const uint32_t wmask = W == 32 ? FULL : 0xFFFFu;
+  const uint32_t gmask = wmask << goff;
+  const uint32_t gidx = lane / W;
+  for (uint32_t base = warp * G; base < nb; base += NW * G) {  // warp uniform
+    const uint32_t slot = base + gidx;
+    bool act = slot < nb;
+    uint32_t nfu = 0, nfv = 0;
+    if (act) { nfu = sh.win[slot].cnt[0]; nfv = sh.win[slot].cnt[1]; }
+    const bool big = nfu > 16u || nfv > 16u;
+    if (W == 16) {
+      if (act && big && gl == 0) atomicAdd(&sh.nbig, 1u);
+      act = act && !big;
+    } else {
+      act = act && big;
+    }
+    uint32_t fu = 0, fv = 0, u = 0, v = 0, hl = 0, k = 0;
+    bool ok = false;
+    if (act) {
+      if (gl < nfu && gl < (uint32_t)S_MAXV) fu = L.ring[(2 * slot) * S_MAXV + gl];
+      if (gl < nfv && gl < (uint32_t)S_MAXV) fv = L.ring[(2 * slot + 1) * S_MAXV + gl];
+      u = sh.win[slot].u; v = sh.win[slot].v; hl = sh.win[slot].h; k = sh.win[slot].keep;
+      ok = !(sh.win[slot].flags & WF_BAD) && nfu <= (uint32_t)S_MAXV && nfv <= (uint32_t)S_MAXV;
+    }
+    const uint32_t rm = (k == u) ? v : u;
+    // the quadrics of the two endpoints are needed only if the collapse happens, but the L2 round
+    // trip is as long as the whole link test: request them now
+    double* Qk = A.Q + 10 * (uint64_t)(L.vbase + k);
+    const double* Qr = A.Q + 10 * (uint64_t)(L.vbase + rm);
+    double qk = 0.0, qr = 0.0;
+    if (ok && gl < 10) { qk = Qk[gl]; qr = Qr[gl]; }
+    const bool hu = ok && gl < nfu, hv = ok && gl < nfv;
+    uint32_t au[3] = {0, 0, 0}, av[3] = {0, 0, 0};
+    uint32_t x1 = 0xF0000000u + lane, x2 = 0xF1000000u + lane, y1 = 0xF2000000u + lane, y2 = 0xF3000000u + lane;
+    if (hu) {
+      au[0] = sl_fget<SM>(L, fu, 0); au[1] = sl_fget<SM>(L, fu, 1); au[2] = sl_fget<SM>(L, fu, 2);
+      sl_others(au, u, &x1, &x2);
+    }
+    if (hv) {
+      av[0] = sl_fget<SM>(L, fv, 0); av[1] = sl_fget<SM>(L, fv, 1); av[2] = sl_fget<SM>(L, fv, 2);
+      sl_others(av, v, &y1, &y2);
+    }
+    // (every lane of the warp takes part in the collectives below; n = 0 for groups without a winner)
+    const uint32_t nu = ok ? nfu : 0u, nv = ok ? nfv : 0u;
+    uint32_t nmax = nu > nv ? nu : nv;
+    if (W == 16) {
+      const uint32_t o = __shfl_xor_sync(FULL, nmax, 16);
+      nmax = o > nmax ? o : nmax;
+    }
+    // distinct neighbours of u (first occurrences f1 among x1, f2 among x2 not in x1), same for v
+    const uint32_t mu1 = __match_any_sync(FULL, x1) & gmask, mu2 = __match_any_sync(FULL, x2) & gmask;
+    const uint32_t mv1 = __match_any_sync(FULL, y1) & gmask, mv2 = __match_any_sync(FULL, y2) & gmask;
+    bool inu = false, inv = false, c1 = false, c2 = false;
+    for (uint32_t j = 0; j < nmax; j++) {
+      const uint32_t sx1 = __shfl_sync(FULL, x1, j, W), sy1 = __shfl_sync(FULL, y1, j, W), sy2 = __shfl_sync(FULL, y2, j, W);
+      if (j < nu) inu |= (sx1 == x2);
+      if (j < nv) {
+        inv |= (sy1 == y2);
+        c1 |= (x1 == sy1) | (x1 == sy2);
+        c2 |= (x2 == sy1) | (x2 == sy2);
+      }
+    }
+    const bool f1 = hu && ((int)lane == __ffs(mu1) - 1);
+    const bool f2 = hu && ((int)lane == __ffs(mu2) - 1) && !inu;
+    const bool g1 = hv && ((int)lane == __ffs(mv1) - 1);
+    const bool g2 = hv && ((int)lane == __ffs(mv2) - 1) && !inv;
+    const uint32_t b_f1 = __ballot_sync(FULL, f1), b_f2 = __ballot_sync(FULL, f2);
+    const uint32_t b_g1 = __ballot_sync(FULL, g1), b_g2 = __ballot_sync(FULL, g2);
+    const uint32_t b_c1 = __ballot_sync(FULL, f1 && c1), b_c2 = __ballot_sync(FULL, f2 && c2);
+    const uint32_t b_sh = __ballot_sync(FULL, hu && (x1 == v || x2 == v));
+    const uint32_t nnu = __popc(b_f1 & gmask) + __popc(b_f2 & gmask), nnv = __popc(b_g1 & gmask) + __popc(b_g2 & gmask);
+    const uint32_t common = __popc(b_c1 & gmask) + __popc(b_c2 & gmask), shared = __popc(b_sh & gmask);
+    const bool go = ok && nnu <= (uint32_t)S_MAXV && nnv <= (uint32_t)S_MAXV && shared == 2 && common == 2;
+    if (act && !go && gl == 0) {  // park the edge until one of its endpoints' rings changes
+      const uint32_t f = hl / 3, c = hl - 3 * f;
+      const uint32_t st = L.fstate[f];  // (winners of one pass never share a face: byte accesses are disjoint)
+      L.fstate[f] = (uint8_t)((st & ~(3u << (2 * c))) | (1u << (2 * c)));
+      sl_vclear<SM>(L.vflag, u, VF_END);
+      sl_vclear<SM>(L.vflag, v, VF_END);
+      atomicOr(&sh.progress, 1u);
+    }
+    const bool rm_is_u = (rm == u);
+    const bool hr = go && (rm_is_u ? hu : hv);
+    const uint32_t rf = rm_is_u ? fu : fv;
+    const uint32_t r0 = rm_is_u ? au[0] : av[0], r1 = rm_is_u ? au[1] : av[1], r2 = rm_is_u ? au[2] : av[2];
+    // faces of rm: those that also hold k die, the others get k in rm's corner
+    const bool dies = hr && (r0 == k || r1 == k || r2 == k);
+    if (hr) {
+      if (dies) L.fstate[rf] = (uint8_t)(L.fstate[rf] & 0x7Fu);
+      else sl_fset<SM>(L, rf, r0 == rm ? 0 : (r1 == rm ? 1 : 2), k);
+    }
+    const uint32_t dead = __popc(__ballot_sync(FULL, dies) & gmask);
+    if (go) {
+      // the new ring of k: parked edges around it may be valid now
+      if (hu && x1 != v && x2 != v) { sl_vor<SM>(L.vflag, x1, VF_RDIRTY); sl_vor<SM>(L.vflag, x2, VF_RDIRTY); }
+      if (hv && y1 != u && y2 != u) { sl_vor<SM>(L.vflag, y1, VF_RDIRTY); sl_vor<SM>(L.vflag, y2, VF_RDIRTY); }
+      if (gl < 10) Qk[gl] = qk + qr;
+      if (gl >= 10 && gl < 13) A.pos[3 * (uint64_t)(L.vbase + k) + (gl - 10)] = sh.wbest[3 * slot + (gl - 10)];
+      if (gl == 0) {
+        sl_vor<SM>(L.vflag, k, VF_CDIRTY | VF_RDIRTY);  // k moved: cached costs of its edges are stale
+        sl_vclear<SM>(L.vflag, k, VF_END);
+        sl_vclear<SM>(L.vflag, rm, 0xFFu);
+        atomicSub(&sh.alive, dead);
+        atomicAdd(&sh.ncol, 1u);
+        atomicOr(&sh.progress, 1u);
+      }
+    }
+  }
+}
+
 template <bool SM>
 __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
   if (A.trace != nullptr && threadIdx.x == 0) {
@@ -727,7 +846,7 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
     SL_MARK(2);
     // ---- P4 + E: the round's winners (marked DONE on both endpoints), SL_WCAP per pass
     for (;;) {
-      if (tid == 0) sh.nwin = 0;
+      if (tid == 0) { sh.nwin = 0; sh.nbig = 0; }
       __syncthreads();
       for (uint32_t i = tid; i < nV; i += NT) {
         const uint32_t a = SM ? i : (uint32_t)vlist[i];
@@ -821,96 +940,16 @@ __device__ void sl_run(const SlArgs& A, const SlLab<SM>& L, SlShared& sh) {
       }
       __syncthreads();
       SL_MARK(7);
-      // E2c: one WARP per winner: link condition by ballots / shuffles over the ring lists (a
-      // lane holds one ring face of each endpoint), then the collapse itself.  The ring
-      // entries of the warp's next winner are fetched before the current one is processed.
-      {
-        uint32_t nfu_n = 0, nfv_n = 0, fu_n = 0, fv_n = 0;
-        uint32_t slot = warp;
-        if (slot < nb) {
-          nfu_n = sh.win[slot].cnt[0]; nfv_n = sh.win[slot].cnt[1];
-          if (lane < nfu_n && lane < (uint32_t)S_MAXV) fu_n = L.ring[(2 * slot) * S_MAXV + lane];
-          if (lane < nfv_n && lane < (uint32_t)S_MAXV) fv_n = L.ring[(2 * slot + 1) * S_MAXV + lane];
-        }
-        for (; slot < nb; slot += NW) {
-          const uint32_t nfu = nfu_n, nfv = nfv_n, fu = fu_n, fv = fv_n;
-          const uint32_t nxt = slot + NW;
-          if (nxt < nb) {
-            nfu_n = sh.win[nxt].cnt[0]; nfv_n = sh.win[nxt].cnt[1];
-            if (lane < nfu_n && lane < (uint32_t)S_MAXV) fu_n = L.ring[(2 * nxt) * S_MAXV + lane];
-            if (lane < nfv_n && lane < (uint32_t)S_MAXV) fv_n = L.ring[(2 * nxt + 1) * S_MAXV + lane];
-          }
-          const uint32_t u = sh.win[slot].u, v = sh.win[slot].v, hl = sh.win[slot].h;
-          bool ok = !(sh.win[slot].flags & WF_BAD) && nfu <= (uint32_t)S_MAXV && nfv <= (uint32_t)S_MAXV;  // warp uniform
-          // the quadrics of the two endpoints are needed only if the collapse happens, but the L2 round
-          // trip is as long as the whole link test: request them now
-          const uint32_t k = sh.win[slot].keep, rm = (k == u) ? v : u;
-          double* Qk = A.Q + 10 * (uint64_t)(L.vbase + k);
-          const double* Qr = A.Q + 10 * (uint64_t)(L.vbase + rm);
-          double qk = 0.0, qr = 0.0;
-          if (ok && lane < 10) { qk = Qk[lane]; qr = Qr[lane]; }
-          const bool hu = ok && lane < nfu, hv = ok && lane < nfv;
-          uint32_t au[3] = {0, 0, 0}, av[3] = {0, 0, 0};
-          uint32_t x1 = 0xF0000000u + lane, x2 = 0xF1000000u + lane, y1 = 0xF2000000u + lane,
-                   y2 = 0xF3000000u + lane;
-          if (hu) {
-            au[0] = sl_fget<SM>(L, fu, 0); au[1] = sl_fget<SM>(L, fu, 1); au[2] = sl_fget<SM>(L, fu, 2);
-            sl_others(au, u, &x1, &x2);
-          }
-          if (hv) {
-            av[0] = sl_fget<SM>(L, fv, 0); av[1] = sl_fget<SM>(L, fv, 1); av[2] = sl_fget<SM>(L, fv, 2);
-            sl_others(av, v, &y1, &y2);
-          }
-          if (ok) {
-            bool f1, f2, g1, g2;
-            const uint32_t nnu = sl_distinct(x1, x2, nfu, lane, &f1, &f2);
-            const uint32_t nnv = sl_distinct(y1, y2, nfv, lane, &g1, &g2);
-            bool c1 = false, c2 = false;
-            for (uint32_t j = 0; j < nfv; j++) {
-              const uint32_t t1 = __shfl_sync(FULL, y1, j), t2 = __shfl_sync(FULL, y2, j);
-              c1 |= (x1 == t1) | (x1 == t2);
-              c2 |= (x2 == t1) | (x2 == t2);
-            }
-            const uint32_t common = __popc(__ballot_sync(FULL, f1 && c1)) + __popc(__ballot_sync(FULL, f2 && c2));
-            const uint32_t shared = __popc(__ballot_sync(FULL, hu && (x1 == v || x2 == v)));
-            ok = nnu <= (uint32_t)S_MAXV && nnv <= (uint32_t)S_MAXV && shared == 2 && common == 2;
-          }
-          if (!ok) {  // park the edge until one of its endpoints' rings changes
-            if (lane == 0) {
-              const uint32_t f = hl / 3, c = hl - 3 * f;
-              const uint32_t st = L.fstate[f];
-              L.fstate[f] = (uint8_t)((st & ~(3u << (2 * c))) | (1u << (2 * c)));
-              sl_vclear<SM>(L.vflag, u, VF_END);
-              sl_vclear<SM>(L.vflag, v, VF_END);
-              atomicOr(&sh.progress, 1u);
-            }
-            continue;
-          }
-          const bool rm_is_u = (rm == u);
-          const bool hr = rm_is_u ? hu : hv;
-          const uint32_t rf = rm_is_u ? fu : fv;
-          const uint32_t r0 = rm_is_u ? au[0] : av[0], r1 = rm_is_u ? au[1] : av[1], r2 = rm_is_u ? au[2] : av[2];
-          // faces of rm: those that also hold k die, the others get k in rm's corner
-          const bool dies = hr && (r0 == k || r1 == k || r2 == k);
-          if (hr) {
-            if (dies) L.fstate[rf] = (uint8_t)(L.fstate[rf] & 0x7Fu);
-            else sl_fset<SM>(L, rf, r0 == rm ? 0 : (r1 == rm ? 1 : 2), k);
-          }
-          const uint32_t dead = __popc(__ballot_sync(FULL, dies));
-          // the new ring of k: parked edges around it may be valid now
-          if (hu && x1 != v && x2 != v) { sl_vor<SM>(L.vflag, x1, VF_RDIRTY); sl_vor<SM>(L.vflag, x2, VF_RDIRTY); }
-          if (hv && y1 != u && y2 != u) { sl_vor<SM>(L.vflag, y1, VF_RDIRTY); sl_vor<SM>(L.vflag, y2, VF_RDIRTY); }
-          if (lane < 10) Qk[lane] = qk + qr;
-          if (lane >= 16 && lane < 19) A.pos[3 * (uint64_t)(L.vbase + k) + (lane - 16)] = sh.wbest[3 * slot + (lane - 16)];
-          if (lane == 0) {
-            sl_vor<SM>(L.vflag, k, VF_CDIRTY | VF_RDIRTY);  // k moved: cached costs of its edges are stale
-            sl_vclear<SM>(L.vflag, k, VF_END);
-            sl_vclear<SM>(L.vflag, rm, 0xFFu);
-            atomicSub(&sh.alive, dead);
-            atomicAdd(&sh.ncol, 1u);
-            atomicOr(&sh.progress, 1u);
-          }
-        }
+      // E2c: link condition by ballots / shuffles over the ring lists (a lane holds one ring face of
+      // each endpoint), then the collapse itself.  Winners whose rings have at most 16 faces (almost
+      // all) are handled by HALF warps, two winners per warp at a time: the pass is a chain of
+      // dependent shared-memory accesses per winner, so its duration is the number of winners a warp
+      // handles one after the other.  The few winners with larger rings take a second pass with
+      // whole warps.
+      sl_collapse_pass<SM, 16>(A, L, sh, nb);
+      __syncthreads();
+      if (sh.nbig) {
+        sl_collapse_pass<SM, 32>(A, L, sh, nb);
       }
       __syncthreads();
       SL_MARK(8);
@@ -986,6 +1025,7 @@ extern __shared__ __align__(16) unsigned char sl_smem[];
 __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
   __shared__ SlShared sh;
   do {
+    __syncthreads();  // (persistent mode) the previous label is completely written back; sh.work may be reused
     if (threadIdx.x == 0) sh.work = atomicAdd(&A.counters[0], 1u);
     __syncthreads();
     const uint32_t wi = sh.work;
@@ -994,7 +1034,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
     const uint32_t tbase = A.tri_off[l], T = A.tri_off[l + 1] - tbase;
     const uint32_t vbase = A.vert_off[l], U = A.vert_off[l + 1] - vbase;
     const uint32_t target = A.target[l];
-    if (T == 0 || T <= target) break;  // init left every face / vertex alive
+    if (T == 0 || T <= target) continue;  // init left every face / vertex alive
     // shared-memory layout: cost queues | ring lists | key1 | faces SoA | face list | face state | vertex flags
     const size_t wq_bytes = (size_t)(SL_THREADS / 32) * SL_EQ * 4;
     const size_t ring_sm = (size_t)SL_WCAP * 2 * S_MAXV * 2, ring_gl = (size_t)SL_WCAP * 2 * S_MAXV * 4;
@@ -1054,7 +1094,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_simp_labels(SlArgs A) {
       }
       sl_run<false>(A, L, sh);
     }
-  } while (false);
+  } while (A.persist);
 }
 
 __global__ void __launch_bounds__(256)
@@ -1284,7 +1324,13 @@ extern "C" int ign_mesh_simplify(ign_mesher* m, const float resolution[3], int r
   A.smem_bytes = (force_gmem && force_gmem[0] == '1') ? sl_fixed : (uint32_t)sl_dyn;
   {
     const int slot = prof_begin(ctx, IGN_PROF_SIMP);
-    k_simp_labels<<<(unsigned)K, sl_threads, sl_dyn, ctx->stream>>>(A);
+    // default: one CTA per label (SMs are handed back to the block scheduler after every label, so
+    // higher-priority streams get them quickly); IGN_SIMP_PERSIST=1: one CTA per SM slot loops over labels
+    const char* pe = getenv("IGN_SIMP_PERSIST");
+    A.persist = (pe && pe[0] == '1') ? 1 : 0;
+    const uint64_t slots = (uint64_t)ctx->sm_count * sl_ctas;
+    const unsigned grid = A.persist ? (unsigned)(K < slots ? K : slots) : (unsigned)K;
+    k_simp_labels<<<grid, sl_threads, sl_dyn, ctx->stream>>>(A);
     ctx->launches++;
     prof_end(ctx, slot);
     S_CUDA(cudaGetLastError());
