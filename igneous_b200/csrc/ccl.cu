@@ -977,14 +977,22 @@ static int ccl_structure(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, ui
     const cuuint64_t gstr[2] = {(cuuint64_t)sx * es, (cuuint64_t)sx * sy * es};
     const cuuint32_t box[3] = {(cuuint32_t)MT::PITCH, MT_BY + 1, (cuuint32_t)MT::BZ + 1};
     const cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char* e = getenv("IGN_CCL_L2PROMO")) promo = atoi(e) == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (atoi(e) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (atoi(e) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo));
     const CUresult r = enc(&tmap, tmap_dtype<T>(), 3, (void*)rd.in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IGN_REQUIRE(r == CUDA_SUCCESS, IGN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %ux%ux%u", (int)r, sx, sy, sz);
   }
   {
     const size_t smem = (use_tma ? 2 : 1) * MT::BYTES;
-    const unsigned per_sm = (unsigned)(200 * 1024 / (smem + 1024)) < 8u ? (unsigned)(200 * 1024 / (smem + 1024)) : 8u;
+    unsigned per_sm = (unsigned)(200 * 1024 / (smem + 1024)) < 8u ? (unsigned)(200 * 1024 / (smem + 1024)) : 8u;
+    // Rows of 16 or more tiles (2048 voxels): one CTA per SM.  With two, the halo rows / planes that
+    // neighbouring tiles re-read fall out of L2 (ncu at 2048^3: 57 GB of DRAM reads for a 34 GB volume,
+    // L2 hit rate 5.5 %, against 1.10x and 23 % at 1024^3); measured 13.7 vs 16.3 ms at 2048^3 and
+    // 1.59 vs 1.27 ms at 1024^3, hence the switch.  IGN_CCL_MASK_CTAS overrides it.
+    if (ma.ntx >= 16) per_sm = 1;
+    if (const char* e = getenv("IGN_CCL_MASK_CTAS")) per_sm = (unsigned)atoi(e) ? (unsigned)atoi(e) : per_sm;
     const uint64_t cap = (uint64_t)ctx->sm_count * (per_sm ? per_sm : 1);
     const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
     IGN_CUDA(cudaMemsetAsync(p.S + W, 0, 8, ctx->stream));  // sentinel words S[W], S[W+1]

@@ -217,7 +217,10 @@ class VolumePipeline:
     sx, sy, sz = self.shape
     es = self.dtype.itemsize
     mz = self.mesh_shape[2]
-    n_layers = -(-sz // mz)
+    # upload granularity: a quarter of the mesh task height -- a task needs its own planes and ONE plane
+    # of the layer above, so it can start after 5 quarter-layers instead of 2 whole layers
+    lz = max(1, mz // 4)
+    n_layers = -(-sz // lz)
     cond = threading.Condition()
     state = {"ready": 0, "error": None}
 
@@ -225,7 +228,8 @@ class VolumePipeline:
       return 16 + k % 48
 
     def wait_for(task):
-      need = min(n_layers, task[2] // mz + 2)
+      top = min(sz, task[2] + task[5])          # first plane the task does not read (2x2x1 pooling keeps z)
+      need = min(n_layers, -(-top // lz))
       with cond:
         cond.wait_for(lambda: state["ready"] >= need or state["error"] is not None)
         if state["error"] is not None:
@@ -256,7 +260,7 @@ class VolumePipeline:
       if trace:
         self.ctx.timer_start(10)
       for k in range(n_layers):
-        z0, z1 = k * mz, min(sz, (k + 1) * mz)
+        z0, z1 = k * lz, min(sz, (k + 1) * lz)
         off = z0 * sx * sy * es
         _shim.check(self.lib.ign_h2d(self.ctx.handle, c.c_void_p(self.d_in.ptr + off),
                                      c.c_void_p(src + off), _u64((z1 - z0) * sx * sy * es)))
