@@ -643,9 +643,9 @@ def main():
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures (profiles/)
 NCU_TRAFFIC = {
   # dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full captures (profiles/)
-  "simp_labels": {"bytes_per_launch": 9.512e9, "source": "profiles/r02_simp_labels_v5_full_summary.txt (one 257^3 MeshTask at mip 2)"},
-  "ccl_local": {"bytes_per_launch": 5.268e9, "source": "profiles/r02_k_ccl_masks_v2_full_summary.txt (1024^3 u32; scales with voxels)"},
-  "ccl_label": {"bytes_per_launch": 4.733e9, "source": "profiles/r02_trip3_k_ccl_expand4_v1_full_summary.txt (1024^3 u32)"},
+  "simp_labels": {"bytes_per_launch": 3.926e9, "source": "profiles/r02_simp_labels_v8_full_summary.txt (one 257^3 MeshTask at mip 2)"},
+  "ccl_local": {"bytes_per_launch": 6.517e10, "source": "profiles/r02_ccl2048_metrics.csv (2048^3 u32, two CTAs per SM; 1024^3: 5.27e9)"},
+  "ccl_label": {"bytes_per_launch": 3.826e10, "source": "profiles/r02_ccl2048_metrics.csv (2048^3 u32)"},
 }
 
 
