@@ -164,6 +164,7 @@ struct MaskArgs {
   uint32_t sx, sy, sz, wpr;
   uint32_t ntx, nty, ntz, nby, nbz;  // tiles per axis; 8x8 blocks of (y,z) tile columns
   uint32_t ncols;                    // padded number of (y,z) columns = nby*nbz*64
+  uint32_t pair;                     // 1: a CTA takes x-adjacent tile PAIRS and writes whole 32-byte mask sectors
   uint32_t *S, *Z, *Ey, *Ez;
 };
 
@@ -179,7 +180,7 @@ __device__ __forceinline__ bool mask_tile_coords(const MaskArgs& a, uint64_t t, 
   return *ty < a.nty && *tz < a.ntz;
 }
 
-template <typename T, bool THR, bool TMA>
+template <typename T, bool THR, bool TMA, bool PAIR>
 __global__ void __launch_bounds__(MT_THREADS)
     k_ccl_masks(const __grid_constant__ CUtensorMap tmap, const Reader<T, THR> rd, const MaskArgs a) {
   using MT = MaskTile<T>;
@@ -191,12 +192,27 @@ __global__ void __launch_bounds__(MT_THREADS)
   const bool transform = THR || rd.has_rails();
 
   uint32_t tx = 0, ty = 0, tz = 0;
-  auto advance = [&](uint64_t from) {  // first valid tile index >= from in this CTA's stride class
-    uint64_t q = from;
-    while (q < ntiles && !mask_tile_coords(a, q, &tx, &ty, &tz)) q += gridDim.x;
+  // Tile sequence of this CTA.  Unpaired: tiles blockIdx, blockIdx + grid, ... (padding columns are
+  // skipped).  Paired: the same over PAIRS of x-adjacent tiles (2p, 2p + 1), first the even one.
+  auto first_from = [&](uint64_t unit) {  // first valid unit >= `unit` in this CTA's stride class -> tile id
+    const uint64_t step = PAIR ? 2 : 1;
+    uint64_t q = unit * step;
+    while (q < ntiles && !mask_tile_coords(a, q, &tx, &ty, &tz)) q += gridDim.x * step;
     return q;
   };
-  uint64_t t = advance(blockIdx.x);
+  auto advance = [&](uint64_t cur) -> uint64_t {  // tile after `cur` (sets tx / ty / tz)
+    if (PAIR) {
+      if (!(cur & 1u)) {
+        mask_tile_coords(a, cur + 1, &tx, &ty, &tz);  // same column as its partner: valid
+        return cur + 1;
+      }
+      return first_from((cur >> 1) + gridDim.x);
+    }
+    return first_from(cur + gridDim.x);
+  };
+  // masks of the even tile of a pair wait here for the odd one: [warp][row][S, Z, Ey, Ez]
+  __shared__ uint4 stash[PAIR ? MT_THREADS / 32 : 1][PAIR ? MT_BY : 1][4];
+  uint64_t t = first_from(blockIdx.x);
   if constexpr (TMA) {
     if (tid == 0) {
       mbar_init(&bars[0], 1);
@@ -214,7 +230,7 @@ __global__ void __launch_bounds__(MT_THREADS)
     const uint32_t cur = TMA ? (it & 1u) : 0u;  // the cooperative fill is synchronous: one buffer
     const uint32_t x0 = tx * MT_BX, y0 = ty * MT_BY, z0 = tz * MT::BZ;
     // next tile of this CTA (its coordinates replace tx/ty/tz from here on)
-    const uint64_t tn = advance(t + gridDim.x);
+    const uint64_t tn = advance(t);
     T* tile = (T*)(mt_smem + (size_t)cur * MT::BYTES);
     if constexpr (TMA) {
       if (tid == 0 && tn < ntiles) {  // the other buffer was released by the barrier that ended the previous iteration
@@ -286,7 +302,9 @@ __global__ void __launch_bounds__(MT_THREADS)
         const uint32_t gy = y0 + ry0 + k;
         if (lane == 0 && gz < a.sz && gy < a.sy) {
           const uint64_t wi = ((uint64_t)gz * a.sy + gy) * a.wpr + w0;
-          if (vec_ok) {
+          if (PAIR) {
+            // (handled below by lanes 0 and 1 together)
+          } else if (vec_ok) {
             static_assert(NXW == 4, "vector stores cover 4 words");
             *(uint4*)(a.S + wi) = make_uint4(bS[0], bS[1], bS[2], bS[3]);
             *(uint4*)(a.Z + wi) = make_uint4(bZ[0], bZ[1], bZ[2], bZ[3]);
@@ -298,6 +316,26 @@ __global__ void __launch_bounds__(MT_THREADS)
               if (w0 + xw < a.wpr) {
                 a.S[wi + xw] = bS[xw]; a.Z[wi + xw] = bZ[xw]; a.Ey[wi + xw] = bY[xw]; a.Ez[wi + xw] = bB[xw];
               }
+          }
+        }
+        if (PAIR) {
+          // A 128-voxel tile yields 16 bytes per mask and row: half a 32-byte sector.  Written alone,
+          // the half sectors were evicted from L2 before the x-neighbour's half arrived (2048^3:
+          // 7.9 GB of DRAM writes for 4.3 GB of masks plus the fills).  The even tile parks its words
+          // in shared memory; with the odd tile lanes 0 / 1 store both halves in one instruction.
+          const bool rowok = gz < a.sz && gy < a.sy;
+          const uint4 cS = make_uint4(bS[0], bS[1], bS[2], bS[3]), cZ = make_uint4(bZ[0], bZ[1], bZ[2], bZ[3]);
+          const uint4 cY = make_uint4(bY[0], bY[1], bY[2], bY[3]), cB = make_uint4(bB[0], bB[1], bB[2], bB[3]);
+          if (!(t & 1u)) {
+            if (lane == 0) {
+              stash[warp][k][0] = cS; stash[warp][k][1] = cZ; stash[warp][k][2] = cY; stash[warp][k][3] = cB;
+            }
+          } else if (lane < 2 && rowok) {
+            const uint64_t wi = ((uint64_t)gz * a.sy + gy) * a.wpr + w0 - 4u + 4u * lane;  // lane 0: the even tile's words
+            *(uint4*)(a.S + wi) = lane ? cS : stash[warp][k][0];
+            *(uint4*)(a.Z + wi) = lane ? cZ : stash[warp][k][1];
+            *(uint4*)(a.Ey + wi) = lane ? cY : stash[warp][k][2];
+            *(uint4*)(a.Ez + wi) = lane ? cB : stash[warp][k][3];
           }
         }
       }
@@ -965,6 +1003,10 @@ static int ccl_structure(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, ui
   ma.nbz = (ma.ntz + 7) / 8;
   ma.ncols = ma.nby * ma.nbz * 64;
   ma.S = p.S; ma.Z = p.Z; ma.Ey = p.Ey; ma.Ez = p.Ez;
+  // whole-sector mask writes pay off where L2 no longer merges the half sectors of x-neighbours: rows of
+  // 16+ tiles (measured at 2048^3: 12.7 vs 16.3 ms; at 1024^3 the unpaired kernel is faster, 1.27 vs 1.60 ms)
+  ma.pair = (p.wpr % 8 == 0 && sx % MT_BX == 0 && ma.ntx >= 16) ? 1u : 0u;
+  if (const char* e = getenv("IGN_CCL_PAIR")) ma.pair = (atoi(e) != 0 && p.wpr % 8 == 0 && sx % MT_BX == 0) ? 1u : 0u;
   const uint64_t ntiles = (uint64_t)ma.ntx * ma.ncols;
   const size_t es = sizeof(T);
   CUtensorMap tmap;
@@ -987,21 +1029,22 @@ static int ccl_structure(ign_ctx* ctx, const R& rd, uint32_t sx, uint32_t sy, ui
   {
     const size_t smem = (use_tma ? 2 : 1) * MT::BYTES;
     unsigned per_sm = (unsigned)(200 * 1024 / (smem + 1024)) < 8u ? (unsigned)(200 * 1024 / (smem + 1024)) : 8u;
-    // Rows of 16 or more tiles (2048 voxels): one CTA per SM.  With two, the halo rows / planes that
-    // neighbouring tiles re-read fall out of L2 (ncu at 2048^3: 57 GB of DRAM reads for a 34 GB volume,
-    // L2 hit rate 5.5 %, against 1.10x and 23 % at 1024^3); measured 13.7 vs 16.3 ms at 2048^3 and
-    // 1.59 vs 1.27 ms at 1024^3, hence the switch.  IGN_CCL_MASK_CTAS overrides it.
-    if (ma.ntx >= 16) per_sm = 1;
     if (const char* e = getenv("IGN_CCL_MASK_CTAS")) per_sm = (unsigned)atoi(e) ? (unsigned)atoi(e) : per_sm;
     const uint64_t cap = (uint64_t)ctx->sm_count * (per_sm ? per_sm : 1);
-    const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+    const uint64_t units = ma.pair ? ntiles / 2 : ntiles;  // tile pairs when the CTAs write whole mask sectors
+    const unsigned grid = (unsigned)(units < cap ? units : cap);
     IGN_CUDA(cudaMemsetAsync(p.S + W, 0, 8, ctx->stream));  // sentinel words S[W], S[W+1]
+    auto launch = [&](auto kern) -> int {
+      IGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, kern, grid, MT_THREADS, smem, tmap, rd, ma);
+      return IGN_OK;
+    };
     if (use_tma) {
-      IGN_CUDA(cudaFuncSetAttribute(k_ccl_masks<T, R::thresholded, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_masks<T, R::thresholded, true>), grid, MT_THREADS, smem, tmap, rd, ma);
+      if (ma.pair) IGN_TRY(launch(k_ccl_masks<T, R::thresholded, true, true>));
+      else IGN_TRY(launch(k_ccl_masks<T, R::thresholded, true, false>));
     } else {
-      IGN_CUDA(cudaFuncSetAttribute(k_ccl_masks<T, R::thresholded, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      IGN_LAUNCH_PROF(ctx, IGN_PROF_CCL_LOCAL, (k_ccl_masks<T, R::thresholded, false>), grid, MT_THREADS, smem, tmap, rd, ma);
+      if (ma.pair) IGN_TRY(launch(k_ccl_masks<T, R::thresholded, false, true>));
+      else IGN_TRY(launch(k_ccl_masks<T, R::thresholded, false, false>));
     }
   }
   // ---- run ids: exclusive scan of popc(S) over W+1 words (rbase[W] = number of runs)

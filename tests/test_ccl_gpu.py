@@ -195,10 +195,13 @@ def test_ccl_tma_and_cooperative_fill_match_oracle(ctx, oracle, monkeypatch, dty
     v = np.asfortranarray(v)
     want, wn = oracle.connected_components(v, return_N=True)
     for no_tma in (False, True):
-      if no_tma:
-        monkeypatch.setenv("IGN_CCL_NO_TMA", "1")
-      else:
-        monkeypatch.delenv("IGN_CCL_NO_TMA", raising=False)
-      got, n = cc3d.connected_components(v, connectivity=6, out_dtype=np.uint64, return_N=True)
-      assert n == wn and np.array_equal(got, want), (v.shape, no_tma)
+      for pair in ("0", "1"):  # 1: x-adjacent tile pairs with whole-sector mask writes (the default for 2048+ voxel rows)
+        if no_tma:
+          monkeypatch.setenv("IGN_CCL_NO_TMA", "1")
+        else:
+          monkeypatch.delenv("IGN_CCL_NO_TMA", raising=False)
+        monkeypatch.setenv("IGN_CCL_PAIR", pair)
+        got, n = cc3d.connected_components(v, connectivity=6, out_dtype=np.uint64, return_N=True)
+        assert n == wn and np.array_equal(got, want), (v.shape, no_tma, pair)
   monkeypatch.delenv("IGN_CCL_NO_TMA", raising=False)
+  monkeypatch.delenv("IGN_CCL_PAIR", raising=False)
