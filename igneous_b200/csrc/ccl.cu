@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(MT_THREADS)
 // ------------------------------------------------------------------ pass B
 constexpr int TB_WMAX = 4096;   // words of a tile (all words of TY x TZ rows)
 constexpr int TB_RCAP = 8192;   // runs of a tile resolved in shared memory
-constexpr int TB_THREADS = 512;
+constexpr int TB_THREADS = 1024;
 constexpr int TB_QCAP = 128;    // per-warp queue of union tasks (4 per lane per round)
 constexpr uint32_t TB_GFLAG = 0x80000000u;
 
