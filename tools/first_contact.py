@@ -123,6 +123,27 @@ def probe_zmesh(zmesh, O, out, report):
   return report["zmesh"]["canonical_mesh_equals_oracle"] and report["zmesh"]["outward_winding"]
 
 
+def probe_cseg(cseg, O, out, report):
+  """compressed_segmentation wheel: is the oracle's (and therefore the device codec's) byte stream the
+  one the wheel writes, and does each side decode the other's stream?"""
+  rng = np.random.default_rng(3)
+  vols = {"u32": np.asfortranarray(rng.integers(0, 6, size=(40, 33, 17)).astype(np.uint32)),
+          "u64": np.asfortranarray((rng.integers(0, 9, size=(16, 16, 16)).astype(np.uint64) << np.uint64(33)))}
+  res = {}
+  ok = True
+  for name, v in vols.items():
+    theirs = bytes(cseg.compress(v, block_size=(8, 8, 8), order="F"))
+    mine = O.cseg_encode(v[..., np.newaxis], (8, 8, 8)).tobytes()
+    back = np.asarray(cseg.decompress(mine, v.shape, dtype=v.dtype, block_size=(8, 8, 8), order="F")).reshape(v.shape)
+    mine_back = O.cseg_decode(np.frombuffer(theirs, dtype=np.uint32), v.shape + (1,), v.dtype, (8, 8, 8))[..., 0]
+    res[name] = {"bytes_identical": theirs == mine, "wheel_decodes_ours": bool(np.array_equal(back, v)),
+                 "we_decode_wheel": bool(np.array_equal(mine_back, v))}
+    ok = ok and res[name]["wheel_decodes_ours"] and res[name]["we_decode_wheel"]
+    np.savez_compressed(os.path.join(out, "upstream_cseg_%s.npz" % name), vol=v, stream=np.frombuffer(theirs, dtype=np.uint8))
+  report["compressed_segmentation"] = res
+  return ok
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
@@ -130,7 +151,7 @@ def main():
   os.makedirs(args.out, exist_ok=True)
   from oracle import oracle as O
   O.build()
-  mods = {n: try_import(n) for n in ("tinybrain", "cc3d", "zmesh", "fastremap")}
+  mods = {n: try_import(n) for n in ("tinybrain", "cc3d", "zmesh", "fastremap", "compressed_segmentation")}
   report = {"wheels": {n: (getattr(m, "__version__", "present") if m else None) for n, m in mods.items()}}
   verdicts = {}
   if mods["tinybrain"]:
@@ -140,9 +161,11 @@ def main():
     verdicts["cc3d"] = probe_cc3d(mods["cc3d"], mods["fastremap"], O, args.out, report)
   if mods["zmesh"]:
     verdicts["zmesh"] = probe_zmesh(mods["zmesh"], O, args.out, report)
+  if mods["compressed_segmentation"]:
+    verdicts["compressed_segmentation"] = probe_cseg(mods["compressed_segmentation"], O, args.out, report)
   report["agrees_with_frozen_defaults"] = verdicts
   report["not_run"] = [k for k, n in (("averaging", "tinybrain"), ("mode", "tinybrain"), ("cc3d", "cc3d"),
-                                      ("zmesh", "zmesh")) if not mods[n]]
+                                      ("zmesh", "zmesh"), ("compressed_segmentation", "compressed_segmentation")) if not mods[n]]
   with open(os.path.join(args.out, "first_contact_report.json"), "w") as f:
     json.dump(report, f, indent=1)
   print(json.dumps(report, indent=1))
