@@ -11,20 +11,22 @@
 //           merged and compacted on collapse).
 //   round   E  every edge of a label still above its face target computes the cheap
 //              quadric cost (min over {u, v, midpoint} of p^T (Qu+Qv) p) and, if
-//              cost <= max_error^2, posts a (float cost, hashed label-local
-//              half-edge id) key to both endpoints (atomicMin);
-//           K2 per vertex: minimum key over its 1-ring;
-//           C  an edge WINS iff its key is the minimum of both endpoints'
-//              rings -> winners never touch each other's faces or vertices
-//              and are processed concurrently: a winner collapses iff the
-//              link condition holds and no incident face flips, otherwise it
-//              is parked until one of its endpoints' rings changes.
+//              cost <= max_error^2, posts a (cost, per-round hash of the label-local
+//              half-edge id) key to both endpoints (atomic min); labels with at most
+//              65536 half-edges use a 32-bit key (16 cost bits | 16-bit id permutation);
+//           K2 per vertex: is its key the minimum over its face neighbours' keys?
+//           C  an edge WINS iff its key is the minimum of both endpoints' keys and of
+//              all their neighbours' -> winners are two edges apart, never touch each
+//              other's faces or vertices and are processed concurrently: a winner
+//              collapses iff the link condition holds and no incident face flips,
+//              otherwise it is parked until one of its endpoints' rings changes.
 //   stop    per label: faces <= target, or a round without winners, or four
 //           consecutive rounds that each remove < 0.2% of the label's faces.
 //   compact scans renumber surviving vertices / faces per label.
 //
 // Labels are independent, so all rounds of one label run inside ONE CTA with the
-// label's topology in shared memory (k_simp_labels below).
+// label's topology in shared memory (k_simp_labels below: one launch per MeshTask, one
+// CTA per label).
 //
 // All arithmetic is double precision WITHOUT fused multiply-add (this file is
 // compiled with -fmad=false) so that oracle/igneous_oracle.c::orc_simplify
@@ -226,27 +228,33 @@ __global__ void __launch_bounds__(256) k_simp_boundary(Simp s) {
 // One CTA owns one label for ALL of its rounds (labels are independent: keys use
 // label-local half-edge ids and the stop rules are per label).  The topology of the
 // label -- faces as label-local vertex ids (u16 SoA), one state byte per face (alive bit
-// + a 2-bit memo per half-edge), one flag byte per vertex, the 64-bit round keys and the
-// ring lists of the round's winners -- lives in SHARED MEMORY for the whole run; only the
-// double-precision data that a round touches sparsely (positions, quadrics, cached float
-// costs) stays in global memory (L2).  A round is a handful of __syncthreads() phases
-// instead of five launches and a host round trip:
+// + a 2-bit memo per half-edge), a flag byte and a "lose" byte per vertex, the 32-bit round
+// keys and the ring lists of the round's winners -- lives in SHARED MEMORY for the whole
+// run; only the double-precision data that a round touches sparsely (positions, quadrics,
+// cached float costs) stays in global memory (L2).  A round is a handful of
+// __syncthreads() phases instead of five launches and a host round trip:
 //
-//   P1  key1[v] = MAX                                         (vertex parallel)
+//   P1  key1[v] = MAX, lose[v] = 0                             (vertex parallel)
 //   P2  every canonical half-edge (u < v) of an alive face posts its key to both
-//       endpoints with a shared-memory atomicMin; the float cost is memoised until an
-//       endpoint's ring changes (DIRTY)                       (face parallel)
+//       endpoints with a shared-memory min reduction; the float cost is memoised until
+//       an endpoint moves (CDIRTY); dropped memos are re-evaluated by per-warp queues on
+//       dense lanes while other warps keep posting                (face parallel)
 //   P3  a vertex LOSEs if a face neighbour holds a smaller key1 (== key2 test of the
-//       round formulation: key2[w] == key1[w] <=> !LOSE[w])   (face parallel)
+//       round formulation: key2[w] == key1[w] <=> !LOSE[w]); plain byte stores
+//                                                               (face parallel)
 //   P4  a vertex a WINs iff its key's half-edge starts at a, both endpoints hold that
-//       key and neither LOSEs                                 (vertex parallel)
+//       key and neither LOSEs; at most SL_WCAP winners per pass  (vertex parallel)
 //   E1  the faces that touch a winner's endpoints append themselves to the winner's
-//       two ring lists                                        (face parallel)
-//   E2  one WARP per winner: link condition by ballots / shuffles over the ring lists,
-//       one face flip test per lane, then the collapse itself  (warp parallel)
+//       two ring lists; the first warps compute the winners' placement and cost (E2a)
+//       at the same time                                         (face parallel)
+//   E2b one flip test per (winner, side, ring face)              (item parallel)
+//   E2c link condition by ballots / shuffles over the ring lists and the collapse
+//       itself, one HALF warp per winner (whole warps for rings over 16 faces)
 //
-// Labels that do not fit (or have more than 65535 faces / vertices) run the same code
-// on the whole-task arrays in global memory (SM = false).
+// Labels that do not fit (more than 16384 faces, or 6U + 9T + 28 KB over the CTA's shared
+// memory) keep faces and lists in global memory, with keys / flags / states still in
+// shared memory when those fit ("hybrid"), else everything global (SM = false, 64-bit
+// key slots).
 // vertex flags: CDIRTY the vertex moved (cached costs of its edges are stale), RDIRTY its ring
 // changed (parked edges around it may be valid now)
 constexpr uint32_t VF_ALIVE = 1, VF_BOUND = 2, VF_CDIRTY = 4, VF_DONE = 16, VF_END = 32, VF_RDIRTY = 64;
