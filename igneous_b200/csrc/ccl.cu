@@ -21,7 +21,9 @@
 //              take a cooperative-load fill of the same tile).  Per 32-voxel
 //              word four ballots: S run starts (v != 0 && v != left), Z non-zero,
 //              Ey / Ez equal to the y-1 / z-1 neighbour.  threshold_image and
-//              blackout_non_face_rails are applied to the staged tile in place.
+//              blackout_non_face_rails are applied to the staged tile in place.  For rows of
+//              2048+ voxels a CTA takes x-adjacent tile PAIRS and stores whole 32-byte mask
+//              sectors (half sectors written apart did not survive in L2 at that size).
 //      scan    exclusive sum of popc(S): the id of the first run starting in each
 //              word.  Run ids therefore follow voxel raster order.
 //   B  tiles   k_ccl_tiles: a CTA owns all words of 8 x 8 rows; the runs of the tile
